@@ -1,0 +1,85 @@
+"""ctypes binding of libbm_b200.so (include/bm_b200.h).  There is no fallback: if the CUDA library is missing
+or a call fails, this raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbm_b200.so")
+
+P, I, L, F = c_void_p, c_int, c_longlong, c_float
+
+# name -> argtypes, in the order of include/bm_b200.h
+SIGNATURES = {
+    "bm_attention_weights_fwd": [P, P, P, P, F, I, I, I, I, P, P, P],
+    "bm_attention_weights_bwd": [P, P, P, I, I, I, I, P, P, P],
+    "bm_sensor_chain_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P],
+    "bm_sensor_chain_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
+    "bm_conv_weight_prep": [P, I, I, I, P, P, P],
+    "bm_conv1d_fwd": [P, P, P, I, I, I, I, I, I, P, P, P],
+    "bm_bn_stats_finalize": [P, L, F, F, P, P, P, P, I, P],
+    "bm_bn_eval_stats": [P, P, F, P, P, I, P],
+    "bm_bn_gelu_skip_fwd": [P, P, P, P, P, P, P, L, I, P],
+    "bm_bn_gelu_skip_bwd": [P, P, P, P, P, P, I, L, I, P, P, P, P, P],
+    "bm_conv1d_bwd_data": [P, P, P, I, I, I, I, I, I, P, P],
+    "bm_conv1d_bwd_weight": [P, P, I, I, I, I, I, I, P, P, P],
+    "bm_conv1d_glu_fwd": [P, P, P, I, I, I, I, I, P, P, P],
+    "bm_glu_bwd": [P, P, L, I, P, P],
+    "bm_head_fwd": [P, P, P, P, P, I, I, I, I, P, P, P, P],
+    "bm_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
+    "bm_clip_scores": [P, P, I, I, L, P, P, P, P, P],
+    "bm_clip_loss_fwd": [P, P, I, I, L, I, P, P, P, P, P, P, P],
+    "bm_clip_loss_bwd": [P, P, P, P, I, I, L, I, P, P, P],
+}
+
+_lib = None
+
+
+class BmB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library (once).  Raises if it has not been built: there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise BmB200Error(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). brainmagick_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.bm_last_error.restype = ctypes.c_char_p
+    lib.bm_last_error.argtypes = []
+    lib.bm_abi_version.restype = c_int
+    lib.bm_abi_version.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, "brainmagick_b200 kernels need CUDA tensors (no CPU fallback)"
+    assert t.is_contiguous(), "non-contiguous tensor handed to the C ABI"
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise BmB200Error(f"{name} failed (code {rc}): {lib.bm_last_error().decode()}")

@@ -1,0 +1,482 @@
+// C-ABI entry points of libbm_b200.so (see include/bm_b200.h for the contract and the reference citations).
+#include "../../include/bm_b200.h"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm_simt.cuh"
+
+namespace bm {
+thread_local char g_last_error[512] = "";
+}
+using namespace bm;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" const char* bm_last_error(void) { return bm::g_last_error; }
+extern "C" int bm_abi_version(void) { return 1; }
+
+namespace {
+
+// number of z-chunks so that a reduction GEMM with `tiles` output tiles fills the machine ~2x
+inline int pick_chunks(int Z, int tiles) {
+    int want = (2 * num_sms() + tiles - 1) / tiles;
+    if (want < 1) want = 1;
+    if (want > Z) want = Z;
+    return want;
+}
+inline int tiles_of(int M, int N) { return ((M + GBM - 1) / GBM) * ((N + GBN - 1) / GBN); }
+
+}  // namespace
+
+// =================================================================================================
+// K1
+// =================================================================================================
+extern "C" int bm_attention_weights_fwd(const float* positions, const float* freq, const float* heads,
+                                        const float* ban_centre, float radius, int R, int C, int O, int P,
+                                        float* emb, float* weights, bm_stream_t stream) {
+    BM_CHECK_ARG(positions && freq && heads && emb && weights);
+    BM_CHECK_ARG(R > 0 && C > 0 && O > 0 && P > 0 && P % 2 == 0);
+    int n = 0;
+    while ((n + 1) * (n + 1) * 2 <= P) ++n;
+    BM_CHECK_ARG(n * n * 2 == P);
+    cudaStream_t st = ST(stream);
+    fourier_emb_kernel<<<ew_grid((long long)R * C * n * n), 256, 0, st>>>(positions, freq, 0.2f, R * C, n, emb);
+    BM_CHECK_LAUNCH();
+    // scores[r][o][c] = <emb[r][c][:], heads[o][:]>
+    GemmP g = gemm_defaults();
+    g.M = C; g.N = O; g.K = P;
+    g.Z = R; g.nseg = R; g.zchunk = 1; g.kchunk = P;
+    g.A = emb; g.lda_z = (long long)C * P; g.lda_m = P; g.lda_k = 1; g.a_mcontig = 0;
+    g.B = heads; g.ldb_z = 0; g.ldb_n = P; g.ldb_k = 1; g.b_ncontig = 0;
+    g.D = weights; g.ldd_z = (long long)O * C; g.ldd_m = 1; g.ldd_n = C;
+    BM_CUDA(launch_gemm(g, st));
+    int rows = R * O;
+    masked_softmax_kernel<<<(rows + 7) / 8, 256, 0, st>>>(weights, positions, ban_centre, radius, -0.1f, R, O, C);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_attention_weights_bwd(const float* dweights, const float* weights, const float* emb, int R,
+                                        int C, int O, int P, float* dscores, float* dheads, bm_stream_t stream) {
+    BM_CHECK_ARG(dweights && weights && emb && dscores && dheads);
+    cudaStream_t st = ST(stream);
+    int rows = R * O;
+    softmax_bwd_kernel<<<(rows + 7) / 8, 256, 0, st>>>(weights, dweights, dscores, rows, C);
+    BM_CHECK_LAUNCH();
+    // dheads[o][p] = sum_{r,c} ds[r][o][c] emb[r][c][p]
+    BM_CUDA(cudaMemsetAsync(dheads, 0, sizeof(float) * O * P, st));
+    GemmP g = gemm_defaults();
+    g.M = O; g.N = P; g.K = C; g.kchunk = C;
+    g.Z = R; g.zchunk = 1; g.nseg = R;
+    g.A = dscores; g.lda_z = (long long)O * C; g.lda_m = C; g.lda_k = 1; g.a_mcontig = 0;
+    g.B = emb; g.ldb_z = (long long)C * P; g.ldb_n = 1; g.ldb_k = P; g.b_ncontig = 1;
+    g.D = dheads; g.ldd_z = 0; g.ldd_m = P; g.ldd_n = 1; g.atomic = 1;
+    BM_CUDA(launch_gemm(g, st));
+    return 0;
+}
+
+// =================================================================================================
+// K2
+// =================================================================================================
+extern "C" int bm_sensor_chain_fwd(const float* meg, const float* weights, const int* rec_of_sample,
+                                   const float* il_w, const float* il_b, const float* subj_w, const int* subject,
+                                   int B, int C, int T, int O, int IL, int D, float* u, float* v, float* x0,
+                                   bm_stream_t stream) {
+    BM_CHECK_ARG(meg && weights && rec_of_sample && il_w && il_b && subj_w && subject && u && v && x0);
+    cudaStream_t st = ST(stream);
+    {   // u[b][t][o] = sum_c meg[b][c][t] w[rec_b][o][c]
+        GemmP g = gemm_defaults();
+        g.M = T; g.N = O; g.K = C; g.kchunk = C;
+        g.Z = B; g.nseg = B; g.zchunk = 1;
+        g.A = meg; g.lda_z = (long long)C * T; g.lda_m = 1; g.lda_k = T; g.a_mcontig = 1;
+        g.B = weights; g.bsel = rec_of_sample; g.ldb_z = (long long)O * C; g.ldb_n = C; g.ldb_k = 1; g.b_ncontig = 0;
+        g.D = u; g.ldd_z = (long long)T * O; g.ldd_m = O; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // v[row][p] = il_b[p] + sum_o u[row][o] il_w[p][o]
+        GemmP g = gemm_defaults();
+        g.M = B * T; g.N = IL; g.K = O; g.kchunk = O;
+        g.A = u; g.lda_m = O; g.lda_k = 1;
+        g.B = il_w; g.ldb_n = O; g.ldb_k = 1;
+        g.D = v; g.ldd_m = IL; g.ldd_n = 1;
+        g.bias = il_b;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // x0[b][t][d] = sum_p v[b][t][p] M[s_b][p][d]
+        GemmP g = gemm_defaults();
+        g.M = T; g.N = D; g.K = IL; g.kchunk = IL;
+        g.Z = B; g.nseg = B; g.zchunk = 1;
+        g.A = v; g.lda_z = (long long)T * IL; g.lda_m = IL; g.lda_k = 1;
+        g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = 1; g.ldb_k = D; g.b_ncontig = 1;
+        g.D = x0; g.ldd_z = (long long)T * D; g.ldd_m = D; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    return 0;
+}
+
+extern "C" int bm_sensor_chain_bwd(const float* dx0, const float* meg, const float* il_w, const float* subj_w,
+                                   const int* subject, const float* u, const float* v, const int* subj_order,
+                                   const int* subj_off, const int* rec_order, const int* rec_off, int B, int C,
+                                   int T, int O, int IL, int D, int S, int R, float* dv, float* du,
+                                   float* d_subj_w, float* d_il_w, float* d_il_b, float* d_weights,
+                                   bm_stream_t stream) {
+    BM_CHECK_ARG(dx0 && meg && il_w && subj_w && subject && u && v && subj_order && subj_off && rec_order && rec_off);
+    BM_CHECK_ARG(dv && du && d_subj_w && d_il_w && d_il_b && d_weights);
+    cudaStream_t st = ST(stream);
+    {   // dv[b][t][p] = sum_d g[b][t][d] M[s_b][p][d]
+        GemmP g = gemm_defaults();
+        g.M = T; g.N = IL; g.K = D; g.kchunk = D;
+        g.Z = B; g.nseg = B; g.zchunk = 1;
+        g.A = dx0; g.lda_z = (long long)T * D; g.lda_m = D; g.lda_k = 1;
+        g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = D; g.ldb_k = 1;
+        g.D = dv; g.ldd_z = (long long)T * IL; g.ldd_m = IL; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // dM[s][p][d] = sum_{b in s} sum_t v[b][t][p] g[b][t][d]
+        GemmP g = gemm_defaults();
+        g.M = IL; g.N = D; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = S; g.seg_off = subj_off; g.zlist = subj_order;
+        g.A = v; g.lda_z = (long long)T * IL; g.lda_m = 1; g.lda_k = IL; g.a_mcontig = 1;
+        g.B = dx0; g.ldb_z = (long long)T * D; g.ldb_n = 1; g.ldb_k = D; g.b_ncontig = 1;
+        g.D = d_subj_w; g.ldd_z = (long long)IL * D; g.ldd_m = D; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // d_il_w[p][o] = sum_{b,t} dv[b][t][p] u[b][t][o]
+        BM_CUDA(cudaMemsetAsync(d_il_w, 0, sizeof(float) * IL * O, st));
+        GemmP g = gemm_defaults();
+        g.M = IL; g.N = O; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = pick_chunks(B, tiles_of(IL, O)); g.zchunk = (B + g.nseg - 1) / g.nseg;
+        g.nseg = (B + g.zchunk - 1) / g.zchunk;
+        g.A = dv; g.lda_z = (long long)T * IL; g.lda_m = 1; g.lda_k = IL; g.a_mcontig = 1;
+        g.B = u; g.ldb_z = (long long)T * O; g.ldb_n = 1; g.ldb_k = O; g.b_ncontig = 1;
+        g.D = d_il_w; g.ldd_z = 0; g.ldd_m = O; g.ldd_n = 1; g.atomic = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // d_il_b[p] = sum dv
+        BM_CUDA(cudaMemsetAsync(d_il_b, 0, sizeof(float) * IL, st));
+        long long rows = (long long)B * T;
+        dim3 grid((unsigned)((rows + 255) / 256), (IL + 127) / 128);
+        colsum_cl_kernel<<<grid, 128, 0, st>>>(dv, d_il_b, rows, IL, 256);
+        BM_CHECK_LAUNCH();
+    }
+    {   // du[row][o] = sum_p dv[row][p] il_w[p][o]
+        GemmP g = gemm_defaults();
+        g.M = B * T; g.N = O; g.K = IL; g.kchunk = IL;
+        g.A = dv; g.lda_m = IL; g.lda_k = 1;
+        g.B = il_w; g.ldb_n = 1; g.ldb_k = O; g.b_ncontig = 1;
+        g.D = du; g.ldd_m = O; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // dw[r][o][c] = sum_{b in r} sum_t du[b][t][o] meg[b][c][t]
+        GemmP g = gemm_defaults();
+        g.M = O; g.N = C; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = R; g.seg_off = rec_off; g.zlist = rec_order;
+        g.A = du; g.lda_z = (long long)T * O; g.lda_m = 1; g.lda_k = O; g.a_mcontig = 1;
+        g.B = meg; g.ldb_z = (long long)C * T; g.ldb_n = T; g.ldb_k = 1; g.b_ncontig = 0;
+        g.D = d_weights; g.ldd_z = (long long)O * C; g.ldd_m = C; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    return 0;
+}
+
+// =================================================================================================
+// K3 / K4
+// =================================================================================================
+extern "C" int bm_conv_weight_prep(const float* w, int Cout, int Cin, int Kw, float* wf, float* wb,
+                                   bm_stream_t stream) {
+    BM_CHECK_ARG(w && (wf || wb) && Cout > 0 && Cin > 0 && Kw > 0);
+    weight_prep_kernel<<<ew_grid((long long)Cout * Cin * Kw), 256, 0, ST(stream)>>>(w, wf, wb, Cout, Cin, Kw);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+static int conv_gemm(const float* x, const float* wmat, const float* bias, const float* addend, int B, int T,
+                     int K, int N, int Kw, int dilation, int sign, float* y, double* stats, int glu, float* glu_out,
+                     cudaStream_t st) {
+    BM_CHECK_ARG(Kw >= 1 && Kw <= 3 && (Kw % 2) == 1);
+    GemmP g = gemm_defaults();
+    g.M = T; g.N = N; g.K = K; g.kchunk = K; g.taps = Kw;
+    g.Z = B; g.nseg = B; g.zchunk = 1;
+    g.A = x; g.lda_z = (long long)T * K; g.lda_m = K; g.lda_k = 1;
+    for (int j = 0; j < Kw; ++j) g.a_shift_m[j] = sign * (j - Kw / 2) * dilation;
+    g.B = wmat; g.ldb_z = 0; g.ldb_tap = (long long)K * N; g.ldb_k = N; g.ldb_n = 1; g.b_ncontig = 1;
+    g.D = y; g.ldd_z = (long long)T * N; g.ldd_m = N; g.ldd_n = 1;
+    g.bias = bias; g.addend = addend; g.stats = stats;
+    if (glu) {
+        g.glu = 1; g.glu_out = glu_out;
+        g.ldg_z = (long long)T * (N / 2); g.ldg_m = N / 2; g.ldg_n = 1;
+    }
+    BM_CUDA(launch_gemm(g, st));
+    return 0;
+}
+
+extern "C" int bm_conv1d_fwd(const float* x, const float* wf, const float* bias, int B, int T, int Cin, int Cout,
+                             int Kw, int dilation, float* y, double* stats, bm_stream_t stream) {
+    BM_CHECK_ARG(x && wf && y && B > 0 && T > 0 && Cin > 0 && Cout > 0 && dilation >= 1);
+    cudaStream_t st = ST(stream);
+    if (stats) BM_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * Cout, st));
+    return conv_gemm(x, wf, bias, nullptr, B, T, Cin, Cout, Kw, dilation, +1, y, stats, 0, nullptr, st);
+}
+
+extern "C" int bm_bn_stats_finalize(const double* stats, long long n, float eps, float momentum,
+                                    float* running_mean, float* running_var, float* mean, float* invstd, int C,
+                                    bm_stream_t stream) {
+    BM_CHECK_ARG(stats && mean && invstd && C > 0 && n > 0);
+    BM_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr));
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(stats, (double)n, eps, momentum, running_mean,
+                                                               running_var, mean, invstd, C);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean,
+                                float* invstd, int C, bm_stream_t stream) {
+    BM_CHECK_ARG(running_mean && running_var && mean && invstd && C > 0);
+    bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, ST(stream)>>>(running_mean, running_var, eps, mean, invstd, C);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_bn_gelu_skip_fwd(const float* y, const float* mean, const float* invstd, const float* gamma,
+                                   const float* beta, const float* x_old, float* x_new, long long rows, int C,
+                                   bm_stream_t stream) {
+    BM_CHECK_ARG(y && mean && invstd && gamma && beta && x_new && rows > 0 && C > 0);
+    long long total = rows * C;
+    bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x_new) |
+                                 reinterpret_cast<uintptr_t>(x_old)) % 16 == 0);
+    if (vec)
+        bn_gelu_skip_fwd_kernel<4><<<ew_grid(total, 256, 4), 256, 0, ST(stream)>>>(y, mean, invstd, gamma, beta,
+                                                                                 x_old, x_new, total, C);
+    else
+        bn_gelu_skip_fwd_kernel<1><<<ew_grid(total), 256, 0, ST(stream)>>>(y, mean, invstd, gamma, beta, x_old,
+                                                                          x_new, total, C);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* mean, const float* invstd,
+                                   const float* gamma, const float* beta, int batch_stats, long long rows, int C,
+                                   double* sums, float* dy, float* dgamma, float* dbeta, bm_stream_t stream) {
+    BM_CHECK_ARG(g && y && mean && invstd && gamma && beta && sums && dy && dgamma && dbeta && rows > 0 && C > 0);
+    cudaStream_t st = ST(stream);
+    BM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    const int rpb = 128;
+    dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
+    bn_gelu_bwd_reduce_kernel<<<grid, 128, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, rows, C, rpb);
+    BM_CHECK_LAUNCH();
+    bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, C);
+    BM_CHECK_LAUNCH();
+    long long total = rows * C;
+    bn_gelu_bwd_apply_kernel<<<ew_grid(total), 256, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, (double)rows,
+                                                           batch_stats, dy, total, C);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_conv1d_bwd_data(const float* dy, const float* wb, const float* addend, int B, int T, int Cin,
+                                  int Cout, int Kw, int dilation, float* dx, bm_stream_t stream) {
+    BM_CHECK_ARG(dy && wb && dx && B > 0 && T > 0 && Cin > 0 && Cout > 0 && dilation >= 1);
+    return conv_gemm(dy, wb, nullptr, addend, B, T, Cout, Cin, Kw, dilation, -1, dx, nullptr, 0, nullptr,
+                     ST(stream));
+}
+
+extern "C" int bm_conv1d_bwd_weight(const float* dy, const float* x, int B, int T, int Cin, int Cout, int Kw,
+                                    int dilation, float* dw, float* dbias, bm_stream_t stream) {
+    BM_CHECK_ARG(dy && x && dw && B > 0 && T > 0 && Cin > 0 && Cout > 0 && Kw >= 1 && Kw <= 3);
+    cudaStream_t st = ST(stream);
+    BM_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * Cin * Kw, st));
+    int nseg = pick_chunks(B, tiles_of(Cout, Cin) * Kw);
+    int zchunk = (B + nseg - 1) / nseg;
+    nseg = (B + zchunk - 1) / zchunk;
+    for (int j = 0; j < Kw; ++j) {
+        GemmP g = gemm_defaults();
+        g.M = Cout; g.N = Cin; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = nseg; g.zchunk = zchunk;
+        g.A = dy; g.lda_z = (long long)T * Cout; g.lda_m = 1; g.lda_k = Cout; g.a_mcontig = 1;
+        g.B = x; g.ldb_z = (long long)T * Cin; g.ldb_n = 1; g.ldb_k = Cin; g.b_ncontig = 1;
+        g.b_shift_k[0] = (j - Kw / 2) * dilation;
+        g.D = dw + j; g.ldd_z = 0; g.ldd_m = (long long)Cin * Kw; g.ldd_n = Kw; g.atomic = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    if (dbias) {
+        BM_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Cout, st));
+        long long rows = (long long)B * T;
+        dim3 grid((unsigned)((rows + 255) / 256), (Cout + 127) / 128);
+        colsum_cl_kernel<<<grid, 128, 0, st>>>(dy, dbias, rows, Cout, 256);
+        BM_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int bm_conv1d_glu_fwd(const float* x, const float* wf, const float* bias, int B, int T, int Cin, int H,
+                                 int Kw, float* h, float* out, bm_stream_t stream) {
+    BM_CHECK_ARG(x && wf && out && B > 0 && T > 0 && Cin > 0 && H > 0);
+    return conv_gemm(x, wf, bias, nullptr, B, T, Cin, 2 * H, Kw, 1, +1, h, nullptr, 1, out, ST(stream));
+}
+
+extern "C" int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh, bm_stream_t stream) {
+    BM_CHECK_ARG(g && h && dh && rows > 0 && H > 0);
+    glu_bwd_kernel<<<ew_grid(rows * H), 256, 0, ST(stream)>>>(g, h, dh, rows, H);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+// =================================================================================================
+// K5
+// =================================================================================================
+extern "C" int bm_head_fwd(const float* x, const float* w0, const float* b0, const float* w2, const float* b2,
+                           int B, int T, int H, int F, float* h1, float* q, float* est, bm_stream_t stream) {
+    BM_CHECK_ARG(x && w0 && b0 && w2 && b2 && q && est && B > 0 && T > 0 && H > 0 && F > 0);
+    cudaStream_t st = ST(stream);
+    const int H2 = 2 * H;
+    {   // h1 = x w0^T + b0 ; q = GELU(h1)
+        GemmP g = gemm_defaults();
+        g.M = B * T; g.N = H2; g.K = H; g.kchunk = H;
+        g.A = x; g.lda_m = H; g.lda_k = 1;
+        g.B = w0; g.ldb_n = H; g.ldb_k = 1;
+        g.D = q; g.ldd_m = H2; g.ldd_n = 1;
+        g.bias = b0; g.aux = h1; g.act = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // est[b][f][t] = b2[f] + sum_i q[b][t][i] w2[i][f]
+        GemmP g = gemm_defaults();
+        g.M = T; g.N = F; g.K = H2; g.kchunk = H2;
+        g.Z = B; g.nseg = B; g.zchunk = 1;
+        g.A = q; g.lda_z = (long long)T * H2; g.lda_m = H2; g.lda_k = 1;
+        g.B = w2; g.ldb_n = 1; g.ldb_k = F; g.b_ncontig = 1;
+        g.D = est; g.ldd_z = (long long)F * T; g.ldd_m = 1; g.ldd_n = T;
+        g.bias = b2;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    return 0;
+}
+
+extern "C" int bm_head_bwd(const float* dest, const float* x, const float* w0, const float* w2, const float* h1,
+                           const float* q, int B, int T, int H, int F, float* dq, float* dx, float* dw0,
+                           float* db0, float* dw2, float* db2, bm_stream_t stream) {
+    BM_CHECK_ARG(dest && x && w0 && w2 && h1 && q && dq && dx && dw0 && db0 && dw2 && db2);
+    cudaStream_t st = ST(stream);
+    const int H2 = 2 * H;
+    const long long rows = (long long)B * T;
+    {   // dw2[i][f] = sum_{b,t} q[b][t][i] dest[b][f][t]
+        BM_CUDA(cudaMemsetAsync(dw2, 0, sizeof(float) * (size_t)H2 * F, st));
+        GemmP g = gemm_defaults();
+        g.M = H2; g.N = F; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = pick_chunks(B, tiles_of(H2, F)); g.zchunk = (B + g.nseg - 1) / g.nseg;
+        g.nseg = (B + g.zchunk - 1) / g.zchunk;
+        g.A = q; g.lda_z = (long long)T * H2; g.lda_m = 1; g.lda_k = H2; g.a_mcontig = 1;
+        g.B = dest; g.ldb_z = (long long)F * T; g.ldb_n = T; g.ldb_k = 1; g.b_ncontig = 0;
+        g.D = dw2; g.ldd_m = F; g.ldd_n = 1; g.atomic = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // db2[f] = sum_{b,t} dest[b][f][t]
+        BM_CUDA(cudaMemsetAsync(db2, 0, sizeof(float) * F, st));
+        long long nrows = (long long)B * F;
+        rowsum_cm_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(dest, db2, B, F, T);
+        BM_CHECK_LAUNCH();
+    }
+    {   // dq[b][t][i] = sum_f dest[b][f][t] w2[i][f]
+        GemmP g = gemm_defaults();
+        g.M = T; g.N = H2; g.K = F; g.kchunk = F;
+        g.Z = B; g.nseg = B; g.zchunk = 1;
+        g.A = dest; g.lda_z = (long long)F * T; g.lda_m = 1; g.lda_k = T; g.a_mcontig = 1;
+        g.B = w2; g.ldb_n = F; g.ldb_k = 1;
+        g.D = dq; g.ldd_z = (long long)T * H2; g.ldd_m = H2; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    gelu_bwd_kernel<<<ew_grid(rows * H2), 256, 0, st>>>(dq, h1, dq, rows * H2);   // dq <- dh1
+    BM_CHECK_LAUNCH();
+    {   // dw0[n][k] = sum_rows dh1[row][n] x[row][k]
+        BM_CUDA(cudaMemsetAsync(dw0, 0, sizeof(float) * (size_t)H2 * H, st));
+        GemmP g = gemm_defaults();
+        g.M = H2; g.N = H; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = pick_chunks(B, tiles_of(H2, H)); g.zchunk = (B + g.nseg - 1) / g.nseg;
+        g.nseg = (B + g.zchunk - 1) / g.zchunk;
+        g.A = dq; g.lda_z = (long long)T * H2; g.lda_m = 1; g.lda_k = H2; g.a_mcontig = 1;
+        g.B = x; g.ldb_z = (long long)T * H; g.ldb_n = 1; g.ldb_k = H; g.b_ncontig = 1;
+        g.D = dw0; g.ldd_m = H; g.ldd_n = 1; g.atomic = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    {   // db0
+        BM_CUDA(cudaMemsetAsync(db0, 0, sizeof(float) * H2, st));
+        dim3 grid((unsigned)((rows + 255) / 256), (H2 + 127) / 128);
+        colsum_cl_kernel<<<grid, 128, 0, st>>>(dq, db0, rows, H2, 256);
+        BM_CHECK_LAUNCH();
+    }
+    {   // dx[row][k] = sum_n dh1[row][n] w0[n][k]
+        GemmP g = gemm_defaults();
+        g.M = (int)rows; g.N = H; g.K = H2; g.kchunk = H2;
+        g.A = dq; g.lda_m = H2; g.lda_k = 1;
+        g.B = w0; g.ldb_n = 1; g.ldb_k = H; g.b_ncontig = 1;
+        g.D = dx; g.ldd_m = H; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    return 0;
+}
+
+// =================================================================================================
+// K6
+// =================================================================================================
+extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss,
+                              float* inv_norm, float* scores, float* probs, bm_stream_t stream) {
+    BM_CHECK_ARG(est && cand && ss && inv_norm && scores && Bn > 0 && Bc > 0 && KT > 0);
+    BM_CHECK_ARG(KT < (1ll << 31));
+    cudaStream_t st = ST(stream);
+    BM_CUDA(cudaMemsetAsync(ss, 0, sizeof(double) * Bc, st));
+    int splits = (int)((KT + 65535) / 65536);
+    if (splits > 32) splits = 32;
+    row_sumsq_kernel<<<dim3(Bc, splits), 256, 0, st>>>(cand, ss, KT);
+    BM_CHECK_LAUNCH();
+    inv_norm_kernel<<<(Bc + 127) / 128, 128, 0, st>>>(ss, inv_norm, Bc);
+    BM_CHECK_LAUNCH();
+    BM_CUDA(cudaMemsetAsync(scores, 0, sizeof(float) * (size_t)Bn * Bc, st));
+    GemmP g = gemm_defaults();
+    g.M = Bn; g.N = Bc; g.K = (int)KT;
+    int tiles = tiles_of(Bn, Bc);
+    int ks = (2 * num_sms() + tiles - 1) / tiles;
+    long long kchunk = (KT + ks - 1) / ks;
+    kchunk = ((kchunk + GBK - 1) / GBK) * GBK;
+    ks = (int)((KT + kchunk - 1) / kchunk);
+    g.ksplit = ks; g.kchunk = (int)kchunk;
+    g.A = est; g.lda_m = KT; g.lda_k = 1;
+    g.B = cand; g.ldb_n = KT; g.ldb_k = 1;
+    g.D = scores; g.ldd_m = Bc; g.ldd_n = 1; g.atomic = 1;
+    g.colscale = inv_norm;
+    BM_CUDA(launch_gemm(g, st));
+    if (probs) {
+        clip_ce_rows_kernel<<<Bn, 256, 0, st>>>(scores, Bn, Bc, 0, nullptr, probs);
+        BM_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long long KT,
+                                int target_offset, double* ss, float* inv_norm, float* scores, float* probs,
+                                float* row_loss, float* loss, bm_stream_t stream) {
+    BM_CHECK_ARG(probs && row_loss && loss);
+    BM_CHECK_ARG(target_offset >= 0 && target_offset + Bn <= Bc);
+    int rc = bm_clip_scores(est, cand, Bn, Bc, KT, ss, inv_norm, scores, nullptr, stream);
+    if (rc) return rc;
+    cudaStream_t st = ST(stream);
+    clip_ce_rows_kernel<<<Bn, 256, 0, st>>>(scores, Bn, Bc, target_offset, row_loss, probs);
+    BM_CHECK_LAUNCH();
+    mean_kernel<<<1, 256, 0, st>>>(row_loss, Bn, loss);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* cand, const float* gout,
+                                int Bn, int Bc, long long KT, int target_offset, float* G, float* dest,
+                                bm_stream_t stream) {
+    BM_CHECK_ARG(probs && inv_norm && cand && gout && G && dest && Bn > 0 && Bc > 0 && KT > 0);
+    BM_CHECK_ARG(KT < (1ll << 31));
+    cudaStream_t st = ST(stream);
+    clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G);
+    BM_CHECK_LAUNCH();
+    GemmP g = gemm_defaults();
+    g.M = Bn; g.N = (int)KT; g.K = Bc; g.kchunk = Bc;
+    g.A = G; g.lda_m = Bc; g.lda_k = 1;
+    g.B = cand; g.ldb_n = 1; g.ldb_k = KT; g.b_ncontig = 1;
+    g.D = dest; g.ldd_m = KT; g.ldd_n = 1;
+    BM_CUDA(launch_gemm(g, st));
+    return 0;
+}

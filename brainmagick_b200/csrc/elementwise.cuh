@@ -1,0 +1,380 @@
+// HBM-bound kernels of the hot path: everything that is not a contraction.
+// Activations are channels-last [B, T, C] inside the encoder (rows = B*T), so a warp always walks
+// contiguous channels; per-channel parameters are read through the read-only path.
+#pragma once
+#include "common.cuh"
+
+namespace bm {
+
+// ------------------------------------------------------------------------------------------------
+// K1 pieces: Fourier embedding of sensor positions and the masked softmax (common.py:254-271,339-357)
+// ------------------------------------------------------------------------------------------------
+// emb[rc][k*n+l] = cos(loc), emb[rc][P/2 + k*n+l] = sin(loc), loc = (x+margin)*f[k] + (y+margin)*f[l]
+// `freq` is the table 2*pi*arange(n)/(1+2*margin) built by the host with the reference's own op order, and
+// the products/sum are rounded separately (no FMA contraction) so that `loc` is bit-identical to torch's.
+__global__ void fourier_emb_kernel(const float* __restrict__ pos, const float* __restrict__ freq, float margin,
+                                   int RC, int n, float* __restrict__ emb) {
+    const int P2 = n * n;
+    long long total = (long long)RC * P2;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int rc = (int)(idx / P2);
+        int kl = (int)(idx - (long long)rc * P2);
+        int k = kl / n, l = kl - k * n;
+        float x = __fadd_rn(pos[2 * rc], margin), y = __fadd_rn(pos[2 * rc + 1], margin);
+        float loc = __fadd_rn(__fmul_rn(x, freq[k]), __fmul_rn(y, freq[l]));
+        float s, c;
+        sincosf(loc, &s, &c);
+        emb[(long long)rc * 2 * P2 + kl] = c;
+        emb[(long long)rc * 2 * P2 + P2 + kl] = s;
+    }
+}
+
+// in-place softmax over c of scores[r][o][:] with -inf on invalid (pos == INVALID) and banned sensors
+// (||pos - centre|| <= radius, training only).  One warp per (r, o) row.
+__global__ void masked_softmax_kernel(float* __restrict__ w, const float* __restrict__ pos,
+                                      const float* __restrict__ centre, float radius, float invalid, int R, int O,
+                                      int C) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= R * O) return;
+    int r = row / O;
+    float* s = w + (long long)row * C;
+    const float* pr = pos + (long long)r * C * 2;
+    float cx = 0.f, cy = 0.f;
+    if (centre) { cx = centre[0]; cy = centre[1]; }
+    float mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) {
+        float x = pr[2 * c], y = pr[2 * c + 1];
+        bool masked = (x == invalid) && (y == invalid);
+        if (centre) {
+            float dx = x - cx, dy = y - cy;
+            masked = masked || (sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy))) <= radius);
+        }
+        float v = masked ? -INFINITY : s[c];
+        s[c] = v;
+        mx = fmaxf(mx, v);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float e = expf(s[c] - mx);
+        s[c] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    float inv = 1.f / sum;
+    for (int c = lane; c < C; c += 32) s[c] *= inv;
+}
+
+// dscore = w * (dw - sum_c w*dw)   (softmax backward, one warp per row)
+__global__ void softmax_bwd_kernel(const float* __restrict__ w, const float* __restrict__ dw,
+                                   float* __restrict__ ds, int rows, int C) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* wr = w + (long long)row * C;
+    const float* dr = dw + (long long)row * C;
+    float dot = 0.f;
+    for (int c = lane; c < C; c += 32) dot += wr[c] * dr[c];
+    dot = warp_sum(dot);
+    for (int c = lane; c < C; c += 32) ds[(long long)row * C + c] = wr[c] * (dr[c] - dot);
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d + GELU + skip  (common.py:118-120,146-147)
+// ------------------------------------------------------------------------------------------------
+// stats[0:C] = sum y, stats[C:2C] = sum y^2 (fp64) over n = B*T rows  ->  mean, invstd (biased var),
+// running stats update with the unbiased variance (momentum), as nn.BatchNorm1d in training mode.
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, double n, float eps, float momentum,
+                                   float* running_mean, float* running_var, float* __restrict__ mean,
+                                   float* __restrict__ invstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double m = stats[c] / n;
+    double var = stats[C + c] / n - m * m;
+    if (var < 0) var = 0;
+    mean[c] = (float)m;
+    invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+        double unb = n > 1 ? var * n / (n - 1) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+
+// eval mode: mean = running_mean, invstd = 1/sqrt(running_var + eps)
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                     float* __restrict__ mean, float* __restrict__ invstd, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = rm[c];
+    invstd[c] = 1.f / sqrtf(rv[c] + eps);
+}
+
+// x_new = GELU((y - mean) * invstd * gamma + beta) (+ x_old)
+template <int VEC>
+__global__ void bn_gelu_skip_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean,
+                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, const float* __restrict__ x_old,
+                                        float* __restrict__ x_new, long long total, int C) {
+    for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * VEC; i < total;
+         i += (long long)gridDim.x * blockDim.x * VEC) {
+        int c = (int)(i % C);
+        float v[VEC], o[VEC];
+        if (VEC == 4) {
+            float4 t = *reinterpret_cast<const float4*>(y + i);
+            v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+            if (x_old) {
+                float4 u = *reinterpret_cast<const float4*>(x_old + i);
+                o[0] = u.x; o[1 % VEC] = u.y; o[2 % VEC] = u.z; o[3 % VEC] = u.w;
+            }
+        } else {
+            v[0] = y[i];
+            if (x_old) o[0] = x_old[i];
+        }
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            float z = (v[j] - mean[c + j]) * invstd[c + j] * gamma[c + j] + beta[c + j];
+            float a = gelu_f(z);
+            v[j] = x_old ? a + o[j] : a;
+        }
+        if (VEC == 4) *reinterpret_cast<float4*>(x_new + i) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+        else x_new[i] = v[0];
+    }
+}
+
+// backward pass 1: sums[c] += sum dz, sums[C+c] += sum dz*yhat  with dz = g * GELU'(z)
+__global__ void bn_gelu_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                          double* __restrict__ sums, long long rows, int C, int rows_per_block) {
+    int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = min(rows, r0 + rows_per_block);
+    float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+        float yh = (y[r * C + c] - mu) * is;
+        float z = yh * ga + be;
+        float dz = g[r * C + c] * gelu_grad_f(z);
+        s1 += dz;
+        s2 += dz * yh;
+    }
+    atomicAdd(sums + c, (double)s1);
+    atomicAdd(sums + C + c, (double)s2);
+}
+
+// dgamma = sum dz*yhat, dbeta = sum dz  (float outputs from the fp64 sums)
+__global__ void bn_param_grad_kernel(const double* __restrict__ sums, float* __restrict__ dgamma,
+                                     float* __restrict__ dbeta, int C) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    dbeta[c] = (float)sums[c];
+    dgamma[c] = (float)sums[C + c];
+}
+
+// backward pass 2: dy = gamma*invstd*(dz - mean(dz) - yhat*mean(dz*yhat))
+// eval mode (use_batch_stats = 0): dy = gamma*invstd*dz
+__global__ void bn_gelu_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                         const double* __restrict__ sums, double n, int use_batch_stats,
+                                         float* __restrict__ dy, long long total, int C) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        float is = invstd[c], ga = gamma[c];
+        float yh = (y[i] - mean[c]) * is;
+        float z = yh * ga + beta[c];
+        float dz = g[i] * gelu_grad_f(z);
+        float v = dz;
+        if (use_batch_stats) v = dz - (float)(sums[c] / n) - yh * (float)(sums[C + c] / n);
+        dy[i] = ga * is * v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GLU backward (common.py:133-138): h = [a | b] per row (2H columns), out = a*sigmoid(b)
+// ------------------------------------------------------------------------------------------------
+__global__ void glu_bwd_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ dh,
+                               long long rows, int H) {
+    long long total = rows * H;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i / H;
+        int c = (int)(i - r * H);
+        float a = h[r * 2 * H + c], b = h[r * 2 * H + H + c];
+        float s = sigmoid_f(b);
+        float gg = g[i];
+        dh[r * 2 * H + c] = gg * s;
+        dh[r * 2 * H + H + c] = gg * a * s * (1.f - s);
+    }
+}
+
+// dh = dq * GELU'(h)   (head, simpleconv.py:185-189)
+__global__ void gelu_bwd_kernel(const float* __restrict__ dq, const float* __restrict__ h, float* __restrict__ dh,
+                                long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x)
+        dh[i] = dq[i] * gelu_grad_f(h[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// bias gradients
+// ------------------------------------------------------------------------------------------------
+// out[c] += sum_r X[r][c]   (channels-last rows); out must be zeroed by the caller
+__global__ void colsum_cl_kernel(const float* __restrict__ X, float* __restrict__ out, long long rows, int C,
+                                 int rows_per_block) {
+    int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f;
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) s += X[r * C + c];
+    atomicAdd(out + c, s);
+}
+
+// out[n] += sum_{z,t} X[z][n][t]  (channel-major [Z,N,T]); one warp per (z, n) row
+__global__ void rowsum_cm_kernel(const float* __restrict__ X, float* __restrict__ out, int Z, int N, int T) {
+    long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= (long long)Z * N) return;
+    const float* x = X + row * T;
+    float s = 0.f;
+    for (int t = lane; t < T; t += 32) s += x[t];
+    s = warp_sum(s);
+    if (lane == 0) atomicAdd(out + (int)(row % N), s);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv weight re-layout: W[o][i][j] -> Wf[j][i][o] (forward B operand) and Wb[j][o][i] (data-gradient B operand)
+// ------------------------------------------------------------------------------------------------
+__global__ void weight_prep_kernel(const float* __restrict__ W, float* __restrict__ Wf, float* __restrict__ Wb,
+                                   int O, int I, int Kw) {
+    long long total = (long long)O * I * Kw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(idx % Kw);
+        long long oi = idx / Kw;
+        int i = (int)(oi % I), o = (int)(oi / I);
+        float v = W[idx];
+        if (Wf) Wf[((long long)j * I + i) * O + o] = v;
+        if (Wb) Wb[((long long)j * O + o) * I + i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ClipLoss pieces (losses.py:91-114)
+// ------------------------------------------------------------------------------------------------
+// ss[o] += sum_k cand[o][k]^2 (fp64 atomics; grid = (rows, splits))
+__global__ void row_sumsq_kernel(const float* __restrict__ X, double* __restrict__ ss, long long K) {
+    __shared__ double red[32];
+    const float* x = X + (long long)blockIdx.x * K;
+    long long chunk = (K + gridDim.y - 1) / gridDim.y;
+    long long k0 = (long long)blockIdx.y * chunk, k1 = min(K, k0 + chunk);
+    float s = 0.f;
+    double acc = 0.0;
+    int cnt = 0;
+    for (long long k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+        float v = x[k];
+        s = fmaf(v, v, s);
+        if (++cnt == 64) { acc += (double)s; s = 0.f; cnt = 0; }
+    }
+    acc += (double)s;
+    acc = warp_sum_d(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = warp_sum_d(v);
+        if (threadIdx.x == 0) atomicAdd(ss + blockIdx.x, v);
+    }
+}
+
+// inv_norm[o] = 1 / (1e-8 + sqrt(ss[o]))    (losses.py:91)
+__global__ void inv_norm_kernel(const double* __restrict__ ss, float* __restrict__ inv, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[i] = 1.f / (1e-8f + (float)sqrt(ss[i]));
+}
+
+// per row b: lse, row_loss[b] = lse - s[b][b+off]; optional probs = softmax(s)   (one block per row)
+__global__ void clip_ce_rows_kernel(const float* __restrict__ scores, int Bn, int Bc, int target_offset,
+                                    float* __restrict__ row_loss, float* __restrict__ probs) {
+    __shared__ float red[32];
+    __shared__ float bcast;
+    int b = blockIdx.x;
+    const float* s = scores + (long long)b * Bc;
+    float mx = -INFINITY;
+    for (int o = threadIdx.x; o < Bc; o += blockDim.x) mx = fmaxf(mx, s[o]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+        v = warp_max(v);
+        if (threadIdx.x == 0) bcast = v;
+    }
+    __syncthreads();
+    mx = bcast;
+    __syncthreads();
+    float sum = 0.f;
+    for (int o = threadIdx.x; o < Bc; o += blockDim.x) sum += expf(s[o] - mx);
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) bcast = v;
+    }
+    __syncthreads();
+    sum = bcast;
+    if (row_loss && threadIdx.x == 0) row_loss[b] = (logf(sum) + mx) - s[b + target_offset];
+    if (probs) {
+        float inv = 1.f / sum;
+        for (int o = threadIdx.x; o < Bc; o += blockDim.x) probs[(long long)b * Bc + o] = expf(s[o] - mx) * inv;
+    }
+}
+
+// loss = mean(row_loss)  (single block, deterministic order)
+__global__ void mean_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)x[i];
+    s = warp_sum_d(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+        v = warp_sum_d(v);
+        if (threadIdx.x == 0) out[0] = (float)(v / n);
+    }
+}
+
+// G[b][o] = gout * (softmax(s)[b][o] - [o == b+off]) / Bn * inv_norm[o]    (A.6 of SURVEY.md)
+__global__ void clip_ce_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ inv_norm,
+                                   const float* __restrict__ gout, int Bn, int Bc, int target_offset,
+                                   float* __restrict__ G) {
+    long long total = (long long)Bn * Bc;
+    float gs = gout[0] / (float)Bn;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int b = (int)(i / Bc), o = (int)(i - (long long)b * Bc);
+        float p = probs[i] - (o == b + target_offset ? 1.f : 0.f);
+        G[i] = gs * p * inv_norm[o];
+    }
+}
+
+inline int ew_grid(long long total, int block = 256, int per_thread = 1) {
+    long long g = (total / per_thread + block - 1) / block;
+    long long cap = (long long)num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace bm

@@ -1,0 +1,54 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed/NCCL over NVLink).
+
+The path shards by batch row: each rank encodes its rows (BatchNorm statistics stay per-rank,
+like the reference which never converts to SyncBatchNorm), then
+  * `all_gather_candidates`: the ONE forward exchange -- NCCL all-gather of the candidate block so every rank
+    scores its rows against the global batch (new semantic; the reference keeps negatives local, README.md:139-143);
+  * `sync_gradients`: the reference's gradient all-reduce(avg) (flashy.distrib.sync_model, bm/solver.py:386),
+    done on one flat bucket.
+"""
+from __future__ import annotations
+
+import typing as tp
+
+import torch
+import torch.distributed as dist
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def all_gather_candidates(candidate: torch.Tensor) -> tp.Tuple[torch.Tensor, int]:
+    """[B_loc, F, T] per rank -> ([W*B_loc, F, T], target offset of this rank's rows).  Candidates carry no
+    gradient on this path (no feature_model), so a plain all-gather is enough."""
+    W = world_size()
+    if W == 1:
+        return candidate, 0
+    candidate = candidate.contiguous()
+    out = torch.empty((W * candidate.shape[0],) + tuple(candidate.shape[1:]), dtype=candidate.dtype,
+                      device=candidate.device)
+    dist.all_gather_into_tensor(out, candidate)
+    return out, rank() * candidate.shape[0]
+
+
+def sync_gradients(params: tp.Iterable[torch.nn.Parameter]) -> None:
+    """all-reduce(avg) of every .grad through one flat fp32 bucket."""
+    W = world_size()
+    if W == 1:
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat.div_(W)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

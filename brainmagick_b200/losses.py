@@ -1,0 +1,79 @@
+"""Drop-in `ClipLoss` (reference: bm/losses.py:29-114): same constructor, `forward(estimate, candidate, mask)`,
+`get_scores`, `get_probabilities`, `trim_samples`.  Scores, softmax / cross-entropy and their gradient run in
+CUDA through the C ABI (`functional.clip_loss`, `functional.clip_scores`).
+
+Reference semantics kept on purpose: only the CANDIDATES are L2-normalised (losses.py:91-94), no temperature,
+the `linear` projection is constructed but never applied (losses.py:35,82), targets are the first B candidates.
+
+Extension (not in the reference): `global_negatives=True` all-gathers the candidates over the
+default process group before scoring, so every rank contrasts against the global batch.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import functional as BF
+from . import distrib
+
+
+class ClipLoss(torch.nn.Module):
+    def __init__(self, linear=None, twin=True, pool=False, tmin=None, tmax=None,
+                 tmin_train=None, tmax_train=None, dset_args=None, center=False, global_negatives=False):
+        super().__init__()
+        self.linear = None                      # the reference never applies its projection (losses.py:35)
+        self.pool = pool
+        self.center = center
+        if linear is not None:                  # kept for state_dict compatibility only
+            self.linear_est = torch.nn.LazyLinear(linear)
+            self.linear_gt = self.linear_est if twin else torch.nn.LazyLinear(linear)
+        self.tmin, self.tmax = tmin, tmax
+        self.tmin_train, self.tmax_train = tmin_train, tmax_train
+        self.dset_args = dset_args
+        self.global_negatives = global_negatives
+
+    # -- time cropping (losses.py:50-75) ---------------------------------------------------------------
+    def _window(self, n_samples: int):
+        use_train = self.training and (self.tmin_train is not None or self.tmax_train is not None)
+        tmin, tmax = (self.tmin_train, self.tmax_train) if use_train else (self.tmin, self.tmax)
+        start, stop = 0, n_samples
+        if tmin is not None or tmax is not None:
+            assert self.dset_args is not None and self.dset_args.tmin is not None
+            origin, rate = self.dset_args.tmin, self.dset_args.sample_rate
+            if tmin is not None:
+                assert tmin >= origin, 'clip.tmin should be above dset.tmin'
+                start = int((tmin - origin) * rate)
+            if tmax is not None:
+                stop = int((tmax - origin) * rate)
+        return start, stop
+
+    def trim_samples(self, estimates, candidates):
+        start, stop = self._window(estimates.shape[-1])
+        return estimates[..., start:stop], candidates[..., start:stop]
+
+    def _prepare(self, estimates, candidates):
+        estimates, candidates = self.trim_samples(estimates, candidates)
+        if self.pool:                            # losses.py:85-87
+            estimates = estimates.mean(dim=2, keepdim=True)
+            candidates = candidates.mean(dim=2, keepdim=True)
+        if self.center:                          # losses.py:88-90
+            estimates = estimates - estimates.mean(dim=(1, 2), keepdim=True)
+            candidates = candidates - candidates.mean(dim=(1, 2), keepdim=True)
+        return estimates, candidates
+
+    def get_scores(self, estimates: torch.Tensor, candidates: torch.Tensor):
+        """[B, C, T] x [B', C, T] -> [B, B'] matching scores (no autograd; use forward() for training)."""
+        estimates, candidates = self._prepare(estimates, candidates)
+        return BF.clip_scores(estimates, candidates)
+
+    def get_probabilities(self, estimates, candidates):
+        estimates, candidates = self._prepare(estimates, candidates)
+        return BF.clip_scores(estimates, candidates, want_probs=True)
+
+    def forward(self, estimate, candidate, mask=None):
+        assert mask.all(), "mask is not supported for now"
+        assert estimate.size(0) <= candidate.size(0), "need at least as many targets as estimates"
+        estimate, candidate = self._prepare(estimate, candidate)
+        offset = 0
+        if self.global_negatives and distrib.world_size() > 1:
+            candidate, offset = distrib.all_gather_candidates(candidate)
+        return BF.clip_loss(estimate, candidate, offset)

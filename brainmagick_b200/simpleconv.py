@@ -1,0 +1,179 @@
+"""Drop-in `SimpleConv` brain encoder (reference: bm/models/simpleconv.py:22-249).
+
+Same constructor signature, submodule/parameter names (=> interchangeable `state_dict`), construction order
+(=> identical parameters for a given `torch.manual_seed`), `forward(inputs, batch) -> [B, F, T]`, train/eval
+semantics (BatchNorm running statistics, one spatial-dropout centre per training forward).  The arithmetic runs in
+hand-written sm_100a CUDA through the C ABI (`functional.encoder_forward`); there is no PyTorch/CPU fallback.
+
+Accelerated configuration = the `clip_conv` family of conf/model/clip_conv.yaml (merger + initial_linear +
+subject_layers + ConvSequence(batch_norm, skip, gelu, glu) + complex_out).  Options outside that family are
+accepted by the signature but raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import typing as tp
+
+import torch
+from torch import nn
+
+from . import functional as BF
+from .common import ChannelMerger, ConvSequence, SubjectLayers, require_library
+
+
+class SimpleConv(nn.Module):
+    def __init__(self,
+                 # Channels
+                 in_channels: tp.Dict[str, int],
+                 out_channels: int,
+                 hidden: tp.Dict[str, int],
+                 # Overall structure
+                 depth: int = 4,
+                 concatenate: bool = False,
+                 linear_out: bool = False,
+                 complex_out: bool = False,
+                 # Conv layer
+                 kernel_size: int = 5,
+                 growth: float = 1.,
+                 dilation_growth: int = 2,
+                 dilation_period: tp.Optional[int] = None,
+                 skip: bool = False,
+                 post_skip: bool = False,
+                 scale: tp.Optional[float] = None,
+                 rewrite: bool = False,
+                 groups: int = 1,
+                 glu: int = 0,
+                 glu_context: int = 0,
+                 glu_glu: bool = True,
+                 gelu: bool = False,
+                 # Dual path RNN
+                 dual_path: int = 0,
+                 # Dropouts, BN, activations
+                 conv_dropout: float = 0.0,
+                 dropout_input: float = 0.0,
+                 batch_norm: bool = False,
+                 relu_leakiness: float = 0.0,
+                 # Subject specific settings
+                 n_subjects: int = 200,
+                 subject_dim: int = 64,
+                 subject_layers: bool = False,
+                 subject_layers_dim: str = "input",
+                 subject_layers_id: bool = False,
+                 embedding_scale: float = 1.0,
+                 # stft transform
+                 n_fft: tp.Optional[int] = None,
+                 fft_complex: bool = True,
+                 # Attention multi-dataset support
+                 merger: bool = False,
+                 merger_pos_dim: int = 256,
+                 merger_channels: int = 270,
+                 merger_dropout: float = 0.2,
+                 merger_penalty: float = 0.,
+                 merger_per_subject: bool = False,
+                 dropout: float = 0.,
+                 dropout_rescale: bool = True,
+                 initial_linear: int = 0,
+                 initial_depth: int = 1,
+                 initial_nonlin: bool = False,
+                 subsample_meg_channels: int = 0,
+                 ):
+        super().__init__()
+        if set(in_channels.keys()) != set(hidden.keys()):
+            raise ValueError("Channels and hidden keys must match "
+                             f"({set(in_channels.keys())} and {set(hidden.keys())})")
+        assert kernel_size % 2 == 1, "For padding to work, this must be verified"
+        off_path = dict(
+            concatenate=concatenate, linear_out=linear_out, complex_out=not complex_out, growth=growth != 1.,
+            dual_path=bool(dual_path), gelu=not gelu, subject_dim=bool(subject_dim),
+            subject_layers=not subject_layers, n_fft=n_fft is not None, merger=not merger, dropout=dropout > 0.,
+            initial_linear=not initial_linear, initial_depth=initial_depth != 1, initial_nonlin=initial_nonlin,
+            subsample_meg_channels=bool(subsample_meg_channels), inputs=set(in_channels) != {"meg"})
+        bad = [k for k, v in off_path.items() if v]
+        if bad:
+            raise NotImplementedError(
+                f"SimpleConv options outside the accelerated clip_conv family: {bad}; see SURVEY.md 8(f) row 4")
+        require_library()
+
+        self._concatenate = concatenate
+        self.out_channels = out_channels
+        self.subsampled_meg_channels: tp.Optional[list] = None
+        self.dropout = None
+        self.stft = None
+        self.subject_embedding = None
+        self.dual_path = None
+        self.n_input_channels = in_channels["meg"]
+
+        # construction order == the reference's (simpleconv.py:104-196), so a seeded constructor is RNG-identical
+        self.merger = ChannelMerger(merger_channels, pos_dim=merger_pos_dim, dropout=merger_dropout,
+                                    usage_penalty=merger_penalty, n_subjects=n_subjects,
+                                    per_subject=merger_per_subject)
+        in_channels["meg"] = merger_channels
+        self.initial_linear = nn.Sequential(nn.Conv1d(in_channels["meg"], initial_linear, 1))
+        in_channels["meg"] = initial_linear
+        meg_dim = in_channels["meg"]
+        dim = {"hidden": hidden["meg"], "input": meg_dim}[subject_layers_dim]
+        self.subject_layers = SubjectLayers(meg_dim, dim, n_subjects, subject_layers_id)
+        in_channels["meg"] = dim
+
+        sizes = [in_channels["meg"]] + [int(round(hidden["meg"] * growth ** k)) for k in range(depth)]
+        final_channels = sizes[-1]
+        self.final = nn.Sequential(
+            nn.Conv1d(final_channels, 2 * final_channels, 1),
+            nn.GELU(),
+            nn.ConvTranspose1d(2 * final_channels, out_channels, 1, 1, 0))
+        self.encoders = nn.ModuleDict({"meg": ConvSequence(
+            sizes, kernel=kernel_size, stride=1, leakiness=relu_leakiness, dropout=conv_dropout,
+            dropout_input=dropout_input, batch_norm=batch_norm, dilation_growth=dilation_growth, groups=groups,
+            dilation_period=dilation_period, skip=skip, post_skip=post_skip, scale=scale, rewrite=rewrite, glu=glu,
+            glu_context=glu_context, glu_glu=glu_glu, activation=nn.GELU)})
+        self._freq: tp.Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _layer_params(self):
+        seq: ConvSequence = self.encoders["meg"]
+        out = []
+        for block in seq.sequence:
+            conv, bn = block[0], block[1]
+            out += [conv.weight, conv.bias, bn.weight, bn.bias]
+        for glu in seq.glus:
+            if glu is not None:
+                out += [glu[0].weight, glu[0].bias]
+        return out
+
+    def _plan(self, meg: torch.Tensor, batch) -> BF.EncoderPlan:
+        seq: ConvSequence = self.encoders["meg"]
+        device = meg.device
+        B, C, _ = meg.shape
+        pos, rec_of_sample, rec_order, rec_off = self.merger.position_getter.batch_layout(batch, C, device)
+        if self._freq is None or self._freq.device != device:
+            self._freq = self.merger.embedding.frequencies().to(device)
+        bn_buffers = [(blk[1].running_mean, blk[1].running_var) for blk in seq.sequence]
+        bn0 = seq.sequence[0][1]
+        if bn0.momentum is None:
+            raise NotImplementedError("BatchNorm cumulative-average mode (momentum=None)")
+        return BF.EncoderPlan(
+            dilations=list(seq.dilations), glu_after=seq.glu_after(), kernel_size=seq.kernel,
+            glu_kernel=seq.glu_kernel, training=self.training, bn_eps=bn0.eps, bn_momentum=bn0.momentum,
+            rec_positions=pos, rec_of_sample=rec_of_sample, rec_order=rec_order, rec_off=rec_off,
+            subject=batch.subject_index.to(device=device, dtype=torch.int32).contiguous(),
+            freq=self._freq, ban_centre=self.merger.draw_ban_centre(device), ban_radius=float(self.merger.dropout),
+            bn_buffers=bn_buffers, keep_for_backward=torch.is_grad_enabled())
+
+    def forward(self, inputs, batch):
+        meg = inputs["meg"]
+        if not meg.is_cuda:
+            raise RuntimeError("brainmagick_b200.SimpleConv runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if meg.dtype != torch.float32:
+            raise TypeError("brainmagick_b200.SimpleConv computes in fp32, like the reference")
+        assert meg.shape[1] == self.n_input_channels, "number of MEG channels differs from in_channels['meg']"
+        length = meg.shape[-1]
+        plan = self._plan(meg, batch)
+        il = self.initial_linear[0]
+        est = BF.encoder_forward(
+            plan, meg, self.merger.heads, il.weight, il.bias, self.subject_layers.weights,
+            self.final[0].weight, self.final[0].bias, self.final[2].weight, self.final[2].bias,
+            self._layer_params())
+        if self.training:
+            seq: ConvSequence = self.encoders["meg"]
+            for blk in seq.sequence:          # nn.BatchNorm1d bookkeeping (running stats were updated on device)
+                blk[1].num_batches_tracked += 1
+        return est[:, :, :length]

@@ -1,0 +1,121 @@
+/* brainmagick_b200 -- C ABI of the B200-native contrastive training step (SimpleConv + ClipLoss).
+ *
+ * The reference (facebookresearch/brainmagick) has no FFI: its boundary for this path is the Python object
+ * surface of `bm.models.SimpleConv` (bm/models/simpleconv.py:22-249) and `bm.losses.ClipLoss`
+ * (bm/losses.py:29-114), called from bm/solver.py:297,373 and bm/train.py:84-86.  The drop-in modules in
+ * `brainmagick_b200/` keep that surface and call THIS library through ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless stated; fp32 data, int32 indices,
+ *     fp64 only for the small statistics scratch buffers;
+ *   - the caller owns every buffer (inputs, outputs, saved activations, scratch); the library never allocates;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises;
+ *   - returns 0 on success, non-zero on error; `bm_last_error()` gives the message (thread local);
+ *   - activations inside the encoder are channels-last [B, T, C]; the model input `meg` [B, C, T], the encoder
+ *     output `estimate` [B, F, T] and the `candidates` [B', F, T] keep the reference's channel-major layout.
+ * There is no CPU fallback anywhere in this library.
+ */
+#ifndef BM_B200_H_
+#define BM_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* bm_stream_t;
+
+const char* bm_last_error(void);
+int bm_abi_version(void);
+
+/* ---- K1: spatial-attention weights, once per recording ------------------------------------------------
+ * replaces FourierEmb.forward (bm/models/common.py:254-271) + the score/softmax half of ChannelMerger.forward
+ * (common.py:337-357).  positions [R,C,2] (INVALID=-0.1 marks padded sensors), freq [n] = 2*pi*arange(n)/1.4
+ * with n = sqrt(P/2), heads [O,P], ban_centre [2] or NULL (eval / dropout 0).
+ * out: emb [R,C,P] (saved for backward), weights [R,O,C] = softmax over C. */
+int bm_attention_weights_fwd(const float* positions, const float* freq, const float* heads,
+                             const float* ban_centre, float radius, int R, int C, int O, int P, float* emb,
+                             float* weights, bm_stream_t stream);
+/* dweights [R,O,C] -> dheads [O,P]; dscores is [R,O,C] scratch. */
+int bm_attention_weights_bwd(const float* dweights, const float* weights, const float* emb, int R, int C, int O,
+                             int P, float* dscores, float* dheads, bm_stream_t stream);
+
+/* ---- K2: sensor chain ----------------------------------------------------------------------------------
+ * replaces the mixing einsum of ChannelMerger.forward (common.py:358), `initial_linear` (simpleconv.py:113-120,
+ * 213-214) and SubjectLayers.forward (common.py:55-58):
+ *   u[b,t,o] = sum_c weights[rec[b],o,c] meg[b,c,t];  v = il_w u + il_b;  x0[b,t,d] = sum_p subj_w[subj[b],p,d] v[b,t,p]
+ * meg [B,C,T]; il_w [IL,O]; subj_w [S,IL,D]; out u [B,T,O], v [B,T,IL], x0 [B,T,D] (channels-last). */
+int bm_sensor_chain_fwd(const float* meg, const float* weights, const int* rec_of_sample, const float* il_w,
+                        const float* il_b, const float* subj_w, const int* subject, int B, int C, int T, int O,
+                        int IL, int D, float* u, float* v, float* x0, bm_stream_t stream);
+/* dx0 [B,T,D] -> d_subj_w [S,IL,D], d_il_w [IL,O], d_il_b [IL], d_weights [R,O,C].
+ * (subj_order, subj_off[S+1]) and (rec_order, rec_off[R+1]) are CSR groupings of the samples by subject and by
+ * recording; dv [B,T,IL] and du [B,T,O] are scratch. */
+int bm_sensor_chain_bwd(const float* dx0, const float* meg, const float* il_w, const float* subj_w,
+                        const int* subject, const float* u, const float* v, const int* subj_order,
+                        const int* subj_off, const int* rec_order, const int* rec_off, int B, int C, int T, int O,
+                        int IL, int D, int S, int R, float* dv, float* du, float* d_subj_w, float* d_il_w,
+                        float* d_il_b, float* d_weights, bm_stream_t stream);
+
+/* ---- K3: dilated Conv1d + train-mode BatchNorm + GELU + skip (ConvSequence, common.py:98-151) ------------
+ * w [Cout,Cin,Kw] -> wf [Kw,Cin,Cout] (forward operand), wb [Kw,Cout,Cin] (data-gradient operand). */
+int bm_conv_weight_prep(const float* w, int Cout, int Cin, int Kw, float* wf, float* wb, bm_stream_t stream);
+/* y[b,t,o] = bias[o] + sum_{i,j} w[o,i,j] x[b, t+(j-Kw/2)*dilation, i]  (zero outside [0,T)); x,y channels-last.
+ * stats (nullable): fp64 [2*Cout] receiving sum(y), sum(y^2) over (b,t) -- zeroed by this call. */
+int bm_conv1d_fwd(const float* x, const float* wf, const float* bias, int B, int T, int Cin, int Cout, int Kw,
+                  int dilation, float* y, double* stats, bm_stream_t stream);
+/* batch statistics -> mean, invstd; updates running stats (nullable) like nn.BatchNorm1d(momentum). */
+int bm_bn_stats_finalize(const double* stats, long long n, float eps, float momentum, float* running_mean,
+                         float* running_var, float* mean, float* invstd, int C, bm_stream_t stream);
+int bm_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* invstd,
+                     int C, bm_stream_t stream);
+/* x_new = GELU(gamma*(y-mean)*invstd + beta) (+ x_old if not NULL); rows = B*T. */
+int bm_bn_gelu_skip_fwd(const float* y, const float* mean, const float* invstd, const float* gamma,
+                        const float* beta, const float* x_old, float* x_new, long long rows, int C,
+                        bm_stream_t stream);
+/* g = dL/dx_new -> dy (through GELU and BN), dgamma, dbeta.  batch_stats=1: training-mode BN backward.
+ * sums: fp64 [2*C] scratch. */
+int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* mean, const float* invstd,
+                        const float* gamma, const float* beta, int batch_stats, long long rows, int C,
+                        double* sums, float* dy, float* dgamma, float* dbeta, bm_stream_t stream);
+/* dx = conv_transpose(dy) (+ addend, the skip-path gradient, if not NULL). */
+int bm_conv1d_bwd_data(const float* dy, const float* wb, const float* addend, int B, int T, int Cin, int Cout,
+                       int Kw, int dilation, float* dx, bm_stream_t stream);
+/* dw [Cout,Cin,Kw] (reference layout), dbias [Cout]. */
+int bm_conv1d_bwd_weight(const float* dy, const float* x, int B, int T, int Cin, int Cout, int Kw, int dilation,
+                         float* dw, float* dbias, bm_stream_t stream);
+
+/* ---- K4: Conv1d(H -> 2H, Kw, pad=Kw/2) + GLU (common.py:133-138) ----------------------------------------
+ * wf [Kw,Cin,2H]; h (nullable, saved for backward) [B,T,2H]; out [B,T,H] = h[:, :H] * sigmoid(h[:, H:]). */
+int bm_conv1d_glu_fwd(const float* x, const float* wf, const float* bias, int B, int T, int Cin, int H, int Kw,
+                      float* h, float* out, bm_stream_t stream);
+int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh, bm_stream_t stream);
+
+/* ---- K5: head Conv1d(H,2H,1) -> GELU -> ConvTranspose1d(2H,F,1) (simpleconv.py:185-189,246-249) --------
+ * x [B,T,H]; w0 [2H,H]; w2 [2H,F] (ConvTranspose1d weight is input-major); out h1,q [B,T,2H], est [B,F,T]. */
+int bm_head_fwd(const float* x, const float* w0, const float* b0, const float* w2, const float* b2, int B, int T,
+                int H, int F, float* h1, float* q, float* est, bm_stream_t stream);
+/* dest [B,F,T] -> dx [B,T,H], dw0 [2H,H], db0 [2H], dw2 [2H,F], db2 [F]; dq [B,T,2H] scratch. */
+int bm_head_bwd(const float* dest, const float* x, const float* w0, const float* w2, const float* h1,
+                const float* q, int B, int T, int H, int F, float* dq, float* dx, float* dw0, float* db0,
+                float* dw2, float* db2, bm_stream_t stream);
+
+/* ---- K6: ClipLoss (bm/losses.py:77-114) -----------------------------------------------------------------
+ * est [Bn,KT], cand [Bc,KT] (KT = F*T, any consistent flattening).
+ * bm_clip_scores = ClipLoss.get_scores (+ get_probabilities when probs != NULL):
+ *   inv_norm[o] = 1/(1e-8+||cand_o||), scores[b,o] = inv_norm[o] <est_b, cand_o>, probs = softmax_o(scores).
+ * ss: fp64 [Bc] scratch. */
+int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss, float* inv_norm,
+                   float* scores, float* probs, bm_stream_t stream);
+/* ClipLoss.forward: loss = mean_b CE(scores[b,:], target_offset + b).  target_offset = 0 is the reference;
+ * rank*Bn is the multi-GPU extension with all-gathered candidates.  row_loss [Bn] scratch, loss [1]. */
+int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long long KT, int target_offset,
+                     double* ss, float* inv_norm, float* scores, float* probs, float* row_loss, float* loss,
+                     bm_stream_t stream);
+/* dL/dest [Bn,KT] = gout * ((probs - onehot)/Bn * inv_norm) @ cand ; G [Bn,Bc] scratch; gout [1] on device. */
+int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* cand, const float* gout, int Bn,
+                     int Bc, long long KT, int target_offset, float* G, float* dest, bm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BM_B200_H_ */

@@ -1,0 +1,127 @@
+"""GPU parity tests proper: the drop-in modules (CUDA through the C ABI) against
+  (1) the golden vectors produced by the verbatim reference (tests/golden, oracle/make_golden.py), and
+  (2) the oracle restatement on freshly seeded inputs at sizes the oracle finishes in seconds.
+Tolerance: 1e-4 relative (north-star), measured as ||x - ref||_F / ||ref||_F."""
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _build_model(cfg, params, device="cuda"):
+    import brainmagick_b200 as bb
+    model = bb.SimpleConv(
+        in_channels=dict(meg=cfg.in_channels), out_channels=cfg.out_channels, hidden=dict(meg=cfg.hidden),
+        depth=cfg.depth, dilation_period=cfg.dilation_period, kernel_size=cfg.kernel_size, skip=True,
+        subject_layers=True, subject_dim=0, complex_out=True, glu=cfg.glu, glu_context=cfg.glu_context, merger=True,
+        initial_linear=cfg.initial_linear, merger_channels=cfg.merger_channels, gelu=True, batch_norm=True,
+        merger_pos_dim=cfg.merger_pos_dim, merger_dropout=cfg.merger_dropout, n_subjects=cfg.n_subjects)
+    missing = model.load_state_dict(params, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model.to(device)
+
+
+def _run_step(model, cfg, t, train, target_offset=0):
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic
+    dev = "cuda"
+    meg = t["meg"].to(dev)
+    batch = synthetic.make_batch(meg, t["subject_index"].to(dev), t["rec_positions"], t["rec_of_sample"])
+    model.train(train)
+    model.merger.ban_centre_override = t["ban_centre"]
+    clip = bb.ClipLoss().to(dev)
+    clip.train(train)
+    est = model(dict(meg=meg), batch)
+    cand = t["candidates"].to(dev)
+    mask = torch.ones(meg.shape[0], 1, meg.shape[2], dtype=torch.bool, device=dev)
+    loss = clip(est, cand, mask)
+    loss.backward()
+    scores = clip.get_scores(est.detach(), cand)
+    probs = clip.get_probabilities(est.detach(), cand)
+    torch.cuda.synchronize()
+    return est.detach().cpu(), loss.detach().cpu(), scores.cpu(), probs.cpu()
+
+
+def _check_grads(model, ref_grads, train, tol):
+    wscale = max(v.norm().item() for k, v in ref_grads.items() if k.endswith("weight") and v.numel())
+    for name, p in model.named_parameters():
+        ref = ref_grads[name]
+        assert p.grad is not None, name
+        g = p.grad.detach().cpu()
+        if train and "sequence" in name and name.endswith(".0.bias"):
+            assert g.abs().max().item() < 1e-4 * wscale + 1e-6, name      # true gradient is 0 (BN follows)
+            continue
+        assert rel_err(g, ref) < 5 * tol, (name, rel_err(g, ref))
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_drop_in_matches_reference_golden(name):
+    cfg, train, t = load_golden(name)
+    params = {k[2:]: v for k, v in t.items() if k.startswith("p.")}
+    model = _build_model(cfg, params)
+    est, loss, scores, probs = _run_step(model, cfg, t, train)
+    assert est.shape == t["estimate"].shape
+    assert rel_err(est, t["estimate"]) < TOL
+    assert rel_err(scores, t["scores"]) < TOL
+    assert abs(loss.item() - t["loss"].item()) < TOL * max(1.0, abs(t["loss"].item()))
+    assert rel_err(probs, t["probs"]) < TOL
+    k = min(5, probs.shape[1])
+    assert torch.equal(probs.topk(k, dim=1).indices, t["probs"].topk(k, dim=1).indices)
+    _check_grads(model, {k2[2:]: v for k2, v in t.items() if k2.startswith("g.")}, train, TOL)
+    sd = model.state_dict()
+    for key, v in t.items():
+        if key.startswith("bn."):
+            got = sd[key[3:]].cpu()
+            if "num_batches" in key:
+                assert int(got) == int(v)
+            else:
+                assert rel_err(got, v) < TOL, key
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=16, C=64, T=120, F=40, S=4, hidden=64, MC=48, IL=56, P=288, n_valid=()),          # cfg1-like (mock, 64 sensors)
+    dict(B=12, C=37, T=91, F=33, S=5, hidden=40, MC=30, IL=34, P=128, n_valid=(37, 20, 11)),   # ragged / padded
+])
+@pytest.mark.parametrize("train", [True, False])
+def test_drop_in_matches_oracle(shape, train):
+    from oracle import bm_oracle
+    cfg = bm_oracle.Config(in_channels=shape["C"], out_channels=shape["F"], n_subjects=shape["S"],
+                           hidden=shape["hidden"], merger_channels=shape["MC"], initial_linear=shape["IL"],
+                           merger_pos_dim=shape["P"])
+    params = bm_oracle.init_state_dict(cfg, seed=11)
+    from brainmagick_b200 import synthetic
+    d = bm_oracle.synthetic_batch(cfg, batch=shape["B"], T=shape["T"], seed=5, n_valid=shape["n_valid"])
+    d["rec_positions"] = synthetic.normalised_positions(cfg.n_subjects, cfg.in_channels, shape["n_valid"], seed=3)
+    ref = bm_oracle.training_step(params, cfg, d["meg"], d["rec_positions"], d["rec_of_sample"], d["subject_index"],
+                                  d["candidates"], ban_centre=d["ban_centre"], training=train)
+    model = _build_model(cfg, params)
+    est, loss, scores, probs = _run_step(model, cfg, d, train)
+    assert rel_err(est, ref["estimate"]) < TOL
+    assert rel_err(scores, ref["scores"]) < TOL
+    assert abs(loss.item() - ref["loss"].item()) < TOL * max(1.0, abs(ref["loss"].item()))
+    _check_grads(model, ref["grads"], train, TOL)
+    if train:
+        sd = model.state_dict()
+        for key, v in ref["bn_updates"].items():
+            assert rel_err(sd[key].cpu(), v) < TOL, key
+
+
+def test_extra_negatives_and_target_offset():
+    """B' > B (negatives beyond the targets, losses.py:105-109) and the multi-GPU target offset."""
+    import brainmagick_b200.functional as BF
+    from oracle import bm_oracle
+    torch.manual_seed(0)
+    est = torch.randn(6, 9, 31)
+    cand = torch.randn(20, 9, 31)
+    for off in (0, 6, 14):
+        e = est.clone().cuda().requires_grad_(True)
+        loss = BF.clip_loss(e, cand.cuda(), off)
+        loss.backward()
+        e_ref = est.clone().requires_grad_(True)
+        ref = bm_oracle.clip_loss(e_ref, cand, off)
+        ref.backward()
+        assert abs(loss.item() - ref.item()) < 1e-5
+        assert rel_err(e.grad.cpu(), e_ref.grad) < TOL
