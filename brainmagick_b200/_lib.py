@@ -57,6 +57,8 @@ def load():
     lib.bm_last_error.argtypes = []
     lib.bm_abi_version.restype = c_int
     lib.bm_abi_version.argtypes = []
+    lib.bm_launch_count.restype = ctypes.c_ulonglong
+    lib.bm_launch_count.argtypes = []
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = c_int
@@ -76,6 +78,10 @@ def ptr(t):
 
 def stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().bm_launch_count())
 
 
 def call(name, *args):

@@ -6,6 +6,7 @@
 
 namespace bm {
 thread_local char g_last_error[512] = "";
+unsigned long long g_launches = 0;
 }
 using namespace bm;
 
@@ -13,6 +14,7 @@ using namespace bm;
 
 extern "C" const char* bm_last_error(void) { return bm::g_last_error; }
 extern "C" int bm_abi_version(void) { return 1; }
+extern "C" unsigned long long bm_launch_count(void) { return bm::g_launches; }
 
 namespace {
 

@@ -9,6 +9,7 @@ namespace bm {
 
 // ---- error plumbing (C-ABI returns an int, message kept for bm_last_error()) -------------------
 extern thread_local char g_last_error[512];
+extern unsigned long long g_launches;   // kernels launched by this library since load (bm_launch_count())
 inline int set_error(int code, const char* fmt, const char* a = "", const char* b = "") {
     snprintf(g_last_error, sizeof(g_last_error), fmt, a, b);
     return code;
@@ -20,6 +21,7 @@ inline int set_error(int code, const char* fmt, const char* a = "", const char* 
 #define BM_CHECK_LAUNCH()                                                                           \
     do {                                                                                            \
         cudaError_t e_ = cudaGetLastError();                                                        \
+        ++::bm::g_launches;                                                                         \
         if (e_ != cudaSuccess) return ::bm::set_error(3, "%s: launch failed: %s", __func__, cudaGetErrorString(e_)); \
     } while (0)
 #define BM_CUDA(call)                                                                               \

@@ -269,6 +269,7 @@ inline cudaError_t launch_gemm(const GemmP& p, cudaStream_t st) {
     if (q.kchunk <= 0) q.kchunk = q.K;
     dim3 grid(gx, gy, gz);
     gemm_simt_kernel<<<grid, GNT, 0, st>>>(q);
+    ++g_launches;
     return cudaGetLastError();
 }
 

@@ -26,6 +26,8 @@ typedef void* bm_stream_t;
 
 const char* bm_last_error(void);
 int bm_abi_version(void);
+/* number of CUDA kernels this library has launched since it was loaded (bench.py's `gpu_launches`). */
+unsigned long long bm_launch_count(void);
 
 /* ---- K1: spatial-attention weights, once per recording ------------------------------------------------
  * replaces FourierEmb.forward (bm/models/common.py:254-271) + the score/softmax half of ChannelMerger.forward

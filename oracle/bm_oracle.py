@@ -299,3 +299,31 @@ def synthetic_batch(cfg: Config, batch: int, T: int = 360, seed: int = 2036, n_v
     ban = torch.rand(2, generator=g)
     return dict(meg=meg, candidates=cand, subject_index=subj, rec_positions=pos,
                 rec_of_sample=subj.clone(), ban_centre=ban)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the same training step on the host cores (restates solver.py:297,373,384-387 + train.py:119)
+# ------------------------------------------------------------------------------------------------
+class CpuTrainer:
+    """forward + ClipLoss + backward + Adam(lr=3e-4, betas=(0.9, 0.999)) on CPU tensors, with BatchNorm running
+    statistics carried across steps -- what `bench.py --impl reference` and the `cpu_baseline` leg time."""
+
+    def __init__(self, cfg: Config, params: tp.Dict[str, torch.Tensor], lr: float = 3e-4):
+        self.cfg = cfg
+        self.p = {k: v.clone() for k, v in params.items()}
+        self.leaves = {k: v.requires_grad_(True) for k, v in self.p.items()
+                       if v.is_floating_point() and "running" not in k}
+        self.opt = torch.optim.Adam(list(self.leaves.values()), lr=lr, betas=(0.9, 0.999))
+
+    def step(self, meg, rec_positions, rec_of_sample, subject_index, candidates, ban_centre=None) -> float:
+        self.opt.zero_grad(set_to_none=True)
+        bn_updates: dict = {}
+        est = simpleconv_forward(self.p, self.cfg, meg, rec_positions, rec_of_sample, subject_index, True,
+                                 ban_centre, bn_updates)
+        loss = clip_loss(est, candidates)
+        loss.backward()
+        self.opt.step()
+        with torch.no_grad():
+            for k, v in bn_updates.items():
+                self.p[k].copy_(v)
+        return float(loss.detach())
