@@ -17,8 +17,8 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 SIGNATURES = {
     "bm_attention_weights_fwd": [P, P, P, P, F, I, I, I, I, P, P, P],
     "bm_attention_weights_bwd": [P, P, P, I, I, I, I, P, P, P],
-    "bm_sensor_chain_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P],
-    "bm_sensor_chain_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
+    "bm_sensor_chain_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P],
+    "bm_sensor_chain_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
     "bm_conv_weight_prep": [P, I, I, I, P, P, P],
     "bm_conv1d_fwd": [P, P, P, I, I, I, I, I, I, P, P, P],
     "bm_bn_stats_finalize": [P, L, F, F, P, P, P, P, I, P],
@@ -31,9 +31,15 @@ SIGNATURES = {
     "bm_glu_bwd": [P, P, L, I, P, P],
     "bm_head_fwd": [P, P, P, P, P, I, I, I, I, P, P, P, P],
     "bm_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
+    "bm_head_bwd_params": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],
     "bm_clip_scores": [P, P, I, I, L, P, P, P, P, P],
     "bm_clip_loss_fwd": [P, P, I, I, L, I, P, P, P, P, P, P, P],
     "bm_clip_loss_bwd": [P, P, P, P, I, I, L, I, P, P, P],
+    "bm_tc_conv_supported": [I, I, I, I, I],
+    "bm_tc_weight_split": [P, I, I, I, P, P, P, P, P],
+    "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P],
+    "bm_col_stats": [P, L, I, P, P],
+    "bm_transpose_nt": [P, I, I, I, P, P],
 }
 
 _lib = None

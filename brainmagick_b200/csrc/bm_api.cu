@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
+#include "tc_conv.cuh"
 
 namespace bm {
 thread_local char g_last_error[512] = "";
@@ -81,9 +82,10 @@ extern "C" int bm_attention_weights_bwd(const float* dweights, const float* weig
 // =================================================================================================
 extern "C" int bm_sensor_chain_fwd(const float* meg, const float* weights, const int* rec_of_sample,
                                    const float* il_w, const float* il_b, const float* subj_w, const int* subject,
-                                   int B, int C, int T, int O, int IL, int D, float* u, float* v, float* x0,
-                                   bm_stream_t stream) {
+                                   int B, int C, int T, int O, int IL, int D, int ld_x0, float* u, float* v,
+                                   float* x0, bm_stream_t stream) {
     BM_CHECK_ARG(meg && weights && rec_of_sample && il_w && il_b && subj_w && subject && u && v && x0);
+    BM_CHECK_ARG(ld_x0 >= D);
     cudaStream_t st = ST(stream);
     {   // u[b][t][o] = sum_c meg[b][c][t] w[rec_b][o][c]
         GemmP g = gemm_defaults();
@@ -109,7 +111,7 @@ extern "C" int bm_sensor_chain_fwd(const float* meg, const float* weights, const
         g.Z = B; g.nseg = B; g.zchunk = 1;
         g.A = v; g.lda_z = (long long)T * IL; g.lda_m = IL; g.lda_k = 1;
         g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = 1; g.ldb_k = D; g.b_ncontig = 1;
-        g.D = x0; g.ldd_z = (long long)T * D; g.ldd_m = D; g.ldd_n = 1;
+        g.D = x0; g.ldd_z = (long long)T * ld_x0; g.ldd_m = ld_x0; g.ldd_n = 1;
         BM_CUDA(launch_gemm(g, st));
     }
     return 0;
@@ -118,9 +120,10 @@ extern "C" int bm_sensor_chain_fwd(const float* meg, const float* weights, const
 extern "C" int bm_sensor_chain_bwd(const float* dx0, const float* meg, const float* il_w, const float* subj_w,
                                    const int* subject, const float* u, const float* v, const int* subj_order,
                                    const int* subj_off, const int* rec_order, const int* rec_off, int B, int C,
-                                   int T, int O, int IL, int D, int S, int R, float* dv, float* du,
+                                   int T, int O, int IL, int D, int ld_x0, int S, int R, float* dv, float* du,
                                    float* d_subj_w, float* d_il_w, float* d_il_b, float* d_weights,
                                    bm_stream_t stream) {
+    BM_CHECK_ARG(ld_x0 >= D);
     BM_CHECK_ARG(dx0 && meg && il_w && subj_w && subject && u && v && subj_order && subj_off && rec_order && rec_off);
     BM_CHECK_ARG(dv && du && d_subj_w && d_il_w && d_il_b && d_weights);
     cudaStream_t st = ST(stream);
@@ -128,7 +131,7 @@ extern "C" int bm_sensor_chain_bwd(const float* dx0, const float* meg, const flo
         GemmP g = gemm_defaults();
         g.M = T; g.N = IL; g.K = D; g.kchunk = D;
         g.Z = B; g.nseg = B; g.zchunk = 1;
-        g.A = dx0; g.lda_z = (long long)T * D; g.lda_m = D; g.lda_k = 1;
+        g.A = dx0; g.lda_z = (long long)T * ld_x0; g.lda_m = ld_x0; g.lda_k = 1;
         g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = D; g.ldb_k = 1;
         g.D = dv; g.ldd_z = (long long)T * IL; g.ldd_m = IL; g.ldd_n = 1;
         BM_CUDA(launch_gemm(g, st));
@@ -138,7 +141,7 @@ extern "C" int bm_sensor_chain_bwd(const float* dx0, const float* meg, const flo
         g.M = IL; g.N = D; g.K = T; g.kchunk = T;
         g.Z = B; g.nseg = S; g.seg_off = subj_off; g.zlist = subj_order;
         g.A = v; g.lda_z = (long long)T * IL; g.lda_m = 1; g.lda_k = IL; g.a_mcontig = 1;
-        g.B = dx0; g.ldb_z = (long long)T * D; g.ldb_n = 1; g.ldb_k = D; g.b_ncontig = 1;
+        g.B = dx0; g.ldb_z = (long long)T * ld_x0; g.ldb_n = 1; g.ldb_k = ld_x0; g.b_ncontig = 1;
         g.D = d_subj_w; g.ldd_z = (long long)IL * D; g.ldd_m = D; g.ldd_n = 1;
         BM_CUDA(launch_gemm(g, st));
     }
@@ -352,10 +355,11 @@ extern "C" int bm_head_fwd(const float* x, const float* w0, const float* b0, con
     return 0;
 }
 
-extern "C" int bm_head_bwd(const float* dest, const float* x, const float* w0, const float* w2, const float* h1,
-                           const float* q, int B, int T, int H, int F, float* dq, float* dx, float* dw0,
-                           float* db0, float* dw2, float* db2, bm_stream_t stream) {
-    BM_CHECK_ARG(dest && x && w0 && w2 && h1 && q && dq && dx && dw0 && db0 && dw2 && db2);
+// dW2, db2, dh1 = dq*GELU'(h1) (in place in dq), dW0, db0 -- the parameter-gradient half of the head backward
+extern "C" int bm_head_bwd_params(const float* dest, const float* x, const float* h1, const float* q, int B, int T,
+                                  int H, int F, float* dq, float* dw0, float* db0, float* dw2, float* db2,
+                                  bm_stream_t stream) {
+    BM_CHECK_ARG(dest && x && h1 && q && dq && dw0 && db0 && dw2 && db2);
     cudaStream_t st = ST(stream);
     const int H2 = 2 * H;
     const long long rows = (long long)B * T;
@@ -376,15 +380,6 @@ extern "C" int bm_head_bwd(const float* dest, const float* x, const float* w0, c
         rowsum_cm_kernel<<<(unsigned)((nrows + 7) / 8), 256, 0, st>>>(dest, db2, B, F, T);
         BM_CHECK_LAUNCH();
     }
-    {   // dq[b][t][i] = sum_f dest[b][f][t] w2[i][f]
-        GemmP g = gemm_defaults();
-        g.M = T; g.N = H2; g.K = F; g.kchunk = F;
-        g.Z = B; g.nseg = B; g.zchunk = 1;
-        g.A = dest; g.lda_z = (long long)F * T; g.lda_m = 1; g.lda_k = T; g.a_mcontig = 1;
-        g.B = w2; g.ldb_n = F; g.ldb_k = 1;
-        g.D = dq; g.ldd_z = (long long)T * H2; g.ldd_m = H2; g.ldd_n = 1;
-        BM_CUDA(launch_gemm(g, st));
-    }
     gelu_bwd_kernel<<<ew_grid(rows * H2), 256, 0, st>>>(dq, h1, dq, rows * H2);   // dq <- dh1
     BM_CHECK_LAUNCH();
     {   // dw0[n][k] = sum_rows dh1[row][n] x[row][k]
@@ -404,6 +399,27 @@ extern "C" int bm_head_bwd(const float* dest, const float* x, const float* w0, c
         colsum_cl_kernel<<<grid, 128, 0, st>>>(dq, db0, rows, H2, 256);
         BM_CHECK_LAUNCH();
     }
+    return 0;
+}
+
+extern "C" int bm_head_bwd(const float* dest, const float* x, const float* w0, const float* w2, const float* h1,
+                           const float* q, int B, int T, int H, int F, float* dq, float* dx, float* dw0,
+                           float* db0, float* dw2, float* db2, bm_stream_t stream) {
+    BM_CHECK_ARG(dest && x && w0 && w2 && h1 && q && dq && dx && dw0 && db0 && dw2 && db2);
+    cudaStream_t st = ST(stream);
+    const int H2 = 2 * H;
+    const long long rows = (long long)B * T;
+    {   // dq[b][t][i] = sum_f dest[b][f][t] w2[i][f]
+        GemmP g = gemm_defaults();
+        g.M = T; g.N = H2; g.K = F; g.kchunk = F;
+        g.Z = B; g.nseg = B; g.zchunk = 1;
+        g.A = dest; g.lda_z = (long long)F * T; g.lda_m = 1; g.lda_k = T; g.a_mcontig = 1;
+        g.B = w2; g.ldb_n = F; g.ldb_k = 1;
+        g.D = dq; g.ldd_z = (long long)T * H2; g.ldd_m = H2; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    int rc = bm_head_bwd_params(dest, x, h1, q, B, T, H, F, dq, dw0, db0, dw2, db2, stream);
+    if (rc) return rc;
     {   // dx[row][k] = sum_n dh1[row][n] w0[n][k]
         GemmP g = gemm_defaults();
         g.M = (int)rows; g.N = H; g.K = H2; g.kchunk = H2;
@@ -480,5 +496,59 @@ extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const
     g.B = cand; g.ldb_n = 1; g.ldb_k = KT; g.b_ncontig = 1;
     g.D = dest; g.ldd_m = KT; g.ldd_n = 1;
     BM_CUDA(launch_gemm(g, st));
+    return 0;
+}
+
+// =================================================================================================
+// tcgen05 (tensor-core) versions of K3/K4
+// =================================================================================================
+extern "C" int bm_tc_conv_supported(int T, int Cin, int Ntot, int Kw, int glu) {
+    return tc::conv_tc_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
+}
+
+extern "C" int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, float* f_hi, float* f_lo, float* g_hi,
+                                  float* g_lo, bm_stream_t stream) {
+    BM_CHECK_ARG(w && Cout > 0 && Cin > 0 && Kw > 0);
+    BM_CHECK_ARG((f_hi == nullptr) == (f_lo == nullptr) && (g_hi == nullptr) == (g_lo == nullptr) && (f_hi || g_hi));
+    tc::weight_split_kernel<<<ew_grid((long long)Cout * Cin * Kw), 256, 0, ST(stream)>>>(w, f_hi, f_lo, g_hi, g_lo,
+                                                                                       Cout, Cin, Kw);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const float* bias,
+                            const float* addend, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
+                            int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, int* status,
+                            bm_stream_t stream) {
+    BM_CHECK_ARG(x && w_hi && w_lo && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
+    BM_CHECK_ARG(tc::conv_tc_supported(T, Cin, Ntot, Kw, glu));
+    BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
+    BM_CHECK_ARG(B <= 65535);
+    tc::ConvTcP p;
+    p.B = B; p.T = T; p.Cin = Cin; p.Ntot = Ntot; p.taps = Kw; p.dilation = dilation; p.sign = sign; p.glu = glu;
+    p.bias = bias; p.addend = addend; p.y = y; p.glu_out = glu_out; p.err = status;
+    p.act = act; p.out_tmajor = out_tmajor; p.aux = aux; p.bn = 0;
+    BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
+    return tc::launch_conv_tc(x, w_hi, w_lo, p, ST(stream));
+}
+
+// per-column sum / sum of squares of a channels-last matrix (BatchNorm batch statistics after the tcgen05 conv)
+extern "C" int bm_col_stats(const float* y, long long rows, int C, double* stats, bm_stream_t stream) {
+    BM_CHECK_ARG(y && stats && rows > 0 && C > 0);
+    cudaStream_t st = ST(stream);
+    BM_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
+    const int rpb = 128;
+    dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
+    col_stats_kernel<<<grid, 128, 0, st>>>(y, stats, rows, C, rpb);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+// [Z, N, T] (channel-major) -> [Z, T, N] (channels-last)
+extern "C" int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream) {
+    BM_CHECK_ARG(in && out && Z > 0 && N > 0 && T > 0 && Z <= 65535);
+    dim3 grid((T + 31) / 32, (N + 31) / 32, Z);
+    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T);
+    BM_CHECK_LAUNCH();
     return 0;
 }

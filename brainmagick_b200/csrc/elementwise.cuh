@@ -238,6 +238,24 @@ __global__ void colsum_cl_kernel(const float* __restrict__ X, float* __restrict_
     atomicAdd(out + c, s);
 }
 
+// stats[c] += sum_r X[r][c], stats[C+c] += sum_r X[r][c]^2   (fp64 atomics; BatchNorm batch statistics)
+__global__ void col_stats_kernel(const float* __restrict__ X, double* __restrict__ stats, long long rows, int C,
+                                 int rows_per_block) {
+    int c = blockIdx.y * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    long long r0 = (long long)blockIdx.x * rows_per_block;
+    long long r1 = min(rows, r0 + rows_per_block);
+    float s = 0.f, q = 0.f;
+#pragma unroll 4
+    for (long long r = r0; r < r1; ++r) {
+        float v = X[r * C + c];
+        s += v;
+        q = fmaf(v, v, q);
+    }
+    atomicAdd(stats + c, (double)s);
+    atomicAdd(stats + C + c, (double)q);
+}
+
 // out[n] += sum_{z,t} X[z][n][t]  (channel-major [Z,N,T]); one warp per (z, n) row
 __global__ void rowsum_cm_kernel(const float* __restrict__ X, float* __restrict__ out, int Z, int N, int T) {
     long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -366,6 +384,25 @@ __global__ void clip_ce_bwd_kernel(const float* __restrict__ probs, const float*
         int b = (int)(i / Bc), o = (int)(i - (long long)b * Bc);
         float p = probs[i] - (o == b + target_offset ? 1.f : 0.f);
         G[i] = gs * p * inv_norm[o];
+    }
+}
+
+// in [Z][N][T] -> out [Z][T][N]   (32x32 tiles through shared memory, both sides coalesced)
+__global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int T) {
+    __shared__ float tile[32][33];
+    const long long zoff = (long long)blockIdx.z * N * T;
+    int t = blockIdx.x * 32 + threadIdx.x;
+#pragma unroll
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int n = blockIdx.y * 32 + i;
+        tile[i][threadIdx.x] = (n < N && t < T) ? in[zoff + (long long)n * T + t] : 0.f;
+    }
+    __syncthreads();
+    int n = blockIdx.y * 32 + threadIdx.x;
+#pragma unroll
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        int tt = blockIdx.x * 32 + i;
+        if (n < N && tt < T) out[zoff + (long long)tt * N + n] = tile[threadIdx.x][i];
     }
 }
 

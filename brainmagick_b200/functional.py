@@ -4,6 +4,10 @@
 autograd node: its backward launches the hand-written gradient kernels in reverse order, so `loss.backward()`
 leaves ordinary dense `.grad` tensors on every parameter (what bm/solver.py:384-387 and
 flashy.distrib.sync_model expect).  `clip_loss` / `clip_scores` are ClipLoss (bm/losses.py:77-114).
+
+Kernel selection is by shape only: contractions whose channel counts fit the tcgen05 tiling (K % 32 == 0 and an
+N tile of 64..160 dividing N -- every layer of the real clip_conv model) run on the tensor-core kernels
+(3xTF32, `bm_tc_*`); other shapes (the tiny unit-test models) run on the FP32-FMA kernels of the same library.
 """
 from __future__ import annotations
 
@@ -36,10 +40,105 @@ class EncoderPlan:
     ban_radius: float
     bn_buffers: tp.List[tp.Tuple[torch.Tensor, torch.Tensor]]   # (running_mean, running_var) per layer
     keep_for_backward: bool = True
+    use_tensor_cores: bool = True
 
 
 def _empty(shape, like, dtype=torch.float32):
     return torch.empty(shape, device=like.device, dtype=dtype)
+
+
+_status: tp.Dict[torch.device, torch.Tensor] = {}
+
+
+def tc_status_tensor(device) -> torch.Tensor:
+    """Device int32 word the tcgen05 kernels set if their bounded pipeline waits ever time out."""
+    device = torch.device(device)
+    if device not in _status:
+        _status[device] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _status[device]
+
+
+def check_tc_status(device=None) -> None:
+    """Synchronising check (tests, bench, end of epoch): raises if a tensor-core kernel reported a timeout."""
+    for dev, t in _status.items():
+        if device is None or torch.device(device) == dev:
+            code = int(t.item())
+            if code != 0:
+                raise _lib.BmB200Error(f"a tcgen05 kernel reported a pipeline timeout (barrier code {code}) on {dev}")
+
+
+def _round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+class _Conv:
+    """One conv layer's prepared operands + the kernel choice (tensor-core or FP32-FMA)."""
+
+    def __init__(self, w: torch.Tensor, T: int, glu: bool, allow_tc: bool, pad_cin_to: int = 0, want_bwd=True):
+        self.cout, self.cin_true, self.kw = w.shape
+        self.glu = glu
+        w = w.contiguous()
+        if pad_cin_to and pad_cin_to != self.cin_true:
+            wp = torch.zeros(self.cout, pad_cin_to, self.kw, device=w.device, dtype=w.dtype)
+            wp[:, :self.cin_true] = w
+            w = wp
+        self.cin = w.shape[1]
+        st = stream()
+        lib = _lib.load()
+        fwd_tc = allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, 1 if glu else 0))
+        bwd_tc = allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0))
+        self.fwd_tc, self.bwd_tc = fwd_tc, bwd_tc
+        self.f_hi = self.f_lo = self.g_hi = self.g_lo = self.wf = self.wb = None
+        if fwd_tc or (bwd_tc and want_bwd):
+            if fwd_tc:
+                self.f_hi, self.f_lo = _empty((self.kw, self.cout, self.cin), w), _empty((self.kw, self.cout, self.cin), w)
+            if bwd_tc and want_bwd:
+                self.g_hi, self.g_lo = _empty((self.kw, self.cin, self.cout), w), _empty((self.kw, self.cin, self.cout), w)
+            call("bm_tc_weight_split", ptr(w), self.cout, self.cin, self.kw, ptr(self.f_hi), ptr(self.f_lo),
+                 ptr(self.g_hi), ptr(self.g_lo), st)
+        if (not fwd_tc) or (want_bwd and not bwd_tc):
+            self.wf = _empty((self.kw, self.cin, self.cout), w) if not fwd_tc else None
+            self.wb = _empty((self.kw, self.cout, self.cin), w) if (want_bwd and not bwd_tc) else None
+            call("bm_conv_weight_prep", ptr(w), self.cout, self.cin, self.kw, ptr(self.wf), ptr(self.wb), st)
+
+    # y = conv(x) (+bias); optionally BatchNorm statistics into `stats`
+    def forward(self, x, bias, B, T, dilation, y, stats, status):
+        st = stream()
+        if self.fwd_tc:
+            call("bm_tc_conv1d", ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
+                 self.kw, dilation, 1, 0, 0, 0, ptr(y), None, None, ptr(status), st)
+            if stats is not None:
+                call("bm_col_stats", ptr(y), B * T, self.cout, ptr(stats), st)
+        else:
+            call("bm_conv1d_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout, self.kw, dilation,
+                 ptr(y), ptr(stats), st)
+
+    def forward_glu(self, x, bias, B, T, h, out, status):
+        st = stream()
+        if self.fwd_tc:
+            call("bm_tc_conv1d", ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
+                 self.kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out), ptr(status), st)
+        else:
+            call("bm_conv1d_glu_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout // 2, self.kw,
+                 ptr(h), ptr(out), st)
+
+    def backward_data(self, dy, addend, B, T, dilation, dx, status):
+        st = stream()
+        if self.bwd_tc:
+            call("bm_tc_conv1d", ptr(dy), ptr(self.g_hi), ptr(self.g_lo), None, ptr(addend), B, T, self.cout,
+                 self.cin, self.kw, dilation, -1, 0, 0, 0, ptr(dx), None, None, ptr(status), st)
+        else:
+            call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
+                 dilation, ptr(dx), st)
+
+    def backward_weight(self, dy, x, B, T, dilation, like):
+        dw = _empty((self.cout, self.cin, self.kw), like)
+        db = _empty((self.cout,), like)
+        call("bm_conv1d_bwd_weight", ptr(dy), ptr(x), B, T, self.cin, self.cout, self.kw, dilation, ptr(dw), ptr(db),
+             stream())
+        if self.cin != self.cin_true:
+            dw = dw[:, :self.cin_true].contiguous()
+        return dw, db
 
 
 class _EncoderFn(torch.autograd.Function):
@@ -67,76 +166,87 @@ class _EncoderFn(torch.autograd.Function):
         F = w2.shape[1]
         rows = B * T
         save = plan.keep_for_backward
+        tc = plan.use_tensor_cores
+        status = tc_status_tensor(meg.device)
 
         # K1 attention weights per recording
         emb = _empty((R, C, P), meg)
         att = _empty((R, O, C), meg)
         call("bm_attention_weights_fwd", ptr(plan.rec_positions), ptr(plan.freq), ptr(heads.contiguous()),
              ptr(plan.ban_centre), float(plan.ban_radius), R, C, O, P, ptr(emb), ptr(att), st)
-        # K2 sensor chain
+        # K2 sensor chain; x0 is kept zero-padded to a multiple of 32 channels when the tensor-core conv follows
+        Dp = _round_up(D, 32)
+        conv0 = _Conv(conv_p[0][0], T, False, tc, pad_cin_to=Dp, want_bwd=save)
+        if not conv0.fwd_tc:
+            Dp = D
+            conv0 = _Conv(conv_p[0][0], T, False, False, want_bwd=save)
         u = _empty((B, T, O), meg)
         v = _empty((B, T, IL), meg)
-        x = _empty((B, T, D), meg)
+        x = torch.zeros((B, T, Dp), device=meg.device) if Dp != D else _empty((B, T, D), meg)
         il_w2 = il_w.reshape(IL, O).contiguous()
         call("bm_sensor_chain_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), ptr(il_w2), ptr(il_b.contiguous()),
-             ptr(subj_w.contiguous()), ptr(plan.subject), B, C, T, O, IL, D, ptr(u), ptr(v), ptr(x), st)
+             ptr(subj_w.contiguous()), ptr(plan.subject), B, C, T, O, IL, D, Dp, ptr(u), ptr(v), ptr(x), st)
 
         # K3/K4 ConvSequence
         stats = _empty((2 * H,), meg, torch.float64)
         saved_layers = []
         for k in range(depth):
             cw, cb, gamma, beta = conv_p[k]
-            cout, cin, kw = cw.shape
-            wf = _empty((kw, cin, cout), meg)
-            wb = _empty((kw, cout, cin), meg)
-            call("bm_conv_weight_prep", ptr(cw.contiguous()), cout, cin, kw, ptr(wf), ptr(wb), st)
+            conv = conv0 if k == 0 else _Conv(cw, T, False, tc, want_bwd=save)
+            cout = conv.cout
             y = _empty((B, T, cout), meg)
             mean = _empty((cout,), meg)
             invstd = _empty((cout,), meg)
             rm, rv = plan.bn_buffers[k]
             if plan.training:
-                call("bm_conv1d_fwd", ptr(x), ptr(wf), ptr(cb.contiguous()), B, T, cin, cout, kw, plan.dilations[k],
-                     ptr(y), ptr(stats), st)
+                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, stats, status)
                 call("bm_bn_stats_finalize", ptr(stats), rows, float(plan.bn_eps), float(plan.bn_momentum),
                      ptr(rm), ptr(rv), ptr(mean), ptr(invstd), cout, st)
             else:
-                call("bm_conv1d_fwd", ptr(x), ptr(wf), ptr(cb.contiguous()), B, T, cin, cout, kw, plan.dilations[k],
-                     ptr(y), None, st)
+                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, None, status)
                 call("bm_bn_eval_stats", ptr(rm), ptr(rv), float(plan.bn_eps), ptr(mean), ptr(invstd), cout, st)
-            skip = cin == cout
+            skip = conv.cin_true == cout
             x_new = _empty((B, T, cout), meg)
             call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
                  ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, st)
-            rec = dict(x_in=x, y=y, mean=mean, invstd=invstd, wb=wb, skip=skip, x_new=x_new)
+            rec = dict(x_in=x, y=y, mean=mean, invstd=invstd, conv=conv, skip=skip, x_new=x_new)
             x = x_new
             if plan.glu_after[k]:
                 gw, gb = glu_p[k]
-                g2h, gcin, gkw = gw.shape
-                gwf = _empty((gkw, gcin, g2h), meg)
-                gwb = _empty((gkw, g2h, gcin), meg)
-                call("bm_conv_weight_prep", ptr(gw.contiguous()), g2h, gcin, gkw, ptr(gwf), ptr(gwb), st)
-                h = _empty((B, T, g2h), meg) if save else None
-                out = _empty((B, T, g2h // 2), meg)
-                call("bm_conv1d_glu_fwd", ptr(x), ptr(gwf), ptr(gb.contiguous()), B, T, gcin, g2h // 2, gkw,
-                     ptr(h), ptr(out), st)
-                rec.update(h=h, gwb=gwb)
+                gconv = _Conv(gw, T, True, tc, want_bwd=save)
+                h = _empty((B, T, gconv.cout), meg) if save else None
+                out = _empty((B, T, gconv.cout // 2), meg)
+                gconv.forward_glu(x, gb.contiguous(), B, T, h, out, status)
+                rec.update(h=h, gconv=gconv)
                 x = out
             saved_layers.append(rec if save else None)
 
         # K5 head
-        w0_2 = w0.reshape(2 * H, H).contiguous()
-        w2_2 = w2.reshape(2 * H, F).contiguous()
-        h1 = _empty((B, T, 2 * H), meg)
-        q = _empty((B, T, 2 * H), meg)
+        H2 = 2 * H
+        head0 = _Conv(w0, T, False, tc, want_bwd=save)                       # [2H, H, 1]
+        w2_as_conv = w2.permute(1, 0, 2).contiguous()                        # ConvTranspose1d [2H,F,1] -> [F,2H,1]
+        head2 = _Conv(w2_as_conv, T, False, tc, want_bwd=save)
+        head_tc = head0.fwd_tc and head2.fwd_tc and head0.bwd_tc and head2.bwd_tc
+        h1 = _empty((B, T, H2), meg)
+        q = _empty((B, T, H2), meg)
         est = _empty((B, F, T), meg)
-        call("bm_head_fwd", ptr(x), ptr(w0_2), ptr(b0.contiguous()), ptr(w2_2), ptr(b2.contiguous()), B, T, H, F,
-             ptr(h1), ptr(q), ptr(est), st)
+        w0_2 = w0.reshape(H2, H).contiguous()
+        w2_2 = w2.reshape(H2, F).contiguous()
+        if head_tc:
+            call("bm_tc_conv1d", ptr(x), ptr(head0.f_hi), ptr(head0.f_lo), ptr(b0.contiguous()), None, B, T, H, H2, 1,
+                 1, 1, 0, 1, 0, ptr(q), ptr(h1), None, ptr(status), st)
+            call("bm_tc_conv1d", ptr(q), ptr(head2.f_hi), ptr(head2.f_lo), ptr(b2.contiguous()), None, B, T, H2, F, 1,
+                 1, 1, 0, 0, 1, ptr(est), None, None, ptr(status), st)
+        else:
+            call("bm_head_fwd", ptr(x), ptr(w0_2), ptr(b0.contiguous()), ptr(w2_2), ptr(b2.contiguous()), B, T, H, F,
+                 ptr(h1), ptr(q), ptr(est), st)
 
         if save:
             ctx.plan = plan
-            ctx.dims = (B, C, T, R, O, P, IL, S, D, H, F)
+            ctx.dims = (B, C, T, R, O, P, IL, S, D, Dp, H, F)
             ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(),
                              layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q,
+                             head0=head0, head2=head2, head_tc=head_tc,
                              conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape, w0_shape=w0.shape, w2_shape=w2.shape)
         return est
 
@@ -144,22 +254,37 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, dest):
         plan: EncoderPlan = ctx.plan
         s = ctx.saved
-        B, C, T, R, O, P, IL, S, D, H, F = ctx.dims
+        B, C, T, R, O, P, IL, S, D, Dp, H, F = ctx.dims
         depth = len(plan.dilations)
         st = stream()
         meg = s["meg"]
         rows = B * T
+        H2 = 2 * H
         dest = dest.contiguous()
+        status = tc_status_tensor(meg.device)
 
-        # head
-        dq = _empty((B, T, 2 * H), meg)
+        # ---- head ----
         g = _empty((B, T, H), meg)
-        dw0 = _empty((2 * H, H), meg)
-        db0 = _empty((2 * H,), meg)
-        dw2 = _empty((2 * H, F), meg)
+        dw0 = _empty((H2, H), meg)
+        db0 = _empty((H2,), meg)
+        dw2 = _empty((H2, F), meg)
         db2 = _empty((F,), meg)
-        call("bm_head_bwd", ptr(dest), ptr(s["x_last"]), ptr(s["w0_2"]), ptr(s["w2_2"]), ptr(s["h1"]), ptr(s["q"]),
-             B, T, H, F, ptr(dq), ptr(g), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)
+        dq = _empty((B, T, H2), meg)
+        if s["head_tc"]:
+            head0, head2 = s["head0"], s["head2"]
+            dest_t = _empty((B, T, F), meg)
+            call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
+            # dq = dest_t @ w2^T  (w2_as_conv [F,2H,1]: its data-gradient operand is [1][2H][F])
+            call("bm_tc_conv1d", ptr(dest_t), ptr(head2.g_hi), ptr(head2.g_lo), None, None, B, T, F, H2, 1, 1, -1, 0, 0,
+                 0, ptr(dq), None, None, ptr(status), st)
+            call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F, ptr(dq),
+                 ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)          # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
+            call("bm_tc_conv1d", ptr(dq), ptr(head0.g_hi), ptr(head0.g_lo), None, None, B, T, H2, H, 1, 1, -1, 0, 0, 0,
+                 ptr(g), None, None, ptr(status), st)
+            del dest_t
+        else:
+            call("bm_head_bwd", ptr(dest), ptr(s["x_last"]), ptr(s["w0_2"]), ptr(s["w2_2"]), ptr(s["h1"]), ptr(s["q"]),
+                 B, T, H, F, ptr(dq), ptr(g), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)
         del dq
 
         sums = _empty((2 * H,), meg, torch.float64)
@@ -168,18 +293,15 @@ class _EncoderFn(torch.autograd.Function):
         for k in reversed(range(depth)):
             rec = s["layers"][k]
             cw, cb, gamma, beta = s["conv_p"][k]
-            cout, cin, kw = cw.shape
+            conv: _Conv = rec["conv"]
+            cout = conv.cout
             if plan.glu_after[k]:
-                gw, gb = s["glu_p"][k]
-                g2h, gcin, gkw = gw.shape
-                dh = _empty((B, T, g2h), meg)
-                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, g2h // 2, ptr(dh), st)
-                dgw = _empty(gw.shape, meg)
-                dgb = _empty((g2h,), meg)
-                call("bm_conv1d_bwd_weight", ptr(dh), ptr(rec["x_new"]), B, T, gcin, g2h, gkw, 1, ptr(dgw), ptr(dgb), st)
-                g = _empty((B, T, gcin), meg)
-                call("bm_conv1d_bwd_data", ptr(dh), ptr(rec["gwb"]), None, B, T, gcin, g2h, gkw, 1, ptr(g), st)
-                glu_grads[k] = (dgw, dgb)
+                gconv: _Conv = rec["gconv"]
+                dh = _empty((B, T, gconv.cout), meg)
+                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), st)
+                glu_grads[k] = gconv.backward_weight(dh, rec["x_new"], B, T, 1, meg)
+                g = _empty((B, T, gconv.cin), meg)
+                gconv.backward_data(dh, None, B, T, 1, g, status)
                 del dh
             dy = _empty((B, T, cout), meg)
             dgamma = _empty((cout,), meg)
@@ -187,18 +309,14 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                  ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
                  ptr(dy), ptr(dgamma), ptr(dbeta), st)
-            dcw = _empty(cw.shape, meg)
-            dcb = _empty((cout,), meg)
-            call("bm_conv1d_bwd_weight", ptr(dy), ptr(rec["x_in"]), B, T, cin, cout, kw, plan.dilations[k],
-                 ptr(dcw), ptr(dcb), st)
-            g_in = _empty((B, T, cin), meg)
-            call("bm_conv1d_bwd_data", ptr(dy), ptr(rec["wb"]), ptr(g) if rec["skip"] else None, B, T, cin, cout, kw,
-                 plan.dilations[k], ptr(g_in), st)
+            dcw, dcb = conv.backward_weight(dy, rec["x_in"], B, T, plan.dilations[k], meg)
+            g_in = _empty((B, T, conv.cin), meg)
+            conv.backward_data(dy, g if rec["skip"] else None, B, T, plan.dilations[k], g_in, status)
             g = g_in
             layer_grads[k] = (dcw, dcb, dgamma, dbeta)
             del dy
 
-        # sensor chain + attention
+        # ---- sensor chain + attention ----
         subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
         counts = torch.bincount(plan.subject, minlength=S)
         subj_off = torch.zeros(S + 1, dtype=torch.int32, device=meg.device)
@@ -211,7 +329,7 @@ class _EncoderFn(torch.autograd.Function):
         d_att = _empty((R, O, C), meg)
         call("bm_sensor_chain_bwd", ptr(g), ptr(meg), ptr(s["il_w2"]), ptr(s["subj_w"]), ptr(plan.subject),
              ptr(s["u"]), ptr(s["v"]), ptr(subj_order), ptr(subj_off), ptr(plan.rec_order), ptr(plan.rec_off),
-             B, C, T, O, IL, D, S, R, ptr(dv), ptr(du), ptr(d_subj), ptr(d_il_w), ptr(d_il_b), ptr(d_att), st)
+             B, C, T, O, IL, D, Dp, S, R, ptr(dv), ptr(du), ptr(d_subj), ptr(d_il_w), ptr(d_il_b), ptr(d_att), st)
         dscores = _empty((R, O, C), meg)
         dheads = _empty((O, P), meg)
         call("bm_attention_weights_bwd", ptr(d_att), ptr(s["att"]), ptr(s["emb"]), R, C, O, P, ptr(dscores),

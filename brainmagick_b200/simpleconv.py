@@ -126,6 +126,7 @@ class SimpleConv(nn.Module):
             dilation_period=dilation_period, skip=skip, post_skip=post_skip, scale=scale, rewrite=rewrite, glu=glu,
             glu_context=glu_context, glu_glu=glu_glu, activation=nn.GELU)})
         self._freq: tp.Optional[torch.Tensor] = None
+        self.use_tensor_cores = True     # False forces the FP32-FMA kernels everywhere (debugging / A-B timing)
 
     # ------------------------------------------------------------------------------------------------
     def _layer_params(self):
@@ -156,7 +157,8 @@ class SimpleConv(nn.Module):
             rec_positions=pos, rec_of_sample=rec_of_sample, rec_order=rec_order, rec_off=rec_off,
             subject=batch.subject_index.to(device=device, dtype=torch.int32).contiguous(),
             freq=self._freq, ban_centre=self.merger.draw_ban_centre(device), ban_radius=float(self.merger.dropout),
-            bn_buffers=bn_buffers, keep_for_backward=torch.is_grad_enabled())
+            bn_buffers=bn_buffers, keep_for_backward=torch.is_grad_enabled(),
+            use_tensor_cores=self.use_tensor_cores)
 
     def forward(self, inputs, batch):
         meg = inputs["meg"]

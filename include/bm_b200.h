@@ -45,17 +45,18 @@ int bm_attention_weights_bwd(const float* dweights, const float* weights, const 
  * replaces the mixing einsum of ChannelMerger.forward (common.py:358), `initial_linear` (simpleconv.py:113-120,
  * 213-214) and SubjectLayers.forward (common.py:55-58):
  *   u[b,t,o] = sum_c weights[rec[b],o,c] meg[b,c,t];  v = il_w u + il_b;  x0[b,t,d] = sum_p subj_w[subj[b],p,d] v[b,t,p]
- * meg [B,C,T]; il_w [IL,O]; subj_w [S,IL,D]; out u [B,T,O], v [B,T,IL], x0 [B,T,D] (channels-last). */
+ * meg [B,C,T]; il_w [IL,O]; subj_w [S,IL,D]; out u [B,T,O], v [B,T,IL], x0 [B,T,ld_x0] (channels-last; ld_x0 >= D
+ * lets the caller keep x0 zero-padded to a multiple of 32 channels for the tensor-core conv that follows). */
 int bm_sensor_chain_fwd(const float* meg, const float* weights, const int* rec_of_sample, const float* il_w,
                         const float* il_b, const float* subj_w, const int* subject, int B, int C, int T, int O,
-                        int IL, int D, float* u, float* v, float* x0, bm_stream_t stream);
+                        int IL, int D, int ld_x0, float* u, float* v, float* x0, bm_stream_t stream);
 /* dx0 [B,T,D] -> d_subj_w [S,IL,D], d_il_w [IL,O], d_il_b [IL], d_weights [R,O,C].
  * (subj_order, subj_off[S+1]) and (rec_order, rec_off[R+1]) are CSR groupings of the samples by subject and by
  * recording; dv [B,T,IL] and du [B,T,O] are scratch. */
 int bm_sensor_chain_bwd(const float* dx0, const float* meg, const float* il_w, const float* subj_w,
                         const int* subject, const float* u, const float* v, const int* subj_order,
                         const int* subj_off, const int* rec_order, const int* rec_off, int B, int C, int T, int O,
-                        int IL, int D, int S, int R, float* dv, float* du, float* d_subj_w, float* d_il_w,
+                        int IL, int D, int ld_x0, int S, int R, float* dv, float* du, float* d_subj_w, float* d_il_w,
                         float* d_il_b, float* d_weights, bm_stream_t stream);
 
 /* ---- K3: dilated Conv1d + train-mode BatchNorm + GELU + skip (ConvSequence, common.py:98-151) ------------
@@ -101,6 +102,11 @@ int bm_head_bwd(const float* dest, const float* x, const float* w0, const float*
                 const float* q, int B, int T, int H, int F, float* dq, float* dx, float* dw0, float* db0,
                 float* dw2, float* db2, bm_stream_t stream);
 
+/* parameter-gradient half of bm_head_bwd, for callers that compute dq and dx themselves (tensor-core path):
+ * in: dq = d(loss)/dq [B,T,2H]; out: dw2, db2, dq <- dq*GELU'(h1) (in place), dw0, db0. */
+int bm_head_bwd_params(const float* dest, const float* x, const float* h1, const float* q, int B, int T, int H, int F,
+                       float* dq, float* dw0, float* db0, float* dw2, float* db2, bm_stream_t stream);
+
 /* ---- K6: ClipLoss (bm/losses.py:77-114) -----------------------------------------------------------------
  * est [Bn,KT], cand [Bc,KT] (KT = F*T, any consistent flattening).
  * bm_clip_scores = ClipLoss.get_scores (+ get_probabilities when probs != NULL):
@@ -116,6 +122,27 @@ int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long l
 /* dL/dest [Bn,KT] = gout * ((probs - onehot)/Bn * inv_norm) @ cand ; G [Bn,Bc] scratch; gout [1] on device. */
 int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* cand, const float* gout, int Bn,
                      int Bc, long long KT, int target_offset, float* G, float* dest, bm_stream_t stream);
+
+/* ---- tcgen05 (5th-gen tensor core) versions of K3/K4: 3xTF32 implicit-GEMM conv ---------------------------
+ * Same arithmetic contract as bm_conv1d_fwd / bm_conv1d_bwd_data / bm_conv1d_glu_fwd (fp32-faithful: every
+ * product is hi*hi + lo*hi + hi*lo of tf32 splits, fp32 accumulation in tensor memory).
+ * bm_tc_weight_split: w [Cout,Cin,Kw] -> forward operand f_hi/f_lo [Kw,Cout,Cin] and data-gradient operand
+ * g_hi/g_lo [Kw,Cin,Cout] (either pair may be NULL).
+ * bm_tc_conv1d: x [B,T,Cin], w_hi/w_lo [Kw,Ntot,Cin]; sign=+1 forward taps, -1 data gradient; glu=1: Ntot = 2H,
+ * y (nullable) receives h, glu_out [B,T,H].  status: device int (nullable) set non-zero if the kernel's pipeline
+ * timed out (never hangs).  bm_tc_conv_supported: shape gate (Cin % 32, Ntot % 160 or H % 80). */
+int bm_tc_conv_supported(int T, int Cin, int Ntot, int Kw, int glu);
+int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, float* f_hi, float* f_lo, float* g_hi,
+                       float* g_lo, bm_stream_t stream);
+int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* addend,
+                 int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
+                 float* y, float* aux, float* glu_out, int* status, bm_stream_t stream);
+/* act=1: y = GELU(.) and aux (nullable) receives the pre-activation; out_tmajor=1: y is [B,Ntot,T] (the head's
+ * channel-major `estimate`).  With Kw=1 this is the pointwise (1x1) contraction of the head (K5).
+ * bm_col_stats: stats[0:C] = sum_r y[r,c], stats[C:2C] = sum_r y[r,c]^2 (fp64), the BatchNorm batch statistics. */
+int bm_col_stats(const float* y, long long rows, int C, double* stats, bm_stream_t stream);
+/* in [Z,N,T] (channel-major) -> out [Z,T,N] (channels-last): the gradient of `estimate` enters the head backward. */
+int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream);
 
 #ifdef __cplusplus
 }

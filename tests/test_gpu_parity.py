@@ -42,6 +42,8 @@ def _run_step(model, cfg, t, train, target_offset=0):
     scores = clip.get_scores(est.detach(), cand)
     probs = clip.get_probabilities(est.detach(), cand)
     torch.cuda.synchronize()
+    from brainmagick_b200 import functional as BF
+    BF.check_tc_status()
     return est.detach().cpu(), loss.detach().cpu(), scores.cpu(), probs.cpu()
 
 
@@ -84,6 +86,7 @@ def test_drop_in_matches_reference_golden(name):
 @pytest.mark.parametrize("shape", [
     dict(B=16, C=64, T=120, F=40, S=4, hidden=64, MC=48, IL=56, P=288, n_valid=()),          # cfg1-like (mock, 64 sensors)
     dict(B=12, C=37, T=91, F=33, S=5, hidden=40, MC=30, IL=34, P=128, n_valid=(37, 20, 11)),   # ragged / padded
+    dict(B=8, C=40, T=130, F=128, S=3, hidden=160, MC=48, IL=24, P=128, n_valid=()),           # tcgen05-eligible widths
 ])
 @pytest.mark.parametrize("train", [True, False])
 def test_drop_in_matches_oracle(shape, train):
@@ -125,3 +128,51 @@ def test_extra_negatives_and_target_offset():
         ref.backward()
         assert abs(loss.item() - ref.item()) < 1e-5
         assert rel_err(e.grad.cpu(), e_ref.grad) < TOL
+
+
+def test_full_size_tensor_core_path_agrees_with_fp32_fma_path():
+    """BASELINE.json configs[1] shapes (208 sensors, T=360, F=1024, hidden 320) at B=32: the tcgen05 (3xTF32) kernels
+    and the FP32-FMA kernels are two independent implementations; estimate, loss and every gradient must agree to
+    the parity bar.  (The oracle cannot run this size in seconds; this is the size-independent cross-check.)"""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic, functional as BF
+    torch.manual_seed(3)
+    B, C, T, F, S = 32, 208, 360, 1024, 27
+    kw = dict(hidden=dict(meg=320), batch_norm=True, depth=10, dilation_period=5, kernel_size=3, skip=True,
+              subject_layers=True, subject_dim=0, complex_out=True, glu=2, glu_context=1, merger=True,
+              initial_linear=270, gelu=True, merger_pos_dim=2048)
+    model = bb.SimpleConv(in_channels=dict(meg=C), out_channels=F, n_subjects=S, **kw).cuda().train()
+    clip = bb.ClipLoss().cuda().train()
+    meg = torch.randn(B, C, T).clamp_(-20, 20).cuda()
+    cand = torch.randn(B, F, T).cuda()
+    subj = torch.randint(0, S, (B,))
+    pos = synthetic.normalised_positions(S, C, seed=1)
+    batch = synthetic.make_batch(meg, subj.cuda(), pos, subj.tolist())
+    mask = torch.ones(B, 1, T, dtype=torch.bool, device="cuda")
+    model.merger.ban_centre_override = torch.tensor([0.3, 0.6])
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    results = []
+    for use_tc in (True, False):
+        model.load_state_dict(state)
+        model.zero_grad(set_to_none=True)
+        model.use_tensor_cores = use_tc
+        est = model(dict(meg=meg), batch)
+        loss = clip(est, cand, mask)
+        loss.backward()
+        torch.cuda.synchronize()
+        BF.check_tc_status()
+        results.append((est.detach().clone(), loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (e1, l1, g1), (e0, l0, g0) = results
+    print(f"estimate rel_err(tc vs fma) = {rel_err(e1.cpu(), e0.cpu()):.2e}; loss {l1:.6f} vs {l0:.6f}")
+    assert rel_err(e1.cpu(), e0.cpu()) < TOL
+    assert abs(l1 - l0) < TOL * max(1.0, abs(l0))
+    wscale = max(v.norm().item() for k, v in g0.items() if k.endswith("weight"))
+    worst = 0.0
+    for name in g0:
+        if "sequence" in name and name.endswith(".0.bias"):
+            assert g1[name].abs().max().item() < 1e-4 * wscale + 1e-6
+            continue
+        e = rel_err(g1[name].cpu(), g0[name].cpu())
+        worst = max(worst, e)
+        assert e < 5 * TOL, (name, e)
+    print(f"worst gradient rel_err(tc vs fma) = {worst:.2e}")
