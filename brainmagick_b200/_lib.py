@@ -40,6 +40,10 @@ SIGNATURES = {
     "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_transpose_nt": [P, I, I, I, P, P],
+    "bm_tc_wgrad_supported": [I, I],
+    "bm_tc_wgrad": [P, P, I, I, I, I, I, I, I, P, P, P, P],
+    "bm_col_sum": [P, L, I, P, P],
+    "bm_gelu_bwd": [P, P, L, P, P],
 }
 
 _lib = None
@@ -65,6 +69,8 @@ def load():
     lib.bm_abi_version.argtypes = []
     lib.bm_launch_count.restype = ctypes.c_ulonglong
     lib.bm_launch_count.argtypes = []
+    lib.bm_tc_wgrad_workspace.restype = c_longlong
+    lib.bm_tc_wgrad_workspace.argtypes = [I, I, I, I]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = c_int

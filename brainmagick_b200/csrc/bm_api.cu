@@ -4,6 +4,7 @@
 #include "elementwise.cuh"
 #include "gemm_simt.cuh"
 #include "tc_conv.cuh"
+#include "tc_wgrad.cuh"
 
 namespace bm {
 thread_local char g_last_error[512] = "";
@@ -549,6 +550,36 @@ extern "C" int bm_transpose_nt(const float* in, int Z, int N, int T, float* out,
     BM_CHECK_ARG(in && out && Z > 0 && N > 0 && T > 0 && Z <= 65535);
     dim3 grid((T + 31) / 32, (N + 31) / 32, Z);
     transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+// weight gradient of a (dilated) conv / pointwise layer on the tensor cores: dW[m][n][tap] = sum_{b,t} dY[b,t,m] X[b,t+s,n]
+extern "C" int bm_tc_wgrad_supported(int M, int N) { return tc::wgrad_tc_supported(M, N) ? 1 : 0; }
+extern "C" long long bm_tc_wgrad_workspace(int B, int M, int N, int Kw) {
+    return (long long)tc::wgrad_workspace_floats(B, M, N, Kw);
+}
+extern "C" int bm_tc_wgrad(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw,
+                           int dilation, float* workspace, float* dw, int* status, bm_stream_t stream) {
+    BM_CHECK_ARG(dy && x && workspace && dw && B > 0 && T > 0 && Kw >= 1 && Kw <= 3 && dilation >= 1);
+    BM_CHECK_ARG(tc::wgrad_tc_supported(M, N) && Ntrue > 0 && Ntrue <= N);
+    return tc::launch_wgrad_tc(dy, x, B, T, M, N, Ntrue, Kw, dilation, workspace, dw, status, ST(stream));
+}
+
+extern "C" int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream) {
+    BM_CHECK_ARG(x && out && rows > 0 && C > 0);
+    cudaStream_t st = ST(stream);
+    BM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
+    dim3 grid((unsigned)((rows + 255) / 256), (C + 127) / 128);
+    colsum_cl_kernel<<<grid, 128, 0, st>>>(x, out, rows, C, 256);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+// dh = dq * GELU'(h)  (elementwise; dh may alias dq)
+extern "C" int bm_gelu_bwd(const float* dq, const float* h, long long n, float* dh, bm_stream_t stream) {
+    BM_CHECK_ARG(dq && h && dh && n > 0);
+    gelu_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(dq, h, dh, n);
     BM_CHECK_LAUNCH();
     return 0;
 }

@@ -186,7 +186,7 @@ inline PFN_bm_encodeTiled get_encode_tiled() {
 
 // fp32 tensor, innermost dimension first; strides in BYTES for dims 1..rank-1; SWIZZLE_128B; OOB reads give 0.
 inline bool make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                          const uint32_t* box) {
+                          const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_bm_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     cuuint64_t gd[5], gs[5];
@@ -194,7 +194,7 @@ inline bool make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_b[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }

@@ -71,6 +71,14 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
+def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status):
+    """dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-kw//2)*dilation,n] on the tensor cores -> [M, Ntrue, kw]."""
+    ws = _empty((int(_lib.load().bm_tc_wgrad_workspace(B, M, N, kw)),), dy)
+    dw = _empty((M, Ntrue, kw), dy)
+    call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(status), stream())
+    return dw
+
+
 class _Conv:
     """One conv layer's prepared operands + the kernel choice (tensor-core or FP32-FMA)."""
 
@@ -88,6 +96,7 @@ class _Conv:
         fwd_tc = allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, 1 if glu else 0))
         bwd_tc = allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0))
         self.fwd_tc, self.bwd_tc = fwd_tc, bwd_tc
+        self.wgrad_tc = allow_tc and bool(lib.bm_tc_wgrad_supported(self.cout, self.cin))
         self.f_hi = self.f_lo = self.g_hi = self.g_lo = self.wf = self.wb = None
         if fwd_tc or (bwd_tc and want_bwd):
             if fwd_tc:
@@ -131,9 +140,13 @@ class _Conv:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
                  dilation, ptr(dx), st)
 
-    def backward_weight(self, dy, x, B, T, dilation, like):
-        dw = _empty((self.cout, self.cin, self.kw), like)
+    def backward_weight(self, dy, x, B, T, dilation, like, status):
         db = _empty((self.cout,), like)
+        if self.wgrad_tc:
+            dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status)
+            call("bm_col_sum", ptr(dy), B * T, self.cout, ptr(db), stream())
+            return dw, db
+        dw = _empty((self.cout, self.cin, self.kw), like)
         call("bm_conv1d_bwd_weight", ptr(dy), ptr(x), B, T, self.cin, self.cout, self.kw, dilation, ptr(dw), ptr(db),
              stream())
         if self.cin != self.cin_true:
@@ -174,8 +187,8 @@ class _EncoderFn(torch.autograd.Function):
         att = _empty((R, O, C), meg)
         call("bm_attention_weights_fwd", ptr(plan.rec_positions), ptr(plan.freq), ptr(heads.contiguous()),
              ptr(plan.ban_centre), float(plan.ban_radius), R, C, O, P, ptr(emb), ptr(att), st)
-        # K2 sensor chain; x0 is kept zero-padded to a multiple of 32 channels when the tensor-core conv follows
-        Dp = _round_up(D, 32)
+        # K2 sensor chain; x0 is kept zero-padded to a multiple of 64 channels when the tensor-core conv follows
+        Dp = _round_up(D, 64)
         conv0 = _Conv(conv_p[0][0], T, False, tc, pad_cin_to=Dp, want_bwd=save)
         if not conv0.fwd_tc:
             Dp = D
@@ -277,8 +290,16 @@ class _EncoderFn(torch.autograd.Function):
             # dq = dest_t @ w2^T  (w2_as_conv [F,2H,1]: its data-gradient operand is [1][2H][F])
             call("bm_tc_conv1d", ptr(dest_t), ptr(head2.g_hi), ptr(head2.g_lo), None, None, B, T, F, H2, 1, 1, -1, 0, 0,
                  0, ptr(dq), None, None, ptr(status), st)
-            call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F, ptr(dq),
-                 ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)          # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
+            lib = _lib.load()
+            if lib.bm_tc_wgrad_supported(H2, F) and lib.bm_tc_wgrad_supported(H2, H):
+                dw2 = tc_wgrad(s["q"], dest_t, B, T, H2, F, F, 1, 1, status).reshape(H2, F)
+                call("bm_col_sum", ptr(dest_t), rows, F, ptr(db2), st)
+                call("bm_gelu_bwd", ptr(dq), ptr(s["h1"]), rows * H2, ptr(dq), st)           # dq <- dh1
+                dw0 = tc_wgrad(dq, s["x_last"], B, T, H2, H, H, 1, 1, status).reshape(H2, H)
+                call("bm_col_sum", ptr(dq), rows, H2, ptr(db0), st)
+            else:
+                call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F,
+                     ptr(dq), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)   # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
             call("bm_tc_conv1d", ptr(dq), ptr(head0.g_hi), ptr(head0.g_lo), None, None, B, T, H2, H, 1, 1, -1, 0, 0, 0,
                  ptr(g), None, None, ptr(status), st)
             del dest_t
@@ -299,7 +320,7 @@ class _EncoderFn(torch.autograd.Function):
                 gconv: _Conv = rec["gconv"]
                 dh = _empty((B, T, gconv.cout), meg)
                 call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), st)
-                glu_grads[k] = gconv.backward_weight(dh, rec["x_new"], B, T, 1, meg)
+                glu_grads[k] = gconv.backward_weight(dh, rec["x_new"], B, T, 1, meg, status)
                 g = _empty((B, T, gconv.cin), meg)
                 gconv.backward_data(dh, None, B, T, 1, g, status)
                 del dh
@@ -309,7 +330,7 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                  ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
                  ptr(dy), ptr(dgamma), ptr(dbeta), st)
-            dcw, dcb = conv.backward_weight(dy, rec["x_in"], B, T, plan.dilations[k], meg)
+            dcw, dcb = conv.backward_weight(dy, rec["x_in"], B, T, plan.dilations[k], meg, status)
             g_in = _empty((B, T, conv.cin), meg)
             conv.backward_data(dy, g if rec["skip"] else None, B, T, plan.dilations[k], g_in, status)
             g = g_in

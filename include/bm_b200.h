@@ -141,6 +141,17 @@ int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const flo
  * channel-major `estimate`).  With Kw=1 this is the pointwise (1x1) contraction of the head (K5).
  * bm_col_stats: stats[0:C] = sum_r y[r,c], stats[C:2C] = sum_r y[r,c]^2 (fp64), the BatchNorm batch statistics. */
 int bm_col_stats(const float* y, long long rows, int C, double* stats, bm_stream_t stream);
+/* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]
+ * for n < Ntrue (x may be channel-padded to N); dy [B,T,M], x [B,T,N] channels-last; dw in nn.Conv1d layout
+ * [M][Ntrue][Kw].  workspace: bm_tc_wgrad_workspace() floats (per-batch-slice partial tiles, reduced in a fixed
+ * order => deterministic).  bm_col_sum: out[c] = sum_r x[r,c] (bias gradients). */
+int bm_tc_wgrad_supported(int M, int N);
+long long bm_tc_wgrad_workspace(int B, int M, int N, int Kw);
+int bm_tc_wgrad(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw, int dilation,
+                float* workspace, float* dw, int* status, bm_stream_t stream);
+int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream);
+/* dh = dq * GELU'(h), elementwise over n values (dh may alias dq): the head's activation backward. */
+int bm_gelu_bwd(const float* dq, const float* h, long long n, float* dh, bm_stream_t stream);
 /* in [Z,N,T] (channel-major) -> out [Z,T,N] (channels-last): the gradient of `estimate` enters the head backward. */
 int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream);
 

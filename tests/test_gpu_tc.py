@@ -108,3 +108,60 @@ def test_tc_conv_speed_report(capsys):
     tf = 2.0 * C * C * Kw * T * B / (ms * 1e-3) / 1e12
     with capsys.disabled():
         print(f"\n[tc conv 320->320 k3 B=256 T=360] {ms:.3f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=5, T=360, M=320, N=320, Kw=3, dil=1),
+    dict(B=3, T=343, M=320, N=320, Kw=3, dil=16),
+    dict(B=4, T=100, M=640, N=320, Kw=3, dil=2),
+    dict(B=3, T=360, M=640, N=1024, Kw=1, dil=1),
+])
+def test_tc_wgrad(case):
+    call, ptr, stream = _call()
+    from brainmagick_b200 import _lib
+    torch.manual_seed(11)
+    B, T, M, N, Kw, dil = (case[k] for k in ("B", "T", "M", "N", "Kw", "dil"))
+    dev = "cuda"
+    dy = torch.randn(B, T, M, device=dev)
+    x = torch.randn(B, T, N, device=dev)
+    ws = torch.empty(_lib.load().bm_tc_wgrad_workspace(B, M, N, Kw), device=dev)
+    dw = torch.full((M, N, Kw), float("nan"), device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw), ptr(status), stream())
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
+    # fp64 reference: dw[m,n,j] = sum_{b,t} dy[b,t,m] x[b,t+(j-Kw//2)*dil,n]
+    ref = torch.zeros(M, N, Kw, dtype=torch.float64, device=dev)
+    xd, dyd = x.double(), dy.double()
+    for j in range(Kw):
+        s = (j - Kw // 2) * dil
+        lo, hi = max(0, -s), min(T, T - s)
+        ref[:, :, j] = torch.einsum("btm,btn->mn", dyd[:, lo:hi], xd[:, lo + s:hi + s])
+    e = rel_err(dw.cpu(), ref.cpu())
+    print(f"[tc wgrad {case}] rel_err vs fp64 = {e:.2e}")
+    assert e < TOL
+
+
+def test_tc_wgrad_speed_report(capsys):
+    call, ptr, stream = _call()
+    from brainmagick_b200 import _lib
+    B, T, M, N, Kw = 256, 360, 320, 320, 3
+    dev = "cuda"
+    dy = torch.randn(B, T, M, device=dev)
+    x = torch.randn(B, T, N, device=dev)
+    ws = torch.empty(_lib.load().bm_tc_wgrad_workspace(B, M, N, Kw), device=dev)
+    dw = torch.empty(M, N, Kw, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws), ptr(dw), ptr(status), stream())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws), ptr(dw), ptr(status), stream())
+    e1.record()
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    ms = e0.elapsed_time(e1) / 10
+    tf = 2.0 * M * N * Kw * T * B / (ms * 1e-3) / 1e12
+    with capsys.disabled():
+        print(f"\n[tc wgrad 320x320 k3 B=256 T=360] {ms:.3f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
