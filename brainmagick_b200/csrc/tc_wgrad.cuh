@@ -254,7 +254,7 @@ inline void wgrad_geometry(int B, int M, int N, int taps, int* nh, int* mblocks,
     *nh = wgrad_pick_nh(N);
     *mblocks = (M + WG_BM - 1) / WG_BM;
     int tiles = (*mblocks) * (N / (2 * *nh)) * taps;
-    int want = (num_sms() + tiles - 1) / tiles;
+    int want = num_sms() / tiles;                 // floor: the whole grid must fit in ONE wave (1 CTA per SM)
     if (want < 1) want = 1;
     if (want > B) want = B;
     *bchunk = (B + want - 1) / want;

@@ -1,0 +1,61 @@
+"""CPU, world_size 2, gloo: the N>1 host logic (candidate all-gather + target offsets, gradient all-reduce) and the
+multi-GPU oracle of SURVEY.md 8(e): per-rank encoder (local BatchNorm statistics) + global negatives."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from brainmagick_b200 import distrib
+        torch.manual_seed(100 + rank)
+        cand = torch.randn(3, 4, 5)
+        gathered, off = distrib.all_gather_candidates(cand)
+        assert gathered.shape == (3 * world, 4, 5) and off == 3 * rank
+        assert torch.equal(gathered[off:off + 3], cand)
+        # gradient all-reduce(avg) over a flat bucket
+        p1, p2 = torch.nn.Parameter(torch.zeros(4, 3)), torch.nn.Parameter(torch.zeros(7))
+        p1.grad = torch.full((4, 3), float(rank + 1))
+        p2.grad = torch.arange(7.) * (rank + 1)
+        distrib.sync_gradients([p1, p2])
+        mean_scale = sum(r + 1 for r in range(world)) / world
+        assert torch.allclose(p1.grad, torch.full((4, 3), mean_scale))
+        assert torch.allclose(p2.grad, torch.arange(7.) * mean_scale)
+        ret[rank] = (gathered.clone(), off)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_allgather_and_grad_sync():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        g0, off0 = ret[0]
+        g1, off1 = ret[1]
+        assert torch.equal(g0, g1) and (off0, off1) == (0, 3)
+
+
+def test_multi_gpu_oracle_decomposes_into_per_rank_losses():
+    """global loss = mean over ranks of CE(scores_r[B/W, B], targets r*B/W + arange); with ONE
+    rank it equals the reference loss."""
+    from oracle import bm_oracle
+    torch.manual_seed(0)
+    est = torch.randn(8, 5, 12)
+    cand = torch.randn(8, 5, 12)
+    ref = bm_oracle.clip_loss(est, cand)
+    parts = [bm_oracle.clip_loss(est[r * 4:(r + 1) * 4], cand, target_offset=r * 4) for r in range(2)]
+    assert abs(float(sum(parts) / 2) - float(ref)) < 1e-6
