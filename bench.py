@@ -233,7 +233,7 @@ def run_b200(args):
 
 
 def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
-    """Times the dominant kernel alone -- bm_tc_conv1d, the tcgen05 3xTF32 implicit-GEMM conv (K3: 320->320, k=3) --
+    """Times the dominant kernel alone -- bm_tc_conv1d_pair, the tcgen05 3xTF32 implicit-GEMM conv (K3: 320->320, k=3) --
     with CUDA events on the launching stream, L2 flushed between launches.  Algorithmic work: 2*H*H*Kw*T FLOP per
     segment (221.2 MFLOP/seg); the tensor pipe executes 3x that (hi*hi + lo*hi + hi*lo)."""
     from brainmagick_b200._lib import call, ptr, stream
@@ -251,8 +251,8 @@ def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
         flush.zero_()                                                   # L2 flush between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call("bm_tc_conv1d", ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
-             ptr(status), stream())
+        call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None,
+             None, ptr(status), stream())
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -262,7 +262,7 @@ def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
     flops = 2.0 * H * H * Kw * T * B
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops"]
-    return dict(kernel="conv_tc_kernel via bm_tc_conv1d (K3: Conv1d 320->320 k3 d4, tcgen05 kind::tf32, 3xTF32)",
+    return dict(kernel="conv_tc3_kernel via bm_tc_conv1d_pair (K3: Conv1d 320->320 k3 d4, tcgen05 cta_group::2 kind::tf32, 3xTF32)",
                 bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
                 ms_per_launch=ms, peak_source=peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
                 executed_tflops=3 * achieved, tf32_pipe_peak=peak / 2, frac_of_tf32_pipe_executed=3 * achieved / (peak / 2),

@@ -35,9 +35,13 @@ SIGNATURES = {
     "bm_clip_scores": [P, P, I, I, L, P, P, P, P, P],
     "bm_clip_loss_fwd": [P, P, I, I, L, I, P, P, P, P, P, P, P],
     "bm_clip_loss_bwd": [P, P, P, P, I, I, L, I, P, P, P],
+    "bm_set_debug_flags": [I],
     "bm_tc_conv_supported": [I, I, I, I, I],
+    "bm_tc_conv2_supported": [I, I, I, I, I],
     "bm_tc_weight_split": [P, I, I, I, P, P, P, P, P],
     "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P],
+    "bm_tc_conv3_supported": [I, I, I, I, I],
+    "bm_tc_conv1d_pair": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_transpose_nt": [P, I, I, I, P, P],
     "bm_tc_wgrad_supported": [I, I],

@@ -5,10 +5,13 @@
 #include "gemm_simt.cuh"
 #include "tc_conv.cuh"
 #include "tc_wgrad.cuh"
+#include "tc_conv2.cuh"
+#include "tc_conv3.cuh"
 
 namespace bm {
 thread_local char g_last_error[512] = "";
 unsigned long long g_launches = 0;
+int g_debug_flags = 0;
 }
 using namespace bm;
 
@@ -17,6 +20,7 @@ using namespace bm;
 extern "C" const char* bm_last_error(void) { return bm::g_last_error; }
 extern "C" int bm_abi_version(void) { return 1; }
 extern "C" unsigned long long bm_launch_count(void) { return bm::g_launches; }
+extern "C" int bm_set_debug_flags(int flags) { int old = bm::g_debug_flags; bm::g_debug_flags = flags; return old; }
 
 namespace {
 
@@ -507,10 +511,14 @@ extern "C" int bm_tc_conv_supported(int T, int Cin, int Ntot, int Kw, int glu) {
     return tc::conv_tc_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
 }
 
+extern "C" int bm_tc_conv2_supported(int T, int Cin, int Ntot, int Kw, int glu) {
+    return tc::conv_tc2_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
+}
+
 extern "C" int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, float* f_hi, float* f_lo, float* g_hi,
                                   float* g_lo, bm_stream_t stream) {
     BM_CHECK_ARG(w && Cout > 0 && Cin > 0 && Kw > 0);
-    BM_CHECK_ARG((f_hi == nullptr) == (f_lo == nullptr) && (g_hi == nullptr) == (g_lo == nullptr) && (f_hi || g_hi));
+    BM_CHECK_ARG((f_hi || g_hi) && !(f_lo && !f_hi) && !(g_lo && !g_hi));
     tc::weight_split_kernel<<<ew_grid((long long)Cout * Cin * Kw), 256, 0, ST(stream)>>>(w, f_hi, f_lo, g_hi, g_lo,
                                                                                        Cout, Cin, Kw);
     BM_CHECK_LAUNCH();
@@ -521,10 +529,19 @@ extern "C" int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo
                             const float* addend, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
                             int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, int* status,
                             bm_stream_t stream) {
-    BM_CHECK_ARG(x && w_hi && w_lo && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
-    BM_CHECK_ARG(tc::conv_tc_supported(T, Cin, Ntot, Kw, glu));
+    BM_CHECK_ARG(x && w_hi && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
     BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
     BM_CHECK_ARG(B <= 65535);
+    BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
+    if (w_lo == nullptr) {      // second-generation kernel: raw fp32 weights, split in shared memory
+        BM_CHECK_ARG(tc::conv_tc2_supported(T, Cin, Ntot, Kw, glu));
+        tc::Conv2P q;
+        q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
+        q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
+        q.glu_out = glu_out; q.err = status;
+        return tc::launch_conv_tc2(x, w_hi, q, ST(stream));
+    }
+    BM_CHECK_ARG(tc::conv_tc_supported(T, Cin, Ntot, Kw, glu));
     tc::ConvTcP p;
     p.B = B; p.T = T; p.Cin = Cin; p.Ntot = Ntot; p.taps = Kw; p.dilation = dilation; p.sign = sign; p.glu = glu;
     p.bias = bias; p.addend = addend; p.y = y; p.glu_out = glu_out; p.err = status;
@@ -582,4 +599,23 @@ extern "C" int bm_gelu_bwd(const float* dq, const float* h, long long n, float* 
     gelu_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(dq, h, dh, n);
     BM_CHECK_LAUNCH();
     return 0;
+}
+
+// third-generation conv kernel: CTA pairs (tcgen05 cta_group::2); same contract as bm_tc_conv1d with pre-split weights
+extern "C" int bm_tc_conv3_supported(int T, int Cin, int Ntot, int Kw, int glu) {
+    return tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
+}
+extern "C" int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, const float* bias,
+                                 const float* addend, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
+                                 int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, int* status,
+                                 bm_stream_t stream) {
+    BM_CHECK_ARG(x && w_hi && w_lo && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
+    BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
+    BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
+    BM_CHECK_ARG(tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu));
+    tc::Conv3P q;
+    q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
+    q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
+    q.glu_out = glu_out; q.err = status;
+    return tc::launch_conv_tc3(x, w_hi, w_lo, q, ST(stream));
 }

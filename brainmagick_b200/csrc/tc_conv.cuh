@@ -242,8 +242,9 @@ __global__ void weight_split_kernel(const float* __restrict__ W, float* __restri
         float v = W[idx];
         float h = tf32_rna(v), l = tf32_rna(v - h);
         long long fi = ((long long)j * O + o) * I + i, gi = ((long long)j * I + i) * O + o;
-        if (f_hi) { f_hi[fi] = h; f_lo[fi] = l; }
-        if (g_hi) { g_hi[gi] = h; g_lo[gi] = l; }
+        // a NULL lo pointer asks for the RAW fp32 value in the re-laid array (the v2 kernel splits in shared memory)
+        if (f_hi) { if (f_lo) { f_hi[fi] = h; f_lo[fi] = l; } else f_hi[fi] = v; }
+        if (g_hi) { if (g_lo) { g_hi[gi] = h; g_lo[gi] = l; } else g_hi[gi] = v; }
     }
 }
 

@@ -35,6 +35,8 @@ struct WgradP {
     const float* dY;            // [B,T,M]
     float* P;                   // [taps][ksplit][Mpad][N] partial tiles, Mpad = gridDim.y*128
     int* err;
+    int trunc_hi;               // 1: leave X raw in smem as the hi operand (the tensor core ignores the 13 low mantissa
+                                //    bits) and write only lo = x - trunc(x): one third less converter smem traffic
 };
 
 // MN-major tf32 operand: the only legal shared-memory layout is SWIZZLE_128B_BASE32B (cutlass sm100_common.inl:92):
@@ -190,12 +192,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
             float4* bh = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES);
             float4* bl = reinterpret_cast<float4*>(smem + s * WG_STAGE_BYTES + WG_B_BYTES_MAX);
             const int nvec = (int)(b_bytes / 16);
-            for (int idx = ct; idx < nvec; idx += 128) {
-                float4 v = bh[idx], h, l;
-                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
-                bh[idx] = h;
-                bl[idx] = l;
+            if (p.trunc_hi) {
+#pragma unroll 4
+                for (int idx = ct; idx < nvec; idx += 128) {
+                    const float4 v = bh[idx];
+                    float4 l;
+                    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    bl[idx] = l;
+                }
+            } else {
+#pragma unroll 2
+                for (int idx = ct; idx < nvec; idx += 128) {
+                    float4 v = bh[idx], h, l;
+                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    bh[idx] = h;
+                    bl[idx] = l;
+                }
             }
             fence_proxy_async();
             tc_fence_before();
@@ -289,6 +305,7 @@ inline int launch_wgrad_tc(const float* dY, const float* X, int B, int T, int M,
     WgradP p;
     p.B = B; p.T = T; p.M = M; p.N = N; p.nh = nh; p.taps = taps; p.dilation = dilation;
     p.ksplit = ksplit; p.bchunk = bchunk; p.dY = dY; p.err = err; p.P = ws;
+    p.trunc_hi = (g_debug_flags & 1) ? 0 : 1;     // default ON; debug bit 0 restores the explicit rna split
     dim3 grid(N / (2 * nh) * taps, mblocks, ksplit);
     wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(tmX, p);
     ++g_launches;

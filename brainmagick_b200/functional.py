@@ -67,6 +67,10 @@ def check_tc_status(device=None) -> None:
                 raise _lib.BmB200Error(f"a tcgen05 kernel reported a pipeline timeout (barrier code {code}) on {dev}")
 
 
+USE_CONV_V2 = False    # single-CTA 128x320 kernel (tc_conv2.cuh): validated, but shared-memory-bandwidth bound
+USE_CONV_V3 = True     # CTA-pair kernel (tc_conv3.cuh, tcgen05 cta_group::2): the fastest where its tiling fits
+
+
 def _round_up(n, m):
     return (n + m - 1) // m * m
 
@@ -93,16 +97,28 @@ class _Conv:
         self.cin = w.shape[1]
         st = stream()
         lib = _lib.load()
-        fwd_tc = allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, 1 if glu else 0))
-        bwd_tc = allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0))
+        g = 1 if glu else 0
+        fwd_v2 = allow_tc and USE_CONV_V2 and bool(lib.bm_tc_conv2_supported(T, self.cin, self.cout, self.kw, g))
+        bwd_v2 = allow_tc and USE_CONV_V2 and bool(lib.bm_tc_conv2_supported(T, self.cout, self.cin, self.kw, 0))
+        self.fwd_v3 = allow_tc and USE_CONV_V3 and bool(lib.bm_tc_conv3_supported(T, self.cin, self.cout, self.kw, g))
+        self.bwd_v3 = allow_tc and USE_CONV_V3 and bool(lib.bm_tc_conv3_supported(T, self.cout, self.cin, self.kw, 0))
+        fwd_v2 = fwd_v2 and not self.fwd_v3
+        bwd_v2 = bwd_v2 and not self.bwd_v3
+        fwd_tc = self.fwd_v3 or fwd_v2 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, g)))
+        bwd_tc = self.bwd_v3 or bwd_v2 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0)))
         self.fwd_tc, self.bwd_tc = fwd_tc, bwd_tc
+        self.fwd_fn = "bm_tc_conv1d_pair" if self.fwd_v3 else "bm_tc_conv1d"
+        self.bwd_fn = "bm_tc_conv1d_pair" if self.bwd_v3 else "bm_tc_conv1d"
         self.wgrad_tc = allow_tc and bool(lib.bm_tc_wgrad_supported(self.cout, self.cin))
         self.f_hi = self.f_lo = self.g_hi = self.g_lo = self.wf = self.wb = None
         if fwd_tc or (bwd_tc and want_bwd):
+            # v2 kernels take the RAW re-laid weights (lo = None); v1 kernels take the pre-split tf32 hi/lo pair
             if fwd_tc:
-                self.f_hi, self.f_lo = _empty((self.kw, self.cout, self.cin), w), _empty((self.kw, self.cout, self.cin), w)
+                self.f_hi = _empty((self.kw, self.cout, self.cin), w)
+                self.f_lo = None if fwd_v2 else _empty((self.kw, self.cout, self.cin), w)
             if bwd_tc and want_bwd:
-                self.g_hi, self.g_lo = _empty((self.kw, self.cin, self.cout), w), _empty((self.kw, self.cin, self.cout), w)
+                self.g_hi = _empty((self.kw, self.cin, self.cout), w)
+                self.g_lo = None if bwd_v2 else _empty((self.kw, self.cin, self.cout), w)
             call("bm_tc_weight_split", ptr(w), self.cout, self.cin, self.kw, ptr(self.f_hi), ptr(self.f_lo),
                  ptr(self.g_hi), ptr(self.g_lo), st)
         if (not fwd_tc) or (want_bwd and not bwd_tc):
@@ -114,7 +130,7 @@ class _Conv:
     def forward(self, x, bias, B, T, dilation, y, stats, status):
         st = stream()
         if self.fwd_tc:
-            call("bm_tc_conv1d", ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
+            call(self.fwd_fn, ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
                  self.kw, dilation, 1, 0, 0, 0, ptr(y), None, None, ptr(status), st)
             if stats is not None:
                 call("bm_col_stats", ptr(y), B * T, self.cout, ptr(stats), st)
@@ -125,7 +141,7 @@ class _Conv:
     def forward_glu(self, x, bias, B, T, h, out, status):
         st = stream()
         if self.fwd_tc:
-            call("bm_tc_conv1d", ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
+            call(self.fwd_fn, ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
                  self.kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out), ptr(status), st)
         else:
             call("bm_conv1d_glu_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout // 2, self.kw,
@@ -134,7 +150,7 @@ class _Conv:
     def backward_data(self, dy, addend, B, T, dilation, dx, status):
         st = stream()
         if self.bwd_tc:
-            call("bm_tc_conv1d", ptr(dy), ptr(self.g_hi), ptr(self.g_lo), None, ptr(addend), B, T, self.cout,
+            call(self.bwd_fn, ptr(dy), ptr(self.g_hi), ptr(self.g_lo), None, ptr(addend), B, T, self.cout,
                  self.cin, self.kw, dilation, -1, 0, 0, 0, ptr(dx), None, None, ptr(status), st)
         else:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
@@ -246,9 +262,9 @@ class _EncoderFn(torch.autograd.Function):
         w0_2 = w0.reshape(H2, H).contiguous()
         w2_2 = w2.reshape(H2, F).contiguous()
         if head_tc:
-            call("bm_tc_conv1d", ptr(x), ptr(head0.f_hi), ptr(head0.f_lo), ptr(b0.contiguous()), None, B, T, H, H2, 1,
+            call(head0.fwd_fn, ptr(x), ptr(head0.f_hi), ptr(head0.f_lo), ptr(b0.contiguous()), None, B, T, H, H2, 1,
                  1, 1, 0, 1, 0, ptr(q), ptr(h1), None, ptr(status), st)
-            call("bm_tc_conv1d", ptr(q), ptr(head2.f_hi), ptr(head2.f_lo), ptr(b2.contiguous()), None, B, T, H2, F, 1,
+            call(head2.fwd_fn, ptr(q), ptr(head2.f_hi), ptr(head2.f_lo), ptr(b2.contiguous()), None, B, T, H2, F, 1,
                  1, 1, 0, 0, 1, ptr(est), None, None, ptr(status), st)
         else:
             call("bm_head_fwd", ptr(x), ptr(w0_2), ptr(b0.contiguous()), ptr(w2_2), ptr(b2.contiguous()), B, T, H, F,
@@ -288,7 +304,7 @@ class _EncoderFn(torch.autograd.Function):
             dest_t = _empty((B, T, F), meg)
             call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
             # dq = dest_t @ w2^T  (w2_as_conv [F,2H,1]: its data-gradient operand is [1][2H][F])
-            call("bm_tc_conv1d", ptr(dest_t), ptr(head2.g_hi), ptr(head2.g_lo), None, None, B, T, F, H2, 1, 1, -1, 0, 0,
+            call(head2.bwd_fn, ptr(dest_t), ptr(head2.g_hi), ptr(head2.g_lo), None, None, B, T, F, H2, 1, 1, -1, 0, 0,
                  0, ptr(dq), None, None, ptr(status), st)
             lib = _lib.load()
             if lib.bm_tc_wgrad_supported(H2, F) and lib.bm_tc_wgrad_supported(H2, H):
@@ -300,7 +316,7 @@ class _EncoderFn(torch.autograd.Function):
             else:
                 call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F,
                      ptr(dq), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)   # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
-            call("bm_tc_conv1d", ptr(dq), ptr(head0.g_hi), ptr(head0.g_lo), None, None, B, T, H2, H, 1, 1, -1, 0, 0, 0,
+            call(head0.bwd_fn, ptr(dq), ptr(head0.g_hi), ptr(head0.g_lo), None, None, B, T, H2, H, 1, 1, -1, 0, 0, 0,
                  ptr(g), None, None, ptr(status), st)
             del dest_t
         else:

@@ -28,6 +28,10 @@ const char* bm_last_error(void);
 int bm_abi_version(void);
 /* number of CUDA kernels this library has launched since it was loaded (bench.py's `gpu_launches`). */
 unsigned long long bm_launch_count(void);
+/* experiment switches (returns the previous value).  By default bm_tc_wgrad keeps X raw in shared memory as the tf32
+ * `hi` operand (the tensor core ignores the 13 low mantissa bits) and only writes `lo = x - trunc(x)`; bit 0 restores
+ * the explicit round-to-nearest hi/lo split (one third more shared-memory traffic). */
+int bm_set_debug_flags(int flags);
 
 /* ---- K1: spatial-attention weights, once per recording ------------------------------------------------
  * replaces FourierEmb.forward (bm/models/common.py:254-271) + the score/softmax half of ChannelMerger.forward
@@ -132,6 +136,10 @@ int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* can
  * y (nullable) receives h, glu_out [B,T,H].  status: device int (nullable) set non-zero if the kernel's pipeline
  * timed out (never hangs).  bm_tc_conv_supported: shape gate (Cin % 32, Ntot % 160 or H % 80). */
 int bm_tc_conv_supported(int T, int Cin, int Ntot, int Kw, int glu);
+/* second-generation kernel (128 x 2*NH tile, activations through tensor memory, weights split in shared memory):
+ * selected by passing w_lo = NULL and w_hi = the RAW fp32 re-laid weights (bm_tc_weight_split with f_lo/g_lo = NULL).
+ * Shape gate: Cin % 32 == 0 and Ntot % 320 == 0 or Ntot % 256 == 0 (GLU: H % 160 == 0 or H % 128 == 0). */
+int bm_tc_conv2_supported(int T, int Cin, int Ntot, int Kw, int glu);
 int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, float* f_hi, float* f_lo, float* g_hi,
                        float* g_lo, bm_stream_t stream);
 int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* addend,
@@ -141,6 +149,14 @@ int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const flo
  * channel-major `estimate`).  With Kw=1 this is the pointwise (1x1) contraction of the head (K5).
  * bm_col_stats: stats[0:C] = sum_r y[r,c], stats[C:2C] = sum_r y[r,c]^2 (fp64), the BatchNorm batch statistics. */
 int bm_col_stats(const float* y, long long rows, int C, double* stats, bm_stream_t stream);
+/* third-generation kernel: CTA PAIRS (tcgen05.mma.cta_group::2, M = 256 over two SMs; each CTA holds half of every
+ * weight tile, activations go through tensor memory).  Same arithmetic contract and arguments as bm_tc_conv1d with
+ * the pre-split (w_hi, w_lo) weights.  Shape gate as bm_tc_conv2_supported. */
+int bm_tc_conv3_supported(int T, int Cin, int Ntot, int Kw, int glu);
+int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* addend,
+                      int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
+                      float* y, float* aux, float* glu_out, int* status, bm_stream_t stream);
+
 /* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]
  * for n < Ntrue (x may be channel-padded to N); dy [B,T,M], x [B,T,N] channels-last; dw in nn.Conv1d layout
  * [M][Ntrue][Kw].  workspace: bm_tc_wgrad_workspace() floats (per-batch-slice partial tiles, reduced in a fixed

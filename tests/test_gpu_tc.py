@@ -16,6 +16,9 @@ def _call():
     return _lib.call, _lib.ptr, _lib.stream
 
 
+_FN = {1: "bm_tc_conv1d", 2: "bm_tc_conv1d", 3: "bm_tc_conv1d_pair"}
+
+
 def _ref_conv(x, w, bias, dilation):
     """x [B,T,Cin] channels-last, w [Cout,Cin,Kw] -> y [B,T,Cout] in fp64 (torch, test-only)."""
     y = torch.nn.functional.conv1d(x.double().permute(0, 2, 1), w.double(), None if bias is None else bias.double(),
@@ -23,9 +26,10 @@ def _ref_conv(x, w, bias, dilation):
     return y.permute(0, 2, 1).contiguous()
 
 
+@pytest.mark.parametrize("gen", [1, 2, 3])
 @pytest.mark.parametrize("dilation", [1, 2, 16])
 @pytest.mark.parametrize("T", [360, 343, 100])
-def test_tc_conv_forward(dilation, T):
+def test_tc_conv_forward(dilation, T, gen):
     call, ptr, stream = _call()
     torch.manual_seed(dilation * 1000 + T)
     B, Cin, Cout, Kw = 3, 320, 320, 3
@@ -33,21 +37,23 @@ def test_tc_conv_forward(dilation, T):
     x = torch.randn(B, T, Cin, device=dev)
     w = torch.randn(Cout, Cin, Kw, device=dev) / (Cin * Kw) ** 0.5
     bias = torch.randn(Cout, device=dev)
-    fh, fl = torch.empty(Kw, Cout, Cin, device=dev), torch.empty(Kw, Cout, Cin, device=dev)
+    fh = torch.empty(Kw, Cout, Cin, device=dev)
+    fl = torch.empty(Kw, Cout, Cin, device=dev) if gen != 2 else None     # gen 2: raw weights, split in-kernel
     call("bm_tc_weight_split", ptr(w), Cout, Cin, Kw, ptr(fh), ptr(fl), None, None, stream())
     y = torch.full((B, T, Cout), float("nan"), device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("bm_tc_conv1d", ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, Cin, Cout, Kw, dilation, 1, 0, 0, 0, ptr(y), None, None,
+    call(_FN[gen], ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, Cin, Cout, Kw, dilation, 1, 0, 0, 0, ptr(y), None, None,
          ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
     ref = _ref_conv(x, w, bias, dilation)
     err = rel_err(y.cpu(), ref.cpu())
-    print(f'[tc fwd d={dilation} T={T}] rel_err vs fp64 = {err:.2e}')
+    print(f'[tc gen{gen} fwd d={dilation} T={T}] rel_err vs fp64 = {err:.2e}')
     assert err < TOL, err
 
 
-def test_tc_conv_glu_and_data_gradient():
+@pytest.mark.parametrize("gen", [1, 2, 3])
+def test_tc_conv_glu_and_data_gradient(gen):
     call, ptr, stream = _call()
     torch.manual_seed(7)
     B, T, H, Kw = 2, 360, 320, 3
@@ -55,13 +61,14 @@ def test_tc_conv_glu_and_data_gradient():
     x = torch.randn(B, T, H, device=dev)
     w = torch.randn(2 * H, H, Kw, device=dev) / (H * Kw) ** 0.5
     bias = torch.randn(2 * H, device=dev)
-    fh, fl = torch.empty(Kw, 2 * H, H, device=dev), torch.empty(Kw, 2 * H, H, device=dev)
-    gh, gl = torch.empty(Kw, H, 2 * H, device=dev), torch.empty(Kw, H, 2 * H, device=dev)
+    fh, gh = torch.empty(Kw, 2 * H, H, device=dev), torch.empty(Kw, H, 2 * H, device=dev)
+    fl = torch.empty(Kw, 2 * H, H, device=dev) if gen != 2 else None
+    gl = torch.empty(Kw, H, 2 * H, device=dev) if gen != 2 else None
     call("bm_tc_weight_split", ptr(w), 2 * H, H, Kw, ptr(fh), ptr(fl), ptr(gh), ptr(gl), stream())
     h = torch.empty(B, T, 2 * H, device=dev)
     out = torch.empty(B, T, H, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("bm_tc_conv1d", ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out),
+    call(_FN[gen], ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out),
          ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0
@@ -73,7 +80,7 @@ def test_tc_conv_glu_and_data_gradient():
     dy = torch.randn(B, T, 2 * H, device=dev)
     addend = torch.randn(B, T, H, device=dev)
     dx = torch.empty(B, T, H, device=dev)
-    call("bm_tc_conv1d", ptr(dy), ptr(gh), ptr(gl), None, ptr(addend), B, T, 2 * H, H, Kw, 1, -1, 0, 0, 0, ptr(dx), None, None,
+    call(_FN[gen], ptr(dy), ptr(gh), ptr(gl), None, ptr(addend), B, T, 2 * H, H, Kw, 1, -1, 0, 0, 0, ptr(dx), None, None,
          ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0
@@ -84,41 +91,45 @@ def test_tc_conv_glu_and_data_gradient():
     assert e < TOL
 
 
-def test_tc_conv_speed_report(capsys):
+@pytest.mark.parametrize("gen", [1, 2, 3])
+def test_tc_conv_speed_report(capsys, gen):
     """Not a pass/fail on speed: prints the per-launch time at the BASELINE shape for the log."""
     call, ptr, stream = _call()
     B, T, C, Kw = 256, 360, 320, 3
     dev = "cuda"
     x = torch.randn(B, T, C, device=dev)
     w = torch.randn(C, C, Kw, device=dev) / (C * Kw) ** 0.5
-    fh, fl = torch.empty(Kw, C, C, device=dev), torch.empty(Kw, C, C, device=dev)
+    fh = torch.empty(Kw, C, C, device=dev)
+    fl = torch.empty(Kw, C, C, device=dev) if gen != 2 else None
     call("bm_tc_weight_split", ptr(w), C, C, Kw, ptr(fh), ptr(fl), None, None, stream())
     y = torch.empty(B, T, C, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     for _ in range(3):
-        call("bm_tc_conv1d", ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, ptr(status), stream())
+        call(_FN[gen], ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, ptr(status), stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        call("bm_tc_conv1d", ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, ptr(status), stream())
+        call(_FN[gen], ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, ptr(status), stream())
     e1.record()
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     ms = e0.elapsed_time(e1) / 10
     tf = 2.0 * C * C * Kw * T * B / (ms * 1e-3) / 1e12
     with capsys.disabled():
-        print(f"\n[tc conv 320->320 k3 B=256 T=360] {ms:.3f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
+        print(f"\n[tc gen{gen} conv 320->320 k3 B=256 T=360] {ms:.3f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
 
 
+@pytest.mark.parametrize("trunc", [0, 1])
 @pytest.mark.parametrize("case", [
     dict(B=5, T=360, M=320, N=320, Kw=3, dil=1),
     dict(B=3, T=343, M=320, N=320, Kw=3, dil=16),
     dict(B=4, T=100, M=640, N=320, Kw=3, dil=2),
     dict(B=3, T=360, M=640, N=1024, Kw=1, dil=1),
 ])
-def test_tc_wgrad(case):
+def test_tc_wgrad(case, trunc):
     call, ptr, stream = _call()
     from brainmagick_b200 import _lib
+    _lib.load().bm_set_debug_flags(trunc)
     torch.manual_seed(11)
     B, T, M, N, Kw, dil = (case[k] for k in ("B", "T", "M", "N", "Kw", "dil"))
     dev = "cuda"
@@ -129,6 +140,7 @@ def test_tc_wgrad(case):
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw), ptr(status), stream())
     torch.cuda.synchronize()
+    _lib.load().bm_set_debug_flags(0)
     assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
     # fp64 reference: dw[m,n,j] = sum_{b,t} dy[b,t,m] x[b,t+(j-Kw//2)*dil,n]
     ref = torch.zeros(M, N, Kw, dtype=torch.float64, device=dev)
@@ -138,13 +150,15 @@ def test_tc_wgrad(case):
         lo, hi = max(0, -s), min(T, T - s)
         ref[:, :, j] = torch.einsum("btm,btn->mn", dyd[:, lo:hi], xd[:, lo + s:hi + s])
     e = rel_err(dw.cpu(), ref.cpu())
-    print(f"[tc wgrad {case}] rel_err vs fp64 = {e:.2e}")
+    print(f"[tc wgrad rna_split={trunc} {case}] rel_err vs fp64 = {e:.2e}")
     assert e < TOL
 
 
-def test_tc_wgrad_speed_report(capsys):
+@pytest.mark.parametrize("trunc", [0, 1])
+def test_tc_wgrad_speed_report(capsys, trunc):
     call, ptr, stream = _call()
     from brainmagick_b200 import _lib
+    _lib.load().bm_set_debug_flags(trunc)
     B, T, M, N, Kw = 256, 360, 320, 320, 3
     dev = "cuda"
     dy = torch.randn(B, T, M, device=dev)
@@ -164,4 +178,5 @@ def test_tc_wgrad_speed_report(capsys):
     ms = e0.elapsed_time(e1) / 10
     tf = 2.0 * M * N * Kw * T * B / (ms * 1e-3) / 1e12
     with capsys.disabled():
-        print(f"\n[tc wgrad 320x320 k3 B=256 T=360] {ms:.3f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
+        _lib.load().bm_set_debug_flags(0)
+        print(f"\n[tc wgrad rna_split={trunc} 320x320 k3 B=256 T=360] {ms:.3f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
