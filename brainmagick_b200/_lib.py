@@ -32,6 +32,7 @@ SIGNATURES = {
     "bm_head_fwd": [P, P, P, P, P, I, I, I, I, P, P, P, P],
     "bm_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "bm_head_bwd_params": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],
+    "bm_clip_set_workspace": [P, L, P],
     "bm_clip_scores": [P, P, I, I, L, P, P, P, P, P],
     "bm_clip_loss_fwd": [P, P, I, I, L, I, P, P, P, P, P, P, P],
     "bm_clip_loss_bwd": [P, P, P, P, I, I, L, I, P, P, P],

@@ -439,6 +439,18 @@ extern "C" int bm_head_bwd(const float* dest, const float* x, const float* w0, c
 // =================================================================================================
 // K6
 // =================================================================================================
+// Optional tensor-core scratch for the two CLIP contractions (caller-owned, registered once per device/stream user):
+// `ws` holds the split-K partial score tiles ([ksplit][Bn][Bc] floats); `status` is the pipeline-timeout word.
+static float* g_clip_ws = nullptr;
+static size_t g_clip_ws_floats = 0;
+static int* g_clip_status = nullptr;
+extern "C" int bm_clip_set_workspace(float* ws, long long n_floats, int* status) {
+    g_clip_ws = ws;
+    g_clip_ws_floats = ws ? (size_t)n_floats : 0;
+    g_clip_status = status;
+    return 0;
+}
+
 extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss,
                               float* inv_norm, float* scores, float* probs, bm_stream_t stream) {
     BM_CHECK_ARG(est && cand && ss && inv_norm && scores && Bn > 0 && Bc > 0 && KT > 0);
@@ -451,6 +463,30 @@ extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int B
     BM_CHECK_LAUNCH();
     inv_norm_kernel<<<(Bc + 127) / 128, 128, 0, st>>>(ss, inv_norm, Bc);
     BM_CHECK_LAUNCH();
+    if (g_clip_ws && g_clip_ws_floats > 0 && tc::conv_tc2_supported(Bn, (int)KT, Bc, 1, 0)) {
+        // tensor cores: scores = E C^T as a split-K pointwise "conv" (x = E [1,Bn,KT], weights = C [Bc,KT] raw fp32)
+        int mt = (Bn + 127) / 128, nt = Bc / (2 * tc::conv_tc2_pick_nh(Bc, 0));
+        int ks = num_sms() / (mt * nt);
+        if (ks < 1) ks = 1;
+        long long chunks = KT / 32;
+        if (ks > chunks) ks = (int)chunks;
+        if ((size_t)ks * Bn * Bc <= g_clip_ws_floats) {
+            tc::Conv2P q;
+            q.B = 1; q.T = Bn; q.Cin = (int)KT; q.Ntot = Bc; q.taps = 1; q.dilation = 1; q.sign = 1; q.glu = 0; q.nh = 0;
+            q.act = 0; q.out_tmajor = 0; q.ksplit = ks; q.bias = nullptr; q.addend = nullptr; q.y = g_clip_ws;
+            q.aux = nullptr; q.glu_out = nullptr; q.err = g_clip_status;
+            int rc = tc::launch_conv_tc2(est, cand, q, st);
+            if (rc) return rc;
+            tc::splitk_reduce_scale_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(g_clip_ws, inv_norm, scores, ks,
+                                                                                       Bn, Bc);
+            BM_CHECK_LAUNCH();
+            if (probs) {
+                clip_ce_rows_kernel<<<Bn, 256, 0, st>>>(scores, Bn, Bc, 0, nullptr, probs);
+                BM_CHECK_LAUNCH();
+            }
+            return 0;
+        }
+    }
     BM_CUDA(cudaMemsetAsync(scores, 0, sizeof(float) * (size_t)Bn * Bc, st));
     GemmP g = gemm_defaults();
     g.M = Bn; g.N = Bc; g.K = (int)KT;
@@ -493,7 +529,13 @@ extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const
     BM_CHECK_ARG(probs && inv_norm && cand && gout && G && dest && Bn > 0 && Bc > 0 && KT > 0);
     BM_CHECK_ARG(KT < (1ll << 31));
     cudaStream_t st = ST(stream);
-    clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G);
+    if (g_clip_ws && tc::wgrad_tc_supported(Bn, (int)KT)) {
+        // tensor cores: dE[b][k] = sum_o G^T[o][b] C[o][k]  == weight-gradient GEMM with "positions" = candidates
+        clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 1);
+        BM_CHECK_LAUNCH();
+        return tc::launch_wgrad_tc(G, cand, 1, Bc, Bn, (int)KT, (int)KT, 1, 1, g_clip_ws, dest, g_clip_status, st);
+    }
+    clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 0);
     BM_CHECK_LAUNCH();
     GemmP g = gemm_defaults();
     g.M = Bn; g.N = (int)KT; g.K = Bc; g.kchunk = Bc;
@@ -538,7 +580,7 @@ extern "C" int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo
         tc::Conv2P q;
         q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
         q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
-        q.glu_out = glu_out; q.err = status;
+        q.glu_out = glu_out; q.err = status; q.ksplit = 1;
         return tc::launch_conv_tc2(x, w_hi, q, ST(stream));
     }
     BM_CHECK_ARG(tc::conv_tc_supported(T, Cin, Ntot, Kw, glu));

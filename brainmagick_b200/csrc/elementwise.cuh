@@ -374,16 +374,19 @@ __global__ void mean_kernel(const float* __restrict__ x, int n, float* __restric
 }
 
 // G[b][o] = gout * (softmax(s)[b][o] - [o == b+off]) / Bn * inv_norm[o]    (A.6 of SURVEY.md)
+// transposed != 0: G is written as [Bc][Bn] (the dY operand layout of the tensor-core dE GEMM)
 __global__ void clip_ce_bwd_kernel(const float* __restrict__ probs, const float* __restrict__ inv_norm,
                                    const float* __restrict__ gout, int Bn, int Bc, int target_offset,
-                                   float* __restrict__ G) {
+                                   float* __restrict__ G, int transposed) {
     long long total = (long long)Bn * Bc;
     float gs = gout[0] / (float)Bn;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         int b = (int)(i / Bc), o = (int)(i - (long long)b * Bc);
         float p = probs[i] - (o == b + target_offset ? 1.f : 0.f);
-        G[i] = gs * p * inv_norm[o];
+        float v = gs * p * inv_norm[o];
+        if (transposed) G[(long long)o * Bn + b] = v;
+        else G[i] = v;
     }
 }
 

@@ -33,6 +33,8 @@ struct Conv2P {
     int glu;                  // halves = 'a' columns [c0, c0+nh) and gate columns [H+c0, H+c0+nh)
     int nh;                   // 160 or 128
     int act, out_tmajor;
+    int ksplit;               // >1: split the K chunks over gridDim.z = B*ksplit CTAs; y receives [ksplit][B][T][Ntot]
+                              //     partial sums (no bias / activation / addend), reduced by the caller
     const float* bias;
     const float* addend;
     float* y;
@@ -56,9 +58,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    const int n_tile = blockIdx.x, t0 = blockIdx.y * C2_BM, b = blockIdx.z;
+    const int n_tile = blockIdx.x, t0 = blockIdx.y * C2_BM;
+    const int b = blockIdx.z / p.ksplit, split = blockIdx.z - b * p.ksplit;
     const int kchunks = p.Cin / C2_BK;
-    const int total = p.taps * kchunks;
+    const int all_chunks = p.taps * kchunks;
+    const int per_split = (all_chunks + p.ksplit - 1) / p.ksplit;
+    const int it_begin = split * per_split;
+    const int total = max(0, min(all_chunks, it_begin + per_split) - it_begin);     // this CTA's K chunks
     const int H = p.Ntot / 2;
     const int nh = p.nh;
     // weight rows (within one tap) of the two column halves of this tile
@@ -89,7 +95,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int s = it % C2_STAGES;
                 const uint32_t ph = (it / C2_STAGES) & 1;
                 if (!mbar_wait(&empty_bar[s], ph ^ 1, p.err, 21)) break;
-                const int tap = it / kchunks, k0 = (it - tap * kchunks) * C2_BK;
+                const int git = it_begin + it;
+                const int tap = git / kchunks, k0 = (git - tap * kchunks) * C2_BK;
                 const int shift = p.sign * (tap - p.taps / 2) * p.dilation;
                 uint8_t* st = smem + s * C2_STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], C2_A_BYTES + b_bytes);
@@ -183,11 +190,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (!p.glu) {
             const int ncol0 = cset * nh;                 // this warp's accumulator columns [ncol0, ncol0 + nh)
             const int n0 = n_tile * 2 * nh + ncol0;
-            const long long off = ((long long)b * p.T + t) * p.Ntot + n0;
+            const long long off = (((long long)split * p.B + b) * p.T + t) * p.Ntot + n0;
 #pragma unroll 1
             for (int c = 0; c < nh / 16; ++c) {
                 float v[16];
                 tmem_ld16(tq + ncol0 + c * 16, v);
+                if (total == 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -290,7 +301,10 @@ inline int launch_conv_tc2(const float* x, const float* w_raw, Conv2P p, cudaStr
         attr_set = true;
     }
     const int ntiles = p.glu ? (p.Ntot / 2) / p.nh : p.Ntot / (2 * p.nh);
-    dim3 grid(ntiles, (p.T + C2_BM - 1) / C2_BM, p.B);
+    if (p.ksplit < 1) p.ksplit = 1;
+    if (p.ksplit > 1 && (p.glu || p.bias || p.addend || p.act || p.aux || p.out_tmajor))
+        return set_error(2, "%s: split-K supports plain outputs only%s", __func__);
+    dim3 grid(ntiles, (p.T + C2_BM - 1) / C2_BM, p.B * p.ksplit);
     conv_tc2_kernel<<<grid, C2_THREADS, C2_SMEM_BYTES, st>>>(tmA, tmB, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
@@ -298,5 +312,21 @@ inline int launch_conv_tc2(const float* x, const float* w_raw, Conv2P p, cudaStr
     return 0;
 }
 
+}  // namespace tc
+}  // namespace bm
+
+namespace bm {
+namespace tc {
+// out[r][c] = colscale[c] * sum_s P[s][r][c]   (fixed order => deterministic)
+__global__ void splitk_reduce_scale_kernel(const float* __restrict__ P, const float* __restrict__ colscale,
+                                           float* __restrict__ out, int ksplit, long long rows, int cols) {
+    long long total = rows * cols;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < ksplit; ++k) s += P[(long long)k * total + i];
+        out[i] = colscale ? s * colscale[(int)(i % cols)] : s;
+    }
+}
 }  // namespace tc
 }  // namespace bm

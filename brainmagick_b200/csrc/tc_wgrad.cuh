@@ -35,6 +35,7 @@ struct WgradP {
     const float* dY;            // [B,T,M]
     float* P;                   // [taps][ksplit][Mpad][N] partial tiles, Mpad = gridDim.y*128
     int* err;
+    int direct;                 // 1 (taps == 1, ksplit == 1): P IS the output [M][N]; rows >= M are not written
     int trunc_hi;               // 1: leave X raw in smem as the hi operand (the tensor core ignores the 13 low mantissa
                                 //    bits) and write only lo = x - trunc(x): one third less converter smem traffic
 };
@@ -220,7 +221,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
         // ---- epilogue: partial tile -> workspace ----
         mbar_wait(&tmem_full_bar, 0, p.err, 16);
         tc_fence_after();
-        const int Mpad = gridDim.y * WG_BM;
+        const int Mpad = p.direct ? p.M : gridDim.y * WG_BM;
+        const bool row_ok = !p.direct || m_ok;
         float* dst = p.P + (((long long)tap * p.ksplit + ks) * Mpad + (m0 + q * 32 + lane)) * p.N + n0;
 #pragma unroll 1
         for (int c = 0; c < 2 * p.nh / 32; ++c) {
@@ -230,9 +232,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;
             }
+            if (row_ok) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(dst + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + c * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
         }
         tc_fence_before();
     }
@@ -305,12 +309,15 @@ inline int launch_wgrad_tc(const float* dY, const float* X, int B, int T, int M,
     WgradP p;
     p.B = B; p.T = T; p.M = M; p.N = N; p.nh = nh; p.taps = taps; p.dilation = dilation;
     p.ksplit = ksplit; p.bchunk = bchunk; p.dY = dY; p.err = err; p.P = ws;
+    p.direct = (taps == 1 && ksplit == 1 && Ntrue == N) ? 1 : 0;
+    if (p.direct) p.P = dW;
     p.trunc_hi = (g_debug_flags & 1) ? 0 : 1;     // default ON; debug bit 0 restores the explicit rna split
     dim3 grid(N / (2 * nh) * taps, mblocks, ksplit);
     wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(tmX, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(3, "%s: launch failed: %s", __func__, cudaGetErrorString(e));
+    if (p.direct) return 0;
     wgrad_reduce_kernel<<<ew_grid((long long)M * Ntrue * taps), 256, 0, st>>>(ws, dW, taps, ksplit, Mpad, M, N, Ntrue);
     ++g_launches;
     e = cudaGetLastError();

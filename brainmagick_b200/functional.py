@@ -390,6 +390,21 @@ def encoder_forward(plan: EncoderPlan, meg, heads, il_w, il_b, subj_w, w0, b0, w
 # ----------------------------------------------------------------------------------------------------
 # ClipLoss
 # ----------------------------------------------------------------------------------------------------
+_clip_ws: tp.Dict[torch.device, torch.Tensor] = {}
+
+
+def _register_clip_workspace(like: torch.Tensor, Bn: int, Bc: int) -> None:
+    """Scratch for the tensor-core CLIP contractions (split-K partial score tiles); one buffer per device, grown on
+    demand, registered with the library before every CLIP call (one process drives one GPU)."""
+    need = 160 * Bn * Bc
+    dev = like.device
+    ws = _clip_ws.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=dev, dtype=torch.float32)
+        _clip_ws[dev] = ws
+    call("bm_clip_set_workspace", ptr(ws), ws.numel(), ptr(tc_status_tensor(dev)))
+
+
 def clip_scores(estimates: torch.Tensor, candidates: torch.Tensor, want_probs: bool = False):
     """ClipLoss.get_scores / get_probabilities (bm/losses.py:77-102); no autograd."""
     est = estimates.detach().contiguous().float()
@@ -401,6 +416,7 @@ def clip_scores(estimates: torch.Tensor, candidates: torch.Tensor, want_probs: b
     inv = _empty((Bc,), est)
     scores = _empty((Bn, Bc), est)
     probs = _empty((Bn, Bc), est) if want_probs else None
+    _register_clip_workspace(est, Bn, Bc)
     call("bm_clip_scores", ptr(est), ptr(cand), Bn, Bc, KT, ptr(ss), ptr(inv), ptr(scores), ptr(probs), stream())
     return probs if want_probs else scores
 
@@ -418,6 +434,7 @@ class _ClipLossFn(torch.autograd.Function):
         probs = _empty((Bn, Bc), est)
         row_loss = _empty((Bn,), est)
         loss = _empty((1,), est)
+        _register_clip_workspace(est, Bn, Bc)
         call("bm_clip_loss_fwd", ptr(est), ptr(cand), Bn, Bc, KT, int(target_offset), ptr(ss), ptr(inv),
              ptr(scores), ptr(probs), ptr(row_loss), ptr(loss), stream())
         ctx.save_for_backward(probs, inv, cand)
@@ -433,6 +450,7 @@ class _ClipLossFn(torch.autograd.Function):
         G = _empty((Bn, Bc), probs)
         dest = _empty(shape, probs)
         gout = gout.reshape(1).contiguous().float()
+        _register_clip_workspace(probs, Bn, Bc)
         call("bm_clip_loss_bwd", ptr(probs), ptr(inv), ptr(cand), ptr(gout), Bn, Bc, KT, off, ptr(G), ptr(dest),
              stream())
         return dest, None, None

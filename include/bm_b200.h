@@ -118,6 +118,10 @@ int bm_head_bwd_params(const float* dest, const float* x, const float* h1, const
  * ss: fp64 [Bc] scratch. */
 int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss, float* inv_norm,
                    float* scores, float* probs, bm_stream_t stream);
+/* Registers caller-owned scratch that lets bm_clip_scores / bm_clip_loss_fwd / bm_clip_loss_bwd run their two big
+ * contractions on the tensor cores (3xTF32): ws >= 148*Bn*Bc floats (split-K partial score tiles), status = device int
+ * set on a pipeline timeout.  Without it (or for shapes outside the tcgen05 tiling) the FP32-FMA GEMM is used. */
+int bm_clip_set_workspace(float* ws, long long n_floats, int* status);
 /* ClipLoss.forward: loss = mean_b CE(scores[b,:], target_offset + b).  target_offset = 0 is the reference;
  * rank*Bn is the multi-GPU extension with all-gathered candidates.  row_loss [Bn] scratch, loss [1]. */
 int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long long KT, int target_offset,

@@ -176,3 +176,28 @@ def test_full_size_tensor_core_path_agrees_with_fp32_fma_path():
         worst = max(worst, e)
         assert e < 5 * TOL, (name, e)
     print(f"worst gradient rel_err(tc vs fma) = {worst:.2e}")
+
+
+@pytest.mark.parametrize("Bn,Bc", [(256, 256), (64, 512), (100, 256)])
+def test_clip_tensor_core_shapes_match_oracle(Bn, Bc):
+    """ClipLoss at tcgen05-eligible candidate counts (B' % 256 == 0, F*T % 320 == 0), incl. ragged row counts and the
+    multi-GPU target offset, against the CPU oracle (F*T kept small so the oracle is instant)."""
+    import brainmagick_b200.functional as BF
+    from oracle import bm_oracle
+    torch.manual_seed(Bn + Bc)
+    F, T = 40, 64                                    # F*T = 2560 = 8 * 320
+    est = torch.randn(Bn, F, T)
+    cand = torch.randn(Bc, F, T)
+    off = Bc - Bn if Bc > Bn else 0
+    e = est.clone().cuda().requires_grad_(True)
+    loss = BF.clip_loss(e, cand.cuda(), off)
+    loss.backward()
+    scores = BF.clip_scores(est.cuda(), cand.cuda())
+    torch.cuda.synchronize()
+    BF.check_tc_status()
+    e_ref = est.clone().requires_grad_(True)
+    ref = bm_oracle.clip_loss(e_ref, cand, off)
+    ref.backward()
+    assert rel_err(scores.cpu(), bm_oracle.clip_scores(est, cand)) < TOL
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    assert rel_err(e.grad.cpu(), e_ref.grad) < TOL
