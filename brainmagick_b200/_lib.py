@@ -19,6 +19,12 @@ SIGNATURES = {
     "bm_attention_weights_bwd": [P, P, P, I, I, I, I, P, P, P],
     "bm_sensor_chain_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P],
     "bm_sensor_chain_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
+    "bm_sensor_mix_fwd": [P, P, P, I, I, I, I, I, P, P],
+    "bm_initial_linear_fwd": [P, I, P, P, I, I, I, I, I, P, P],
+    "bm_subject_layers_fwd": [P, I, P, P, I, I, I, I, I, P, P],
+    "bm_subject_layers_bwd": [P, I, P, I, P, P, P, P, I, I, I, I, I, I, P, P, P],
+    "bm_initial_linear_bwd": [P, I, P, I, P, I, I, I, I, I, P, P, P, P],
+    "bm_sensor_mix_bwd": [P, I, P, P, P, I, I, I, I, I, P, P],
     "bm_conv_weight_prep": [P, I, I, I, P, P, P],
     "bm_conv1d_fwd": [P, P, P, I, I, I, I, I, I, P, P, P],
     "bm_bn_stats_finalize": [P, L, F, F, P, P, P, P, I, P],

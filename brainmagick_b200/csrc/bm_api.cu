@@ -85,40 +85,135 @@ extern "C" int bm_attention_weights_bwd(const float* dweights, const float* weig
 // =================================================================================================
 // K2
 // =================================================================================================
+// ---- pieces (leading dimensions explicit so that u / v / x0 may be kept channel-padded for the tensor-core layers) ----
+extern "C" int bm_sensor_mix_fwd(const float* meg, const float* weights, const int* rec_of_sample, int B, int C, int T,
+                                 int O, int ld_u, float* u, bm_stream_t stream) {
+    BM_CHECK_ARG(meg && weights && rec_of_sample && u && ld_u >= O);
+    // u[b][t][o] = sum_c meg[b][c][t] w[rec_b][o][c]
+    GemmP g = gemm_defaults();
+    g.M = T; g.N = O; g.K = C; g.kchunk = C;
+    g.Z = B; g.nseg = B; g.zchunk = 1;
+    g.A = meg; g.lda_z = (long long)C * T; g.lda_m = 1; g.lda_k = T; g.a_mcontig = 1;
+    g.B = weights; g.bsel = rec_of_sample; g.ldb_z = (long long)O * C; g.ldb_n = C; g.ldb_k = 1; g.b_ncontig = 0;
+    g.D = u; g.ldd_z = (long long)T * ld_u; g.ldd_m = ld_u; g.ldd_n = 1;
+    BM_CUDA(launch_gemm(g, ST(stream)));
+    return 0;
+}
+
+extern "C" int bm_initial_linear_fwd(const float* u, int ld_u, const float* il_w, const float* il_b, int B, int T, int O,
+                                     int IL, int ld_v, float* v, bm_stream_t stream) {
+    BM_CHECK_ARG(u && il_w && il_b && v && ld_u >= O && ld_v >= IL);
+    // v[row][p] = il_b[p] + sum_o u[row][o] il_w[p][o]
+    GemmP g = gemm_defaults();
+    g.M = B * T; g.N = IL; g.K = O; g.kchunk = O;
+    g.A = u; g.lda_m = ld_u; g.lda_k = 1;
+    g.B = il_w; g.ldb_n = O; g.ldb_k = 1;
+    g.D = v; g.ldd_m = ld_v; g.ldd_n = 1;
+    g.bias = il_b;
+    BM_CUDA(launch_gemm(g, ST(stream)));
+    return 0;
+}
+
+extern "C" int bm_subject_layers_fwd(const float* v, int ld_v, const float* subj_w, const int* subject, int B, int T,
+                                     int IL, int D, int ld_x0, float* x0, bm_stream_t stream) {
+    BM_CHECK_ARG(v && subj_w && subject && x0 && ld_v >= IL && ld_x0 >= D);
+    // x0[b][t][d] = sum_p v[b][t][p] M[s_b][p][d]
+    GemmP g = gemm_defaults();
+    g.M = T; g.N = D; g.K = IL; g.kchunk = IL;
+    g.Z = B; g.nseg = B; g.zchunk = 1;
+    g.A = v; g.lda_z = (long long)T * ld_v; g.lda_m = ld_v; g.lda_k = 1;
+    g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = 1; g.ldb_k = D; g.b_ncontig = 1;
+    g.D = x0; g.ldd_z = (long long)T * ld_x0; g.ldd_m = ld_x0; g.ldd_n = 1;
+    BM_CUDA(launch_gemm(g, ST(stream)));
+    return 0;
+}
+
 extern "C" int bm_sensor_chain_fwd(const float* meg, const float* weights, const int* rec_of_sample,
                                    const float* il_w, const float* il_b, const float* subj_w, const int* subject,
                                    int B, int C, int T, int O, int IL, int D, int ld_x0, float* u, float* v,
                                    float* x0, bm_stream_t stream) {
     BM_CHECK_ARG(meg && weights && rec_of_sample && il_w && il_b && subj_w && subject && u && v && x0);
     BM_CHECK_ARG(ld_x0 >= D);
+    int rc = bm_sensor_mix_fwd(meg, weights, rec_of_sample, B, C, T, O, O, u, stream);
+    if (!rc) rc = bm_initial_linear_fwd(u, O, il_w, il_b, B, T, O, IL, IL, v, stream);
+    if (!rc) rc = bm_subject_layers_fwd(v, IL, subj_w, subject, B, T, IL, D, ld_x0, x0, stream);
+    return rc;
+}
+
+extern "C" int bm_subject_layers_bwd(const float* dx0, int ld_x0, const float* v, int ld_v, const float* subj_w,
+                                     const int* subject, const int* subj_order, const int* subj_off, int B, int T, int IL,
+                                     int D, int S, int ld_dv, float* dv, float* d_subj_w, bm_stream_t stream) {
+    BM_CHECK_ARG(dx0 && v && subj_w && subject && subj_order && subj_off && dv && d_subj_w);
+    BM_CHECK_ARG(ld_x0 >= D && ld_v >= IL && ld_dv >= IL);
     cudaStream_t st = ST(stream);
-    {   // u[b][t][o] = sum_c meg[b][c][t] w[rec_b][o][c]
+    {   // dv[b][t][p] = sum_d g[b][t][d] M[s_b][p][d]
         GemmP g = gemm_defaults();
-        g.M = T; g.N = O; g.K = C; g.kchunk = C;
+        g.M = T; g.N = IL; g.K = D; g.kchunk = D;
         g.Z = B; g.nseg = B; g.zchunk = 1;
-        g.A = meg; g.lda_z = (long long)C * T; g.lda_m = 1; g.lda_k = T; g.a_mcontig = 1;
-        g.B = weights; g.bsel = rec_of_sample; g.ldb_z = (long long)O * C; g.ldb_n = C; g.ldb_k = 1; g.b_ncontig = 0;
-        g.D = u; g.ldd_z = (long long)T * O; g.ldd_m = O; g.ldd_n = 1;
+        g.A = dx0; g.lda_z = (long long)T * ld_x0; g.lda_m = ld_x0; g.lda_k = 1;
+        g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = D; g.ldb_k = 1;
+        g.D = dv; g.ldd_z = (long long)T * ld_dv; g.ldd_m = ld_dv; g.ldd_n = 1;
         BM_CUDA(launch_gemm(g, st));
     }
-    {   // v[row][p] = il_b[p] + sum_o u[row][o] il_w[p][o]
+    {   // dM[s][p][d] = sum_{b in s} sum_t v[b][t][p] g[b][t][d]
         GemmP g = gemm_defaults();
-        g.M = B * T; g.N = IL; g.K = O; g.kchunk = O;
-        g.A = u; g.lda_m = O; g.lda_k = 1;
-        g.B = il_w; g.ldb_n = O; g.ldb_k = 1;
-        g.D = v; g.ldd_m = IL; g.ldd_n = 1;
-        g.bias = il_b;
+        g.M = IL; g.N = D; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = S; g.seg_off = subj_off; g.zlist = subj_order;
+        g.A = v; g.lda_z = (long long)T * ld_v; g.lda_m = 1; g.lda_k = ld_v; g.a_mcontig = 1;
+        g.B = dx0; g.ldb_z = (long long)T * ld_x0; g.ldb_n = 1; g.ldb_k = ld_x0; g.b_ncontig = 1;
+        g.D = d_subj_w; g.ldd_z = (long long)IL * D; g.ldd_m = D; g.ldd_n = 1;
         BM_CUDA(launch_gemm(g, st));
     }
-    {   // x0[b][t][d] = sum_p v[b][t][p] M[s_b][p][d]
+    return 0;
+}
+
+extern "C" int bm_initial_linear_bwd(const float* dv, int ld_dv, const float* u, int ld_u, const float* il_w, int B, int T,
+                                     int O, int IL, int ld_du, float* du, float* d_il_w, float* d_il_b,
+                                     bm_stream_t stream) {
+    BM_CHECK_ARG(dv && u && il_w && du && d_il_w && d_il_b && ld_dv >= IL && ld_u >= O && ld_du >= O);
+    cudaStream_t st = ST(stream);
+    {   // d_il_w[p][o] = sum_{b,t} dv[b][t][p] u[b][t][o]
+        BM_CUDA(cudaMemsetAsync(d_il_w, 0, sizeof(float) * IL * O, st));
         GemmP g = gemm_defaults();
-        g.M = T; g.N = D; g.K = IL; g.kchunk = IL;
-        g.Z = B; g.nseg = B; g.zchunk = 1;
-        g.A = v; g.lda_z = (long long)T * IL; g.lda_m = IL; g.lda_k = 1;
-        g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = 1; g.ldb_k = D; g.b_ncontig = 1;
-        g.D = x0; g.ldd_z = (long long)T * ld_x0; g.ldd_m = ld_x0; g.ldd_n = 1;
+        g.M = IL; g.N = O; g.K = T; g.kchunk = T;
+        g.Z = B; g.nseg = pick_chunks(B, tiles_of(IL, O)); g.zchunk = (B + g.nseg - 1) / g.nseg;
+        g.nseg = (B + g.zchunk - 1) / g.zchunk;
+        g.A = dv; g.lda_z = (long long)T * ld_dv; g.lda_m = 1; g.lda_k = ld_dv; g.a_mcontig = 1;
+        g.B = u; g.ldb_z = (long long)T * ld_u; g.ldb_n = 1; g.ldb_k = ld_u; g.b_ncontig = 1;
+        g.D = d_il_w; g.ldd_z = 0; g.ldd_m = O; g.ldd_n = 1; g.atomic = 1;
         BM_CUDA(launch_gemm(g, st));
     }
+    {   // d_il_b[p] = sum dv
+        BM_CUDA(cudaMemsetAsync(d_il_b, 0, sizeof(float) * IL, st));
+        GemmP g = gemm_defaults();                      // column sums as a 1-row GEMM would waste a tile: dedicated kernel
+        (void)g;
+        long long rows = (long long)B * T;
+        dim3 grid((unsigned)((rows + 255) / 256), (IL + 127) / 128);
+        colsum_strided_kernel<<<grid, 128, 0, st>>>(dv, d_il_b, rows, IL, ld_dv, 256);
+        BM_CHECK_LAUNCH();
+    }
+    {   // du[row][o] = sum_p dv[row][p] il_w[p][o]
+        GemmP g = gemm_defaults();
+        g.M = B * T; g.N = O; g.K = IL; g.kchunk = IL;
+        g.A = dv; g.lda_m = ld_dv; g.lda_k = 1;
+        g.B = il_w; g.ldb_n = 1; g.ldb_k = O; g.b_ncontig = 1;
+        g.D = du; g.ldd_m = ld_du; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    return 0;
+}
+
+extern "C" int bm_sensor_mix_bwd(const float* du, int ld_du, const float* meg, const int* rec_order, const int* rec_off,
+                                 int B, int C, int T, int O, int R, float* d_weights, bm_stream_t stream) {
+    BM_CHECK_ARG(du && meg && rec_order && rec_off && d_weights && ld_du >= O);
+    // dw[r][o][c] = sum_{b in r} sum_t du[b][t][o] meg[b][c][t]
+    GemmP g = gemm_defaults();
+    g.M = O; g.N = C; g.K = T; g.kchunk = T;
+    g.Z = B; g.nseg = R; g.seg_off = rec_off; g.zlist = rec_order;
+    g.A = du; g.lda_z = (long long)T * ld_du; g.lda_m = 1; g.lda_k = ld_du; g.a_mcontig = 1;
+    g.B = meg; g.ldb_z = (long long)C * T; g.ldb_n = T; g.ldb_k = 1; g.b_ncontig = 0;
+    g.D = d_weights; g.ldd_z = (long long)O * C; g.ldd_m = C; g.ldd_n = 1;
+    BM_CUDA(launch_gemm(g, ST(stream)));
     return 0;
 }
 
@@ -128,64 +223,14 @@ extern "C" int bm_sensor_chain_bwd(const float* dx0, const float* meg, const flo
                                    int T, int O, int IL, int D, int ld_x0, int S, int R, float* dv, float* du,
                                    float* d_subj_w, float* d_il_w, float* d_il_b, float* d_weights,
                                    bm_stream_t stream) {
-    BM_CHECK_ARG(ld_x0 >= D);
     BM_CHECK_ARG(dx0 && meg && il_w && subj_w && subject && u && v && subj_order && subj_off && rec_order && rec_off);
     BM_CHECK_ARG(dv && du && d_subj_w && d_il_w && d_il_b && d_weights);
-    cudaStream_t st = ST(stream);
-    {   // dv[b][t][p] = sum_d g[b][t][d] M[s_b][p][d]
-        GemmP g = gemm_defaults();
-        g.M = T; g.N = IL; g.K = D; g.kchunk = D;
-        g.Z = B; g.nseg = B; g.zchunk = 1;
-        g.A = dx0; g.lda_z = (long long)T * ld_x0; g.lda_m = ld_x0; g.lda_k = 1;
-        g.B = subj_w; g.bsel = subject; g.ldb_z = (long long)IL * D; g.ldb_n = D; g.ldb_k = 1;
-        g.D = dv; g.ldd_z = (long long)T * IL; g.ldd_m = IL; g.ldd_n = 1;
-        BM_CUDA(launch_gemm(g, st));
-    }
-    {   // dM[s][p][d] = sum_{b in s} sum_t v[b][t][p] g[b][t][d]
-        GemmP g = gemm_defaults();
-        g.M = IL; g.N = D; g.K = T; g.kchunk = T;
-        g.Z = B; g.nseg = S; g.seg_off = subj_off; g.zlist = subj_order;
-        g.A = v; g.lda_z = (long long)T * IL; g.lda_m = 1; g.lda_k = IL; g.a_mcontig = 1;
-        g.B = dx0; g.ldb_z = (long long)T * ld_x0; g.ldb_n = 1; g.ldb_k = ld_x0; g.b_ncontig = 1;
-        g.D = d_subj_w; g.ldd_z = (long long)IL * D; g.ldd_m = D; g.ldd_n = 1;
-        BM_CUDA(launch_gemm(g, st));
-    }
-    {   // d_il_w[p][o] = sum_{b,t} dv[b][t][p] u[b][t][o]
-        BM_CUDA(cudaMemsetAsync(d_il_w, 0, sizeof(float) * IL * O, st));
-        GemmP g = gemm_defaults();
-        g.M = IL; g.N = O; g.K = T; g.kchunk = T;
-        g.Z = B; g.nseg = pick_chunks(B, tiles_of(IL, O)); g.zchunk = (B + g.nseg - 1) / g.nseg;
-        g.nseg = (B + g.zchunk - 1) / g.zchunk;
-        g.A = dv; g.lda_z = (long long)T * IL; g.lda_m = 1; g.lda_k = IL; g.a_mcontig = 1;
-        g.B = u; g.ldb_z = (long long)T * O; g.ldb_n = 1; g.ldb_k = O; g.b_ncontig = 1;
-        g.D = d_il_w; g.ldd_z = 0; g.ldd_m = O; g.ldd_n = 1; g.atomic = 1;
-        BM_CUDA(launch_gemm(g, st));
-    }
-    {   // d_il_b[p] = sum dv
-        BM_CUDA(cudaMemsetAsync(d_il_b, 0, sizeof(float) * IL, st));
-        long long rows = (long long)B * T;
-        dim3 grid((unsigned)((rows + 255) / 256), (IL + 127) / 128);
-        colsum_cl_kernel<<<grid, 128, 0, st>>>(dv, d_il_b, rows, IL, 256);
-        BM_CHECK_LAUNCH();
-    }
-    {   // du[row][o] = sum_p dv[row][p] il_w[p][o]
-        GemmP g = gemm_defaults();
-        g.M = B * T; g.N = O; g.K = IL; g.kchunk = IL;
-        g.A = dv; g.lda_m = IL; g.lda_k = 1;
-        g.B = il_w; g.ldb_n = 1; g.ldb_k = O; g.b_ncontig = 1;
-        g.D = du; g.ldd_m = O; g.ldd_n = 1;
-        BM_CUDA(launch_gemm(g, st));
-    }
-    {   // dw[r][o][c] = sum_{b in r} sum_t du[b][t][o] meg[b][c][t]
-        GemmP g = gemm_defaults();
-        g.M = O; g.N = C; g.K = T; g.kchunk = T;
-        g.Z = B; g.nseg = R; g.seg_off = rec_off; g.zlist = rec_order;
-        g.A = du; g.lda_z = (long long)T * O; g.lda_m = 1; g.lda_k = O; g.a_mcontig = 1;
-        g.B = meg; g.ldb_z = (long long)C * T; g.ldb_n = T; g.ldb_k = 1; g.b_ncontig = 0;
-        g.D = d_weights; g.ldd_z = (long long)O * C; g.ldd_m = C; g.ldd_n = 1;
-        BM_CUDA(launch_gemm(g, st));
-    }
-    return 0;
+    BM_CHECK_ARG(ld_x0 >= D);
+    int rc = bm_subject_layers_bwd(dx0, ld_x0, v, IL, subj_w, subject, subj_order, subj_off, B, T, IL, D, S, IL, dv,
+                                   d_subj_w, stream);
+    if (!rc) rc = bm_initial_linear_bwd(dv, IL, u, O, il_w, B, T, O, IL, O, du, d_il_w, d_il_b, stream);
+    if (!rc) rc = bm_sensor_mix_bwd(du, O, meg, rec_order, rec_off, B, C, T, O, R, d_weights, stream);
+    return rc;
 }
 
 // =================================================================================================
@@ -269,15 +314,32 @@ extern "C" int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* 
     BM_CHECK_ARG(g && y && mean && invstd && gamma && beta && sums && dy && dgamma && dbeta && rows > 0 && C > 0);
     cudaStream_t st = ST(stream);
     BM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
-    const int rpb = 128;
-    dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
-    bn_gelu_bwd_reduce_kernel<<<grid, 128, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, rows, C, rpb);
+    const long long total = rows * C;
+    const bool vec = (C % 4 == 0) && aligned16(g, y, dy) && aligned16(mean, invstd, gamma) && aligned16(beta);
+    if (vec) {
+        const int rpb = 64, C4 = C / 4;
+        dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C4 + 127) / 128);
+        bn_gelu_bwd_reduce_v4_kernel<<<grid, 128, 0, st>>>(
+            reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(mean),
+            reinterpret_cast<const float4*>(invstd), reinterpret_cast<const float4*>(gamma),
+            reinterpret_cast<const float4*>(beta), sums, rows, C, rpb);
+    } else {
+        const int rpb = 128;
+        dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
+        bn_gelu_bwd_reduce_kernel<<<grid, 128, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, rows, C, rpb);
+    }
     BM_CHECK_LAUNCH();
     bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, C);
     BM_CHECK_LAUNCH();
-    long long total = rows * C;
-    bn_gelu_bwd_apply_kernel<<<ew_grid(total), 256, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, (double)rows,
-                                                           batch_stats, dy, total, C);
+    if (vec)
+        bn_gelu_bwd_apply_v4_kernel<<<ew_grid(total / 4), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(mean),
+            reinterpret_cast<const float4*>(invstd), reinterpret_cast<const float4*>(gamma),
+            reinterpret_cast<const float4*>(beta), sums, (double)rows, batch_stats, reinterpret_cast<float4*>(dy),
+            total / 4, C);
+    else
+        bn_gelu_bwd_apply_kernel<<<ew_grid(total), 256, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, (double)rows,
+                                                               batch_stats, dy, total, C);
     BM_CHECK_LAUNCH();
     return 0;
 }
@@ -325,7 +387,11 @@ extern "C" int bm_conv1d_glu_fwd(const float* x, const float* wf, const float* b
 
 extern "C" int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh, bm_stream_t stream) {
     BM_CHECK_ARG(g && h && dh && rows > 0 && H > 0);
-    glu_bwd_kernel<<<ew_grid(rows * H), 256, 0, ST(stream)>>>(g, h, dh, rows, H);
+    if (H % 4 == 0 && aligned16(g, h, dh))
+        glu_bwd_v4_kernel<<<ew_grid(rows * H / 4), 256, 0, ST(stream)>>>(
+            reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(h), reinterpret_cast<float4*>(dh), rows, H);
+    else
+        glu_bwd_kernel<<<ew_grid(rows * H), 256, 0, ST(stream)>>>(g, h, dh, rows, H);
     BM_CHECK_LAUNCH();
     return 0;
 }
@@ -597,9 +663,15 @@ extern "C" int bm_col_stats(const float* y, long long rows, int C, double* stats
     BM_CHECK_ARG(y && stats && rows > 0 && C > 0);
     cudaStream_t st = ST(stream);
     BM_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * C, st));
-    const int rpb = 128;
-    dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
-    col_stats_kernel<<<grid, 128, 0, st>>>(y, stats, rows, C, rpb);
+    if (C % 4 == 0 && aligned16(y)) {
+        const int rpb = 64, C4 = C / 4;
+        dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C4 + 127) / 128);
+        colsum_v4_kernel<true><<<grid, 128, 0, st>>>(reinterpret_cast<const float4*>(y), nullptr, stats, rows, C, rpb);
+    } else {
+        const int rpb = 128;
+        dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
+        col_stats_kernel<<<grid, 128, 0, st>>>(y, stats, rows, C, rpb);
+    }
     BM_CHECK_LAUNCH();
     return 0;
 }
@@ -629,8 +701,14 @@ extern "C" int bm_col_sum(const float* x, long long rows, int C, float* out, bm_
     BM_CHECK_ARG(x && out && rows > 0 && C > 0);
     cudaStream_t st = ST(stream);
     BM_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, st));
-    dim3 grid((unsigned)((rows + 255) / 256), (C + 127) / 128);
-    colsum_cl_kernel<<<grid, 128, 0, st>>>(x, out, rows, C, 256);
+    if (C % 4 == 0 && aligned16(x)) {
+        const int rpb = 128, C4 = C / 4;
+        dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C4 + 127) / 128);
+        colsum_v4_kernel<false><<<grid, 128, 0, st>>>(reinterpret_cast<const float4*>(x), out, nullptr, rows, C, rpb);
+    } else {
+        dim3 grid((unsigned)((rows + 255) / 256), (C + 127) / 128);
+        colsum_cl_kernel<<<grid, 128, 0, st>>>(x, out, rows, C, 256);
+    }
     BM_CHECK_LAUNCH();
     return 0;
 }
@@ -638,7 +716,11 @@ extern "C" int bm_col_sum(const float* x, long long rows, int C, float* out, bm_
 // dh = dq * GELU'(h)  (elementwise; dh may alias dq)
 extern "C" int bm_gelu_bwd(const float* dq, const float* h, long long n, float* dh, bm_stream_t stream) {
     BM_CHECK_ARG(dq && h && dh && n > 0);
-    gelu_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(dq, h, dh, n);
+    if (n % 4 == 0 && aligned16(dq, h, dh))
+        gelu_bwd_v4_kernel<<<ew_grid(n / 4), 256, 0, ST(stream)>>>(
+            reinterpret_cast<const float4*>(dq), reinterpret_cast<const float4*>(h), reinterpret_cast<float4*>(dh), n / 4);
+    else
+        gelu_bwd_kernel<<<ew_grid(n), 256, 0, ST(stream)>>>(dq, h, dh, n);
     BM_CHECK_LAUNCH();
     return 0;
 }

@@ -156,12 +156,17 @@ class _Conv:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
                  dilation, ptr(dx), st)
 
-    def backward_weight(self, dy, x, B, T, dilation, like, status):
-        db = _empty((self.cout,), like)
+    def backward_weight(self, dy, x, B, T, dilation, like, status, bias_grad_is_zero=False):
+        """`bias_grad_is_zero`: the conv feeds a training-mode BatchNorm, whose backward makes sum(dy) == 0 exactly
+        (the reference's value there is rounding noise around 0); skip the reduction."""
         if self.wgrad_tc:
             dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status)
+            if bias_grad_is_zero:
+                return dw, torch.zeros((self.cout,), device=like.device)
+            db = _empty((self.cout,), like)
             call("bm_col_sum", ptr(dy), B * T, self.cout, ptr(db), stream())
             return dw, db
+        db = _empty((self.cout,), like)
         dw = _empty((self.cout, self.cin, self.kw), like)
         call("bm_conv1d_bwd_weight", ptr(dy), ptr(x), B, T, self.cin, self.cout, self.kw, dilation, ptr(dw), ptr(db),
              stream())
@@ -209,12 +214,33 @@ class _EncoderFn(torch.autograd.Function):
         if not conv0.fwd_tc:
             Dp = D
             conv0 = _Conv(conv_p[0][0], T, False, False, want_bwd=save)
-        u = _empty((B, T, O), meg)
-        v = _empty((B, T, IL), meg)
-        x = torch.zeros((B, T, Dp), device=meg.device) if Dp != D else _empty((B, T, D), meg)
         il_w2 = il_w.reshape(IL, O).contiguous()
-        call("bm_sensor_chain_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), ptr(il_w2), ptr(il_b.contiguous()),
-             ptr(subj_w.contiguous()), ptr(plan.subject), B, C, T, O, IL, D, Dp, ptr(u), ptr(v), ptr(x), st)
+        # `initial_linear` on the tensor cores when the (64-padded) widths fit: u and v are then kept zero-padded
+        Op, ILp = _round_up(O, 64), _round_up(IL, 64)
+        il_conv = None
+        if tc:
+            wpad = torch.zeros((ILp, Op, 1), device=meg.device)
+            wpad[:IL, :O, 0] = il_w2
+            il_conv = _Conv(wpad, T, False, True, want_bwd=save)
+            if not (il_conv.fwd_tc and il_conv.bwd_tc and il_conv.wgrad_tc):
+                il_conv = None
+        x = torch.zeros((B, T, Dp), device=meg.device) if Dp != D else _empty((B, T, D), meg)
+        if il_conv is not None:
+            u = torch.zeros((B, T, Op), device=meg.device) if Op != O else _empty((B, T, O), meg)
+            v = _empty((B, T, ILp), meg)
+            bpad = torch.zeros((ILp,), device=meg.device)
+            bpad[:IL] = il_b
+            call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, Op, ptr(u), st)
+            il_conv.forward(u, bpad, B, T, 1, v, None, status)
+            call("bm_subject_layers_fwd", ptr(v), ILp, ptr(subj_w.contiguous()), ptr(plan.subject), B, T, IL, D, Dp,
+                 ptr(x), st)
+        else:
+            Op, ILp = O, IL
+            u = _empty((B, T, O), meg)
+            v = _empty((B, T, IL), meg)
+            call("bm_sensor_chain_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), ptr(il_w2),
+                 ptr(il_b.contiguous()), ptr(subj_w.contiguous()), ptr(plan.subject), B, C, T, O, IL, D, Dp, ptr(u),
+                 ptr(v), ptr(x), st)
 
         # K3/K4 ConvSequence
         stats = _empty((2 * H,), meg, torch.float64)
@@ -273,7 +299,8 @@ class _EncoderFn(torch.autograd.Function):
         if save:
             ctx.plan = plan
             ctx.dims = (B, C, T, R, O, P, IL, S, D, Dp, H, F)
-            ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(),
+            ctx.pads = (Op, ILp)
+            ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(), il_conv=il_conv,
                              layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q,
                              head0=head0, head2=head2, head_tc=head_tc,
                              conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape, w0_shape=w0.shape, w2_shape=w2.shape)
@@ -346,7 +373,8 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                  ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
                  ptr(dy), ptr(dgamma), ptr(dbeta), st)
-            dcw, dcb = conv.backward_weight(dy, rec["x_in"], B, T, plan.dilations[k], meg, status)
+            dcw, dcb = conv.backward_weight(dy, rec["x_in"], B, T, plan.dilations[k], meg, status,
+                                            bias_grad_is_zero=plan.training)
             g_in = _empty((B, T, conv.cin), meg)
             conv.backward_data(dy, g if rec["skip"] else None, B, T, plan.dilations[k], g_in, status)
             g = g_in
@@ -358,15 +386,30 @@ class _EncoderFn(torch.autograd.Function):
         counts = torch.bincount(plan.subject, minlength=S)
         subj_off = torch.zeros(S + 1, dtype=torch.int32, device=meg.device)
         subj_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        dv = _empty((B, T, IL), meg)
-        du = _empty((B, T, O), meg)
+        Op, ILp = ctx.pads
         d_subj = _empty((S, IL, D), meg)
-        d_il_w = _empty((IL, O), meg)
-        d_il_b = _empty((IL,), meg)
         d_att = _empty((R, O, C), meg)
-        call("bm_sensor_chain_bwd", ptr(g), ptr(meg), ptr(s["il_w2"]), ptr(s["subj_w"]), ptr(plan.subject),
-             ptr(s["u"]), ptr(s["v"]), ptr(subj_order), ptr(subj_off), ptr(plan.rec_order), ptr(plan.rec_off),
-             B, C, T, O, IL, D, Dp, S, R, ptr(dv), ptr(du), ptr(d_subj), ptr(d_il_w), ptr(d_il_b), ptr(d_att), st)
+        il_conv = s["il_conv"]
+        if il_conv is not None:
+            dv = torch.zeros((B, T, ILp), device=meg.device) if ILp != IL else _empty((B, T, IL), meg)
+            call("bm_subject_layers_bwd", ptr(g), Dp, ptr(s["v"]), ILp, ptr(s["subj_w"]), ptr(plan.subject),
+                 ptr(subj_order), ptr(subj_off), B, T, IL, D, S, ILp, ptr(dv), ptr(d_subj), st)
+            du = _empty((B, T, Op), meg)
+            il_conv.backward_data(dv, None, B, T, 1, du, status)
+            d_il_w = tc_wgrad(dv, s["u"], B, T, ILp, Op, O, 1, 1, status)[:IL, :, 0].contiguous()
+            dbp = _empty((ILp,), meg)
+            call("bm_col_sum", ptr(dv), rows, ILp, ptr(dbp), st)
+            d_il_b = dbp[:IL].contiguous()
+            call("bm_sensor_mix_bwd", ptr(du), Op, ptr(meg), ptr(plan.rec_order), ptr(plan.rec_off), B, C, T, O, R,
+                 ptr(d_att), st)
+        else:
+            dv = _empty((B, T, IL), meg)
+            du = _empty((B, T, O), meg)
+            d_il_w = _empty((IL, O), meg)
+            d_il_b = _empty((IL,), meg)
+            call("bm_sensor_chain_bwd", ptr(g), ptr(meg), ptr(s["il_w2"]), ptr(s["subj_w"]), ptr(plan.subject),
+                 ptr(s["u"]), ptr(s["v"]), ptr(subj_order), ptr(subj_off), ptr(plan.rec_order), ptr(plan.rec_off),
+                 B, C, T, O, IL, D, Dp, S, R, ptr(dv), ptr(du), ptr(d_subj), ptr(d_il_w), ptr(d_il_b), ptr(d_att), st)
         dscores = _empty((R, O, C), meg)
         dheads = _empty((O, P), meg)
         call("bm_attention_weights_bwd", ptr(d_att), ptr(s["att"]), ptr(s["emb"]), R, C, O, P, ptr(dscores),

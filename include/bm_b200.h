@@ -63,6 +63,22 @@ int bm_sensor_chain_bwd(const float* dx0, const float* meg, const float* il_w, c
                         int IL, int D, int ld_x0, int S, int R, float* dv, float* du, float* d_subj_w, float* d_il_w,
                         float* d_il_b, float* d_weights, bm_stream_t stream);
 
+/* The same chain as separate stages with explicit leading dimensions (u / v / dv / du / x0 may be kept zero-padded to a
+ * multiple of 64 channels so that `initial_linear` runs on the tensor-core pointwise kernel, bm_tc_conv1d_pair Kw=1). */
+int bm_sensor_mix_fwd(const float* meg, const float* weights, const int* rec_of_sample, int B, int C, int T, int O,
+                      int ld_u, float* u, bm_stream_t stream);
+int bm_initial_linear_fwd(const float* u, int ld_u, const float* il_w, const float* il_b, int B, int T, int O, int IL,
+                          int ld_v, float* v, bm_stream_t stream);
+int bm_subject_layers_fwd(const float* v, int ld_v, const float* subj_w, const int* subject, int B, int T, int IL, int D,
+                          int ld_x0, float* x0, bm_stream_t stream);
+int bm_subject_layers_bwd(const float* dx0, int ld_x0, const float* v, int ld_v, const float* subj_w, const int* subject,
+                          const int* subj_order, const int* subj_off, int B, int T, int IL, int D, int S, int ld_dv,
+                          float* dv, float* d_subj_w, bm_stream_t stream);
+int bm_initial_linear_bwd(const float* dv, int ld_dv, const float* u, int ld_u, const float* il_w, int B, int T, int O,
+                          int IL, int ld_du, float* du, float* d_il_w, float* d_il_b, bm_stream_t stream);
+int bm_sensor_mix_bwd(const float* du, int ld_du, const float* meg, const int* rec_order, const int* rec_off, int B, int C,
+                      int T, int O, int R, float* d_weights, bm_stream_t stream);
+
 /* ---- K3: dilated Conv1d + train-mode BatchNorm + GELU + skip (ConvSequence, common.py:98-151) ------------
  * w [Cout,Cin,Kw] -> wf [Kw,Cin,Cout] (forward operand), wb [Kw,Cout,Cin] (data-gradient operand). */
 int bm_conv_weight_prep(const float* w, int Cout, int Cin, int Kw, float* wf, float* wb, bm_stream_t stream);
