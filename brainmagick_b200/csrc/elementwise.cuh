@@ -425,33 +425,6 @@ __global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restr
 // ------------------------------------------------------------------------------------------------
 // float4 versions (C % 4 == 0, 16-byte aligned rows): one thread owns 4 consecutive channels
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_gelu_bwd_reduce_v4_kernel(const float4* __restrict__ g, const float4* __restrict__ y,
-                                             const float4* __restrict__ mean, const float4* __restrict__ invstd,
-                                             const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                                             double* __restrict__ sums, long long rows, int C, int rows_per_block) {
-    const int C4 = C >> 2;
-    int c4 = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c4 >= C4) return;
-    long long r0 = (long long)blockIdx.x * rows_per_block;
-    long long r1 = min(rows, r0 + rows_per_block);
-    const float4 mu = mean[c4], is = invstd[c4], ga = gamma[c4], be = beta[c4];
-    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll 2
-    for (long long r = r0; r < r1; ++r) {
-        const float4 yv = y[r * C4 + c4], gv = g[r * C4 + c4];
-        float yh, dz;
-        yh = (yv.x - mu.x) * is.x; dz = gv.x * gelu_grad_f(yh * ga.x + be.x); s1.x += dz; s2.x = fmaf(dz, yh, s2.x);
-        yh = (yv.y - mu.y) * is.y; dz = gv.y * gelu_grad_f(yh * ga.y + be.y); s1.y += dz; s2.y = fmaf(dz, yh, s2.y);
-        yh = (yv.z - mu.z) * is.z; dz = gv.z * gelu_grad_f(yh * ga.z + be.z); s1.z += dz; s2.z = fmaf(dz, yh, s2.z);
-        yh = (yv.w - mu.w) * is.w; dz = gv.w * gelu_grad_f(yh * ga.w + be.w); s1.w += dz; s2.w = fmaf(dz, yh, s2.w);
-    }
-    const int c = c4 * 4;
-    atomicAdd(sums + c, (double)s1.x); atomicAdd(sums + c + 1, (double)s1.y);
-    atomicAdd(sums + c + 2, (double)s1.z); atomicAdd(sums + c + 3, (double)s1.w);
-    atomicAdd(sums + C + c, (double)s2.x); atomicAdd(sums + C + c + 1, (double)s2.y);
-    atomicAdd(sums + C + c + 2, (double)s2.z); atomicAdd(sums + C + c + 3, (double)s2.w);
-}
-
 __global__ void bn_gelu_bwd_apply_v4_kernel(const float4* __restrict__ g, const float4* __restrict__ y,
                                             const float4* __restrict__ mean, const float4* __restrict__ invstd,
                                             const float4* __restrict__ gamma, const float4* __restrict__ beta,
@@ -506,33 +479,6 @@ __global__ void gelu_bwd_v4_kernel(const float4* __restrict__ dq, const float4* 
          i += (long long)gridDim.x * blockDim.x) {
         const float4 d = dq[i], x = h[i];
         dh[i] = make_float4(d.x * gelu_grad_f(x.x), d.y * gelu_grad_f(x.y), d.z * gelu_grad_f(x.z), d.w * gelu_grad_f(x.w));
-    }
-}
-
-// out[c] += sum_r X[r][c] and (optionally) stats[C+c] += sum_r X[r][c]^2; SQ selects fp64 statistics mode
-template <bool STATS>
-__global__ void colsum_v4_kernel(const float4* __restrict__ X, float* __restrict__ out, double* __restrict__ stats,
-                                 long long rows, int C, int rows_per_block) {
-    const int C4 = C >> 2;
-    int c4 = blockIdx.y * blockDim.x + threadIdx.x;
-    if (c4 >= C4) return;
-    long long r0 = (long long)blockIdx.x * rows_per_block;
-    long long r1 = min(rows, r0 + rows_per_block);
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-#pragma unroll 4
-    for (long long r = r0; r < r1; ++r) {
-        const float4 v = X[r * C4 + c4];
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        if (STATS) { q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w); }
-    }
-    const int c = c4 * 4;
-    if (STATS) {
-        atomicAdd(stats + c, (double)s.x); atomicAdd(stats + c + 1, (double)s.y);
-        atomicAdd(stats + c + 2, (double)s.z); atomicAdd(stats + c + 3, (double)s.w);
-        atomicAdd(stats + C + c, (double)q.x); atomicAdd(stats + C + c + 1, (double)q.y);
-        atomicAdd(stats + C + c + 2, (double)q.z); atomicAdd(stats + C + c + 3, (double)q.w);
-    } else {
-        atomicAdd(out + c, s.x); atomicAdd(out + c + 1, s.y); atomicAdd(out + c + 2, s.z); atomicAdd(out + c + 3, s.w);
     }
 }
 
