@@ -1,0 +1,84 @@
+"""GPU: top-10 segment-retrieval accuracy parity on the learnable synthetic task (north-star: within +-0.5 pt of the
+reference on the same synthetic eval).  Both implementations start from the same state_dict and see the same batches
+and spatial-dropout centres for 64 Adam steps; the reference side is the CPU oracle (oracle/bm_oracle.py)."""
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_top10_accuracy_parity_on_synthetic_task():
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import functional as BF, synthetic
+    from oracle import accuracy_task as at, bm_oracle
+
+    cfg = bm_oracle.Config(in_channels=32, out_channels=24, n_subjects=4, hidden=160, merger_channels=40,
+                           initial_linear=48, merger_pos_dim=128)
+    task = at.make_task(cfg, n_train=1024, n_eval=2048, T=90, noise=3.0)
+    sched = at.batches(1024, 64, 4)
+    p0 = bm_oracle.init_state_dict(cfg, seed=3)
+
+    # ---- reference side: CPU oracle ----
+    p_ref, loss_ref = at.train_oracle(cfg, p0, task, sched, lr=1e-3)
+    acc_ref, _ = at.eval_oracle(cfg, p_ref, task, k=10)
+    acc1_ref, _ = at.eval_oracle(cfg, p_ref, task, k=1)
+
+    # ---- CUDA drop-in ----
+    model = bb.SimpleConv(
+        in_channels=dict(meg=cfg.in_channels), out_channels=cfg.out_channels, hidden=dict(meg=cfg.hidden), depth=cfg.depth,
+        dilation_period=5, kernel_size=3, skip=True, subject_layers=True, subject_dim=0, complex_out=True, glu=2,
+        glu_context=1, merger=True, initial_linear=cfg.initial_linear, merger_channels=cfg.merger_channels, gelu=True,
+        batch_norm=True, merger_pos_dim=cfg.merger_pos_dim, n_subjects=cfg.n_subjects)
+    model.load_state_dict(p0)
+    model = model.cuda().train()
+    clip = bb.ClipLoss().cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    recs = [synthetic.SyntheticRecording(s, task["positions"][s]) for s in range(cfg.n_subjects)]
+    d = {k: v.cuda() for k, v in task["train"].items()}
+    losses = []
+    for idx, ban in sched:
+        idx_d = idx.cuda()
+        meg, feats, subj = d["meg"][idx_d], d["feats"][idx_d], d["subj"][idx_d]
+        batch = synthetic.SyntheticBatch(meg, subj, [recs[int(s)] for s in task["train"]["subj"][idx]])
+        model.merger.ban_centre_override = ban
+        opt.zero_grad(set_to_none=True)
+        est = model(dict(meg=meg), batch)
+        loss = clip(est, feats, torch.ones(len(idx), 1, meg.shape[-1], dtype=torch.bool, device="cuda"))
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    BF.check_tc_status()
+
+    model.eval()
+    clip.eval()
+    e = {k: v.cuda() for k, v in task["eval"].items()}
+    ests = []
+    with torch.no_grad():
+        for i in range(0, len(e["meg"]), 256):
+            sl = slice(i, i + 256)
+            batch = synthetic.SyntheticBatch(e["meg"][sl], e["subj"][sl], [recs[int(s)] for s in task["eval"]["subj"][sl]])
+            ests.append(model(dict(meg=e["meg"][sl]), batch))
+    est = torch.cat(ests)
+    hits10 = hits1 = 0
+    for i in range(0, len(est), 256):
+        probs = clip.get_probabilities(est[i:i + 256], e["feats"])
+        top = probs.topk(10, dim=1).indices
+        truth = torch.arange(i, min(i + 256, len(est)), device="cuda")[:, None]
+        hits10 += (top == truth).any(dim=1).sum().item()
+        hits1 += (top[:, :1] == truth).sum().item()
+    acc, acc1 = hits10 / len(est), hits1 / len(est)
+    result = dict(task="synthetic latent retrieval, 2048 held-out segments, 64 Adam steps (lr 1e-3, B=64)",
+                  top10_reference_cpu_oracle=acc_ref, top10_cuda=acc, top1_reference_cpu_oracle=acc1_ref, top1_cuda=acc1,
+                  final_loss_reference=loss_ref[-1], final_loss_cuda=losses[-1], first_loss_reference=loss_ref[0],
+                  first_loss_cuda=losses[0])
+    print("\n[accuracy parity]", json.dumps(result))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "accuracy_parity.json"), "w") as f:
+            json.dump(result, f, indent=1)
+    assert abs(losses[0] - loss_ref[0]) < 1e-4 * max(1.0, abs(loss_ref[0]))
+    assert acc_ref > 0.3, "the task must be learnt for the comparison to mean anything"
+    assert abs(acc - acc_ref) <= 0.005, (acc, acc_ref)          # +-0.5 pt
