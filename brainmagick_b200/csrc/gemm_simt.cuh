@@ -59,7 +59,7 @@ inline GemmP gemm_defaults() {
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GNT = 256, GPAD = 4;
 
-__global__ void __launch_bounds__(GNT) gemm_simt_kernel(const GemmP p) {
+__global__ void __launch_bounds__(GNT, 2) gemm_simt_kernel(const GemmP p) {
     __shared__ __align__(16) float As[2][GBK][GBM + GPAD];
     __shared__ __align__(16) float Bs[2][GBK][GBN + GPAD];
 
@@ -92,23 +92,12 @@ __global__ void __launch_bounds__(GNT) gemm_simt_kernel(const GemmP p) {
         return n < p.N ? n : -1;
     };
 
-    // loader element mapping
-    int a_r[8], a_k[8], b_c[8], b_k[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        if (p.a_mcontig) { a_r[i] = tid & 127; a_k[i] = (tid >> 7) + 2 * i; }
-        else             { a_k[i] = tid & 15;  a_r[i] = (tid >> 4) + 16 * i; }
-        if (p.b_ncontig) { b_c[i] = tid & 127; b_k[i] = (tid >> 7) + 2 * i; }
-        else             { b_k[i] = tid & 15;  b_c[i] = (tid >> 4) + 16 * i; }
-    }
-    long long b_coloff[8];
-    bool b_colok[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int n = gcol(b_c[i]);
-        b_colok[i] = n >= 0;
-        b_coloff[i] = (long long)(n < 0 ? 0 : n) * p.ldb_n;
-    }
+    // loader element mapping (recomputed from tid inside the unrolled loops: keeps the kernel at <= 128 registers so
+    // that two CTAs fit per SM, which is what hides the latency of the scalar tile loads)
+    const int a_r0 = p.a_mcontig ? (tid & 127) : (tid >> 4), a_k0 = p.a_mcontig ? (tid >> 7) : (tid & 15);
+    const int a_rs = p.a_mcontig ? 0 : 16, a_ks = p.a_mcontig ? 2 : 0;
+    const int b_c0 = p.b_ncontig ? (tid & 127) : (tid >> 4), b_k0 = p.b_ncontig ? (tid >> 7) : (tid & 15);
+    const int b_cs = p.b_ncontig ? 0 : 16, b_ks = p.b_ncontig ? 2 : 0;
 
     float ra[8], rb[8];
     auto load_tile = [&](int it) {
@@ -124,25 +113,26 @@ __global__ void __launch_bounds__(GNT) gemm_simt_kernel(const GemmP p) {
         const int k0 = kb + kt * GBK;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            int k = k0 + a_k[i];
-            int m = m0 + a_r[i];
+            int k = k0 + a_k0 + a_ks * i;
+            int m = m0 + a_r0 + a_rs * i;
             int ms = m + sh_m;
             bool ok = (k < ke) && (m < p.M) && (ms >= 0) && (ms < p.M);
             ra[i] = ok ? __ldg(Ab + (long long)ms * p.lda_m + (long long)k * p.lda_k) : 0.f;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            int k = k0 + b_k[i];
+            int k = k0 + b_k0 + b_ks * i;
             int ks = k + sh_k;
-            bool ok = b_colok[i] && (k < ke) && (ks >= 0) && (ks < p.K);
-            rb[i] = ok ? __ldg(Bb + b_coloff[i] + (long long)ks * p.ldb_k) : 0.f;
+            int n = gcol(b_c0 + b_cs * i);
+            bool ok = (n >= 0) && (k < ke) && (ks >= 0) && (ks < p.K);
+            rb[i] = ok ? __ldg(Bb + (long long)n * p.ldb_n + (long long)ks * p.ldb_k) : 0.f;
         }
     };
     auto store_tile = [&](int buf) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            As[buf][a_k[i]][a_r[i]] = ra[i];
-            Bs[buf][b_k[i]][b_c[i]] = rb[i];
+            As[buf][a_k0 + a_ks * i][a_r0 + a_rs * i] = ra[i];
+            Bs[buf][b_k0 + b_ks * i][b_c0 + b_cs * i] = rb[i];
         }
     };
 
