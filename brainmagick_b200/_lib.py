@@ -54,6 +54,8 @@ SIGNATURES = {
     "bm_tc_wgrad_supported": [I, I],
     "bm_tc_wgrad": [P, P, I, I, I, I, I, I, I, P, P, P, P],
     "bm_col_sum": [P, L, I, P, P],
+    "bm_tc_pointwise_sel": [P, P, P, P, I, I, I, I, I, P, P, P],
+    "bm_tc_wgrad_grouped": [P, P, P, P, I, I, I, I, I, P, P, P],
     "bm_gelu_bwd": [P, P, L, P, P],
 }
 

@@ -646,7 +646,7 @@ extern "C" int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo
     tc::ConvTcP p;
     p.B = B; p.T = T; p.Cin = Cin; p.Ntot = Ntot; p.taps = Kw; p.dilation = dilation; p.sign = sign; p.glu = glu;
     p.bias = bias; p.addend = addend; p.y = y; p.glu_out = glu_out; p.err = status;
-    p.act = act; p.out_tmajor = out_tmajor; p.aux = aux; p.bn = 0;
+    p.act = act; p.out_tmajor = out_tmajor; p.aux = aux; p.bn = 0; p.wsel = nullptr; p.n_wsets = 1;
     BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
     return tc::launch_conv_tc(x, w_hi, w_lo, p, ST(stream));
 }
@@ -727,4 +727,26 @@ extern "C" int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float*
     q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
     q.glu_out = glu_out; q.err = status;
     return tc::launch_conv_tc3(x, w_hi, w_lo, q, ST(stream));
+}
+
+// pointwise (1x1) contraction with a per-sample weight set (SubjectLayers.forward / its data gradient, common.py:55-58):
+//   y[b,t,n] = sum_k x[b,t,k] W[wsel[b]][n][k];  w_hi/w_lo are the tf32-split K-major weight sets [S][Ntot][Cin]
+extern "C" int bm_tc_pointwise_sel(const float* x, const float* w_hi, const float* w_lo, const int* wsel, int n_sets,
+                                   int B, int T, int Cin, int Ntot, float* y, int* status, bm_stream_t stream) {
+    BM_CHECK_ARG(x && w_hi && w_lo && wsel && y && n_sets > 0 && B > 0 && B <= 65535 && T > 0);
+    BM_CHECK_ARG(tc::conv_tc_supported(T, Cin, Ntot, 1, 0));
+    tc::ConvTcP p;
+    p.B = B; p.T = T; p.Cin = Cin; p.Ntot = Ntot; p.taps = 1; p.dilation = 1; p.sign = 1; p.glu = 0;
+    p.bias = nullptr; p.addend = nullptr; p.y = y; p.glu_out = nullptr; p.err = status;
+    p.act = 0; p.out_tmajor = 0; p.aux = nullptr; p.bn = 0; p.wsel = wsel; p.n_wsets = n_sets;
+    return tc::launch_conv_tc(x, w_hi, w_lo, p, ST(stream));
+}
+
+// per-group pointwise weight gradient (SubjectLayers: dM[s] = sum over the samples of subject s), tensor cores:
+//   out[g][m][n] = sum_{b in group g} sum_t dy[b,t,m] x[b,t,n];  out is [G][ceil(M/128)*128][N]
+extern "C" int bm_tc_wgrad_grouped(const float* dy, const float* x, const int* order, const int* seg_off, int G, int B,
+                                   int T, int M, int N, float* out, int* status, bm_stream_t stream) {
+    BM_CHECK_ARG(dy && x && order && seg_off && out && G > 0 && B > 0 && T > 0);
+    BM_CHECK_ARG(tc::wgrad_tc_supported(M, N));
+    return tc::launch_wgrad_tc_grouped(dy, x, order, seg_off, G, B, T, M, N, out, status, ST(stream));
 }

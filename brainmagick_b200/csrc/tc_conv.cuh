@@ -35,6 +35,8 @@ struct ConvTcP {
     float* y;                 // [B,T,Ntot] (pre-GLU h when glu; may be null then)
     float* aux;               // [B,T,Ntot] or null
     float* glu_out;           // [B,T,Ntot/2]
+    int n_wsets;              // number of weight sets when wsel != null
+    const int* wsel;          // per-sample weight set (SubjectLayers): weight rows are offset by wsel[b]*taps*Ntot; or null
     int* err;
 };
 
@@ -80,6 +82,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             prefetch_tmap(&tmA);
             prefetch_tmap(&tmBhi);
             prefetch_tmap(&tmBlo);
+            const int wsel_base = p.wsel ? p.wsel[b] * p.taps : 0;
             for (int it = 0; it < total; ++it) {
                 const int s = it % CV_STAGES;
                 const uint32_t ph = (it / CV_STAGES) & 1;
@@ -92,7 +95,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* bh = st + 2 * CV_A_BYTES;
                 uint8_t* bl = bh + CV_B_BYTES;
                 if (!p.glu) {
-                    const int row = tap * p.Ntot + n_tile * p.bn;
+                    const int row = (wsel_base + tap) * p.Ntot + n_tile * p.bn;
                     tma_load_2d(bh, &tmBhi, &full_bar[s], k0, row);
                     tma_load_2d(bl, &tmBlo, &full_bar[s], k0, row);
                 } else {
@@ -273,7 +276,7 @@ inline int launch_conv_tc(const float* x, const float* w_hi, const float* w_lo, 
         if (!make_tmap_f32(&tmA, x, 3, dims, str, box)) return set_error(4, "%s: cuTensorMapEncodeTiled(A) failed%s", __func__);
     }
     {
-        uint64_t dims[2] = {(uint64_t)p.Cin, (uint64_t)p.taps * p.Ntot};
+        uint64_t dims[2] = {(uint64_t)p.Cin, (uint64_t)p.taps * p.Ntot * (uint64_t)(p.wsel ? p.n_wsets : 1)};
         uint64_t str[1] = {(uint64_t)p.Cin * 4};
         uint32_t box[2] = {CV_BK, (uint32_t)(p.glu ? CV_BN / 2 : p.bn)};
         if (!make_tmap_f32(&tmBh, w_hi, 2, dims, str, box) || !make_tmap_f32(&tmBl, w_lo, 2, dims, str, box))

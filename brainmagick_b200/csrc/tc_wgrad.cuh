@@ -36,6 +36,8 @@ struct WgradP {
     float* P;                   // [taps][ksplit][Mpad][N] partial tiles, Mpad = gridDim.y*128
     int* err;
     int direct;                 // 1 (taps == 1, ksplit == 1): P IS the output [M][N]; rows >= M are not written
+    const int* zlist;           // grouped mode (per-subject gradients): slice ks = samples zlist[seg_off[ks] .. seg_off[ks+1])
+    const int* seg_off;         //   and P [ksplit][Mpad][N] is the per-group output (no reduction)
     int trunc_hi;               // 1: leave X raw in smem as the hi operand (the tensor core ignores the 13 low mantissa
                                 //    bits) and write only lo = x - trunc(x): one third less converter smem traffic
 };
@@ -94,7 +96,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
     const int tap = blockIdx.x / ntiles;
     const int shift = (tap - p.taps / 2) * p.dilation;
     const int n0 = (blockIdx.x - tap * ntiles) * 2 * p.nh, m0 = blockIdx.y * WG_BM, ks = blockIdx.z;
-    const int b_begin = ks * p.bchunk, b_end = min(p.B, b_begin + p.bchunk);
+    const int b_begin = p.seg_off ? p.seg_off[ks] : ks * p.bchunk;
+    const int b_end = p.seg_off ? p.seg_off[ks + 1] : min(p.B, b_begin + p.bchunk);
     const int tchunks = (p.T + WG_BK - 1) / WG_BK;
     const int total = max(0, b_end - b_begin) * tchunks;
     const int nblk = 2 * p.nh / 32;                          // 32-channel blocks in the B tile
@@ -122,7 +125,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
                 const int s = it % WG_STAGES;
                 const uint32_t ph = (it / WG_STAGES) & 1;
                 if (!mbar_wait(&empty_bar[s], ph ^ 1, p.err, 11)) break;
-                const int b = b_begin + it / tchunks, t0 = (it % tchunks) * WG_BK;
+                int b = b_begin + it / tchunks;
+                if (p.zlist) b = p.zlist[b];
+                const int t0 = (it % tchunks) * WG_BK;
                 uint8_t* st = smem + s * WG_STAGE_BYTES;
                 mbar_expect_tx(&full_bar[s], b_bytes);
                 for (int k = 0; k < nblk; ++k)
@@ -166,7 +171,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         float nxt[WG_BK];
         auto load_a = [&](int it) {
-            const int b = b_begin + it / tchunks, t0 = (it % tchunks) * WG_BK;
+            int b = b_begin + it / tchunks;
+            if (p.zlist) b = p.zlist[b];
+            const int t0 = (it % tchunks) * WG_BK;
             const float* src = p.dY + ((long long)b * p.T + t0) * p.M + m;
 #pragma unroll
             for (int j = 0; j < WG_BK; ++j) nxt[j] = (m_ok && t0 + j < p.T) ? __ldg(src + (long long)j * p.M) : 0.f;
@@ -310,6 +317,7 @@ inline int launch_wgrad_tc(const float* dY, const float* X, int B, int T, int M,
     p.B = B; p.T = T; p.M = M; p.N = N; p.nh = nh; p.taps = taps; p.dilation = dilation;
     p.ksplit = ksplit; p.bchunk = bchunk; p.dY = dY; p.err = err; p.P = ws;
     p.direct = (taps == 1 && ksplit == 1 && Ntrue == N) ? 1 : 0;
+    p.zlist = nullptr; p.seg_off = nullptr;
     if (p.direct) p.P = dW;
     p.trunc_hi = (g_debug_flags & 1) ? 0 : 1;     // default ON; debug bit 0 restores the explicit rna split
     dim3 grid(N / (2 * nh) * taps, mblocks, ksplit);
@@ -322,6 +330,40 @@ inline int launch_wgrad_tc(const float* dY, const float* X, int B, int T, int M,
     ++g_launches;
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(3, "%s: reduce launch failed: %s", __func__, cudaGetErrorString(e));
+    return 0;
+}
+
+// grouped pointwise weight gradient: out[g][m][n] = sum_{b in group g} sum_t dY[b,t,m] X[b,t,n]; out is [G][Mpad][N] with
+// Mpad = ceil(M/128)*128 (rows >= M are zero); groups given as CSR (zlist, seg_off[G+1]) over the samples.
+inline int launch_wgrad_tc_grouped(const float* dY, const float* X, const int* zlist, const int* seg_off, int G, int B,
+                                   int T, int M, int N, float* out, int* err, cudaStream_t st) {
+    const int nh = wgrad_pick_nh(N);
+    if (nh == 0) return set_error(2, "%s: unsupported N%s", __func__);
+    CUtensorMap tmX;
+    {
+        uint64_t dims[3] = {(uint64_t)N, (uint64_t)T, (uint64_t)B};
+        uint64_t str[2] = {(uint64_t)N * 4, (uint64_t)T * N * 4};
+        uint32_t box[3] = {32, 32, 1};
+        if (!make_tmap_f32(&tmX, X, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+            return set_error(4, "%s: cuTensorMapEncodeTiled failed%s", __func__);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(3, "%s: cudaFuncSetAttribute: %s", __func__, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    WgradP p;
+    p.B = B; p.T = T; p.M = M; p.N = N; p.nh = nh; p.taps = 1; p.dilation = 1;
+    p.ksplit = G; p.bchunk = 0; p.dY = dY; p.err = err; p.P = out; p.direct = 0;
+    p.zlist = zlist; p.seg_off = seg_off;
+    p.trunc_hi = (g_debug_flags & 1) ? 0 : 1;
+    dim3 grid(N / (2 * nh), (M + WG_BM - 1) / WG_BM, G);
+    if (G > 65535) return set_error(2, "%s: too many groups%s", __func__);
+    wgrad_tc_kernel<<<grid, WG_THREADS, WG_SMEM_BYTES, st>>>(tmX, p);
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(3, "%s: launch failed: %s", __func__, cudaGetErrorString(e));
     return 0;
 }
 

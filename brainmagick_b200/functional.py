@@ -232,9 +232,24 @@ class _EncoderFn(torch.autograd.Function):
             bpad[:IL] = il_b
             call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, Op, ptr(u), st)
             il_conv.forward(u, bpad, B, T, 1, v, None, status)
-            call("bm_subject_layers_fwd", ptr(v), ILp, ptr(subj_w.contiguous()), ptr(plan.subject), B, T, IL, D, Dp,
-                 ptr(x), st)
+            lib = _lib.load()
+            subj_tc = (Dp != D or D % 64 == 0) and bool(lib.bm_tc_conv_supported(T, ILp, Dp, 1, 0)) and \
+                bool(lib.bm_tc_conv_supported(T, Dp, ILp, 1, 0)) and bool(lib.bm_tc_wgrad_supported(ILp, Dp))
+            if subj_tc:
+                # per-subject weights, zero-padded; forward operand [s][d][p] (K-major in p), tf32-split
+                subj_pad = torch.zeros((S, ILp, Dp), device=meg.device)
+                subj_pad[:, :IL, :D] = subj_w
+                mt = subj_pad.transpose(1, 2).contiguous()
+                sf_hi, sf_lo = _empty((S * Dp, ILp), meg), _empty((S * Dp, ILp), meg)
+                call("bm_tc_weight_split", ptr(mt), S * Dp, ILp, 1, ptr(sf_hi), ptr(sf_lo), None, None, st)
+                call("bm_tc_pointwise_sel", ptr(v), ptr(sf_hi), ptr(sf_lo), ptr(plan.subject), S, B, T, ILp, Dp, ptr(x),
+                     ptr(status), st)
+            else:
+                subj_pad = None
+                call("bm_subject_layers_fwd", ptr(v), ILp, ptr(subj_w.contiguous()), ptr(plan.subject), B, T, IL, D, Dp,
+                     ptr(x), st)
         else:
+            subj_pad = None
             Op, ILp = O, IL
             u = _empty((B, T, O), meg)
             v = _empty((B, T, IL), meg)
@@ -301,6 +316,7 @@ class _EncoderFn(torch.autograd.Function):
             ctx.dims = (B, C, T, R, O, P, IL, S, D, Dp, H, F)
             ctx.pads = (Op, ILp)
             ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(), il_conv=il_conv,
+                             subj_pad=subj_pad,
                              layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q,
                              head0=head0, head2=head2, head_tc=head_tc,
                              conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape, w0_shape=w0.shape, w2_shape=w2.shape)
@@ -391,9 +407,22 @@ class _EncoderFn(torch.autograd.Function):
         d_att = _empty((R, O, C), meg)
         il_conv = s["il_conv"]
         if il_conv is not None:
-            dv = torch.zeros((B, T, ILp), device=meg.device) if ILp != IL else _empty((B, T, IL), meg)
-            call("bm_subject_layers_bwd", ptr(g), Dp, ptr(s["v"]), ILp, ptr(s["subj_w"]), ptr(plan.subject),
-                 ptr(subj_order), ptr(subj_off), B, T, IL, D, S, ILp, ptr(dv), ptr(d_subj), st)
+            if s["subj_pad"] is not None:
+                subj_pad = s["subj_pad"]                                   # [S][ILp][Dp]: data-gradient operand as is
+                sb_hi, sb_lo = _empty((S * ILp, Dp), meg), _empty((S * ILp, Dp), meg)
+                call("bm_tc_weight_split", ptr(subj_pad), S * ILp, Dp, 1, ptr(sb_hi), ptr(sb_lo), None, None, st)
+                dv = _empty((B, T, ILp), meg)
+                call("bm_tc_pointwise_sel", ptr(g), ptr(sb_hi), ptr(sb_lo), ptr(plan.subject), S, B, T, Dp, ILp, ptr(dv),
+                     ptr(status), st)
+                mpad = _round_up(ILp, 128)
+                dm = _empty((S, mpad, Dp), meg)
+                call("bm_tc_wgrad_grouped", ptr(s["v"]), ptr(g), ptr(subj_order), ptr(subj_off), S, B, T, ILp, Dp,
+                     ptr(dm), ptr(status), st)
+                d_subj = dm[:, :IL, :D].contiguous()
+            else:
+                dv = torch.zeros((B, T, ILp), device=meg.device) if ILp != IL else _empty((B, T, IL), meg)
+                call("bm_subject_layers_bwd", ptr(g), Dp, ptr(s["v"]), ILp, ptr(s["subj_w"]), ptr(plan.subject),
+                     ptr(subj_order), ptr(subj_off), B, T, IL, D, S, ILp, ptr(dv), ptr(d_subj), st)
             du = _empty((B, T, Op), meg)
             il_conv.backward_data(dv, None, B, T, 1, du, status)
             d_il_w = tc_wgrad(dv, s["u"], B, T, ILp, Op, O, 1, 1, status)[:IL, :, 0].contiguous()

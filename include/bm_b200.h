@@ -186,6 +186,14 @@ long long bm_tc_wgrad_workspace(int B, int M, int N, int Kw);
 int bm_tc_wgrad(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw, int dilation,
                 float* workspace, float* dw, int* status, bm_stream_t stream);
 int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream);
+/* SubjectLayers (common.py:55-58) on the tensor cores.
+ * bm_tc_pointwise_sel: y[b,t,n] = sum_k x[b,t,k] W[wsel[b]][n][k] with tf32-split weight sets w_hi/w_lo [S][Ntot][Cin].
+ * bm_tc_wgrad_grouped: out[g][m][n] = sum_{b in group g} sum_t dy[b,t,m] x[b,t,n], groups as CSR (order, seg_off[G+1]);
+ * out is [G][ceil(M/128)*128][N] (rows >= M are zero). */
+int bm_tc_pointwise_sel(const float* x, const float* w_hi, const float* w_lo, const int* wsel, int n_sets, int B, int T,
+                        int Cin, int Ntot, float* y, int* status, bm_stream_t stream);
+int bm_tc_wgrad_grouped(const float* dy, const float* x, const int* order, const int* seg_off, int G, int B, int T, int M,
+                        int N, float* out, int* status, bm_stream_t stream);
 /* dh = dq * GELU'(h), elementwise over n values (dh may alias dq): the head's activation backward. */
 int bm_gelu_bwd(const float* dq, const float* h, long long n, float* dh, bm_stream_t stream);
 /* in [Z,N,T] (channel-major) -> out [Z,T,N] (channels-last): the gradient of `estimate` enters the head backward. */
