@@ -7,6 +7,7 @@
 #include "tc_wgrad.cuh"
 #include "tc_conv2.cuh"
 #include "tc_conv3.cuh"
+#include "tc_conv4.cuh"
 
 namespace bm {
 thread_local char g_last_error[512] = "";
@@ -721,6 +722,15 @@ extern "C" int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float*
     BM_CHECK_ARG(x && w_hi && w_lo && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
     BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
     BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
+    if ((g_debug_flags & 2) && tc::conv_tc4_supported(T, Cin, Ntot, Kw, glu)) {
+        // fourth generation (persistent CTA pairs, double-buffered accumulators, half-width tiles): correct but measured
+        // slower than generation 3 (it streams every x tile twice and becomes L2->SM bound); kept behind debug bit 1<<1
+        tc::Conv4P q;
+        q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
+        q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
+        q.glu_out = glu_out; q.err = status;
+        return tc::launch_conv_tc4(x, w_hi, w_lo, q, ST(stream));
+    }
     BM_CHECK_ARG(tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu));
     tc::Conv3P q;
     q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;

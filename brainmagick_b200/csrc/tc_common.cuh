@@ -163,6 +163,14 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(r);
 }
 
+// The same split with full-rate integer/FP32 instructions (cvt.rna.tf32 issues at a fraction of the FMA rate and made
+// the converter warps the bottleneck): hi = round-to-nearest(ties away) of x to 10 mantissa bits = (bits + 0x1000) &
+// ~0x1FFF, lo = x - hi exactly (the tensor core ignores lo's 13 low mantissa bits: error <= 2^-21 |x|).
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
+}
+
 }  // namespace tc
 
 // ---------------------------------------------------------------------------------------------------

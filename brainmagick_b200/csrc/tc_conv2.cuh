@@ -153,10 +153,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-                    hi[4 * c + 0] = tf32_rna(v.x); hi[4 * c + 1] = tf32_rna(v.y);
-                    hi[4 * c + 2] = tf32_rna(v.z); hi[4 * c + 3] = tf32_rna(v.w);
-                    lo[4 * c + 0] = tf32_rna(v.x - hi[4 * c + 0]); lo[4 * c + 1] = tf32_rna(v.y - hi[4 * c + 1]);
-                    lo[4 * c + 2] = tf32_rna(v.z - hi[4 * c + 2]); lo[4 * c + 3] = tf32_rna(v.w - hi[4 * c + 3]);
+                    tf32_split(v.x, hi[4 * c + 0], lo[4 * c + 0]); tf32_split(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+                    tf32_split(v.z, hi[4 * c + 2], lo[4 * c + 2]); tf32_split(v.w, hi[4 * c + 3], lo[4 * c + 3]);
                 }
                 tmem_st32(tq + C2_ACC_COLS + s * C2_A_COLS, hi);
                 tmem_st32(tq + C2_ACC_COLS + s * C2_A_COLS + C2_BK, lo);
@@ -171,8 +169,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const int idx = ct + C2_CONV_THREADS * j;
                 if (idx < nvec) {
                     float4 v = bh[idx], h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
                     bh[idx] = h;
                     bl[idx] = l;
                 }

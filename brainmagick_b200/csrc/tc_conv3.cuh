@@ -200,10 +200,8 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
-                    hi[4 * c + 0] = tf32_rna(v.x); hi[4 * c + 1] = tf32_rna(v.y);
-                    hi[4 * c + 2] = tf32_rna(v.z); hi[4 * c + 3] = tf32_rna(v.w);
-                    lo[4 * c + 0] = tf32_rna(v.x - hi[4 * c + 0]); lo[4 * c + 1] = tf32_rna(v.y - hi[4 * c + 1]);
-                    lo[4 * c + 2] = tf32_rna(v.z - hi[4 * c + 2]); lo[4 * c + 3] = tf32_rna(v.w - hi[4 * c + 3]);
+                    tf32_split(v.x, hi[4 * c + 0], lo[4 * c + 0]); tf32_split(v.y, hi[4 * c + 1], lo[4 * c + 1]);
+                    tf32_split(v.z, hi[4 * c + 2], lo[4 * c + 2]); tf32_split(v.w, hi[4 * c + 3], lo[4 * c + 3]);
                 }
                 tmem_st32(tq + C3_ACC_COLS + s * C3_A_COLS, hi);
                 tmem_st32(tq + C3_ACC_COLS + s * C3_A_COLS + C3_BK, lo);

@@ -186,8 +186,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
             float hi[WG_BK], lo[WG_BK];
 #pragma unroll
             for (int j = 0; j < WG_BK; ++j) {
-                hi[j] = tf32_rna(nxt[j]);
-                lo[j] = tf32_rna(nxt[j] - hi[j]);
+                tf32_split(nxt[j], hi[j], lo[j]);
             }
             if (it + 1 < total) load_a(it + 1);              // prefetch the next chunk's dY column
             // the TMEM A slot and the smem stage are free once the MMAs of iteration it-STAGES have completed
@@ -215,8 +214,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
 #pragma unroll 2
                 for (int idx = ct; idx < nvec; idx += 128) {
                     float4 v = bh[idx], h, l;
-                    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+                    tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y); tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
                     bh[idx] = h;
                     bl[idx] = l;
                 }

@@ -11,12 +11,25 @@ from conftest import rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _reset_debug_flags():
+    yield
+    from brainmagick_b200 import _lib
+    _lib.load().bm_set_debug_flags(0)
+
+
 def _call():
     from brainmagick_b200 import _lib
     return _lib.call, _lib.ptr, _lib.stream
 
 
-_FN = {1: "bm_tc_conv1d", 2: "bm_tc_conv1d", 3: "bm_tc_conv1d_pair"}
+_FN = {1: "bm_tc_conv1d", 2: "bm_tc_conv1d", 3: "bm_tc_conv1d_pair", 4: "bm_tc_conv1d_pair"}
+
+
+def _gen_flags(gen):
+    """generation 3 = the CTA-pair kernel (default), 4 = the persistent half-tile variant (debug bit 2)."""
+    from brainmagick_b200 import _lib
+    _lib.load().bm_set_debug_flags(2 if gen == 4 else 0)
 
 
 def _ref_conv(x, w, bias, dilation):
@@ -26,11 +39,12 @@ def _ref_conv(x, w, bias, dilation):
     return y.permute(0, 2, 1).contiguous()
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3])
+@pytest.mark.parametrize("gen", [1, 2, 3, 4])
 @pytest.mark.parametrize("dilation", [1, 2, 16])
 @pytest.mark.parametrize("T", [360, 343, 100])
 def test_tc_conv_forward(dilation, T, gen):
     call, ptr, stream = _call()
+    _gen_flags(gen)
     torch.manual_seed(dilation * 1000 + T)
     B, Cin, Cout, Kw = 3, 320, 320, 3
     dev = "cuda"
@@ -52,9 +66,10 @@ def test_tc_conv_forward(dilation, T, gen):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3])
+@pytest.mark.parametrize("gen", [1, 2, 3, 4])
 def test_tc_conv_glu_and_data_gradient(gen):
     call, ptr, stream = _call()
+    _gen_flags(gen)
     torch.manual_seed(7)
     B, T, H, Kw = 2, 360, 320, 3
     dev = "cuda"
@@ -91,10 +106,11 @@ def test_tc_conv_glu_and_data_gradient(gen):
     assert e < TOL
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3])
+@pytest.mark.parametrize("gen", [1, 2, 3, 4])
 def test_tc_conv_speed_report(capsys, gen):
     """Not a pass/fail on speed: prints the per-launch time at the BASELINE shape for the log."""
     call, ptr, stream = _call()
+    _gen_flags(gen)
     B, T, C, Kw = 256, 360, 320, 3
     dev = "cuda"
     x = torch.randn(B, T, C, device=dev)
