@@ -271,6 +271,27 @@ def run_b200(args):
     print(json.dumps(out))
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
+    (profiles/*_ncu_conv3_summary.csv, `ncu --set full` of profiles/profile_kernels.py conv); None if absent."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_conv3_summary.csv")))
+    if not files:
+        return None
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        hdr, units, vals = rows[0], rows[1], rows[-1]
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+            tot += float(vals[i]) * scale
+        return tot
+    except Exception:
+        return None
+
+
 def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
     """Times the dominant kernel alone -- bm_tc_conv1d_pair, the tcgen05 3xTF32 implicit-GEMM conv (K3: 320->320, k=3) --
     with CUDA events on the launching stream, L2 flushed between launches.  Algorithmic work: 2*H*H*Kw*T FLOP per
@@ -302,9 +323,11 @@ def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops"]
     return dict(kernel="conv_tc3_kernel via bm_tc_conv1d_pair (K3: Conv1d 320->320 k3 d4, tcgen05 cta_group::2 kind::tf32, 3xTF32)",
-                bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                traffic=ncu_traffic_bytes(), algorithmic_bytes=2.0 * B * T * H * 4,
                 ms_per_launch=ms, peak_source=peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
                 executed_tflops=3 * achieved, tf32_pipe_peak=peak / 2, frac_of_tf32_pipe_executed=3 * achieved / (peak / 2),
+                frac_of_3xtf32_ceiling=achieved / (peak / 6),
                 note="achieved = ALGORITHMIC fp32 FLOPs (2*320*320*3*T*B per launch) / time. fp32-faithful parity (1e-4) "
                      "needs 3 tf32 MMAs per product, and kind::tf32 runs at half the bf16 rate, so the ceiling of "
                      "`frac` for this scheme is 1/6; frac_of_tf32_pipe_executed is the tensor-pipe view")
