@@ -39,7 +39,24 @@ struct Conv3P {
     float* aux;
     float* glu_out;
     int* err;
+    int tma_epi;              // 0: per-thread stores; 1: TMA store of 32x32 blocks; 2: TMA reduce-add (y += tile, in place)
 };
+
+// smem (128B-swizzled 32x32 fp32 block) -> global through the TMA: full-line, asynchronous stores; rows/samples outside
+// the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -88,7 +105,7 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                const __grid_constant__ CUtensorMap tmBlo, const Conv3P p) {
+                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY, const Conv3P p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[C3_STAGES], conv_bar[C3_STAGES], empty_bar[C3_STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
@@ -217,7 +234,44 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int cset = cw >> 2;
             const int t = t0 + row;
             const bool valid = t < p.T && b < p.B;
-            if (!p.glu) {
+            if (p.tma_epi) {
+                // Measured: the per-thread 16-byte stores below (1280 B apart) made the epilogue 18 % of the kernel.  Here each
+                // warp writes its 32x32 accumulator block into a 128B-swizzled shared-memory tile (the pipeline stages are
+                // free once tmem_full has fired in both CTAs) and one lane hands it to the TMA: full-line asynchronous
+                // stores, or a reduce-add straight into the skip-path gradient (y += tile) with no addend loads at all.
+                const int ncol0 = cset * nh;
+                const int n0 = n_tile * 2 * nh + ncol0;
+                uint8_t* stg = smem + cw * 8192;                       // two 4 KB buffers per warp
+                if (lane == 0) prefetch_tmap(&tmY);
+#pragma unroll 1
+                for (int c = 0; c < nh / 32; ++c) {
+                    float v[32];
+                    tmem_ld32(tq + ncol0 + c * 32, v);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 bb = *reinterpret_cast<const float4*>(p.bias + n0 + c * 32 + j);
+                            v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+                        }
+                    }
+                    uint8_t* buf = stg + (c & 1) * 4096;
+                    if (lane == 0) bulk_wait_read<1>();                // the store that used this buffer two chunks ago
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.tma_epi == 2) tma_reduce_add_3d(&tmY, buf, n0 + c * 32, t0 + q * 32, b);
+                        else tma_store_3d(&tmY, buf, n0 + c * 32, t0 + q * 32, b);
+                        bulk_commit();
+                    }
+                }
+                if (lane == 0) bulk_wait<0>();
+                __syncwarp();
+            } else if (!p.glu) {
                 const int ncol0 = cset * nh;
                 const int n0 = n_tile * 2 * nh + ncol0;
                 const long long off = ((long long)b * p.T + t) * p.Ntot + n0;
@@ -309,7 +363,7 @@ inline bool conv_tc3_supported(int T, int Cin, int Ntot, int Kw, int glu) {
 inline int launch_conv_tc3(const float* x, const float* w_hi, const float* w_lo, Conv3P p, cudaStream_t st) {
     p.nh = conv_tc3_pick_nh(p.Ntot, p.glu);
     if (p.nh == 0) return set_error(2, "%s: unsupported N%s", __func__);
-    CUtensorMap tmA, tmBh, tmBl;
+    CUtensorMap tmA, tmBh, tmBl, tmY;
     {
         uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.T, (uint64_t)p.B};
         uint64_t str[2] = {(uint64_t)p.Cin * 4, (uint64_t)p.T * p.Cin * 4};
@@ -323,6 +377,18 @@ inline int launch_conv_tc3(const float* x, const float* w_hi, const float* w_lo,
         if (!make_tmap_f32(&tmBh, w_hi, 2, dims, str, box) || !make_tmap_f32(&tmBl, w_lo, 2, dims, str, box))
             return set_error(4, "%s: cuTensorMapEncodeTiled(B) failed%s", __func__);
     }
+    // TMA epilogue for the plain modes: store, or in-place accumulate when the caller passes addend == y
+    p.tma_epi = 0;
+    if (!p.glu && !p.act && !p.aux && !p.out_tmajor && p.y && (p.nh % 32 == 0) && (p.addend == nullptr || p.addend == p.y))
+        p.tma_epi = p.addend ? 2 : 1;
+    {
+        uint64_t dims[3] = {(uint64_t)p.Ntot, (uint64_t)p.T, (uint64_t)p.B};
+        uint64_t str[2] = {(uint64_t)p.Ntot * 4, (uint64_t)p.T * p.Ntot * 4};
+        uint32_t box[3] = {32, 32, 1};
+        const void* base = p.tma_epi ? (const void*)p.y : (const void*)x;       // any valid tensor when unused
+        if (!p.tma_epi) { dims[0] = (uint64_t)p.Cin; str[0] = (uint64_t)p.Cin * 4; str[1] = (uint64_t)p.T * p.Cin * 4; }
+        if (!make_tmap_f32(&tmY, base, 3, dims, str, box)) return set_error(4, "%s: cuTensorMapEncodeTiled(Y) failed%s", __func__);
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES);
@@ -333,7 +399,7 @@ inline int launch_conv_tc3(const float* x, const float* w_hi, const float* w_lo,
     const int mtiles = (p.T + C3_BM - 1) / C3_BM;
     const int pairs = mtiles * ((p.B + 1) / 2);
     dim3 grid(2 * pairs, ntiles, 1);
-    conv_tc3_kernel<<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p);
+    conv_tc3_kernel<<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmY, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(3, "%s: launch failed: %s", __func__, cudaGetErrorString(e));

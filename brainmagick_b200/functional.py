@@ -391,9 +391,13 @@ class _EncoderFn(torch.autograd.Function):
                  ptr(dy), ptr(dgamma), ptr(dbeta), st)
             dcw, dcb = conv.backward_weight(dy, rec["x_in"], B, T, plan.dilations[k], meg, status,
                                             bias_grad_is_zero=plan.training)
-            g_in = _empty((B, T, conv.cin), meg)
-            conv.backward_data(dy, g if rec["skip"] else None, B, T, plan.dilations[k], g_in, status)
-            g = g_in
+            if rec["skip"]:
+                # in place: g += conv_transpose(dy) (addend == output: the pair kernel turns this into a TMA reduce-add)
+                conv.backward_data(dy, g, B, T, plan.dilations[k], g, status)
+            else:
+                g_in = _empty((B, T, conv.cin), meg)
+                conv.backward_data(dy, None, B, T, plan.dilations[k], g_in, status)
+                g = g_in
             layer_grads[k] = (dcw, dcb, dgamma, dbeta)
             del dy
 

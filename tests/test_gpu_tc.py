@@ -104,6 +104,13 @@ def test_tc_conv_glu_and_data_gradient(gen):
     e = rel_err(dx.cpu(), ref_dx.cpu())
     print(f'[tc dgrad K=1920] rel_err vs fp64 = {e:.2e}')
     assert e < TOL
+    # in-place skip-gradient accumulation (addend == output): the pair kernel uses a TMA reduce-add
+    acc = addend.clone()
+    call(_FN[gen], ptr(dy), ptr(gh), ptr(gl), None, ptr(acc), B, T, 2 * H, H, Kw, 1, -1, 0, 0, 0, ptr(acc), None, None,
+         ptr(status), stream())
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0
+    assert rel_err(acc.cpu(), ref_dx.cpu()) < TOL
 
 
 @pytest.mark.parametrize("gen", [1, 2, 3, 4])
