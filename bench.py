@@ -143,6 +143,7 @@ def run_b200(args):
     def step(meg_d, feats_d, subj_d, subj_h):
         opt.zero_grad(set_to_none=True)
         batch = make_batch(meg_d, subj_d, subj_h)
+        clip.prefetch_candidates(feats_d)          # N > 1: the candidate all-gather overlaps the encoder forward
         est = model(dict(meg=meg_d), batch)
         loss = clip(est, feats_d, mask)
         loss.backward()

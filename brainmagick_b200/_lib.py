@@ -17,6 +17,9 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 SIGNATURES = {
     "bm_attention_weights_fwd": [P, P, P, P, F, I, I, I, I, P, P, P],
     "bm_attention_weights_bwd": [P, P, P, I, I, I, I, P, P, P],
+    "bm_fourier_emb": [P, P, I, I, I, P, P],
+    "bm_masked_softmax": [P, P, P, F, I, I, I, P],
+    "bm_softmax_bwd": [P, P, L, I, P, P],
     "bm_sensor_chain_fwd": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, P, P, P, P],
     "bm_sensor_chain_bwd": [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
     "bm_sensor_mix_fwd": [P, P, P, I, I, I, I, I, P, P],
@@ -51,6 +54,7 @@ SIGNATURES = {
     "bm_tc_conv1d_pair": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_transpose_nt": [P, I, I, I, P, P],
+    "bm_transpose_nt_ld": [P, I, I, I, I, P, P],
     "bm_tc_wgrad_supported": [I, I],
     "bm_tc_wgrad": [P, P, I, I, I, I, I, I, I, P, P, P, P],
     "bm_col_sum": [P, L, I, P, P],

@@ -670,7 +670,16 @@ extern "C" int bm_col_stats(const float* y, long long rows, int C, double* stats
 extern "C" int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream) {
     BM_CHECK_ARG(in && out && Z > 0 && N > 0 && T > 0 && Z <= 65535);
     dim3 grid((T + 31) / 32, (N + 31) / 32, Z);
-    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T);
+    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T, N);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+// same with an output row stride ld_out >= N (columns N..ld_out-1 are left untouched: zero them once for padding)
+extern "C" int bm_transpose_nt_ld(const float* in, int Z, int N, int T, int ld_out, float* out, bm_stream_t stream) {
+    BM_CHECK_ARG(in && out && Z > 0 && N > 0 && T > 0 && Z <= 65535 && ld_out >= N);
+    dim3 grid((T + 31) / 32, (N + 31) / 32, Z);
+    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T, ld_out);
     BM_CHECK_LAUNCH();
     return 0;
 }
@@ -759,4 +768,33 @@ extern "C" int bm_tc_wgrad_grouped(const float* dy, const float* x, const int* o
     BM_CHECK_ARG(dy && x && order && seg_off && out && G > 0 && B > 0 && T > 0);
     BM_CHECK_ARG(tc::wgrad_tc_supported(M, N));
     return tc::launch_wgrad_tc_grouped(dy, x, order, seg_off, G, B, T, M, N, out, status, ST(stream));
+}
+
+// ---- K1 pieces, for callers that run the two attention contractions on the tensor cores -------------------------
+extern "C" int bm_fourier_emb(const float* positions, const float* freq, int R, int C, int P, float* emb,
+                              bm_stream_t stream) {
+    BM_CHECK_ARG(positions && freq && emb && R > 0 && C > 0 && P > 0 && P % 2 == 0);
+    int n = 0;
+    while ((n + 1) * (n + 1) * 2 <= P) ++n;
+    BM_CHECK_ARG(n * n * 2 == P);
+    fourier_emb_kernel<<<ew_grid((long long)R * C * n * n), 256, 0, ST(stream)>>>(positions, freq, 0.2f, R * C, n, emb);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+// in-place: weights[r][o][:] = softmax_c(scores + mask), mask = -inf on INVALID / banned sensors (common.py:339-357)
+extern "C" int bm_masked_softmax(float* weights, const float* positions, const float* ban_centre, float radius, int R,
+                                 int O, int C, bm_stream_t stream) {
+    BM_CHECK_ARG(weights && positions && R > 0 && O > 0 && C > 0);
+    int rows = R * O;
+    masked_softmax_kernel<<<(rows + 7) / 8, 256, 0, ST(stream)>>>(weights, positions, ban_centre, radius, -0.1f, R, O, C);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+// dscores = w * (dw - sum_c w dw), rows of length C
+extern "C" int bm_softmax_bwd(const float* weights, const float* dweights, long long rows, int C, float* dscores,
+                              bm_stream_t stream) {
+    BM_CHECK_ARG(weights && dweights && dscores && rows > 0 && C > 0);
+    softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ST(stream)>>>(weights, dweights, dscores, (int)rows, C);
+    BM_CHECK_LAUNCH();
+    return 0;
 }

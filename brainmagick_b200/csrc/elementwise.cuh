@@ -404,9 +404,10 @@ __global__ void clip_ce_bwd_kernel(const float* __restrict__ probs, const float*
 }
 
 // in [Z][N][T] -> out [Z][T][N]   (32x32 tiles through shared memory, both sides coalesced)
-__global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int T) {
+__global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int T, int ld_out) {
     __shared__ float tile[32][33];
     const long long zoff = (long long)blockIdx.z * N * T;
+    const long long zout = (long long)blockIdx.z * T * ld_out;
     int t = blockIdx.x * 32 + threadIdx.x;
 #pragma unroll
     for (int i = threadIdx.y; i < 32; i += 8) {
@@ -418,7 +419,7 @@ __global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restr
 #pragma unroll
     for (int i = threadIdx.y; i < 32; i += 8) {
         int tt = blockIdx.x * 32 + i;
-        if (n < N && tt < T) out[zoff + (long long)tt * N + n] = tile[threadIdx.x][i];
+        if (n < N && tt < T) out[zout + (long long)tt * ld_out + n] = tile[threadIdx.x][i];
     }
 }
 

@@ -36,6 +36,29 @@ def all_gather_candidates(candidate: torch.Tensor) -> tp.Tuple[torch.Tensor, int
     return out, rank() * candidate.shape[0]
 
 
+class CandidateGather:
+    """The candidate all-gather started EARLY (it does not depend on the encoder): NCCL moves the blocks over NVLink while
+    the encoder's forward kernels run; `wait()` joins it on the current stream just before the contrastive matmul."""
+
+    def __init__(self, candidate: torch.Tensor):
+        self.source = candidate
+        W = world_size()
+        self.offset = rank() * candidate.shape[0]
+        if W == 1:
+            self.out, self.work = candidate, None
+            return
+        candidate = candidate.contiguous()
+        self.out = torch.empty((W * candidate.shape[0],) + tuple(candidate.shape[1:]), dtype=candidate.dtype,
+                               device=candidate.device)
+        self.work = dist.all_gather_into_tensor(self.out, candidate, async_op=True)
+
+    def wait(self) -> tp.Tuple[torch.Tensor, int]:
+        if self.work is not None:
+            self.work.wait()          # current stream waits for NCCL's stream; the host does not block
+            self.work = None
+        return self.out, self.offset
+
+
 def sync_gradients(params: tp.Iterable[torch.nn.Parameter]) -> None:
     """all-reduce(avg) of every .grad through one flat fp32 bucket."""
     W = world_size()

@@ -203,11 +203,29 @@ class _EncoderFn(torch.autograd.Function):
         tc = plan.use_tensor_cores
         status = tc_status_tensor(meg.device)
 
-        # K1 attention weights per recording
+        # K1 attention weights per recording (the score contraction on the tensor cores when the widths fit)
         emb = _empty((R, C, P), meg)
-        att = _empty((R, O, C), meg)
-        call("bm_attention_weights_fwd", ptr(plan.rec_positions), ptr(plan.freq), ptr(heads.contiguous()),
-             ptr(plan.ban_centre), float(plan.ban_radius), R, C, O, P, ptr(emb), ptr(att), st)
+        lib = _lib.load()
+        Opad = _round_up(O, 64)
+        heads_conv = None
+        if tc and bool(lib.bm_tc_conv3_supported(C, P, Opad, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Opad, P)):
+            hpad = torch.zeros((Opad, P, 1), device=meg.device)
+            hpad[:O, :, 0] = heads
+            heads_conv = _Conv(hpad, C, False, True, want_bwd=False)
+            if not heads_conv.fwd_v3:
+                heads_conv = None
+        if heads_conv is not None:
+            call("bm_fourier_emb", ptr(plan.rec_positions), ptr(plan.freq), R, C, P, ptr(emb), st)
+            att_full = _empty((R, Opad, C), meg)          # scores[r][o][c] = <emb[r][c], heads[o]> written channel-major
+            call(heads_conv.fwd_fn, ptr(emb), ptr(heads_conv.f_hi), ptr(heads_conv.f_lo), None, None, R, C, P, Opad, 1, 1, 1,
+                 0, 0, 1, ptr(att_full), None, None, ptr(status), st)
+            call("bm_masked_softmax", ptr(att_full), ptr(plan.rec_positions), ptr(plan.ban_centre), float(plan.ban_radius),
+                 R, Opad, C, st)
+            att = att_full[:, :O].contiguous()
+        else:
+            att = _empty((R, O, C), meg)
+            call("bm_attention_weights_fwd", ptr(plan.rec_positions), ptr(plan.freq), ptr(heads.contiguous()),
+                 ptr(plan.ban_centre), float(plan.ban_radius), R, C, O, P, ptr(emb), ptr(att), st)
         # K2 sensor chain; x0 is kept zero-padded to a multiple of 64 channels when the tensor-core conv follows
         Dp = _round_up(D, 64)
         conv0 = _Conv(conv_p[0][0], T, False, tc, pad_cin_to=Dp, want_bwd=save)
@@ -230,9 +248,24 @@ class _EncoderFn(torch.autograd.Function):
             v = _empty((B, T, ILp), meg)
             bpad = torch.zeros((ILp,), device=meg.device)
             bpad[:IL] = il_b
-            call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, Op, ptr(u), st)
-            il_conv.forward(u, bpad, B, T, 1, v, None, status)
             lib = _lib.load()
+            # sensor mix on the tensor cores: meg transposed once to channels-last (sensor count padded to 128), then
+            # u = megT @ w[rec]^T is a pointwise contraction with a per-sample weight set (one per recording)
+            Cp = _round_up(C, 128)
+            mix_tc = bool(lib.bm_tc_conv_supported(T, Cp, Op, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Op, Cp))
+            megT = None
+            if mix_tc:
+                megT = torch.zeros((B, T, Cp), device=meg.device) if Cp != C else _empty((B, T, C), meg)
+                call("bm_transpose_nt_ld", ptr(meg), B, C, T, Cp, ptr(megT), st)
+                att_pad = torch.zeros((R, Op, Cp), device=meg.device)
+                att_pad[:, :O, :C] = att
+                aw_hi, aw_lo = _empty((R * Op, Cp), meg), _empty((R * Op, Cp), meg)
+                call("bm_tc_weight_split", ptr(att_pad), R * Op, Cp, 1, ptr(aw_hi), ptr(aw_lo), None, None, st)
+                call("bm_tc_pointwise_sel", ptr(megT), ptr(aw_hi), ptr(aw_lo), ptr(plan.rec_of_sample), R, B, T, Cp, Op,
+                     ptr(u), ptr(status), st)
+            else:
+                call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, Op, ptr(u), st)
+            il_conv.forward(u, bpad, B, T, 1, v, None, status)
             subj_tc = (Dp != D or D % 64 == 0) and bool(lib.bm_tc_conv_supported(T, ILp, Dp, 1, 0)) and \
                 bool(lib.bm_tc_conv_supported(T, Dp, ILp, 1, 0)) and bool(lib.bm_tc_wgrad_supported(ILp, Dp))
             if subj_tc:
@@ -250,6 +283,7 @@ class _EncoderFn(torch.autograd.Function):
                      ptr(x), st)
         else:
             subj_pad = None
+            megT = None
             Op, ILp = O, IL
             u = _empty((B, T, O), meg)
             v = _empty((B, T, IL), meg)
@@ -316,7 +350,7 @@ class _EncoderFn(torch.autograd.Function):
             ctx.dims = (B, C, T, R, O, P, IL, S, D, Dp, H, F)
             ctx.pads = (Op, ILp)
             ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(), il_conv=il_conv,
-                             subj_pad=subj_pad,
+                             subj_pad=subj_pad, megT=megT, heads_tc=heads_conv is not None,
                              layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q,
                              head0=head0, head2=head2, head_tc=head_tc,
                              conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape, w0_shape=w0.shape, w2_shape=w2.shape)
@@ -433,8 +467,16 @@ class _EncoderFn(torch.autograd.Function):
             dbp = _empty((ILp,), meg)
             call("bm_col_sum", ptr(dv), rows, ILp, ptr(dbp), st)
             d_il_b = dbp[:IL].contiguous()
-            call("bm_sensor_mix_bwd", ptr(du), Op, ptr(meg), ptr(plan.rec_order), ptr(plan.rec_off), B, C, T, O, R,
-                 ptr(d_att), st)
+            if s["megT"] is not None:
+                megT = s["megT"]
+                Cp = megT.shape[2]
+                dwp = _empty((R, _round_up(Op, 128), Cp), meg)
+                call("bm_tc_wgrad_grouped", ptr(du), ptr(megT), ptr(plan.rec_order), ptr(plan.rec_off), R, B, T, Op, Cp,
+                     ptr(dwp), ptr(status), st)
+                d_att = dwp[:, :O, :C].contiguous()
+            else:
+                call("bm_sensor_mix_bwd", ptr(du), Op, ptr(meg), ptr(plan.rec_order), ptr(plan.rec_off), B, C, T, O, R,
+                     ptr(d_att), st)
         else:
             dv = _empty((B, T, IL), meg)
             du = _empty((B, T, O), meg)
@@ -444,9 +486,16 @@ class _EncoderFn(torch.autograd.Function):
                  ptr(s["u"]), ptr(s["v"]), ptr(subj_order), ptr(subj_off), ptr(plan.rec_order), ptr(plan.rec_off),
                  B, C, T, O, IL, D, Dp, S, R, ptr(dv), ptr(du), ptr(d_subj), ptr(d_il_w), ptr(d_il_b), ptr(d_att), st)
         dscores = _empty((R, O, C), meg)
-        dheads = _empty((O, P), meg)
-        call("bm_attention_weights_bwd", ptr(d_att), ptr(s["att"]), ptr(s["emb"]), R, C, O, P, ptr(dscores),
-             ptr(dheads), st)
+        if s["heads_tc"]:
+            Opad = _round_up(O, 64)
+            call("bm_softmax_bwd", ptr(s["att"]), ptr(d_att), R * O, C, ptr(dscores), st)
+            ds_t = torch.zeros((R, C, Opad), device=meg.device)
+            call("bm_transpose_nt_ld", ptr(dscores), R, O, C, Opad, ptr(ds_t), st)
+            dheads = tc_wgrad(ds_t, s["emb"], R, C, Opad, P, P, 1, 1, status)[:O, :, 0].contiguous()
+        else:
+            dheads = _empty((O, P), meg)
+            call("bm_attention_weights_bwd", ptr(d_att), ptr(s["att"]), ptr(s["emb"]), R, C, O, P, ptr(dscores),
+                 ptr(dheads), st)
 
         grads = [None, None, dheads, d_il_w.reshape(s["il_shape"]), d_il_b, d_subj,
                  dw0.reshape(s["w0_shape"]), db0, dw2.reshape(s["w2_shape"]), db2]

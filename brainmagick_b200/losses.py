@@ -30,6 +30,7 @@ class ClipLoss(torch.nn.Module):
         self.tmin_train, self.tmax_train = tmin_train, tmax_train
         self.dset_args = dset_args
         self.global_negatives = global_negatives
+        self._prefetched = None
 
     # -- time cropping (losses.py:50-75) ---------------------------------------------------------------
     def _window(self, n_samples: int):
@@ -69,9 +70,22 @@ class ClipLoss(torch.nn.Module):
         estimates, candidates = self._prepare(estimates, candidates)
         return BF.clip_scores(estimates, candidates, want_probs=True)
 
+    def prefetch_candidates(self, candidate: torch.Tensor) -> None:
+        """Optional (multi-GPU, global_negatives): start the candidate all-gather now -- e.g. right after the batch reaches
+        the device, before the encoder forward -- so that it overlaps compute.  `forward` picks it up when it is called
+        with the same tensor; without this call the gather simply happens inside `forward`."""
+        if self.global_negatives and distrib.world_size() > 1 and not (self.pool or self.center) \
+                and self._window(candidate.shape[-1]) == (0, candidate.shape[-1]):
+            self._prefetched = distrib.CandidateGather(candidate)
+
     def forward(self, estimate, candidate, mask=None):
         assert mask.all(), "mask is not supported for now"
         assert estimate.size(0) <= candidate.size(0), "need at least as many targets as estimates"
+        pre, self._prefetched = self._prefetched, None
+        if pre is not None and pre.source is candidate:
+            estimate, _ = self._prepare(estimate, candidate)
+            candidate, offset = pre.wait()
+            return BF.clip_loss(estimate, candidate, offset)
         estimate, candidate = self._prepare(estimate, candidate)
         offset = 0
         if self.global_negatives and distrib.world_size() > 1:

@@ -45,6 +45,14 @@ int bm_attention_weights_fwd(const float* positions, const float* freq, const fl
 int bm_attention_weights_bwd(const float* dweights, const float* weights, const float* emb, int R, int C, int O,
                              int P, float* dscores, float* dheads, bm_stream_t stream);
 
+/* K1 in pieces (the two contractions -- scores = emb heads^T and dheads = dscores^T emb -- then run on the tensor-core
+ * kernels bm_tc_conv1d_pair(out_tmajor) / bm_tc_wgrad): Fourier embedding, in-place masked softmax, softmax backward. */
+int bm_fourier_emb(const float* positions, const float* freq, int R, int C, int P, float* emb, bm_stream_t stream);
+int bm_masked_softmax(float* weights, const float* positions, const float* ban_centre, float radius, int R, int O, int C,
+                      bm_stream_t stream);
+int bm_softmax_bwd(const float* weights, const float* dweights, long long rows, int C, float* dscores,
+                   bm_stream_t stream);
+
 /* ---- K2: sensor chain ----------------------------------------------------------------------------------
  * replaces the mixing einsum of ChannelMerger.forward (common.py:358), `initial_linear` (simpleconv.py:113-120,
  * 213-214) and SubjectLayers.forward (common.py:55-58):
@@ -198,6 +206,8 @@ int bm_tc_wgrad_grouped(const float* dy, const float* x, const int* order, const
 int bm_gelu_bwd(const float* dq, const float* h, long long n, float* dh, bm_stream_t stream);
 /* in [Z,N,T] (channel-major) -> out [Z,T,N] (channels-last): the gradient of `estimate` enters the head backward. */
 int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream);
+/* same with an output row stride ld_out >= N (pad columns untouched): meg [B,C,T] -> channels-last, channel-padded. */
+int bm_transpose_nt_ld(const float* in, int Z, int N, int T, int ld_out, float* out, bm_stream_t stream);
 
 #ifdef __cplusplus
 }

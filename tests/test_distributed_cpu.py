@@ -33,6 +33,9 @@ def _worker(rank, world, port, ret):
         mean_scale = sum(r + 1 for r in range(world)) / world
         assert torch.allclose(p1.grad, torch.full((4, 3), mean_scale))
         assert torch.allclose(p2.grad, torch.arange(7.) * mean_scale)
+        early = distrib.CandidateGather(cand)              # the prefetched (async) form used by ClipLoss.prefetch_candidates
+        g2, off2 = early.wait()
+        assert torch.equal(g2, gathered) and off2 == off
         ret[rank] = (gathered.clone(), off)
     finally:
         dist.destroy_process_group()
