@@ -130,6 +130,58 @@ def test_extra_negatives_and_target_offset():
         assert rel_err(e.grad.cpu(), e_ref.grad) < TOL
 
 
+@pytest.mark.parametrize("case", [
+    dict(name="cfg3 audio_mous-like", B=6, C=273, T=360, F=1024, S=8, n_valid=()),
+    dict(name="cfg4 broderick mel", B=6, C=128, T=360, F=120, S=5, n_valid=()),
+    dict(name="cfg5 mixed studies, real T", B=9, C=273, T=343, F=1024, S=6, n_valid=(273, 208, 128, 60)),
+])
+def test_other_baseline_configs_tensor_core_vs_fma(case):
+    """BASELINE.json configs 3-5 at small batch (odd batch, ragged T=343, padded sensors, F=120): tcgen05 path vs the
+    FP32-FMA path of the same library on identical inputs and parameters."""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic, functional as BF
+    torch.manual_seed(5)
+    B, C, T, F, S = case["B"], case["C"], case["T"], case["F"], case["S"]
+    kw = dict(hidden=dict(meg=320), batch_norm=True, depth=10, dilation_period=5, kernel_size=3, skip=True,
+              subject_layers=True, subject_dim=0, complex_out=True, glu=2, glu_context=1, merger=True,
+              initial_linear=270, gelu=True, merger_pos_dim=2048)
+    model = bb.SimpleConv(in_channels=dict(meg=C), out_channels=F, n_subjects=S, **kw).cuda().train()
+    clip = bb.ClipLoss().cuda().train()
+    pos = synthetic.normalised_positions(S, C, case["n_valid"], seed=2)
+    subj = torch.randint(0, S, (B,))
+    meg = torch.randn(B, C, T).clamp_(-20, 20)
+    if case["n_valid"]:
+        for b in range(B):
+            meg[b, case["n_valid"][int(subj[b]) % len(case["n_valid"])]:] = 0
+    meg = meg.cuda()
+    cand = torch.randn(B, F, T).cuda()
+    batch = synthetic.make_batch(meg, subj.cuda(), pos, subj.tolist())
+    mask = torch.ones(B, 1, T, dtype=torch.bool, device="cuda")
+    model.merger.ban_centre_override = torch.tensor([0.7, 0.2])
+    state = {k: v.clone() for k, v in model.state_dict().items()}
+    res = []
+    for use_tc in (True, False):
+        model.load_state_dict(state)
+        model.zero_grad(set_to_none=True)
+        model.use_tensor_cores = use_tc
+        est = model(dict(meg=meg), batch)
+        loss = clip(est, cand, mask)
+        loss.backward()
+        torch.cuda.synchronize()
+        BF.check_tc_status()
+        res.append((est.detach().clone(), loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()}))
+    (e1, l1, g1), (e0, l0, g0) = res
+    assert torch.isfinite(e1).all()
+    assert rel_err(e1.cpu(), e0.cpu()) < TOL, case["name"]
+    assert abs(l1 - l0) < TOL * max(1.0, abs(l0))
+    wscale = max(v.norm().item() for k, v in g0.items() if k.endswith("weight"))
+    for name in g0:
+        if "sequence" in name and name.endswith(".0.bias"):
+            assert g1[name].abs().max().item() < 1e-4 * wscale + 1e-6
+            continue
+        assert rel_err(g1[name].cpu(), g0[name].cpu()) < 5 * TOL, (case["name"], name)
+
+
 def test_full_size_tensor_core_path_agrees_with_fp32_fma_path():
     """BASELINE.json configs[1] shapes (208 sensors, T=360, F=1024, hidden 320) at B=32: the tcgen05 (3xTF32) kernels
     and the FP32-FMA kernels are two independent implementations; estimate, loss and every gradient must agree to
