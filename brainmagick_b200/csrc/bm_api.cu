@@ -720,6 +720,8 @@ extern "C" int bm_gelu_bwd(const float* dq, const float* h, long long n, float* 
     return 0;
 }
 
+static double* g_pair_stats = nullptr;
+
 // third-generation conv kernel: CTA pairs (tcgen05 cta_group::2); same contract as bm_tc_conv1d with pre-split weights
 extern "C" int bm_tc_conv3_supported(int T, int Cin, int Ntot, int Kw, int glu) {
     return tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
@@ -744,8 +746,20 @@ extern "C" int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float*
     tc::Conv3P q;
     q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
     q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
-    q.glu_out = glu_out; q.err = status;
+    q.glu_out = glu_out; q.err = status; q.stats = g_pair_stats;
+    g_pair_stats = nullptr;
+    if (q.stats) {
+        BM_CHECK_ARG(!glu && !act && !aux && !out_tmajor && !addend);
+        BM_CUDA(cudaMemsetAsync(q.stats, 0, sizeof(double) * 2 * Ntot, ST(stream)));
+    }
     return tc::launch_conv_tc3(x, w_hi, w_lo, q, ST(stream));
+}
+
+// Arms the NEXT bm_tc_conv1d_pair call (plain forward mode) to also accumulate the BatchNorm batch statistics
+// sum(y), sum(y^2) per output channel into stats[2*Ntot] (fp64) from its epilogue tiles.
+extern "C" int bm_tc_pair_want_stats(double* stats) {
+    g_pair_stats = stats;
+    return 0;
 }
 
 // pointwise (1x1) contraction with a per-sample weight set (SubjectLayers.forward / its data gradient, common.py:55-58):

@@ -40,6 +40,8 @@ struct Conv3P {
     float* glu_out;
     int* err;
     int tma_epi;              // 0: per-thread stores; 1: TMA store of 32x32 blocks; 2: TMA reduce-add (y += tile, in place)
+    double* stats;            // [2*Ntot] or null: BatchNorm batch statistics sum(y), sum(y^2) accumulated from the staged
+                              // epilogue blocks (fp64 atomics; only with tma_epi == 1; zeroed by the launcher)
 };
 
 // smem (128B-swizzled 32x32 fp32 block) -> global through the TMA: full-line, asynchronous stores; rows/samples outside
@@ -267,6 +269,22 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         if (p.tma_epi == 2) tma_reduce_add_3d(&tmY, buf, n0 + c * 32, t0 + q * 32, b);
                         else tma_store_3d(&tmY, buf, n0 + c * 32, t0 + q * 32, b);
                         bulk_commit();
+                    }
+                    if (p.stats) {
+                        // column sums of this 32x32 block straight from the staged tile (lane = column): the separate
+                        // statistics pass over y (118 MB per layer) disappears
+                        const int nrows = (b < p.B) ? min(32, p.T - (t0 + q * 32)) : 0;
+                        float s1 = 0.f, s2 = 0.f;
+                        for (int r = 0; r < nrows; ++r) {
+                            const float x = *reinterpret_cast<const float*>(buf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) +
+                                                                              (lane & 3) * 4);
+                            s1 += x;
+                            s2 = fmaf(x, x, s2);
+                        }
+                        if (nrows > 0) {
+                            atomicAdd(p.stats + n0 + c * 32 + lane, (double)s1);
+                            atomicAdd(p.stats + p.Ntot + n0 + c * 32 + lane, (double)s2);
+                        }
                     }
                 }
                 if (lane == 0) bulk_wait<0>();

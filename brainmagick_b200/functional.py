@@ -130,9 +130,12 @@ class _Conv:
     def forward(self, x, bias, B, T, dilation, y, stats, status):
         st = stream()
         if self.fwd_tc:
+            fused = stats is not None and self.fwd_v3
+            if fused:
+                call("bm_tc_pair_want_stats", ptr(stats))       # BatchNorm statistics out of the conv epilogue
             call(self.fwd_fn, ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
                  self.kw, dilation, 1, 0, 0, 0, ptr(y), None, None, ptr(status), st)
-            if stats is not None:
+            if stats is not None and not fused:
                 call("bm_col_stats", ptr(y), B * T, self.cout, ptr(stats), st)
         else:
             call("bm_conv1d_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout, self.kw, dilation,

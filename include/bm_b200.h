@@ -185,6 +185,11 @@ int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, cons
                       int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
                       float* y, float* aux, float* glu_out, int* status, bm_stream_t stream);
 
+/* Arms the NEXT bm_tc_conv1d_pair call (plain forward: no glu/act/aux/addend) to accumulate the BatchNorm batch
+ * statistics stats[0:Ntot] = sum(y), stats[Ntot:2Ntot] = sum(y^2) (fp64, zeroed by that call) from its epilogue tiles,
+ * replacing the separate bm_col_stats pass over y. */
+int bm_tc_pair_want_stats(double* stats);
+
 /* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]
  * for n < Ntrue (x may be channel-padded to N); dy [B,T,M], x [B,T,N] channels-last; dw in nn.Conv1d layout
  * [M][Ntrue][Kw].  workspace: bm_tc_wgrad_workspace() floats (per-batch-slice partial tiles, reduced in a fixed
