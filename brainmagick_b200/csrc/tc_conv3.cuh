@@ -107,7 +107,8 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C3_THREADS, 1)
 conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY, const Conv3P p) {
+                const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmY,
+                const __grid_constant__ CUtensorMap tmO, const Conv3P p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[C3_STAGES], conv_bar[C3_STAGES], empty_bar[C3_STAGES], tmem_full_bar;
     __shared__ uint32_t tmem_base_smem;
@@ -236,7 +237,57 @@ conv_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const int cset = cw >> 2;
             const int t = t0 + row;
             const bool valid = t < p.T && b < p.B;
-            if (p.tma_epi) {
+            if (p.tma_epi == 3) {
+                // GLU through the TMA: per 32-column chunk three staged 32x32 blocks -- h's `a` part, h's gate part (both
+                // only when the pre-activation is saved for backward) and out = a * sigmoid(gate)
+                const int nch = nh / 32;
+                const int ch_begin = cset == 0 ? 0 : (nch + 1) / 2, ch_end = cset == 0 ? (nch + 1) / 2 : nch;
+                const int c0 = n_tile * nh;
+                uint8_t* stg = smem + cw * 12288;
+                if (lane == 0) { prefetch_tmap(&tmY); prefetch_tmap(&tmO); }
+#pragma unroll 1
+                for (int c = ch_begin; c < ch_end; ++c) {
+                    float a[32], g[32];
+                    tmem_ld32(tq + c * 32, a);
+                    tmem_ld32(tq + nh + c * 32, g);
+                    if (p.bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 ba = *reinterpret_cast<const float4*>(p.bias + c0 + c * 32 + j);
+                            const float4 bg = *reinterpret_cast<const float4*>(p.bias + H + c0 + c * 32 + j);
+                            a[j] += ba.x; a[j + 1] += ba.y; a[j + 2] += ba.z; a[j + 3] += ba.w;
+                            g[j] += bg.x; g[j + 1] += bg.y; g[j + 2] += bg.z; g[j + 3] += bg.w;
+                        }
+                    }
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int sw = (j ^ (lane & 7)) << 4;
+                        if (p.y) {
+                            *reinterpret_cast<float4*>(rowp + sw) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+                            *reinterpret_cast<float4*>(rowp + 4096 + sw) =
+                                make_float4(g[4 * j], g[4 * j + 1], g[4 * j + 2], g[4 * j + 3]);
+                        }
+                        *reinterpret_cast<float4*>(rowp + 8192 + sw) =
+                            make_float4(a[4 * j] * sigmoid_f(g[4 * j]), a[4 * j + 1] * sigmoid_f(g[4 * j + 1]),
+                                        a[4 * j + 2] * sigmoid_f(g[4 * j + 2]), a[4 * j + 3] * sigmoid_f(g[4 * j + 3]));
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (p.y) {
+                            tma_store_3d(&tmY, stg, c0 + c * 32, t0 + q * 32, b);
+                            tma_store_3d(&tmY, stg + 4096, H + c0 + c * 32, t0 + q * 32, b);
+                        }
+                        tma_store_3d(&tmO, stg + 8192, c0 + c * 32, t0 + q * 32, b);
+                        bulk_commit();
+                    }
+                }
+                if (lane == 0) bulk_wait<0>();
+                __syncwarp();
+            } else if (p.tma_epi) {
                 // Measured: the per-thread 16-byte stores below (1280 B apart) made the epilogue 18 % of the kernel.  Here each
                 // warp writes its 32x32 accumulator block into a 128B-swizzled shared-memory tile (the pipeline stages are
                 // free once tmem_full has fired in both CTAs) and one lane hands it to the TMA: full-line asynchronous
@@ -381,7 +432,7 @@ inline bool conv_tc3_supported(int T, int Cin, int Ntot, int Kw, int glu) {
 inline int launch_conv_tc3(const float* x, const float* w_hi, const float* w_lo, Conv3P p, cudaStream_t st) {
     p.nh = conv_tc3_pick_nh(p.Ntot, p.glu);
     if (p.nh == 0) return set_error(2, "%s: unsupported N%s", __func__);
-    CUtensorMap tmA, tmBh, tmBl, tmY;
+    CUtensorMap tmA, tmBh, tmBl, tmY, tmO;
     {
         uint64_t dims[3] = {(uint64_t)p.Cin, (uint64_t)p.T, (uint64_t)p.B};
         uint64_t str[2] = {(uint64_t)p.Cin * 4, (uint64_t)p.T * p.Cin * 4};
@@ -406,6 +457,21 @@ inline int launch_conv_tc3(const float* x, const float* w_hi, const float* w_lo,
         const void* base = p.tma_epi ? (const void*)p.y : (const void*)x;       // any valid tensor when unused
         if (!p.tma_epi) { dims[0] = (uint64_t)p.Cin; str[0] = (uint64_t)p.Cin * 4; str[1] = (uint64_t)p.T * p.Cin * 4; }
         if (!make_tmap_f32(&tmY, base, 3, dims, str, box)) return set_error(4, "%s: cuTensorMapEncodeTiled(Y) failed%s", __func__);
+        tmO = tmY;
+    }
+    if (p.glu && p.nh % 32 == 0 && p.glu_out && !p.stats) {
+        // GLU through the TMA: tmY describes h [B,T,2H] (when saved), tmO the gated output [B,T,H]
+        p.tma_epi = 3;
+        const int Hh = p.Ntot / 2;
+        uint32_t box[3] = {32, 32, 1};
+        uint64_t dimo[3] = {(uint64_t)Hh, (uint64_t)p.T, (uint64_t)p.B};
+        uint64_t stro[2] = {(uint64_t)Hh * 4, (uint64_t)p.T * Hh * 4};
+        if (!make_tmap_f32(&tmO, p.glu_out, 3, dimo, stro, box)) return set_error(4, "%s: cuTensorMapEncodeTiled(O) failed%s", __func__);
+        if (p.y) {
+            uint64_t dimh[3] = {(uint64_t)p.Ntot, (uint64_t)p.T, (uint64_t)p.B};
+            uint64_t strh[2] = {(uint64_t)p.Ntot * 4, (uint64_t)p.T * p.Ntot * 4};
+            if (!make_tmap_f32(&tmY, p.y, 3, dimh, strh, box)) return set_error(4, "%s: cuTensorMapEncodeTiled(H) failed%s", __func__);
+        }
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -417,7 +483,7 @@ inline int launch_conv_tc3(const float* x, const float* w_hi, const float* w_lo,
     const int mtiles = (p.T + C3_BM - 1) / C3_BM;
     const int pairs = mtiles * ((p.B + 1) / 2);
     dim3 grid(2 * pairs, ntiles, 1);
-    conv_tc3_kernel<<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmY, p);
+    conv_tc3_kernel<<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, tmY, tmO, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(3, "%s: launch failed: %s", __func__, cudaGetErrorString(e));
