@@ -57,7 +57,7 @@ SIGNATURES = {
     "bm_transpose_nt": [P, I, I, I, P, P],
     "bm_transpose_nt_ld": [P, I, I, I, I, P, P],
     "bm_tc_wgrad_supported": [I, I],
-    "bm_tc_wgrad": [P, P, I, I, I, I, I, I, I, P, P, P, P],
+    "bm_tc_wgrad": [P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "bm_col_sum": [P, L, I, P, P],
     "bm_tc_pointwise_sel": [P, P, P, P, I, I, I, I, I, P, P, P],
     "bm_tc_wgrad_grouped": [P, P, P, P, I, I, I, I, I, P, P, P],

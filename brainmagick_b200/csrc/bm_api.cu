@@ -690,10 +690,10 @@ extern "C" long long bm_tc_wgrad_workspace(int B, int M, int N, int Kw) {
     return (long long)tc::wgrad_workspace_floats(B, M, N, Kw);
 }
 extern "C" int bm_tc_wgrad(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw,
-                           int dilation, float* workspace, float* dw, int* status, bm_stream_t stream) {
+                           int dilation, float* workspace, float* dw, float* dbias, int* status, bm_stream_t stream) {
     BM_CHECK_ARG(dy && x && workspace && dw && B > 0 && T > 0 && Kw >= 1 && Kw <= 3 && dilation >= 1);
     BM_CHECK_ARG(tc::wgrad_tc_supported(M, N) && Ntrue > 0 && Ntrue <= N);
-    return tc::launch_wgrad_tc(dy, x, B, T, M, N, Ntrue, Kw, dilation, workspace, dw, status, ST(stream));
+    return tc::launch_wgrad_tc(dy, x, B, T, M, N, Ntrue, Kw, dilation, workspace, dw, status, ST(stream), dbias);
 }
 
 extern "C" int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream) {

@@ -38,6 +38,8 @@ struct WgradP {
     int direct;                 // 1 (taps == 1, ksplit == 1): P IS the output [M][N]; rows >= M are not written
     const int* zlist;           // grouped mode (per-subject gradients): slice ks = samples zlist[seg_off[ks] .. seg_off[ks+1])
     const int* seg_off;         //   and P [ksplit][Mpad][N] is the per-group output (no reduction)
+    float* dbias;               // [M] or null: bias gradient sum_{b,t} dY[b,t,m], accumulated for free from the dY values the
+                                //   converter threads already hold (atomicAdd; zeroed by the launcher)
     int trunc_hi;               // 1: leave X raw in smem as the hi operand (the tensor core ignores the 13 low mantissa
                                 //    bits) and write only lo = x - trunc(x): one third less converter smem traffic
 };
@@ -180,6 +182,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
         };
         if (total > 0) load_a(0);
         bool ok = true;
+        float bias_acc = 0.f;
         for (int it = 0; it < total && ok; ++it) {
             const int s = it % WG_STAGES;
             const uint32_t ph = (it / WG_STAGES) & 1;
@@ -187,6 +190,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
 #pragma unroll
             for (int j = 0; j < WG_BK; ++j) {
                 tf32_split(nxt[j], hi[j], lo[j]);
+                bias_acc += nxt[j];
             }
             if (it + 1 < total) load_a(it + 1);              // prefetch the next chunk's dY column
             // the TMEM A slot and the smem stage are free once the MMAs of iteration it-STAGES have completed
@@ -223,6 +227,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
             tc_fence_before();
             mbar_arrive(&conv_bar[s]);
         }
+        if (p.dbias && m_ok && tap == p.taps / 2 && n0 == 0) atomicAdd(p.dbias + m, bias_acc);
         // ---- epilogue: partial tile -> workspace ----
         mbar_wait(&tmem_full_bar, 0, p.err, 16);
         tc_fence_after();
@@ -293,7 +298,7 @@ inline size_t wgrad_workspace_floats(int B, int M, int N, int taps) {
 
 // dY [B,T,M], X [B,T,N] -> dW [M][Ntrue][taps]; ws: wgrad_workspace_floats() floats
 inline int launch_wgrad_tc(const float* dY, const float* X, int B, int T, int M, int N, int Ntrue, int taps,
-                           int dilation, float* ws, float* dW, int* err, cudaStream_t st) {
+                           int dilation, float* ws, float* dW, int* err, cudaStream_t st, float* dbias = nullptr) {
     int nh, mblocks, ksplit, bchunk;
     wgrad_geometry(B, M, N, taps, &nh, &mblocks, &ksplit, &bchunk);
     if (nh == 0) return set_error(2, "%s: unsupported N%s", __func__);
@@ -316,6 +321,11 @@ inline int launch_wgrad_tc(const float* dY, const float* X, int B, int T, int M,
     p.ksplit = ksplit; p.bchunk = bchunk; p.dY = dY; p.err = err; p.P = ws;
     p.direct = (taps == 1 && ksplit == 1 && Ntrue == N) ? 1 : 0;
     p.zlist = nullptr; p.seg_off = nullptr;
+    p.dbias = dbias;
+    if (dbias) {
+        cudaError_t em = cudaMemsetAsync(dbias, 0, sizeof(float) * M, st);
+        if (em != cudaSuccess) return set_error(3, "%s: memset: %s", __func__, cudaGetErrorString(em));
+    }
     if (p.direct) p.P = dW;
     p.trunc_hi = (g_debug_flags & 1) ? 0 : 1;     // default ON; debug bit 0 restores the explicit rna split
     dim3 grid(N / (2 * nh) * taps, mblocks, ksplit);
@@ -354,7 +364,7 @@ inline int launch_wgrad_tc_grouped(const float* dY, const float* X, const int* z
     WgradP p;
     p.B = B; p.T = T; p.M = M; p.N = N; p.nh = nh; p.taps = 1; p.dilation = 1;
     p.ksplit = G; p.bchunk = 0; p.dY = dY; p.err = err; p.P = out; p.direct = 0;
-    p.zlist = zlist; p.seg_off = seg_off;
+    p.zlist = zlist; p.seg_off = seg_off; p.dbias = nullptr;
     p.trunc_hi = (g_debug_flags & 1) ? 0 : 1;
     dim3 grid(N / (2 * nh), (M + WG_BM - 1) / WG_BM, G);
     if (G > 65535) return set_error(2, "%s: too many groups%s", __func__);

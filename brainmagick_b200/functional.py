@@ -75,11 +75,13 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
-def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status):
-    """dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-kw//2)*dilation,n] on the tensor cores -> [M, Ntrue, kw]."""
+def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None):
+    """dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-kw//2)*dilation,n] on the tensor cores -> [M, Ntrue, kw];
+    `dbias` [M] (optional) receives sum_{b,t} dy[b,t,m] from the same kernel."""
     ws = _empty((int(_lib.load().bm_tc_wgrad_workspace(B, M, N, kw)),), dy)
     dw = _empty((M, Ntrue, kw), dy)
-    call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(status), stream())
+    call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(dbias), ptr(status),
+         stream())
     return dw
 
 
@@ -163,11 +165,11 @@ class _Conv:
         """`bias_grad_is_zero`: the conv feeds a training-mode BatchNorm, whose backward makes sum(dy) == 0 exactly
         (the reference's value there is rounding noise around 0); skip the reduction."""
         if self.wgrad_tc:
-            dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status)
             if bias_grad_is_zero:
+                dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status)
                 return dw, torch.zeros((self.cout,), device=like.device)
             db = _empty((self.cout,), like)
-            call("bm_col_sum", ptr(dy), B * T, self.cout, ptr(db), stream())
+            dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status, dbias=db)
             return dw, db
         db = _empty((self.cout,), like)
         dw = _empty((self.cout, self.cin, self.kw), like)
@@ -391,8 +393,7 @@ class _EncoderFn(torch.autograd.Function):
                 dw2 = tc_wgrad(s["q"], dest_t, B, T, H2, F, F, 1, 1, status).reshape(H2, F)
                 call("bm_col_sum", ptr(dest_t), rows, F, ptr(db2), st)
                 call("bm_gelu_bwd", ptr(dq), ptr(s["h1"]), rows * H2, ptr(dq), st)           # dq <- dh1
-                dw0 = tc_wgrad(dq, s["x_last"], B, T, H2, H, H, 1, 1, status).reshape(H2, H)
-                call("bm_col_sum", ptr(dq), rows, H2, ptr(db0), st)
+                dw0 = tc_wgrad(dq, s["x_last"], B, T, H2, H, H, 1, 1, status, dbias=db0).reshape(H2, H)
             else:
                 call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F,
                      ptr(dq), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)   # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
@@ -466,9 +467,8 @@ class _EncoderFn(torch.autograd.Function):
                      ptr(subj_order), ptr(subj_off), B, T, IL, D, S, ILp, ptr(dv), ptr(d_subj), st)
             du = _empty((B, T, Op), meg)
             il_conv.backward_data(dv, None, B, T, 1, du, status)
-            d_il_w = tc_wgrad(dv, s["u"], B, T, ILp, Op, O, 1, 1, status)[:IL, :, 0].contiguous()
             dbp = _empty((ILp,), meg)
-            call("bm_col_sum", ptr(dv), rows, ILp, ptr(dbp), st)
+            d_il_w = tc_wgrad(dv, s["u"], B, T, ILp, Op, O, 1, 1, status, dbias=dbp)[:IL, :, 0].contiguous()
             d_il_b = dbp[:IL].contiguous()
             if s["megT"] is not None:
                 megT = s["megT"]

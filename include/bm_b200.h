@@ -193,11 +193,12 @@ int bm_tc_pair_want_stats(double* stats);
 /* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]
  * for n < Ntrue (x may be channel-padded to N); dy [B,T,M], x [B,T,N] channels-last; dw in nn.Conv1d layout
  * [M][Ntrue][Kw].  workspace: bm_tc_wgrad_workspace() floats (per-batch-slice partial tiles, reduced in a fixed
- * order => deterministic).  bm_col_sum: out[c] = sum_r x[r,c] (bias gradients). */
+ * order => deterministic).  dbias (nullable) [M] receives the bias gradient sum_{b,t} dy[b,t,m], accumulated from the dy
+ * values the kernel already holds in registers.  bm_col_sum: out[c] = sum_r x[r,c] (other bias gradients). */
 int bm_tc_wgrad_supported(int M, int N);
 long long bm_tc_wgrad_workspace(int B, int M, int N, int Kw);
 int bm_tc_wgrad(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw, int dilation,
-                float* workspace, float* dw, int* status, bm_stream_t stream);
+                float* workspace, float* dw, float* dbias, int* status, bm_stream_t stream);
 int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream);
 /* SubjectLayers (common.py:55-58) on the tensor cores.
  * bm_tc_pointwise_sel: y[b,t,n] = sum_k x[b,t,k] W[wsel[b]][n][k] with tf32-split weight sets w_hi/w_lo [S][Ntot][Cin].

@@ -29,7 +29,7 @@ elif which == "wgrad":
     ws = torch.empty(_lib.load().bm_tc_wgrad_workspace(B, H, H, Kw), device=dev)
     dw = torch.empty(H, H, Kw, device=dev)
     for _ in range(6):
-        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(ws), ptr(dw), ptr(status), stream())
+        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(ws), ptr(dw), None, ptr(status), stream())
 torch.cuda.synchronize()
 assert int(status.item()) == 0
 print("done", which)

@@ -161,9 +161,11 @@ def test_tc_wgrad(case, trunc):
     ws = torch.empty(_lib.load().bm_tc_wgrad_workspace(B, M, N, Kw), device=dev)
     dw = torch.full((M, N, Kw), float("nan"), device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw), ptr(status), stream())
+    db = torch.full((M,), float("nan"), device=dev)
+    call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw), ptr(db), ptr(status), stream())
     torch.cuda.synchronize()
     _lib.load().bm_set_debug_flags(0)
+    assert rel_err(db.cpu(), dy.double().sum(dim=(0, 1)).cpu()) < 1e-5
     assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
     # fp64 reference: dw[m,n,j] = sum_{b,t} dy[b,t,m] x[b,t+(j-Kw//2)*dil,n]
     ref = torch.zeros(M, N, Kw, dtype=torch.float64, device=dev)
@@ -190,11 +192,11 @@ def test_tc_wgrad_speed_report(capsys, trunc):
     dw = torch.empty(M, N, Kw, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     for _ in range(3):
-        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws), ptr(dw), ptr(status), stream())
+        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws), ptr(dw), None, ptr(status), stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws), ptr(dw), ptr(status), stream())
+        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws), ptr(dw), None, ptr(status), stream())
     e1.record()
     torch.cuda.synchronize()
     assert int(status.item()) == 0
