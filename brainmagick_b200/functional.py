@@ -67,8 +67,19 @@ def check_tc_status(device=None) -> None:
                 raise _lib.BmB200Error(f"a tcgen05 kernel reported a pipeline timeout (barrier code {code}) on {dev}")
 
 
+OVERLAP_WGRAD = True   # weight-gradient kernels on a side stream, concurrent with the data-gradient kernels of the layer
 USE_CONV_V2 = False    # single-CTA 128x320 kernel (tc_conv2.cuh): validated, but shared-memory-bandwidth bound
 USE_CONV_V3 = True     # CTA-pair kernel (tc_conv3.cuh, tcgen05 cta_group::2): the fastest where its tiling fits
+
+
+_side_streams: tp.Dict[torch.device, torch.cuda.Stream] = {}
+
+
+def _side_stream(device) -> torch.cuda.Stream:
+    device = torch.device(device)
+    if device not in _side_streams:
+        _side_streams[device] = torch.cuda.Stream(device=device)
+    return _side_streams[device]
 
 
 def _round_up(n, m):
@@ -408,6 +419,23 @@ class _EncoderFn(torch.autograd.Function):
         sums = _empty((2 * H,), meg, torch.float64)
         layer_grads: tp.List[tp.Any] = [None] * depth
         glu_grads = {}
+        # The weight gradient and the data gradient of a layer are independent given dy: the weight-gradient kernels go to
+        # a side stream so that their CTAs fill the SMs left idle by the partial last wave of the data-gradient kernel.
+        main = torch.cuda.current_stream()
+        side = _side_stream(meg.device) if (OVERLAP_WGRAD and plan.use_tensor_cores) else None
+
+        def weight_grad(conv_obj, dy_t, x_t, dil, bias_zero):
+            if side is None:
+                return conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                out = conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero)
+            dy_t.record_stream(side)
+            x_t.record_stream(side)
+            for o in out:
+                o.record_stream(main)
+            return out
+
         for k in reversed(range(depth)):
             rec = s["layers"][k]
             cw, cb, gamma, beta = s["conv_p"][k]
@@ -417,7 +445,7 @@ class _EncoderFn(torch.autograd.Function):
                 gconv: _Conv = rec["gconv"]
                 dh = _empty((B, T, gconv.cout), meg)
                 call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), st)
-                glu_grads[k] = gconv.backward_weight(dh, rec["x_new"], B, T, 1, meg, status)
+                glu_grads[k] = weight_grad(gconv, dh, rec["x_new"], 1, False)
                 g = _empty((B, T, gconv.cin), meg)
                 gconv.backward_data(dh, None, B, T, 1, g, status)
                 del dh
@@ -427,8 +455,7 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                  ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
                  ptr(dy), ptr(dgamma), ptr(dbeta), st)
-            dcw, dcb = conv.backward_weight(dy, rec["x_in"], B, T, plan.dilations[k], meg, status,
-                                            bias_grad_is_zero=plan.training)
+            dcw, dcb = weight_grad(conv, dy, rec["x_in"], plan.dilations[k], plan.training)
             if rec["skip"]:
                 # in place: g += conv_transpose(dy) (addend == output: the pair kernel turns this into a TMA reduce-add)
                 conv.backward_data(dy, g, B, T, plan.dilations[k], g, status)
@@ -439,6 +466,8 @@ class _EncoderFn(torch.autograd.Function):
             layer_grads[k] = (dcw, dcb, dgamma, dbeta)
             del dy
 
+        if side is not None:
+            main.wait_stream(side)
         # ---- sensor chain + attention ----
         subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
         counts = torch.bincount(plan.subject, minlength=S)
