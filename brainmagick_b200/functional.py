@@ -385,6 +385,7 @@ class _EncoderFn(torch.autograd.Function):
         dest = dest.contiguous()
         status = tc_status_tensor(meg.device)
 
+        ctx_keep: tp.List[tp.Any] = []          # operands of side-stream kernels, released after the streams join
         # ---- head ----
         g = _empty((B, T, H), meg)
         dw0 = _empty((H2, H), meg)
@@ -401,10 +402,26 @@ class _EncoderFn(torch.autograd.Function):
                  0, ptr(dq), None, None, ptr(status), st)
             lib = _lib.load()
             if lib.bm_tc_wgrad_supported(H2, F) and lib.bm_tc_wgrad_supported(H2, H):
-                dw2 = tc_wgrad(s["q"], dest_t, B, T, H2, F, F, 1, 1, status).reshape(H2, F)
+                main0 = torch.cuda.current_stream()
+                side0 = _side_stream(meg.device) if OVERLAP_WGRAD else None
+
+                def on_side(fn, *tensors):
+                    """runs fn() on the side stream after everything queued so far on the main stream"""
+                    if side0 is None:
+                        return fn()
+                    side0.wait_stream(main0)
+                    with torch.cuda.stream(side0):
+                        out = fn()
+                    ctx_keep.append(tensors)
+                    out.record_stream(main0)
+                    return out
+
+                # dW2 / db2 only need dest_t and q: they overlap the dq contraction queued just before
+                dw2 = on_side(lambda: tc_wgrad(s["q"], dest_t, B, T, H2, F, F, 1, 1, status), s["q"], dest_t).reshape(H2, F)
                 call("bm_col_sum", ptr(dest_t), rows, F, ptr(db2), st)
                 call("bm_gelu_bwd", ptr(dq), ptr(s["h1"]), rows * H2, ptr(dq), st)           # dq <- dh1
-                dw0 = tc_wgrad(dq, s["x_last"], B, T, H2, H, H, 1, 1, status, dbias=db0).reshape(H2, H)
+                dw0 = on_side(lambda: tc_wgrad(dq, s["x_last"], B, T, H2, H, H, 1, 1, status, dbias=db0), dq,
+                              s["x_last"], db0).reshape(H2, H)
             else:
                 call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F,
                      ptr(dq), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)   # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
@@ -423,6 +440,7 @@ class _EncoderFn(torch.autograd.Function):
         # a side stream so that their CTAs fill the SMs left idle by the partial last wave of the data-gradient kernel.
         main = torch.cuda.current_stream()
         side = _side_stream(meg.device) if (OVERLAP_WGRAD and plan.use_tensor_cores) else None
+        keep_alive: tp.List[tp.Any] = ctx_keep
 
         def weight_grad(conv_obj, dy_t, x_t, dil, bias_zero):
             if side is None:
@@ -430,8 +448,9 @@ class _EncoderFn(torch.autograd.Function):
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 out = conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero)
-            dy_t.record_stream(side)
-            x_t.record_stream(side)
+            # the big operands are kept alive until the streams join (no record_stream: with the host running steps ahead
+            # it would block the allocator from reusing ~3 GB of blocks and force cudaMallocs in the timed loop)
+            keep_alive.append((dy_t, x_t))
             for o in out:
                 o.record_stream(main)
             return out
@@ -468,6 +487,7 @@ class _EncoderFn(torch.autograd.Function):
 
         if side is not None:
             main.wait_stream(side)
+        keep_alive.clear()
         # ---- sensor chain + attention ----
         subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
         counts = torch.bincount(plan.subject, minlength=S)
