@@ -60,13 +60,10 @@ class PositionGetter:
         return positions
 
     def get_positions(self, batch) -> torch.Tensor:
-        meg = batch.meg
-        B, C, _ = meg.shape
-        positions = torch.full((B, C, 2), self.INVALID, device=meg.device)
-        for idx in range(len(batch)):
-            rec_pos = self.get_recording_layout(batch._recordings[idx])
-            positions[idx, :len(rec_pos)] = rec_pos.to(meg.device)
-        return positions
+        """Per-sample positions [B, C, 2] (what the reference's notebooks read); built from one row per recording."""
+        n_channels = batch.meg.shape[1]
+        table, rec_of_sample, _, _ = self.batch_layout(batch, n_channels, batch.meg.device)
+        return table[rec_of_sample.long()]
 
     def is_invalid(self, positions):
         return (positions == self.INVALID).all(dim=-1)
