@@ -62,6 +62,14 @@ SIGNATURES = {
     "bm_tc_pointwise_sel": [P, P, P, P, I, I, I, I, I, P, P, P],
     "bm_tc_wgrad_grouped": [P, P, P, P, I, I, I, I, I, P, P, P],
     "bm_gelu_bwd": [P, P, L, P, P],
+    "bm_candidate_inv_norms": [P, I, L, P, P, P],
+    "bm_retrieval_topk": [P, L, I, I, P, I, I, I, P, P, P, P, P, P, P, P, P, P],
+    "bm_retrieval_probs": [P, L, I, I, P, P],
+    "bm_retrieval_vocab_probs": [P, L, I, P, P, P, P, P, I, P, P, P],
+    "bm_rowdot_scaled": [P, P, I, L, P, P],
+    "bm_scale_clamp_crop": [P, P, P, P, I, I, I, I, I, F, I, I, P, P, P],
+    "bm_reject_compact": [P, P, L, F, I, P, P, P, P],
+    "bm_gather_rows": [P, P, I, L, P, P],
 }
 
 _lib = None
@@ -89,6 +97,8 @@ def load():
     lib.bm_launch_count.argtypes = []
     lib.bm_tc_wgrad_workspace.restype = c_longlong
     lib.bm_tc_wgrad_workspace.argtypes = [I, I, I, I]
+    lib.bm_clip_workspace.restype = c_longlong
+    lib.bm_clip_workspace.argtypes = [I, I, L]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = c_int

@@ -8,6 +8,8 @@
 #include "tc_conv2.cuh"
 #include "tc_conv3.cuh"
 #include "tc_conv4.cuh"
+#include "retrieval.cuh"
+#include "prep.cuh"
 
 namespace bm {
 thread_local char g_last_error[512] = "";
@@ -511,10 +513,27 @@ extern "C" int bm_clip_set_workspace(float* ws, long long n_floats, int* status)
     return 0;
 }
 
-extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss,
-                              float* inv_norm, float* scores, float* probs, bm_stream_t stream) {
-    BM_CHECK_ARG(est && cand && ss && inv_norm && scores && Bn > 0 && Bc > 0 && KT > 0);
-    BM_CHECK_ARG(KT < (1ll << 31));
+namespace {
+// split-K factor of the tensor-core score GEMM: enough K slices to put one CTA on every SM
+inline int clip_tc_ksplit(int Bn, int Bc, long long KT) {
+    int mt = (Bn + 127) / 128, nt = Bc / (2 * tc::conv_tc2_pick_nh(Bc, 0));
+    int ks = num_sms() / (mt * nt);
+    if (ks < 1) ks = 1;
+    long long chunks = KT / 32;
+    if (ks > chunks) ks = (int)chunks;
+    return ks;
+}
+}  // namespace
+
+extern "C" long long bm_clip_workspace(int Bn, int Bc, long long KT) {
+    if (Bn <= 0 || Bc <= 0 || KT <= 0 || KT >= (1ll << 31)) return 0;
+    if (!tc::conv_tc2_supported(Bn, (int)KT, Bc, 1, 0)) return 0;
+    return (long long)clip_tc_ksplit(Bn, Bc, KT) * Bn * Bc;
+}
+
+extern "C" int bm_candidate_inv_norms(const float* cand, int Bc, long long KT, double* ss, float* inv_norm,
+                                      bm_stream_t stream) {
+    BM_CHECK_ARG(cand && ss && inv_norm && Bc > 0 && KT > 0);
     cudaStream_t st = ST(stream);
     BM_CUDA(cudaMemsetAsync(ss, 0, sizeof(double) * Bc, st));
     int splits = (int)((KT + 65535) / 65536);
@@ -523,13 +542,21 @@ extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int B
     BM_CHECK_LAUNCH();
     inv_norm_kernel<<<(Bc + 127) / 128, 128, 0, st>>>(ss, inv_norm, Bc);
     BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss,
+                              float* inv_norm, float* scores, float* probs, bm_stream_t stream) {
+    BM_CHECK_ARG(est && cand && inv_norm && scores && Bn > 0 && Bc > 0 && KT > 0);
+    BM_CHECK_ARG(KT < (1ll << 31));
+    cudaStream_t st = ST(stream);
+    if (ss) {       // ss == NULL: inv_norm is an INPUT (candidate norms computed once, e.g. the retrieval evaluation)
+        int rc = bm_candidate_inv_norms(cand, Bc, KT, ss, inv_norm, stream);
+        if (rc) return rc;
+    }
     if (g_clip_ws && g_clip_ws_floats > 0 && tc::conv_tc2_supported(Bn, (int)KT, Bc, 1, 0)) {
         // tensor cores: scores = E C^T as a split-K pointwise "conv" (x = E [1,Bn,KT], weights = C [Bc,KT] raw fp32)
-        int mt = (Bn + 127) / 128, nt = Bc / (2 * tc::conv_tc2_pick_nh(Bc, 0));
-        int ks = num_sms() / (mt * nt);
-        if (ks < 1) ks = 1;
-        long long chunks = KT / 32;
-        if (ks > chunks) ks = (int)chunks;
+        int ks = clip_tc_ksplit(Bn, Bc, KT);
         if ((size_t)ks * Bn * Bc <= g_clip_ws_floats) {
             tc::Conv2P q;
             q.B = 1; q.T = Bn; q.Cin = (int)KT; q.Ntot = Bc; q.taps = 1; q.dilation = 1; q.sign = 1; q.glu = 0; q.nh = 0;
@@ -603,6 +630,93 @@ extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const
     g.B = cand; g.ldb_n = 1; g.ldb_k = KT; g.b_ncontig = 1;
     g.D = dest; g.ldd_m = KT; g.ldd_n = 1;
     BM_CUDA(launch_gemm(g, st));
+    return 0;
+}
+
+// =================================================================================================
+// Retrieval evaluation
+// =================================================================================================
+extern "C" int bm_retrieval_topk(const float* vals, long long ld, int Bn, int n_cols, const float* own_values,
+                                 int own_col, int is_prob, int k, const long long* labels,
+                                 const long long* own_labels, const long long* targets, long long* top_idx,
+                                 float* top_prob, int* hit, float* soft, float* row_max, float* row_sum,
+                                 bm_stream_t stream) {
+    BM_CHECK_ARG(vals && Bn > 0 && n_cols > 0 && ld >= n_cols && k >= 0);
+    BM_CHECK_ARG(!own_values || (own_col >= 0 && own_col < n_cols));
+    BM_CHECK_ARG(!own_labels || (labels && own_col >= 0 && own_col < n_cols));
+    BM_CHECK_ARG(!(hit || soft) || (labels && targets));
+    BM_CHECK_ARG(k == 0 || top_idx || top_prob || hit);
+    int threads = n_cols >= 4096 ? 512 : 256;
+    retrieval_topk_kernel<<<Bn, threads, 0, ST(stream)>>>(vals, ld, n_cols, own_values, own_col, is_prob, k, labels,
+                                                          own_labels, targets, top_idx, top_prob, hit, soft, row_max,
+                                                          row_sum);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_retrieval_probs(const float* scores, long long ld, int Bn, int n_cols, float* probs,
+                                  bm_stream_t stream) {
+    BM_CHECK_ARG(scores && probs && Bn > 0 && n_cols > 0 && ld >= n_cols);
+    softmax_rows_ld_kernel<<<Bn, 256, 0, ST(stream)>>>(scores, ld, n_cols, probs);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_retrieval_vocab_probs(const float* scores, long long ld, int Bn, const float* own_scores,
+                                        const float* row_max, const float* row_sum, const int* perm, const int* seg,
+                                        int V, const int* own_word, float* vocab, bm_stream_t stream) {
+    BM_CHECK_ARG(scores && row_max && row_sum && perm && seg && vocab && Bn > 0 && V > 0);
+    BM_CHECK_ARG(!own_scores || own_word);
+    vocab_probs_kernel<<<Bn, 256, 0, ST(stream)>>>(scores, ld, own_scores, row_max, row_sum, perm, seg, V, own_word,
+                                                   vocab);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_rowdot_scaled(const float* a, const float* c, int Bn, long long K, float* own,
+                                bm_stream_t stream) {
+    BM_CHECK_ARG(a && c && own && Bn > 0 && K > 0);
+    rowdot_scaled_kernel<<<Bn, 512, 0, ST(stream)>>>(a, c, K, own);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+// =================================================================================================
+// Batch preparation
+// =================================================================================================
+extern "C" int bm_scale_clamp_crop(const float* x, const int* slot, const float* center, const float* scale, int B,
+                                   int C, int T, int t0, int T_out, float limit, int clip, int inverse, float* y,
+                                   unsigned int* peak_bits, bm_stream_t stream) {
+    BM_CHECK_ARG(x && center && scale && y && B > 0 && C > 0 && T > 0);
+    BM_CHECK_ARG(t0 >= 0 && T_out > 0 && t0 + T_out <= T);
+    BM_CHECK_ARG(!clip || limit >= 0.f);
+    cudaStream_t st = ST(stream);
+    if (peak_bits) BM_CUDA(cudaMemsetAsync(peak_bits, 0, sizeof(unsigned) * B, st));
+    long long rows = (long long)B * C;
+    long long blocks = (rows + 7) / 8;                       // 8 warps (rows) per block
+    long long cap = (long long)num_sms() * 8;                // one full wave of 2048-thread SMs, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    scale_clamp_crop_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, slot, center, scale, B, C, T, t0, T_out, limit, clip,
+                                                             inverse, y, peak_bits);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_reject_compact(const unsigned int* peak_bits, const unsigned char* mask, long long mask_elems,
+                                 float limit, int B, unsigned char* keep, int* keep_rows, int* n_keep,
+                                 bm_stream_t stream) {
+    BM_CHECK_ARG(peak_bits && keep && keep_rows && n_keep && B > 0);
+    BM_CHECK_ARG(!mask || mask_elems > 0);
+    reject_compact_kernel<<<1, 1024, 0, ST(stream)>>>(peak_bits, mask, mask_elems, limit, B, keep, keep_rows, n_keep);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_gather_rows(const float* x, const int* rows, int n_rows, long long row_elems, float* y,
+                              bm_stream_t stream) {
+    BM_CHECK_ARG(x && rows && y && n_rows > 0 && row_elems > 0);
+    gather_rows_kernel<<<ew_grid((long long)n_rows * row_elems), 256, 0, ST(stream)>>>(x, rows, n_rows, row_elems, y);
+    BM_CHECK_LAUNCH();
     return 0;
 }
 

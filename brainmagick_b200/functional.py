@@ -570,10 +570,11 @@ def encoder_forward(plan: EncoderPlan, meg, heads, il_w, il_b, subj_w, w0, b0, w
 _clip_ws: tp.Dict[torch.device, torch.Tensor] = {}
 
 
-def _register_clip_workspace(like: torch.Tensor, Bn: int, Bc: int) -> None:
+def _register_clip_workspace(like: torch.Tensor, Bn: int, Bc: int, floats: tp.Optional[int] = None) -> None:
     """Scratch for the tensor-core CLIP contractions (split-K partial score tiles); one buffer per device, grown on
-    demand, registered with the library before every CLIP call (one process drives one GPU)."""
-    need = 160 * Bn * Bc
+    demand, registered with the library before every CLIP call (one process drives one GPU).  `floats`: exact need when
+    the caller asked the library (`bm_clip_workspace`, forward-only retrieval shapes); default = the training bound."""
+    need = 160 * Bn * Bc if floats is None else max(int(floats), 1)
     dev = like.device
     ws = _clip_ws.get(dev)
     if ws is None or ws.numel() < need:
@@ -596,6 +597,31 @@ def clip_scores(estimates: torch.Tensor, candidates: torch.Tensor, want_probs: b
     _register_clip_workspace(est, Bn, Bc)
     call("bm_clip_scores", ptr(est), ptr(cand), Bn, Bc, KT, ptr(ss), ptr(inv), ptr(scores), ptr(probs), stream())
     return probs if want_probs else scores
+
+
+def candidate_inv_norms(candidates: torch.Tensor) -> torch.Tensor:
+    """inv_norm[o] = 1 / (1e-8 + ||candidate_o||) (bm/losses.py:91), for a candidate set that is scored many times."""
+    cand = candidates.detach().contiguous().float()
+    Bc, KT = cand.shape[0], cand[0].numel()
+    ss = _empty((Bc,), cand, torch.float64)
+    inv = _empty((Bc,), cand)
+    call("bm_candidate_inv_norms", ptr(cand), Bc, KT, ptr(ss), ptr(inv), stream())
+    return inv
+
+
+def clip_scores_prenormed(estimates: torch.Tensor, candidates: torch.Tensor, inv_norms: torch.Tensor) -> torch.Tensor:
+    """ClipLoss.get_scores against a candidate set whose `candidate_inv_norms` are already known (retrieval evaluation:
+    the same candidates serve every query batch, so they are normed once)."""
+    est = estimates.detach().contiguous().float()
+    cand = candidates if (candidates.is_contiguous() and candidates.dtype == torch.float32) \
+        else candidates.contiguous().float()
+    Bn, Bc = est.shape[0], cand.shape[0]
+    KT = est[0].numel()
+    assert cand[0].numel() == KT and inv_norms.numel() == Bc
+    scores = _empty((Bn, Bc), est)
+    _register_clip_workspace(est, Bn, Bc, floats=int(_lib.load().bm_clip_workspace(Bn, Bc, KT)))
+    call("bm_clip_scores", ptr(est), ptr(cand), Bn, Bc, KT, None, ptr(inv_norms), ptr(scores), None, stream())
+    return scores
 
 
 class _ClipLossFn(torch.autograd.Function):

@@ -44,15 +44,43 @@ class SyntheticRecording:
 
 
 class SyntheticBatch:
+    """The part of `SegmentBatch` (bm/dataset.py:209-258) the model, the scaler and the solver's batch preparation touch:
+    tensor fields + the per-sample recordings list, `.to`, `.replace`, indexing by a mask / index tensor, `len`."""
+    TENSORS = ("meg", "features", "features_mask", "subject_index", "recording_index")
+
     def __init__(self, meg: torch.Tensor, subject_index: torch.Tensor, recordings: tp.Sequence[SyntheticRecording],
-                 features: tp.Optional[torch.Tensor] = None):
+                 features: tp.Optional[torch.Tensor] = None, features_mask: tp.Optional[torch.Tensor] = None,
+                 recording_index: tp.Optional[torch.Tensor] = None):
         self.meg = meg
         self.subject_index = subject_index
         self.features = features
+        self.features_mask = features_mask
+        if recording_index is None and len(recordings):
+            recording_index = torch.tensor([r.recording_index for r in recordings], dtype=torch.long)
+        self.recording_index = recording_index
         self._recordings = list(recordings)
 
+    def _rebuild(self, **fields):
+        kw = {name: getattr(self, name) for name in self.TENSORS}
+        kw["recordings"] = self._recordings
+        kw.update(fields)
+        return SyntheticBatch(**kw)
+
+    def to(self, device) -> "SyntheticBatch":
+        return self._rebuild(**{n: getattr(self, n).to(device) for n in self.TENSORS if getattr(self, n) is not None})
+
+    def replace(self, **fields) -> "SyntheticBatch":
+        if "_recordings" in fields:
+            fields["recordings"] = fields.pop("_recordings")
+        return self._rebuild(**fields)
+
+    def __getitem__(self, index) -> "SyntheticBatch":
+        rows = torch.arange(len(self), device=self.meg.device)[index].tolist()
+        picked = {n: getattr(self, n)[index] for n in self.TENSORS if getattr(self, n) is not None}
+        return self._rebuild(recordings=[self._recordings[i] for i in rows] if self._recordings else [], **picked)
+
     def __len__(self):
-        return len(self._recordings)
+        return len(self.meg)
 
 
 def normalised_positions(n_rec: int, n_channels: int, n_valid: tp.Sequence[int] = (), seed: int = 0) -> torch.Tensor:

@@ -139,13 +139,19 @@ int bm_head_bwd_params(const float* dest, const float* x, const float* h1, const
  * est [Bn,KT], cand [Bc,KT] (KT = F*T, any consistent flattening).
  * bm_clip_scores = ClipLoss.get_scores (+ get_probabilities when probs != NULL):
  *   inv_norm[o] = 1/(1e-8+||cand_o||), scores[b,o] = inv_norm[o] <est_b, cand_o>, probs = softmax_o(scores).
- * ss: fp64 [Bc] scratch. */
+ * ss: fp64 [Bc] scratch (NULL: inv_norm is given, see bm_candidate_inv_norms). */
 int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss, float* inv_norm,
                    float* scores, float* probs, bm_stream_t stream);
 /* Registers caller-owned scratch that lets bm_clip_scores / bm_clip_loss_fwd / bm_clip_loss_bwd run their two big
  * contractions on the tensor cores (3xTF32): ws >= 148*Bn*Bc floats (split-K partial score tiles), status = device int
  * set on a pipeline timeout.  Without it (or for shapes outside the tcgen05 tiling) the FP32-FMA GEMM is used. */
 int bm_clip_set_workspace(float* ws, long long n_floats, int* status);
+/* Floats of workspace the tensor-core score GEMM needs for this shape (split-K slices x Bn x Bc); 0 = the shape is
+ * outside the tcgen05 tiling (Bc % 256 and % 320 != 0, or KT % 32 != 0) and the FP32-FMA GEMM will be used. */
+long long bm_clip_workspace(int Bn, int Bc, long long KT);
+/* inv_norm[o] = 1/(1e-8+||cand_o||) alone (losses.py:91); ss fp64 [Bc] scratch.  bm_clip_scores with ss == NULL takes
+ * inv_norm as an INPUT: a fixed candidate set (retrieval evaluation) is normed once, not once per query batch. */
+int bm_candidate_inv_norms(const float* cand, int Bc, long long KT, double* ss, float* inv_norm, bm_stream_t stream);
 /* ClipLoss.forward: loss = mean_b CE(scores[b,:], target_offset + b).  target_offset = 0 is the reference;
  * rank*Bn is the multi-GPU extension with all-gathered candidates.  row_loss [Bn] scratch, loss [1]. */
 int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long long KT, int target_offset,
@@ -154,6 +160,50 @@ int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long l
 /* dL/dest [Bn,KT] = gout * ((probs - onehot)/Bn * inv_norm) @ cand ; G [Bn,Bc] scratch; gout [1] on device. */
 int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* cand, const float* gout, int Bn,
                      int Bc, long long KT, int target_offset, float* G, float* dest, bm_stream_t stream);
+
+/* ---- Retrieval evaluation: scripts/run_eval_probs.py:237-307, bm/wer.py:80-116 ---------
+ * The score matrix comes from bm_clip_scores (queries x candidates, candidate axis optionally zero-padded to the
+ * tensor-core tile: ld >= n_cols); these entry points replace the host-side softmax / topk / scatter_add / label
+ * comparison the reference runs per query (wer.py) or per query batch on the CPU copy (run_eval_probs.py).
+ * bm_retrieval_topk, one row b of `vals` (stride ld) at a time:
+ *   is_prob=0: vals are scores, p = softmax over the n_cols columns (row_max/row_sum, nullable, receive its stats);
+ *   is_prob=1: vals are probabilities already, negative entries are holes;
+ *   own_values [Bn] (nullable): per-row value standing in column own_col -- wer.py:93 overwrites the last negative
+ *     with the query's own true output; own_labels [Bn] likewise for that column's label (wer.py:94);
+ *   top_idx/top_prob [Bn,k] (nullable): the k best columns, best first, ties -> lower column (-1 / 0 if fewer);
+ *   hit[b] = rank (0 = best) of the first of the k selected columns whose label is targets[b], -1 if none: a top-k'
+ *     hit for any k' <= k is 0 <= hit[b] < k' (run_eval_probs.py:253-259, wer.py:107-111);
+ *   soft[b] = sum of p over the columns whose label is targets[b] (wer.py:114-115).
+ * bm_retrieval_probs: probs [Bn,n_cols] = softmax(scores[:, :n_cols])  (ClipLoss.get_probabilities, losses.py:97-102).
+ * bm_retrieval_vocab_probs: per-word probabilities (wer.py:101-104) without atomics: vocab [Bn,V+1],
+ *   vocab[b][w] = sum_{j in seg[w]..seg[w+1]} p[b][perm[j]] (+ the own candidate's p when own_word[b] == w);
+ *   column V = own p when own_word[b] == V (a word no shared negative carries), else -1 (a hole for bm_retrieval_topk).
+ * bm_rowdot_scaled: own[b] = <a_b, c_b> / (1e-8 + ||c_b||): the score of a query against its own true output. */
+int bm_retrieval_topk(const float* vals, long long ld, int Bn, int n_cols, const float* own_values, int own_col,
+                      int is_prob, int k, const long long* labels, const long long* own_labels,
+                      const long long* targets, long long* top_idx, float* top_prob, int* hit, float* soft,
+                      float* row_max, float* row_sum, bm_stream_t stream);
+int bm_retrieval_probs(const float* scores, long long ld, int Bn, int n_cols, float* probs, bm_stream_t stream);
+int bm_retrieval_vocab_probs(const float* scores, long long ld, int Bn, const float* own_scores, const float* row_max,
+                             const float* row_sum, const int* perm, const int* seg, int V, const int* own_word,
+                             float* vocab, bm_stream_t stream);
+int bm_rowdot_scaled(const float* a, const float* c, int Bn, long long K, float* own, bm_stream_t stream);
+
+/* ---- Batch preparation: bm/norm.py:239-275, 325-341; bm/solver.py:262-274 ---------------
+ * bm_scale_clamp_crop: y [B,C,T_out] = op(x [B,C,T])[..., t0:t0+T_out] with op = (x - center[slot[b]][c]) / scale[..]
+ *   (BatchScaler.transform; inverse=1: x*scale + center), then clamp to +-limit when clip (ScaleReject, norm.py:332-333)
+ *   -- one pass, bit-identical to the reference's fp32 arithmetic.  center/scale: [R,C] tables (RobustScaler per
+ *   recording, or one row of per-channel StandardScaler constants with slot = NULL).  peak_bits [B] (nullable): bit
+ *   pattern of max |op(x)| over the whole uncropped sample (what ScaleReject tests, norm.py:334).
+ * bm_reject_compact: keep[b] = !(peak > limit) && (mask == NULL || any(mask[b])) (norm.py:335-339);
+ *   keep_rows = kept sample indices in order, n_keep[0] their count.
+ * bm_gather_rows: y[i] = x[rows[i]] over rows of row_elems floats (batch[keep], norm.py:340). */
+int bm_scale_clamp_crop(const float* x, const int* slot, const float* center, const float* scale, int B, int C, int T,
+                        int t0, int T_out, float limit, int clip, int inverse, float* y, unsigned int* peak_bits,
+                        bm_stream_t stream);
+int bm_reject_compact(const unsigned int* peak_bits, const unsigned char* mask, long long mask_elems, float limit,
+                      int B, unsigned char* keep, int* keep_rows, int* n_keep, bm_stream_t stream);
+int bm_gather_rows(const float* x, const int* rows, int n_rows, long long row_elems, float* y, bm_stream_t stream);
 
 /* ---- tcgen05 (5th-gen tensor core) versions of K3/K4: 3xTF32 implicit-GEMM conv ---------------------------
  * Same arithmetic contract as bm_conv1d_fwd / bm_conv1d_bwd_data / bm_conv1d_glu_fwd (fp32-faithful: every

@@ -98,7 +98,116 @@ def run_case(name, c):
           f"size={os.path.getsize(os.path.join(OUT, name + '.npz')) / 1024:.0f} KiB")
 
 
+def run_prep(name="prep_small"):
+    """bm/norm.py verbatim (RobustScaler.fit/transform, StandardScaler, BatchScaler._transform, ScaleReject) on a
+    small batch that mixes three recordings, holds an out-of-range sample, a zero-padded channel and an empty
+    features mask; plus the offset crop of solver.py:262-274 applied with plain slicing."""
+    norm = ref_loader.load_reference_norm()
+    torch.manual_seed(4242)
+    B, C, T, off = 7, 6, 30, 3
+    fb = ref_loader.FakeFeaturesBuilder({"a": (3, True), "b": (2, False)})
+    rec_ids = [4, 9, 11]
+    out = {}
+    for per_channel in (False, True):
+        scaler = norm.BatchScaler(fb, per_channel=per_channel)
+        torch.manual_seed(4242)
+        for i, r in enumerate(rec_ids):
+            fit = torch.randn(400, C) * (0.5 + i) + 0.3 * i
+            fit[:, C - 1] = 0 if i == 1 else fit[:, C - 1]      # padded channel -> scale_ forced to 1 (norm.py:73-76)
+            s = norm.RobustScaler()
+            s.fit(fit)
+            scaler.meg_scalers[r] = s
+            out[f"fit.meg.{r}"] = fit.numpy()
+        feats_fit = torch.randn(50, fb.dimension, T) * 2 + 1
+        mask_fit = torch.ones(50, 1, T, dtype=torch.bool)
+        mask_fit[::7, :, ::3] = False
+        out["fit.features"], out["fit.features_mask"] = feats_fit.numpy(), mask_fit.numpy()
+        for fname, fs in scaler.feature_scalers.items():
+            fs.fit(norm._as_nd(feats_fit[:, fb.get_slice(fname)]), norm._as_nd(mask_fit))
+        meg = torch.randn(B, C, T) * 2
+        meg[2, 1, 5] = 90.0                                      # > limit after scaling -> rejected / clipped
+        meg[5, 0, 0] = -75.0
+        rec = torch.tensor([4, 11, 9, 9, 4, 11, 4])
+        features = torch.randn(B, fb.dimension, T)
+        fmask = torch.ones(B, 1, T, dtype=torch.bool)
+        fmask[3] = False                                         # empty features (exclude_empty_features)
+        tag = "pc1." if per_channel else "pc0."
+        out[tag + "meg_center"] = np.stack([scaler.meg_scalers[r].center_.numpy() for r in rec_ids])
+        out[tag + "meg_scale"] = np.stack([scaler.meg_scalers[r].scale_.numpy() for r in rec_ids])
+        fc = torch.zeros(fb.dimension)
+        fsc = torch.ones(fb.dimension)
+        for fname, fs in scaler.feature_scalers.items():
+            if isinstance(fs, norm.StandardScaler):
+                fc[fb.get_slice(fname)] = fs.center_
+                fsc[fb.get_slice(fname)] = fs.scale_
+        out[tag + "feat_center"], out[tag + "feat_scale"] = fc.numpy(), fsc.numpy()
+        batch = ref_loader.FakeSegmentBatch(meg.clone(), features.clone(), fmask.clone(), rec.clone())
+        tr = scaler.transform(batch)
+        out[tag + "transform.meg"], out[tag + "transform.features"] = tr.meg.numpy(), tr.features.numpy()
+        inv = scaler.inverse_transform(tr)
+        out[tag + "inverse.meg"], out[tag + "inverse.features"] = inv.meg.numpy(), inv.features.numpy()
+        for clip in (False, True):
+            for excl in (False, True):
+                sr = norm.ScaleReject(scaler, limit=20.0, exclude_empty_features=excl, clip=clip)
+                kept, keep = sr(ref_loader.FakeSegmentBatch(meg.clone(), features.clone(), fmask.clone(), rec.clone()))
+                k = f"{tag}clip{int(clip)}.excl{int(excl)}."
+                out[k + "keep"] = keep.numpy()
+                out[k + "meg"] = kept.meg[..., off:].contiguous().numpy()               # solver.py:264
+                out[k + "features"] = kept.features[..., :-off].contiguous().numpy()    # solver.py:273
+                out[k + "features_mask"] = kept.features_mask[..., :-off].contiguous().numpy()
+                out[k + "rejection_rate"] = np.float64(sr.rejection_rate)
+    out.update(meg=meg.numpy(), features=features.numpy(), features_mask=fmask.numpy(), recording_index=rec.numpy(),
+               rec_ids=np.array(rec_ids), offset=np.int64(off), limit=np.float32(20.0))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: {len(out)} arrays, size={os.path.getsize(os.path.join(OUT, name + '.npz')) / 1024:.0f} KiB")
+
+
+def run_retrieval(name="retrieval_small"):
+    """Verbatim `ClipLoss.get_probabilities` (bm/losses.py:97-102) driven by the evaluation loops of
+    scripts/run_eval_probs.py:237-307 and bm/wer.py:80-116.  Those two files import flashy / dora / omegaconf and a
+    Solver, so the loops themselves are the restatement in `oracle/eval_oracle.py`; the arithmetic is the reference's."""
+    from oracle import eval_oracle
+    _, _, losses = ref_loader.load_reference()
+    clip = losses.ClipLoss().eval()
+    probs_fn = lambda e, c: clip.get_probabilities(e, c)   # noqa: E731
+    torch.manual_seed(777)
+    N, M, F, T = 24, 17, 6, 20
+    trues = torch.randn(M, F, T)
+    seg_of_pred = torch.randint(0, M, (N,))
+    preds = 0.12 * trues[seg_of_pred] + torch.randn(N, F, T)
+    vocab_labels = torch.randperm(10_000)[:M] * 7919 - 31_000_000          # int64 "segment hashes"
+    target_labels = vocab_labels[seg_of_pred]
+    out = dict(preds=preds.numpy(), trues=trues.numpy(), vocab_labels=vocab_labels.numpy(),
+               target_labels=target_labels.numpy())
+    probs = eval_oracle.builds_probs(preds, trues, batch_size=10, probabilities=probs_fn)
+    out["probs"] = probs.numpy()
+    out["acc"] = np.array([eval_oracle.accuracy_from_probs(probs, target_labels, vocab_labels, k) for k in (1, 5, 10)])
+    window = eval_oracle.crop_window(-0.5, 120.0, -0.45, -0.4)
+    out["window"] = np.array(window)
+    out["probs_window"] = eval_oracle.builds_probs(preds, trues, 10, window, probs_fn).numpy()
+    # wer ranking: 12 estimates, 5 distinct words, 9 negatives
+    n, n_neg, topx = 12, 9, 3
+    word_hashes = torch.tensor([11, 23, 11, 35, 47, 23, 59, 11, 35, 47, 23, 59], dtype=torch.int32)
+    outputs = torch.randn(n, F, T)
+    estimates = 0.15 * outputs + torch.randn(n, F, T)
+    kept = torch.randperm(n)[:n_neg]
+    negatives, negative_hashes = outputs[kept], word_hashes[kept]
+    res = eval_oracle.wer_ranking(estimates, word_hashes, outputs, negatives, negative_hashes, topx, probs_fn)
+    out.update(wer_estimates=estimates.numpy(), wer_outputs=outputs.numpy(), wer_word_hashes=word_hashes.numpy(),
+               wer_negatives=negatives.numpy(), wer_negative_hashes=negative_hashes.numpy(), wer_topx=np.int64(topx),
+               wer=np.float64(res["wer"]), wer_vocab=np.float64(res["wer_vocab"]),
+               wer_soft=np.float64(res["soft_correct"]))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: acc@1/5/10={out['acc']} wer={res} window={window}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
+    wanted = sys.argv[1:]
     for name, c in CASES.items():
-        run_case(name, c)
+        if not wanted or name in wanted:
+            run_case(name, c)
+    if not wanted or "prep_small" in wanted:
+        run_prep()
+    if not wanted or "retrieval_small" in wanted:
+        run_retrieval()

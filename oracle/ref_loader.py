@@ -122,3 +122,78 @@ def clip_conv_kwargs(hidden=320, depth=10, merger_channels=270, initial_linear=2
     kw.update(hidden=dict(meg=hidden), depth=depth, merger_channels=merger_channels,
               initial_linear=initial_linear, merger_pos_dim=merger_pos_dim, merger_dropout=merger_dropout)
     return kw
+
+
+# ----------------------------------------------------------------------------------------------
+# bm/norm.py (BatchScaler._transform + ScaleReject), loaded verbatim
+# ----------------------------------------------------------------------------------------------
+_norm = None
+
+
+def load_reference_norm():
+    """Returns the verbatim `bm.norm` module.  It imports `dora.log.LogProgress`, `bm.features.{FeaturesBuilder,
+    Feature}` and `bm.dataset.SegmentBatch` for type annotations and the (unused here) `fit` loop only; empty
+    stand-ins are enough for `RobustScaler` / `StandardScaler` / `BatchScaler._transform` / `ScaleReject`."""
+    global _norm
+    if _norm is not None:
+        return _norm
+    load_reference()
+    if "dora" not in sys.modules:
+        dora = types.ModuleType("dora")
+        dora.__path__ = []
+        sys.modules["dora"] = dora
+    log = types.ModuleType("dora.log")
+    log.LogProgress = lambda logger, it, **kw: it
+    sys.modules["dora.log"] = log
+    feats = types.ModuleType("bm.features")
+    feats.FeaturesBuilder = object
+    feats.Feature = object
+    sys.modules["bm.features"] = feats
+    dset = types.ModuleType("bm.dataset")
+    dset.SegmentBatch = FakeSegmentBatch
+    sys.modules["bm.dataset"] = dset
+    spec = importlib.util.spec_from_file_location("bm.norm", REF + "/norm.py")
+    m = importlib.util.module_from_spec(spec)
+    sys.modules["bm.norm"] = m
+    spec.loader.exec_module(m)
+    _norm = m
+    return m
+
+
+class FakeSegmentBatch:
+    """What BatchScaler._transform / ScaleReject.__call__ touch on a SegmentBatch (norm.py:248-275, 325-341):
+    `.meg`, `.features`, `.features_mask`, `.recording_index`, `.replace(**kw)`, boolean-mask `__getitem__`."""
+
+    def __init__(self, meg, features, features_mask, recording_index):
+        self.meg, self.features, self.features_mask = meg, features, features_mask
+        self.recording_index = recording_index
+
+    def replace(self, **kw):
+        d = dict(meg=self.meg, features=self.features, features_mask=self.features_mask,
+                 recording_index=self.recording_index)
+        d.update(kw)
+        return FakeSegmentBatch(**d)
+
+    def __getitem__(self, keep):
+        return FakeSegmentBatch(self.meg[keep], self.features[keep], self.features_mask[keep],
+                                self.recording_index[keep])
+
+    def __len__(self):
+        return len(self.meg)
+
+
+class FakeFeaturesBuilder(dict):
+    """name -> (slice, normalizable) ; stands in for bm.features.FeaturesBuilder (norm.py:160-162, 232, 264)."""
+
+    def __init__(self, spec):
+        super().__init__()
+        start = 0
+        self._slices = {}
+        for name, (dim, normalizable) in spec.items():
+            self[name] = types.SimpleNamespace(normalizable=normalizable, categorical=False, cardinality=0)
+            self._slices[name] = slice(start, start + dim)
+            start += dim
+        self.dimension = start
+
+    def get_slice(self, name):
+        return self._slices[name]

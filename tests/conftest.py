@@ -37,6 +37,12 @@ def load_golden(name):
     return cfg, bool(train), t
 
 
+def load_arrays(name):
+    """Plain dict of numpy arrays of a fixture without a model configuration (prep_small, retrieval_small)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
 def rel_err(a, b):
     """Relative Frobenius error ||a-b|| / ||b|| (b = reference)."""
     a, b = a.double(), b.double()
