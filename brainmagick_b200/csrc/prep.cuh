@@ -10,6 +10,8 @@
 
 namespace bm {
 
+constexpr int PREP_ILP = 8;
+
 // x [B, C, T] -> y [B, C, T_out] = op(x[..., t0 : t0 + T_out]);  op = (x - center[slot[b]][c]) / scale[slot[b]][c]
 // (or x * scale + center when `inverse`), then clamp to +-limit when `clip`.
 // peak_bits[b] = max over the WHOLE sample (all T, like the reference, which rejects before it crops) of |op(x)|, as
@@ -32,13 +34,24 @@ __global__ void scale_clamp_crop_kernel(const float* __restrict__ x, const int* 
         const float* xr = x + row * T;
         float* yr = y + row * T_out - t0;
         float peak = 0.f;
-#pragma unroll 4
-        for (int t = t_lo + lane; t < t_hi; t += 32) {
-            float v = xr[t];
-            v = inverse ? __fadd_rn(__fmul_rn(v, scl), ctr) : __fdiv_rn(__fsub_rn(v, ctr), scl);
-            if (clip) v = fminf(fmaxf(v, -limit), limit);
-            peak = fmaxf(peak, fabsf(v));
-            if (t >= t0 && t < t0 + T_out) yr[t] = v;
+        // 8 independent 128 B loads in flight per warp before the first use (a row is ~11 such lines)
+        for (int base = t_lo; base < t_hi; base += 32 * PREP_ILP) {
+            float v[PREP_ILP];
+#pragma unroll
+            for (int i = 0; i < PREP_ILP; ++i) {
+                const int t = base + i * 32 + lane;
+                v[i] = t < t_hi ? xr[t] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < PREP_ILP; ++i) {
+                const int t = base + i * 32 + lane;
+                float w = inverse ? __fadd_rn(__fmul_rn(v[i], scl), ctr) : __fdiv_rn(__fsub_rn(v[i], ctr), scl);
+                if (clip) w = fminf(fmaxf(w, -limit), limit);
+                if (t < t_hi) {
+                    peak = fmaxf(peak, fabsf(w));
+                    if (t >= t0 && t < t0 + T_out) yr[t] = w;
+                }
+            }
         }
         if (peak_bits) {
             peak = warp_max(peak);

@@ -256,10 +256,14 @@ class ScaleReject:
         self._count = 0
 
     def _scaled(self, batch, offset_samples: int):
+        can_reject = (not self.clip) or self.exclude_empty_features
         meg, features, peak = self.scaler._apply(batch, False, self.limit, self.clip, t0=offset_samples,
-                                                 crop=offset_samples, want_peak=True)
+                                                 crop=offset_samples, want_peak=can_reject)
         B = meg.shape[0]
         self._count += B
+        if not can_reject:
+            # clamped values cannot exceed the limit (norm.py:332-335): nothing to test, and no host synchronisation
+            return meg, features, torch.ones(B, device=meg.device, dtype=torch.bool), None, B
         keep = torch.empty(B, device=meg.device, dtype=torch.bool)
         rows = torch.empty(B, device=meg.device, dtype=torch.int32)
         n_keep = torch.empty(1, device=meg.device, dtype=torch.int32)
