@@ -176,11 +176,14 @@ class SubjectLayers(nn.Module):
 
 
 class ConvSequence(nn.Module):
-    """Residual dilated Conv1d + BatchNorm + GELU stack with GLU blocks (reference: bm/models/common.py:79-151).
+    """Dilated Conv1d (+ BatchNorm) + activation stack with residual skips and GLU blocks (reference:
+    bm/models/common.py:79-151).  Submodule names (`sequence.{k}.0/1`, `glus.{k}.0`) and construction order match the
+    reference, so `state_dict()` keys and seeded initialisation are interchangeable.
 
-    Only the `clip_conv` family is accelerated: stride 1, odd kernel <= 3, batch_norm, skip, GELU, GLU every
-    `glu` layers with context `glu_context`.  Submodule names (`sequence.{k}.0/1`, `glus.{k}.0`) match the
-    reference so that `state_dict()` keys are interchangeable."""
+    Two users: `SimpleConv` fuses the `clip_conv` family (batch_norm, skip, GELU, GLU) into its own forward/backward;
+    a stand-alone sequence (the `DeepMel` feature model) runs through `forward(x)` -> `convseq.conv_sequence`.
+    Accelerated: stride 1, odd kernel <= 3, GELU / LeakyReLU / ReLU, with or without BatchNorm, skip,
+    activation_on_last, GLU every `glu` layers with context <= 1.  Everything else raises NotImplementedError."""
 
     def __init__(self, channels: tp.Sequence[int], kernel: int = 4, dilation_growth: int = 1,
                  dilation_period: tp.Optional[int] = None, stride: int = 2, dropout: float = 0.0,
@@ -190,29 +193,41 @@ class ConvSequence(nn.Module):
                  glu_context: int = 0, glu_glu: bool = True, activation: tp.Any = None) -> None:
         super().__init__()
         unsupported = dict(stride=stride != 1, dropout=bool(dropout), groups=groups != 1, decode=decode,
-                           batch_norm=not batch_norm, dropout_input=bool(dropout_input), skip=not skip,
-                           scale=scale is not None, rewrite=rewrite, activation_on_last=not activation_on_last,
+                           dropout_input=bool(dropout_input), scale=scale is not None, rewrite=rewrite,
                            post_skip=post_skip, glu_glu=not glu_glu, kernel=kernel % 2 != 1 or kernel > 3,
-                           activation=activation is not nn.GELU, glu_context=bool(glu) and glu_context > 1)
+                           activation=activation not in (None, nn.GELU, nn.ReLU, nn.LeakyReLU),
+                           glu_context=bool(glu) and glu_context > 1)
         bad = [k for k, v in unsupported.items() if v]
         if bad:
-            raise NotImplementedError(f"ConvSequence options outside the accelerated clip_conv family: {bad} "
-                                      "(SURVEY 8(f) row 4)")
+            raise NotImplementedError(f"ConvSequence options without a CUDA implementation: {bad} (SURVEY 8(f) row 4)")
         channels = tuple(channels)
         self.skip = skip
         self.kernel = kernel
         self.glu_kernel = 1 + 2 * glu_context
+        self.batch_norm = batch_norm
+        # activation code / slope understood by the kernels: 0 = GELU, 1 = LeakyReLU(slope) (ReLU = slope 0)
+        self.act_code = 0 if activation is nn.GELU else 1
+        self.act_slope = 0.0 if activation is nn.ReLU else (0.01 if activation is nn.LeakyReLU else float(leakiness))
+        make_act = (lambda: nn.LeakyReLU(leakiness)) if activation is None else activation
+        self.clip_conv_family = batch_norm and skip and activation is nn.GELU and activation_on_last
         self.sequence = nn.ModuleList()
         self.glus = nn.ModuleList()
         self.dilations: tp.List[int] = []
+        self.has_act: tp.List[bool] = []
         dilation = 1
         for k, (chin, chout) in enumerate(zip(channels[:-1], channels[1:])):
             if dilation_period and (k % dilation_period) == 0:
                 dilation = 1
             self.dilations.append(dilation)
-            conv = nn.Conv1d(chin, chout, kernel, 1, (kernel // 2) * dilation, dilation=dilation)
+            layers: tp.List[nn.Module] = [nn.Conv1d(chin, chout, kernel, 1, (kernel // 2) * dilation, dilation=dilation)]
             dilation *= dilation_growth
-            self.sequence.append(nn.Sequential(conv, nn.BatchNorm1d(num_features=chout), nn.GELU()))
+            is_last = k == len(channels) - 2
+            self.has_act.append(activation_on_last or not is_last)
+            if self.has_act[-1]:
+                if batch_norm:
+                    layers.append(nn.BatchNorm1d(num_features=chout))
+                layers.append(make_act())
+            self.sequence.append(nn.Sequential(*layers))
             if glu and (k + 1) % glu == 0:
                 self.glus.append(nn.Sequential(
                     nn.Conv1d(chout, 2 * chout, self.glu_kernel, padding=glu_context), nn.GLU(dim=1)))
@@ -223,7 +238,8 @@ class ConvSequence(nn.Module):
         return [g is not None for g in self.glus]
 
     def forward(self, x):
-        raise RuntimeError("ConvSequence is fused into SimpleConv.forward in brainmagick_b200")
+        from . import convseq
+        return convseq.conv_sequence(self, x)
 
 
 def require_library():

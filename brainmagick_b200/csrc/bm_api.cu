@@ -10,6 +10,7 @@
 #include "tc_conv4.cuh"
 #include "retrieval.cuh"
 #include "prep.cuh"
+#include "convseq.cuh"
 
 namespace bm {
 thread_local char g_last_error[512] = "";
@@ -630,6 +631,69 @@ extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const
     g.B = cand; g.ldb_n = 1; g.ldb_k = KT; g.b_ncontig = 1;
     g.D = dest; g.ldd_m = KT; g.ldd_n = 1;
     BM_CUDA(launch_gemm(g, st));
+    return 0;
+}
+
+// =================================================================================================
+// Stand-alone ConvSequence epilogues + candidate-side ClipLoss gradient (DeepMel)
+// =================================================================================================
+extern "C" int bm_bn_act_skip_fwd(const float* y, const float* mean, const float* invstd, const float* gamma,
+                                  const float* beta, const float* x_old, float* x_new, long long rows, int C, int act,
+                                  float slope, bm_stream_t stream) {
+    BM_CHECK_ARG(y && x_new && rows > 0 && C > 0 && act >= 0 && act <= 2);
+    BM_CHECK_ARG(!mean || (invstd && gamma && beta));
+    bn_act_skip_fwd_kernel<<<ew_grid(rows * C), 256, 0, ST(stream)>>>(y, mean, invstd, gamma, beta, x_old, x_new,
+                                                                      rows * C, C, act, slope);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_bn_act_skip_bwd(const float* g, const float* y, const float* mean, const float* invstd,
+                                  const float* gamma, const float* beta, int batch_stats, long long rows, int C,
+                                  int act, float slope, double* sums, float* dy, float* dgamma, float* dbeta,
+                                  bm_stream_t stream) {
+    BM_CHECK_ARG(g && y && dy && rows > 0 && C > 0 && act >= 0 && act <= 2);
+    BM_CHECK_ARG(!mean || (invstd && gamma && beta && sums && dgamma && dbeta));
+    cudaStream_t st = ST(stream);
+    if (mean) {
+        BM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+        const int rpb = 128;
+        dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
+        bn_act_bwd_reduce_kernel<<<grid, 128, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, rows, C, rpb, act, slope);
+        BM_CHECK_LAUNCH();
+        bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, C);
+        BM_CHECK_LAUNCH();
+    }
+    bn_act_bwd_apply_kernel<<<ew_grid(rows * C), 256, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, (double)rows,
+                                                               batch_stats, dy, rows * C, C, act, slope);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int bm_clip_loss_bwd_cand(const float* probs, const float* scores, const float* inv_norm, const float* est,
+                                     const float* cand, const float* gout, int Bn, int Bc, long long KT,
+                                     int target_offset, float* G, float* coef, float* dcand, bm_stream_t stream) {
+    BM_CHECK_ARG(probs && scores && inv_norm && est && cand && gout && G && coef && dcand);
+    BM_CHECK_ARG(Bn > 0 && Bc > 0 && KT > 0 && KT < (1ll << 31));
+    cudaStream_t st = ST(stream);
+    clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 0);
+    BM_CHECK_LAUNCH();
+    // dcand[o][k] = sum_b G[b][o] est[b][k]: a weight-gradient GEMM whose "positions" are the estimates
+    if (g_clip_ws && tc::wgrad_tc_supported(Bc, (int)KT)) {
+        int rc = tc::launch_wgrad_tc(G, est, 1, Bn, Bc, (int)KT, (int)KT, 1, 1, g_clip_ws, dcand, g_clip_status, st);
+        if (rc) return rc;
+    } else {
+        GemmP g = gemm_defaults();
+        g.M = Bc; g.N = (int)KT; g.K = Bn; g.kchunk = Bn;
+        g.A = G; g.lda_m = 1; g.lda_k = Bc; g.a_mcontig = 1;
+        g.B = est; g.ldb_n = 1; g.ldb_k = KT; g.b_ncontig = 1;
+        g.D = dcand; g.ldd_m = KT; g.ldd_n = 1;
+        BM_CUDA(launch_gemm(g, st));
+    }
+    clip_cand_coef_kernel<<<(Bc + 127) / 128, 128, 0, st>>>(G, scores, inv_norm, Bn, Bc, coef);
+    BM_CHECK_LAUNCH();
+    clip_cand_correct_kernel<<<ew_grid((long long)Bc * KT), 256, 0, st>>>(cand, coef, KT, (long long)Bc * KT, dcand);
+    BM_CHECK_LAUNCH();
     return 0;
 }
 

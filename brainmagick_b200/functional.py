@@ -640,23 +640,33 @@ class _ClipLossFn(torch.autograd.Function):
         _register_clip_workspace(est, Bn, Bc)
         call("bm_clip_loss_fwd", ptr(est), ptr(cand), Bn, Bc, KT, int(target_offset), ptr(ss), ptr(inv),
              ptr(scores), ptr(probs), ptr(row_loss), ptr(loss), stream())
-        ctx.save_for_backward(probs, inv, cand)
-        ctx.meta = (Bn, Bc, KT, int(target_offset), est.shape)
+        if candidate.requires_grad:      # a trainable feature model produced the candidates (solver.py:304-320)
+            ctx.save_for_backward(probs, inv, cand, scores, est)
+        else:
+            ctx.save_for_backward(probs, inv, cand)
+        ctx.meta = (Bn, Bc, KT, int(target_offset), est.shape, cand.shape)
         return loss.reshape(())
 
     @staticmethod
     def backward(ctx, gout):
-        probs, inv, cand = ctx.saved_tensors
-        Bn, Bc, KT, off, shape = ctx.meta
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError("gradient w.r.t. candidates (feature_model) is a later row of SURVEY 8(f)")
-        G = _empty((Bn, Bc), probs)
-        dest = _empty(shape, probs)
+        probs, inv, cand = ctx.saved_tensors[:3]
+        Bn, Bc, KT, off, shape, cand_shape = ctx.meta
         gout = gout.reshape(1).contiguous().float()
         _register_clip_workspace(probs, Bn, Bc)
-        call("bm_clip_loss_bwd", ptr(probs), ptr(inv), ptr(cand), ptr(gout), Bn, Bc, KT, off, ptr(G), ptr(dest),
-             stream())
-        return dest, None, None
+        dest = dcand = None
+        if ctx.needs_input_grad[0]:
+            G = _empty((Bn, Bc), probs)
+            dest = _empty(shape, probs)
+            call("bm_clip_loss_bwd", ptr(probs), ptr(inv), ptr(cand), ptr(gout), Bn, Bc, KT, off, ptr(G), ptr(dest),
+                 stream())
+        if ctx.needs_input_grad[1]:
+            scores, est = ctx.saved_tensors[3:]
+            G = _empty((Bn, Bc), probs)
+            coef = _empty((Bc,), probs)
+            dcand = _empty(cand_shape, probs)
+            call("bm_clip_loss_bwd_cand", ptr(probs), ptr(scores), ptr(inv), ptr(est), ptr(cand), ptr(gout), Bn, Bc, KT,
+                 off, ptr(G), ptr(coef), ptr(dcand), stream())
+        return dest, dcand, None
 
 
 def clip_loss(estimate, candidate, target_offset: int = 0):

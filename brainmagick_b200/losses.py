@@ -81,6 +81,9 @@ class ClipLoss(torch.nn.Module):
     def forward(self, estimate, candidate, mask=None):
         assert mask.all(), "mask is not supported for now"
         assert estimate.size(0) <= candidate.size(0), "need at least as many targets as estimates"
+        if candidate.requires_grad and self.global_negatives and distrib.world_size() > 1:
+            raise NotImplementedError("global_negatives with trainable candidates needs the reduce-scatter of d_cand "
+                                      "(SURVEY 8(e)); train the feature model with local negatives")
         pre, self._prefetched = self._prefetched, None
         if pre is not None and pre.source is candidate:
             estimate, _ = self._prepare(estimate, candidate)

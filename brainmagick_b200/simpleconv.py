@@ -125,6 +125,9 @@ class SimpleConv(nn.Module):
             dropout_input=dropout_input, batch_norm=batch_norm, dilation_growth=dilation_growth, groups=groups,
             dilation_period=dilation_period, skip=skip, post_skip=post_skip, scale=scale, rewrite=rewrite, glu=glu,
             glu_context=glu_context, glu_glu=glu_glu, activation=nn.GELU)})
+        if not self.encoders["meg"].clip_conv_family:
+            raise NotImplementedError("SimpleConv fuses the clip_conv ConvSequence (batch_norm, skip, GELU); "
+                                      "see SURVEY.md 8(f) row 4")
         self._freq: tp.Optional[torch.Tensor] = None
         self.use_tensor_cores = True     # False forces the FP32-FMA kernels everywhere (debugging / A-B timing)
 

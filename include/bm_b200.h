@@ -161,6 +161,25 @@ int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long l
 int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* cand, const float* gout, int Bn,
                      int Bc, long long KT, int target_offset, float* G, float* dest, bm_stream_t stream);
 
+/* ---- Stand-alone ConvSequence / DeepMel: bm/models/common.py:79-151, bm/models/features.py:15-35 --
+ * Layer epilogue x_new = act(bn(y)) (+ x_old) over channels-last rows [rows, C] and its backward, for the cases the
+ * brain encoder's fused BatchNorm+GELU kernels do not cover: act 0 = GELU, 1 = LeakyReLU(slope) (common.py:95),
+ * 2 = none; mean == NULL = no BatchNorm (the layer then only applies the activation / the skip).
+ * bm_bn_act_skip_bwd: dy = d/dy of the above given g = dL/dx_new (the skip branch's gradient is g itself);
+ * batch_stats=1: training-mode BatchNorm (dgamma, dbeta, fp64 sums [2C] scratch), 0: eval statistics. */
+int bm_bn_act_skip_fwd(const float* y, const float* mean, const float* invstd, const float* gamma, const float* beta,
+                       const float* x_old, float* x_new, long long rows, int C, int act, float slope,
+                       bm_stream_t stream);
+int bm_bn_act_skip_bwd(const float* g, const float* y, const float* mean, const float* invstd, const float* gamma,
+                       const float* beta, int batch_stats, long long rows, int C, int act, float slope, double* sums,
+                       float* dy, float* dgamma, float* dbeta, bm_stream_t stream);
+/* Gradient of ClipLoss.forward w.r.t. the CANDIDATES (a trainable feature model, solver.py:304-320): with G as in
+ * bm_clip_loss_bwd, dcand[o] = sum_b G[b,o] est[b] - coef[o] cand[o], coef[o] = (sum_b G[b,o] scores[b,o]) / ||cand_o||
+ * (the derivative of the 1/(1e-8+||.||) normalisation, losses.py:91).  G [Bn,Bc], coef [Bc]: scratch. */
+int bm_clip_loss_bwd_cand(const float* probs, const float* scores, const float* inv_norm, const float* est,
+                          const float* cand, const float* gout, int Bn, int Bc, long long KT, int target_offset,
+                          float* G, float* coef, float* dcand, bm_stream_t stream);
+
 /* ---- Retrieval evaluation: scripts/run_eval_probs.py:237-307, bm/wer.py:80-116 ---------
  * The score matrix comes from bm_clip_scores (queries x candidates, candidate axis optionally zero-padded to the
  * tensor-core tile: ld >= n_cols); these entry points replace the host-side softmax / topk / scatter_add / label

@@ -201,6 +201,67 @@ def run_retrieval(name="retrieval_small"):
     print(f"{name}: acc@1/5/10={out['acc']} wer={res} window={window}")
 
 
+DEEPMEL_CASES = {
+    # conf/feature_model/deep_mel.yaml scaled down; "b" has a residual on its very first layer and GELU
+    "deepmel_small": dict(n_in=10, params=dict(n_hidden_channels=16, n_hidden_layers=4, n_out_channels=24, kernel=3,
+                                                stride=1, dilation_growth=2, dilation_period=5, batch_norm=True,
+                                                activation_on_last=False, skip=True, glu_context=1, glu=2),
+                          B=5, T=20, seed=31),
+    "deepmel_nobn": dict(n_in=12, params=dict(n_hidden_channels=12, n_hidden_layers=3, n_out_channels=12, kernel=3,
+                                               stride=1, dilation_growth=2, dilation_period=2, batch_norm=False,
+                                               activation_on_last=False, skip=True, glu_context=0, glu=3,
+                                               leakiness=0.1),
+                         B=4, T=17, seed=32),
+}
+
+
+def run_deepmel(name, c):
+    """Verbatim DeepMel (bm/models/features.py) -> candidates, verbatim ClipLoss against a random `estimate` that
+    requires grad; one training forward/backward (parameter, estimate AND candidate-side gradients), then an eval-mode
+    forward with the updated running statistics."""
+    import importlib.util
+    _, _, losses = ref_loader.load_reference()
+    spec = importlib.util.spec_from_file_location("bm.models.features", ref_loader.REF + "/models/features.py")
+    feats = importlib.util.module_from_spec(spec)
+    sys.modules["bm.models.features"] = feats
+    spec.loader.exec_module(feats)
+    torch.manual_seed(c["seed"])
+    model = feats.DeepMel(n_in_channels=c["n_in"], **c["params"])
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.add_(0.1 * torch.randn_like(m.weight))
+                m.bias.add_(0.1 * torch.randn_like(m.bias))
+                m.running_mean.add_(0.1 * torch.randn_like(m.running_mean))
+                m.running_var.mul_(1 + 0.2 * torch.rand_like(m.running_var))
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    B, T = c["B"], c["T"]
+    mel = torch.randn(B, c["n_in"], T)
+    n_out = c["params"]["n_out_channels"]
+    estimate = torch.randn(B, n_out, T, requires_grad=True)
+    clip = losses.ClipLoss()
+    model.train()
+    cand = model(mel)
+    cand.retain_grad()
+    loss = clip(estimate, cand, torch.ones(B, 1, T, dtype=torch.bool))
+    loss.backward()
+    out = dict(mel=mel.numpy(), estimate=estimate.detach().numpy(), candidates=cand.detach().numpy(),
+               loss=loss.detach().numpy(), **{"g.estimate": estimate.grad.numpy(), "g.candidates": cand.grad.numpy()})
+    for k, v in state.items():
+        out["p." + k] = v.numpy()
+    for k, v in model.named_parameters():
+        out["g." + k] = v.grad.numpy()
+    for k, v in model.state_dict().items():
+        if "running" in k or "num_batches" in k:
+            out["bn." + k] = v.numpy()
+    model.eval()
+    with torch.no_grad():
+        out["candidates_eval"] = model(mel).numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: loss={float(loss):.6f} cand.std={float(cand.std()):.4f} "
+          f"|d_cand|={float(cand.grad.norm()):.4e} size={os.path.getsize(os.path.join(OUT, name + '.npz')) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     wanted = sys.argv[1:]
@@ -211,3 +272,6 @@ if __name__ == "__main__":
         run_prep()
     if not wanted or "retrieval_small" in wanted:
         run_retrieval()
+    for name, c in DEEPMEL_CASES.items():
+        if not wanted or name in wanted:
+            run_deepmel(name, c)
