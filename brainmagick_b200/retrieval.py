@@ -127,11 +127,13 @@ def retrieval_accuracy(clip, preds: torch.Tensor, trues: torch.Tensor, target_la
                        bank: tp.Optional[CandidateBank] = None) -> tp.Dict[int, float]:
     """`_get_accuracy_from_probs(builds_probs(...), ...)` for several k at once (run_eval_probs.py:331-362) without
     materialising the probabilities: {k: accuracy}."""
-    assert len(target_labels) == len(preds) and len(vocab_labels) == len(trues)
+    assert len(target_labels) == len(preds)
     if tmin is not None or tmax is not None:
         lo, hi = _window(dset_args, tmin, tmax)
-        preds, trues = preds[..., lo:hi], trues[..., lo:hi]
-    bank = bank or CandidateBank(clip, trues)
+        preds = preds[..., lo:hi]
+        trues = None if trues is None else trues[..., lo:hi]
+    bank = bank or CandidateBank(clip, trues)          # `bank`: candidates already resident (cropped like `preds`)
+    assert len(vocab_labels) == bank.n
     dev = bank.rows.device
     labels = _i64(vocab_labels, dev)
     kmax = max(topk)
