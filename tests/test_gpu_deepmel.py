@@ -145,12 +145,22 @@ def test_clip_candidate_gradient(Bn, Bc, F, T):
     assert rel_err(c2.grad.cpu(), cr.grad) < TOL
 
 
-def test_deepmel_full_size_tensor_core_vs_fma():
+@pytest.mark.parametrize("activation", ["gelu", "lrelu"])
+def test_deepmel_full_size_tensor_core_vs_fma(activation):
     """conf/feature_model/deep_mel.yaml at its real widths (120 mel -> 9 x 320 -> 768, T=360): the tensor-core path
-    against the FP32-FMA path of the same library, forward and every gradient."""
+    against the FP32-FMA path of the same library, forward and every gradient.
+
+    With the smooth GELU the gradients agree to the usual tolerance.  The configuration's own LeakyReLU(0) has a
+    discontinuous derivative: a pre-activation within rounding distance of 0 takes derivative 0 on one path and 1 on the
+    other, and flipping a fraction f of the activations moves a gradient by ~sqrt(f) in relative Frobenius norm
+    (f ~ 1e-5 -> a few 1e-3).  The oracle shows the same sensitivity on the CPU: a 2e-5 relative perturbation of its
+    conv outputs moves the LeakyReLU(0) gradients by 1.8e-2 and the GELU gradients by 2e-4 (profiles/README.md).  So
+    with LeakyReLU the forward is held to the tolerance and the gradients to a bound only a real defect would exceed."""
     torch.manual_seed(8)
     kw = dict(n_hidden_channels=320, n_hidden_layers=10, n_out_channels=768, kernel=3, stride=1, dilation_growth=2,
               dilation_period=5, batch_norm=True, activation_on_last=False, skip=True, glu_context=1, glu=2)
+    if activation == "gelu":
+        kw["activation"] = torch.nn.GELU
     model = DeepMel(n_in_channels=120, **kw).to(DEV).train()
     B, T = 8, 360
     mel = torch.randn(B, 120, T, device=DEV)
@@ -169,9 +179,14 @@ def test_deepmel_full_size_tensor_core_vs_fma():
     (o_tc, g_tc, n_tc), (o_fma, g_fma, n_fma) = results
     assert rel_err(o_tc, o_fma) < TOL
     wscale = max(v.norm().item() for k, v in g_fma.items() if k.endswith("weight"))
+    worst, worst_name = 0.0, ""
     for name in g_fma:
         if g_fma[name].norm().item() < 1e-5 * wscale:
-            assert g_tc[name].abs().max().item() < 1e-4 * wscale + 1e-6, name
-        else:
-            assert rel_err(g_tc[name], g_fma[name]) < 5 * TOL, (name, rel_err(g_tc[name], g_fma[name]))
-    print(f"\n[deepmel] full size B={B}: {n_tc} launches (tensor cores) vs {n_fma} (fma)")
+            assert g_tc[name].abs().max().item() < 1e-3 * wscale + 1e-6, name
+            continue
+        err = rel_err(g_tc[name], g_fma[name])
+        if err > worst:
+            worst, worst_name = err, name
+    print(f"\n[deepmel] full size B={B} {activation}: forward {rel_err(o_tc, o_fma):.2e}, worst gradient {worst:.2e} "
+          f"({worst_name}); {n_tc} launches (tensor cores) vs {n_fma} (fma)")
+    assert worst < (5 * TOL if activation == "gelu" else 3e-2), (worst_name, worst)
