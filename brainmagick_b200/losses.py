@@ -6,7 +6,8 @@ Reference semantics kept on purpose: only the CANDIDATES are L2-normalised (loss
 the `linear` projection is constructed but never applied (losses.py:35,82), targets are the first B candidates.
 
 Extension (not in the reference): `global_negatives=True` all-gathers the candidates over the
-default process group before scoring, so every rank contrasts against the global batch.
+default process group before scoring, so every rank contrasts against the global batch; when the candidates require
+grad (a trainable feature model) the gather is differentiable (reduce-scatter of the candidate gradients).
 """
 from __future__ import annotations
 
@@ -74,17 +75,20 @@ class ClipLoss(torch.nn.Module):
         """Optional (multi-GPU, global_negatives): start the candidate all-gather now -- e.g. right after the batch reaches
         the device, before the encoder forward -- so that it overlaps compute.  `forward` picks it up when it is called
         with the same tensor; without this call the gather simply happens inside `forward`."""
-        if self.global_negatives and distrib.world_size() > 1 and not (self.pool or self.center) \
+        if self.global_negatives and distrib.world_size() > 1 and not candidate.requires_grad \
+                and not (self.pool or self.center) \
                 and self._window(candidate.shape[-1]) == (0, candidate.shape[-1]):
             self._prefetched = distrib.CandidateGather(candidate)
 
     def forward(self, estimate, candidate, mask=None):
         assert mask.all(), "mask is not supported for now"
         assert estimate.size(0) <= candidate.size(0), "need at least as many targets as estimates"
-        if candidate.requires_grad and self.global_negatives and distrib.world_size() > 1:
-            raise NotImplementedError("global_negatives with trainable candidates needs the reduce-scatter of d_cand "
-                                      "(SURVEY 8(e)); train the feature model with local negatives")
         pre, self._prefetched = self._prefetched, None
+        if candidate.requires_grad and torch.is_grad_enabled() and self.global_negatives and distrib.world_size() > 1:
+            # a trainable feature model made the candidates: differentiable gather (reduce-scatter of dC in backward)
+            estimate, candidate = self._prepare(estimate, candidate)
+            candidate, offset = distrib.all_gather_candidates_with_grad(candidate)
+            return BF.clip_loss(estimate, candidate, offset)
         if pre is not None and pre.source is candidate:
             estimate, _ = self._prepare(estimate, candidate)
             candidate, offset = pre.wait()

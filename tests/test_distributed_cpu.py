@@ -62,3 +62,47 @@ def test_multi_gpu_oracle_decomposes_into_per_rank_losses():
     ref = bm_oracle.clip_loss(est, cand)
     parts = [bm_oracle.clip_loss(est[r * 4:(r + 1) * 4], cand, target_offset=r * 4) for r in range(2)]
     assert abs(float(sum(parts) / 2) - float(ref)) < 1e-6
+
+
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from brainmagick_b200 import distrib
+        from oracle import bm_oracle
+        torch.manual_seed(7)                      # every rank builds the SAME global tensors and takes its shard
+        est = torch.randn(world * 3, 4, 6)
+        cand = torch.randn(world * 3, 4, 6)
+        mine = slice(rank * 3, rank * 3 + 3)
+        c = cand[mine].clone().requires_grad_(True)
+        e = est[mine].clone().requires_grad_(True)
+        gathered, off = distrib.all_gather_candidates_with_grad(c)
+        assert off == 3 * rank and gathered.requires_grad and torch.equal(gathered.detach(), cand)
+        loss = bm_oracle.clip_loss(e, gathered, target_offset=off)       # this rank's term of the global loss
+        loss.backward()
+        ret[rank] = (float(loss), c.grad.clone(), e.grad.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_with_grad_reduce_scatters_candidate_gradients():
+    """SURVEY 8(e) with trainable candidates: per-rank losses over all-gathered candidates; each rank's candidate gradient
+    must be the sum over ranks of its block == W x the gradient of the global (mean-over-ranks) loss, which the averaging
+    gradient all-reduce of the feature model's parameters then turns into the global gradient."""
+    from oracle import bm_oracle
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+        torch.manual_seed(7)
+        est = torch.randn(world * 3, 4, 6).requires_grad_(True)
+        cand = torch.randn(world * 3, 4, 6).requires_grad_(True)
+        parts = [bm_oracle.clip_loss(est[r * 3:(r + 1) * 3], cand, target_offset=r * 3) for r in range(world)]
+        total = sum(parts) / world
+        total.backward()
+        for r in range(world):
+            loss_r, dc_r, de_r = ret[r]
+            assert abs(loss_r - float(parts[r])) < 1e-6
+            assert torch.allclose(dc_r, world * cand.grad[r * 3:(r + 1) * 3], atol=1e-6)
+            assert torch.allclose(de_r, world * est.grad[r * 3:(r + 1) * 3], atol=1e-6)
