@@ -55,10 +55,15 @@ class SyntheticBatch:
         self.subject_index = subject_index
         self.features = features
         self.features_mask = features_mask
-        if recording_index is None and len(recordings):
-            recording_index = torch.tensor([r.recording_index for r in recordings], dtype=torch.long)
-        self.recording_index = recording_index
+        self._recording_index = recording_index
         self._recordings = list(recordings)
+
+    @property
+    def recording_index(self) -> tp.Optional[torch.Tensor]:
+        """int64 [B]; derived from the recordings on first use (the training step itself never reads it)."""
+        if self._recording_index is None and self._recordings:
+            self._recording_index = torch.tensor([r.recording_index for r in self._recordings], dtype=torch.long)
+        return self._recording_index
 
     def _rebuild(self, **fields):
         kw = {name: getattr(self, name) for name in self.TENSORS}

@@ -1,0 +1,38 @@
+"""Size-independent properties of the retrieval evaluation at the BASELINE feature size (F=1024, T=360: 368 640 values
+per candidate), where the CPU oracle would take minutes: a segment must retrieve itself, probabilities are a distribution,
+the selection is ordered.  (Batch preparation and DeepMel are checked at full size in their own files.)"""
+import pytest
+import torch
+
+from brainmagick_b200 import functional as BF
+from brainmagick_b200 import retrieval
+from brainmagick_b200.losses import ClipLoss
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_self_retrieval_at_baseline_feature_size():
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    M, N, F, T, k = 384, 256, 1024, 360, 10
+    trues = torch.randn(M, F, T, device=DEV, generator=gen)
+    preds = trues[:N]                                    # every query IS one of the candidates
+    labels = torch.arange(M, device=DEV, dtype=torch.int64) * 11 - 7
+    clip = ClipLoss().eval()
+    bank = retrieval.CandidateBank(clip, trues)
+    assert bank.n == M and bank.n_pad == 512
+    scores = bank.scores(clip, preds)
+    BF.check_tc_status()
+    r = retrieval._topk(scores, M, k, labels, labels[:N], want_soft=True)
+    # Cauchy-Schwarz: <c_b, c_o>/||c_o|| <= ||c_b||, with equality only for the segment itself
+    assert torch.equal(r["top_idx"][:, 0], torch.arange(N, device=DEV))
+    assert (r["hit"] == 0).all()
+    assert (r["top_prob"][:, 0] > 0.999).all()
+    assert (r["top_prob"][:, :-1] >= r["top_prob"][:, 1:]).all()
+    assert (r["top_prob"].sum(1) <= 1 + 1e-5).all()
+    assert (r["soft"] - r["top_prob"][:, 0]).abs().max().item() < 1e-6      # distinct labels: soft == p(own column)
+    # the diagonal score is the candidate's own norm
+    own = scores[torch.arange(N), torch.arange(N)]
+    assert torch.allclose(own, trues[:N].reshape(N, -1).norm(dim=1), rtol=1e-4)
+    acc = retrieval.retrieval_accuracy(clip, preds, None, labels[:N], labels, topk=(1, 5), batch_size=128, bank=bank)
+    assert acc == {1: 1.0, 5: 1.0}
