@@ -262,6 +262,61 @@ def run_deepmel(name, c):
           f"|d_cand|={float(cand.grad.norm()):.4e} size={os.path.getsize(os.path.join(OUT, name + '.npz')) / 1024:.0f} KiB")
 
 
+# The ablation table of the paper (grids/nmi/ablation_final.py:42-52), each as a change to the small clip_conv case
+ABLATION_BASE = dict(B=6, C=10, T=24, F=8, S=3, hidden=16, depth=4, MC=12, IL=12, P=32, seed=41)
+ABLATIONS = {
+    "ablation_reference": {},
+    "ablation_no_merger": dict(merger=False),
+    "ablation_no_initial_linear": dict(initial_linear=0),
+    "ablation_no_glu": dict(glu=0),
+    "ablation_relu": dict(gelu=False),
+    "ablation_no_skip": dict(skip=False),
+    "ablation_no_complex_out": dict(complex_out=False),
+    "ablation_no_subject_layers": dict(subject_layers=False),
+    "ablation_subject_embedding": dict(subject_layers=False, subject_dim=5),
+}
+
+
+def run_ablation(name, change):
+    """Verbatim SimpleConv with one constructor change, one training step with the verbatim ClipLoss."""
+    c = dict(ABLATION_BASE)
+    common, simpleconv, losses = ref_loader.load_reference()
+    torch.manual_seed(c["seed"])
+    kw = ref_loader.clip_conv_kwargs(hidden=c["hidden"], depth=c["depth"], merger_channels=c["MC"],
+                                     initial_linear=c["IL"], merger_pos_dim=c["P"])
+    kw.update(change)
+    model = simpleconv.SimpleConv(in_channels=dict(meg=c["C"]), out_channels=c["F"], n_subjects=c["S"], **kw)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.weight.add_(0.1 * torch.randn_like(m.weight))
+                m.bias.add_(0.1 * torch.randn_like(m.bias))
+    state = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    B, C, T, F, S = c["B"], c["C"], c["T"], c["F"], c["S"]
+    meg = torch.randn(B, C, T).clamp_(-20, 20)
+    cand = torch.randn(B, F, T)
+    subj = torch.randint(0, S, (B,))
+    recs = [ref_loader.FakeRecording(s, C, C, seed=c["seed"]) for s in range(S)]
+    batch = ref_loader.FakeBatch(meg, subj, [recs[int(s)] for s in subj])
+    getter = common.PositionGetter()
+    pos = torch.stack([getter.get_recording_layout(r).clone() for r in recs])
+    model.train()
+    torch.manual_seed(9100 + c["seed"])
+    ban = torch.rand(2)
+    torch.manual_seed(9100 + c["seed"])
+    est = model(dict(meg=meg.clone()), batch)
+    loss = losses.ClipLoss()(est, cand, torch.ones(B, 1, T, dtype=torch.bool))
+    loss.backward()
+    out = dict(meg=meg.numpy(), candidates=cand.numpy(), subject_index=subj.numpy(), rec_positions=pos.numpy(),
+               ban_centre=ban.numpy(), estimate=est.detach().numpy(), loss=loss.detach().numpy())
+    for k, v in state.items():
+        out["p." + k] = v.numpy()
+    for k, v in model.named_parameters():
+        out["g." + k] = v.grad.numpy() if v.grad is not None else np.zeros(0, np.float32)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"{name}: loss={loss.item():.6f} est.std={est.std().item():.4f} params={sum(v.numel() for v in state.values())}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     wanted = sys.argv[1:]
@@ -275,3 +330,6 @@ if __name__ == "__main__":
     for name, c in DEEPMEL_CASES.items():
         if not wanted or name in wanted:
             run_deepmel(name, c)
+    for name, change in ABLATIONS.items():
+        if not wanted or name in wanted:
+            run_ablation(name, change)
