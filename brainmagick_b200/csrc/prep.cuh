@@ -30,7 +30,11 @@ __global__ void scale_clamp_crop_kernel(const float* __restrict__ x, const int* 
     for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows; row += warps) {
         const int b = (int)(row / C), c = (int)(row - (long long)b * C);
         const int s = slot ? slot[b] : 0;
-        const float ctr = center[(long long)s * C + c], scl = scale[(long long)s * C + c];
+        // a recording the scaler was never fitted on (the reference raises KeyError, norm.py:256): poison the sample with
+        // NaN instead of reading outside the table; Solver._process_batch asserts finiteness right after (solver.py:256)
+        const bool known = s >= 0;
+        const float ctr = known ? center[(long long)s * C + c] : __int_as_float(0x7fc00000);
+        const float scl = known ? scale[(long long)s * C + c] : 1.f;
         const float* xr = x + row * T;
         float* yr = y + row * T_out - t0;
         float peak = 0.f;
@@ -46,7 +50,7 @@ __global__ void scale_clamp_crop_kernel(const float* __restrict__ x, const int* 
             for (int i = 0; i < PREP_ILP; ++i) {
                 const int t = base + i * 32 + lane;
                 float w = inverse ? __fadd_rn(__fmul_rn(v[i], scl), ctr) : __fdiv_rn(__fsub_rn(v[i], ctr), scl);
-                if (clip) w = fminf(fmaxf(w, -limit), limit);
+                if (clip) w = w < -limit ? -limit : (w > limit ? limit : w);     // NaN stays NaN, like Tensor.clamp_
                 if (t < t_hi) {
                     peak = fmaxf(peak, fabsf(w));
                     if (t >= t0 && t < t0 + T_out) yr[t] = w;

@@ -196,7 +196,12 @@ class BatchScaler:
         return out
 
     def slots(self, recording_index: torch.Tensor, slot_of: torch.Tensor) -> torch.Tensor:
-        return slot_of[recording_index.to(slot_of.device).long()].contiguous()
+        """Table row of each sample; -1 for a recording the scaler was not fitted on (the kernel then poisons the sample
+        with NaN -- the reference raises KeyError there -- without a device-to-host check in the per-batch path)."""
+        idx = recording_index.to(slot_of.device).long()
+        inside = (idx >= 0) & (idx < len(slot_of))
+        rows = slot_of[idx.clamp(0, len(slot_of) - 1)]
+        return torch.where(inside, rows, torch.full_like(rows, -1)).contiguous()
 
     # -- per batch --------------------------------------------------------------------------------------------
     def _apply(self, batch, inverse: bool, limit=0.0, clip=False, t0=0, crop=0, want_peak=False):

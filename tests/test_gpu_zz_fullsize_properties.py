@@ -36,3 +36,39 @@ def test_self_retrieval_at_baseline_feature_size():
     assert torch.allclose(own, trues[:N].reshape(N, -1).norm(dim=1), rtol=1e-4)
     acc = retrieval.retrieval_accuracy(clip, preds, None, labels[:N], labels, topk=(1, 5), batch_size=128, bank=bank)
     assert acc == {1: 1.0, 5: 1.0}
+
+
+def test_prep_nan_and_unknown_recording_semantics():
+    """Tensor.clamp_ propagates NaN (norm.py:333) and a recording without a fitted scaler is an error in the reference
+    (KeyError, norm.py:256): here such a sample comes out all-NaN, which Solver._process_batch's finiteness assert catches."""
+    import types
+    from brainmagick_b200 import norm as bnorm, synthetic
+
+    class Builder(dict):
+        dimension = 2
+
+        def __init__(self):
+            super().__init__(f=types.SimpleNamespace(normalizable=False, categorical=False, cardinality=0))
+
+        def get_slice(self, name):
+            return slice(0, 2)
+
+    sc = bnorm.BatchScaler(Builder())
+    for r in (4, 9):
+        s = bnorm.Scaler()
+        s.center_, s.scale_ = torch.full((3,), 0.5), torch.full((3,), 2.0)
+        sc.meg_scalers[r] = s
+    meg = torch.randn(3, 3, 40, device=DEV)
+    meg[0, 1, 7] = float("nan")
+    batch = synthetic.SyntheticBatch(meg, torch.zeros(3, dtype=torch.long, device=DEV), [],
+                                     features=torch.randn(3, 2, 40, device=DEV),
+                                     features_mask=torch.ones(3, 1, 40, dtype=torch.bool, device=DEV),
+                                     recording_index=torch.tensor([4, 9, 5], device=DEV))
+    out, feats, mask, keep = bnorm.ScaleReject(sc, limit=20.0, clip=True).prepare(batch, 4)
+    assert keep.all() and out.shape == (3, 3, 36)
+    assert torch.isnan(out[0, 1, 3]) and torch.isnan(out[0]).sum() == 1
+    assert torch.isfinite(out[1]).all()
+    assert torch.isnan(out[2]).all()                               # recording 5 was never fitted
+    want = ((meg[1] - 0.5) / 2.0).clamp(-20, 20)[:, 4:]
+    assert torch.equal(out[1], want)
+    assert torch.equal(feats, batch.features[..., :-4])

@@ -164,3 +164,14 @@ def test_retrieval_vocabulary_bookkeeping():
     assert vocab.tolist() == [10, 20, 30]
     assert order.tolist() == [1, 4, 3, 0, 2, 5] and seg.tolist() == [0, 2, 3, 6]
     assert own.tolist() == [0, 3, 2, 3]                  # 99 and 5 occur nowhere among the shared negatives -> slot V
+
+
+def test_batch_scaler_slots_for_unknown_recordings():
+    sc = bnorm.BatchScaler(_Builder())
+    for r in (4, 9):
+        s = bnorm.Scaler()
+        s.center_, s.scale_ = torch.zeros(6), torch.ones(6)
+        sc.meg_scalers[r] = s
+    _, _, slot_of, _, _ = sc.tables("cpu", 6)
+    got = sc.slots(torch.tensor([9, 4, 5, 77, -3]), slot_of)
+    assert got.tolist() == [1, 0, -1, -1, -1] and got.dtype == torch.int32
