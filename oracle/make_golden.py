@@ -94,7 +94,7 @@ def run_case(name, c):
             out["bn." + k] = v.numpy()
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
-    print(f"{name}: loss={float(loss):.6f} est.std={float(est.std()):.4f} "
+    print(f"{name}: loss={loss.item():.6f} est.std={est.std().item():.4f} "
           f"size={os.path.getsize(os.path.join(OUT, name + '.npz')) / 1024:.0f} KiB")
 
 
