@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- loads the *verbatim* brainmagick hot-path modules from /root/reference.
 
 Used by `oracle/make_golden.py` (fixture generation) and by `tests/test_oracle_vs_reference.py`
-(which skips when /root/reference is absent, i.e. on the GPU box).  Nothing in the product package
+(which skips when /root/reference is absent, i.e. on the GPU box).  `load_reference_norm()` adds the verbatim
+`bm/norm.py`; `bm/models/features.py` (DeepMel) is loaded by the generator the same way.  Nothing in the product package
 (`brainmagick_b200/`) imports this file.
 
 The three hot-path files import cleanly once two stub modules exist:
