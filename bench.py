@@ -385,7 +385,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="batch per GPU (256 = BASELINE.json configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--next-rows", action="store_true",
+                    help="instead of the headline step: the SURVEY 8(f) rows (batch preparation, retrieval evaluation, "
+                         "DeepMel), each beside a bounded CPU sample of its oracle; one GPU")
     args = ap.parse_args()
+    if args.next_rows:
+        from profiles import bench_next_rows      # its CPU legs are this file's cpu_baseline leg for those rows
+        bench_next_rows.main()
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

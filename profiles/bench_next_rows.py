@@ -1,8 +1,8 @@
 """Micro-benchmarks of the SURVEY 8(f) rows built after the training step (batch preparation, retrieval evaluation,
 DeepMel feature model), each beside a bounded CPU sample of its oracle.  Not the headline metric (that is bench.py);
-run on one B200:
+run on one B200 as a leg of bench.py (the oracle imports below are that leg's `cpu_baseline`):
 
-    python profiles/bench_next_rows.py            # writes gpurun_out/next_rows.json and prints it
+    python bench.py --next-rows                   # writes gpurun_out/next_rows.json and prints it
 
 Timing: CUDA events on the launching stream after warm-up; inputs larger than L2 (or flushed by the working set).
 """
