@@ -41,6 +41,7 @@ class EncoderPlan:
     bn_buffers: tp.List[tp.Tuple[torch.Tensor, torch.Tensor]]   # (running_mean, running_var) per layer
     keep_for_backward: bool = True
     use_tensor_cores: bool = True
+    skip: bool = True                      # ConvSequence(skip=...): residual where a layer keeps its width (common.py:146-147)
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -325,7 +326,7 @@ class _EncoderFn(torch.autograd.Function):
             else:
                 conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, None, status)
                 call("bm_bn_eval_stats", ptr(rm), ptr(rv), float(plan.bn_eps), ptr(mean), ptr(invstd), cout, st)
-            skip = conv.cin_true == cout
+            skip = plan.skip and conv.cin_true == cout
             x_new = _empty((B, T, cout), meg)
             call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
                  ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, st)

@@ -6,8 +6,9 @@ semantics (BatchNorm running statistics, one spatial-dropout centre per training
 hand-written sm_100a CUDA through the C ABI (`functional.encoder_forward`); there is no PyTorch/CPU fallback.
 
 Accelerated configuration = the `clip_conv` family of conf/model/clip_conv.yaml (merger + initial_linear +
-subject_layers + ConvSequence(batch_norm, skip, gelu, glu) + complex_out).  Options outside that family are
-accepted by the signature but raise NotImplementedError.
+subject_layers + ConvSequence(batch_norm, gelu) + complex_out), with or without `skip` and with any `glu` period
+(two of the paper's ablations, grids/nmi/ablation_final.py:45,48).  Options outside that family are accepted by the
+signature but raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -126,7 +127,7 @@ class SimpleConv(nn.Module):
             dilation_period=dilation_period, skip=skip, post_skip=post_skip, scale=scale, rewrite=rewrite, glu=glu,
             glu_context=glu_context, glu_glu=glu_glu, activation=nn.GELU)})
         if not self.encoders["meg"].clip_conv_family:
-            raise NotImplementedError("SimpleConv fuses the clip_conv ConvSequence (batch_norm, skip, GELU); "
+            raise NotImplementedError("SimpleConv fuses the clip_conv ConvSequence (batch_norm, GELU); "
                                       "see SURVEY.md 8(f) row 4")
         self._freq: tp.Optional[torch.Tensor] = None
         self.use_tensor_cores = True     # False forces the FP32-FMA kernels everywhere (debugging / A-B timing)
@@ -161,7 +162,7 @@ class SimpleConv(nn.Module):
             subject=batch.subject_index.to(device=device, dtype=torch.int32).contiguous(),
             freq=self._freq, ban_centre=self.merger.draw_ban_centre(device), ban_radius=float(self.merger.dropout),
             bn_buffers=bn_buffers, keep_for_backward=torch.is_grad_enabled(),
-            use_tensor_cores=self.use_tensor_cores)
+            use_tensor_cores=self.use_tensor_cores, skip=seq.skip)
 
     def forward(self, inputs, batch):
         meg = inputs["meg"]
