@@ -173,7 +173,7 @@ class BatchScaler:
 
     # -- device tables --------------------------------------------------------------------------------------
     def tables(self, device, n_channels: int):
-        """(center [R, C], scale [R, C], slot_of [max recording_index + 1] int32, feat_center [1, F], feat_scale [1, F])."""
+        """(center [R, C], scale [R, C], slot_of [max recording_index + 3] int32 (see `slots`), feat_center [1, F], feat_scale [1, F])."""
         key = (str(device), n_channels, len(self.meg_scalers))
         hit = self._tables.get(key)
         if hit is not None:
@@ -183,8 +183,9 @@ class BatchScaler:
         center = torch.stack([self.meg_scalers[i].center_.float() for i in ids])
         scale = torch.stack([self.meg_scalers[i].scale_.float() for i in ids])
         assert center.shape[1] == n_channels, f"scalers were fitted on {center.shape[1]} channels, got {n_channels}"
-        slot_of = torch.full((max(ids) + 1,), -1, dtype=torch.int32)
-        slot_of[torch.tensor(ids)] = torch.arange(len(ids), dtype=torch.int32)
+        # slot_of[1 + recording_index]; one sentinel (-1) entry at each end absorbs every out-of-range index after a clamp
+        slot_of = torch.full((max(ids) + 3,), -1, dtype=torch.int32)
+        slot_of[torch.tensor(ids) + 1] = torch.arange(len(ids), dtype=torch.int32)
         dim = self.features_builder.dimension
         fc, fs = torch.zeros(1, dim), torch.ones(1, dim)
         for name, fscaler in self.feature_scalers.items():
@@ -199,9 +200,7 @@ class BatchScaler:
         """Table row of each sample; -1 for a recording the scaler was not fitted on (the kernel then poisons the sample
         with NaN -- the reference raises KeyError there -- without a device-to-host check in the per-batch path)."""
         idx = recording_index.to(slot_of.device).long()
-        inside = (idx >= 0) & (idx < len(slot_of))
-        rows = slot_of[idx.clamp(0, len(slot_of) - 1)]
-        return torch.where(inside, rows, torch.full_like(rows, -1)).contiguous()
+        return slot_of[(idx + 1).clamp_(0, len(slot_of) - 1)].contiguous()
 
     # -- per batch --------------------------------------------------------------------------------------------
     def _apply(self, batch, inverse: bool, limit=0.0, clip=False, t0=0, crop=0, want_peak=False):

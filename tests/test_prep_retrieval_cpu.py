@@ -100,8 +100,8 @@ def test_batch_scaler_tables_and_slots():
     sc.feature_scalers["a"].center_ = torch.tensor(float(g["pc0.feat_center"][0]))
     sc.feature_scalers["a"].scale_ = torch.tensor(float(g["pc0.feat_scale"][0]))
     center, scale, slot_of, fc, fs = sc.tables("cpu", 6)
-    assert center.shape == (3, 6) and slot_of.tolist()[4] == 0 and slot_of.tolist()[9] == 1 and slot_of.tolist()[11] == 2
-    assert slot_of.tolist()[0] == -1
+    assert center.shape == (3, 6) and slot_of.tolist()[5] == 0 and slot_of.tolist()[10] == 1 and slot_of.tolist()[12] == 2
+    assert slot_of.tolist()[0] == -1 and slot_of.tolist()[-1] == -1 and len(slot_of) == 14
     slots = sc.slots(torch.from_numpy(g["recording_index"]), slot_of)
     assert slots.tolist() == [0, 2, 1, 1, 0, 2, 0]
     assert np.array_equal(fc.numpy()[0], g["pc0.feat_center"]) and np.array_equal(fs.numpy()[0], g["pc0.feat_scale"])
