@@ -42,6 +42,8 @@ class EncoderPlan:
     keep_for_backward: bool = True
     use_tensor_cores: bool = True
     skip: bool = True                      # ConvSequence(skip=...): residual where a layer keeps its width (common.py:146-147)
+    act_code: int = 0                      # 0 = GELU (clip_conv); 1 = LeakyReLU(act_slope), i.e. simpleconv.gelu=False
+    act_slope: float = 0.0
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -328,8 +330,13 @@ class _EncoderFn(torch.autograd.Function):
                 call("bm_bn_eval_stats", ptr(rm), ptr(rv), float(plan.bn_eps), ptr(mean), ptr(invstd), cout, st)
             skip = plan.skip and conv.cin_true == cout
             x_new = _empty((B, T, cout), meg)
-            call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
-                 ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, st)
+            if plan.act_code == 0:
+                call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
+                     ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, st)
+            else:
+                call("bm_bn_act_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
+                     ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, plan.act_code,
+                     float(plan.act_slope), st)
             rec = dict(x_in=x, y=y, mean=mean, invstd=invstd, conv=conv, skip=skip, x_new=x_new)
             x = x_new
             if plan.glu_after[k]:
@@ -353,7 +360,19 @@ class _EncoderFn(torch.autograd.Function):
         est = _empty((B, F, T), meg)
         w0_2 = w0.reshape(H2, H).contiguous()
         w2_2 = w2.reshape(H2, F).contiguous()
-        if head_tc:
+        head_generic = plan.act_code != 0
+        if head_generic:
+            # simpleconv.gelu=False (simpleconv.py:85-90,187): conv -> activation kernel -> conv, channels-last, then one
+            # transpose to the channel-major estimate (the fused GELU epilogues below do not apply)
+            head_tc = False
+            head0.forward(x, b0.contiguous(), B, T, 1, h1, None, status)
+            call("bm_bn_act_skip_fwd", ptr(h1), None, None, None, None, None, ptr(q), rows, H2, plan.act_code,
+                 float(plan.act_slope), st)
+            est_cl = _empty((B, T, F), meg)
+            head2.forward(q, b2.contiguous(), B, T, 1, est_cl, None, status)
+            call("bm_transpose_nt", ptr(est_cl), B, T, F, ptr(est), st)
+            del est_cl
+        elif head_tc:
             call(head0.fwd_fn, ptr(x), ptr(head0.f_hi), ptr(head0.f_lo), ptr(b0.contiguous()), None, B, T, H, H2, 1,
                  1, 1, 0, 1, 0, ptr(q), ptr(h1), None, ptr(status), st)
             call(head2.fwd_fn, ptr(q), ptr(head2.f_hi), ptr(head2.f_lo), ptr(b2.contiguous()), None, B, T, H2, F, 1,
@@ -369,7 +388,7 @@ class _EncoderFn(torch.autograd.Function):
             ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(), il_conv=il_conv,
                              subj_pad=subj_pad, megT=megT, heads_tc=heads_conv is not None,
                              layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q,
-                             head0=head0, head2=head2, head_tc=head_tc,
+                             head0=head0, head2=head2, head_tc=head_tc, head_generic=head_generic,
                              conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape, w0_shape=w0.shape, w2_shape=w2.shape)
         return est
 
@@ -394,7 +413,20 @@ class _EncoderFn(torch.autograd.Function):
         dw2 = _empty((H2, F), meg)
         db2 = _empty((F,), meg)
         dq = _empty((B, T, H2), meg)
-        if s["head_tc"]:
+        if s["head_generic"]:
+            head0, head2 = s["head0"], s["head2"]
+            dest_t = _empty((B, T, F), meg)
+            call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
+            head2.backward_data(dest_t, None, B, T, 1, dq, status)                 # dq = dest_t @ w2^T
+            dw2c, db2 = head2.backward_weight(dest_t, s["q"], B, T, 1, meg, status)    # [F, 2H, 1]
+            dw2 = dw2c.permute(1, 0, 2).reshape(H2, F).contiguous()
+            dh1 = _empty((B, T, H2), meg)
+            call("bm_bn_act_skip_bwd", ptr(dq), ptr(s["h1"]), None, None, None, None, 0, rows, H2, plan.act_code,
+                 float(plan.act_slope), None, ptr(dh1), None, None, st)
+            dw0, db0 = head0.backward_weight(dh1, s["x_last"], B, T, 1, meg, status)   # [2H, H, 1]
+            head0.backward_data(dh1, None, B, T, 1, g, status)
+            del dest_t, dh1
+        elif s["head_tc"]:
             head0, head2 = s["head0"], s["head2"]
             dest_t = _empty((B, T, F), meg)
             call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
@@ -472,9 +504,14 @@ class _EncoderFn(torch.autograd.Function):
             dy = _empty((B, T, cout), meg)
             dgamma = _empty((cout,), meg)
             dbeta = _empty((cout,), meg)
-            call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
-                 ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
-                 ptr(dy), ptr(dgamma), ptr(dbeta), st)
+            if plan.act_code == 0:
+                call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
+                     ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
+                     ptr(dy), ptr(dgamma), ptr(dbeta), st)
+            else:
+                call("bm_bn_act_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
+                     ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout,
+                     plan.act_code, float(plan.act_slope), ptr(sums), ptr(dy), ptr(dgamma), ptr(dbeta), st)
             dcw, dcb = weight_grad(conv, dy, rec["x_in"], plan.dilations[k], plan.training)
             if rec["skip"]:
                 # in place: g += conv_transpose(dy) (addend == output: the pair kernel turns this into a TMA reduce-add)

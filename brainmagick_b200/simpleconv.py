@@ -6,8 +6,8 @@ semantics (BatchNorm running statistics, one spatial-dropout centre per training
 hand-written sm_100a CUDA through the C ABI (`functional.encoder_forward`); there is no PyTorch/CPU fallback.
 
 Accelerated configuration = the `clip_conv` family of conf/model/clip_conv.yaml (merger + initial_linear +
-subject_layers + ConvSequence(batch_norm, gelu) + complex_out), with or without `skip` and with any `glu` period
-(two of the paper's ablations, grids/nmi/ablation_final.py:45,48).  Options outside that family are accepted by the
+subject_layers + ConvSequence(batch_norm) + complex_out), with or without `skip`, with any `glu` period and with
+GELU or (Leaky)ReLU (three of the paper's ablations, grids/nmi/ablation_final.py:45,47,48).  Options outside that family are accepted by the
 signature but raise NotImplementedError.
 """
 from __future__ import annotations
@@ -84,7 +84,7 @@ class SimpleConv(nn.Module):
         assert kernel_size % 2 == 1, "For padding to work, this must be verified"
         off_path = dict(
             concatenate=concatenate, linear_out=linear_out, complex_out=not complex_out, growth=growth != 1.,
-            dual_path=bool(dual_path), gelu=not gelu, subject_dim=bool(subject_dim),
+            dual_path=bool(dual_path), subject_dim=bool(subject_dim),
             subject_layers=not subject_layers, n_fft=n_fft is not None, merger=not merger, dropout=dropout > 0.,
             initial_linear=not initial_linear, initial_depth=initial_depth != 1, initial_nonlin=initial_nonlin,
             subsample_meg_channels=bool(subsample_meg_channels), inputs=set(in_channels) != {"meg"})
@@ -115,19 +115,26 @@ class SimpleConv(nn.Module):
         self.subject_layers = SubjectLayers(meg_dim, dim, n_subjects, subject_layers_id)
         in_channels["meg"] = dim
 
+        # simpleconv.py:85-90: GELU, else LeakyReLU(relu_leakiness), else ReLU -- in the ConvSequence and in the head
+        if gelu:
+            activation, make_act = nn.GELU, nn.GELU
+        elif relu_leakiness:
+            activation, make_act = None, (lambda: nn.LeakyReLU(relu_leakiness))    # ConvSequence builds the same module
+        else:
+            activation, make_act = nn.ReLU, nn.ReLU
         sizes = [in_channels["meg"]] + [int(round(hidden["meg"] * growth ** k)) for k in range(depth)]
         final_channels = sizes[-1]
         self.final = nn.Sequential(
             nn.Conv1d(final_channels, 2 * final_channels, 1),
-            nn.GELU(),
+            make_act(),
             nn.ConvTranspose1d(2 * final_channels, out_channels, 1, 1, 0))
         self.encoders = nn.ModuleDict({"meg": ConvSequence(
             sizes, kernel=kernel_size, stride=1, leakiness=relu_leakiness, dropout=conv_dropout,
             dropout_input=dropout_input, batch_norm=batch_norm, dilation_growth=dilation_growth, groups=groups,
             dilation_period=dilation_period, skip=skip, post_skip=post_skip, scale=scale, rewrite=rewrite, glu=glu,
-            glu_context=glu_context, glu_glu=glu_glu, activation=nn.GELU)})
+            glu_context=glu_context, glu_glu=glu_glu, activation=activation)})
         if not self.encoders["meg"].clip_conv_family:
-            raise NotImplementedError("SimpleConv fuses the clip_conv ConvSequence (batch_norm, GELU); "
+            raise NotImplementedError("SimpleConv fuses the clip_conv ConvSequence (batch_norm on every layer); "
                                       "see SURVEY.md 8(f) row 4")
         self._freq: tp.Optional[torch.Tensor] = None
         self.use_tensor_cores = True     # False forces the FP32-FMA kernels everywhere (debugging / A-B timing)
@@ -162,7 +169,7 @@ class SimpleConv(nn.Module):
             subject=batch.subject_index.to(device=device, dtype=torch.int32).contiguous(),
             freq=self._freq, ban_centre=self.merger.draw_ban_centre(device), ban_radius=float(self.merger.dropout),
             bn_buffers=bn_buffers, keep_for_backward=torch.is_grad_enabled(),
-            use_tensor_cores=self.use_tensor_cores, skip=seq.skip)
+            use_tensor_cores=self.use_tensor_cores, skip=seq.skip, act_code=seq.act_code, act_slope=seq.act_slope)
 
     def forward(self, inputs, batch):
         meg = inputs["meg"]

@@ -113,9 +113,9 @@ def test_ablation_reference_configuration():
     _ablation_step("ablation_reference")
 
 
-@pytest.mark.parametrize("name", ["ablation_no_glu", "ablation_no_skip"])
-@pytest.mark.xfail(strict=False, reason="SimpleConv(glu=0) / SimpleConv(skip=False) go through the same fused encoder and "
-                                        "kernels as the reference row, but this path has not had its first GPU run yet")
-def test_ablation_rows_the_fused_encoder_already_covers(name):
-    """grids/nmi/ablation_final.py:45,48 -- `simpleconv.glu=0` and `simpleconv.skip=False`."""
+@pytest.mark.parametrize("name", ["ablation_no_glu", "ablation_no_skip", "ablation_relu"])
+@pytest.mark.xfail(strict=False, reason="SimpleConv(glu=0 | skip=False | gelu=False) go through the fused encoder with kernels "
+                                        "that are each verified elsewhere, but these paths have not had their first GPU run yet")
+def test_ablation_rows_the_fused_encoder_covers(name):
+    """grids/nmi/ablation_final.py:45,47,48 -- `simpleconv.glu=0`, `simpleconv.gelu=False`, `simpleconv.skip=False`."""
     _ablation_step(name)
