@@ -21,6 +21,11 @@ from . import functional as BF
 from .common import ChannelMerger, ConvSequence, SubjectLayers, require_library
 
 
+def _require_cuda(meg: torch.Tensor) -> None:
+    if not meg.is_cuda:
+        raise RuntimeError("brainmagick_b200.SimpleConv runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+
 class SimpleConv(nn.Module):
     def __init__(self,
                  # Channels
@@ -173,8 +178,7 @@ class SimpleConv(nn.Module):
 
     def forward(self, inputs, batch):
         meg = inputs["meg"]
-        if not meg.is_cuda:
-            raise RuntimeError("brainmagick_b200.SimpleConv runs on CUDA (sm_100a) only; there is no CPU fallback")
+        _require_cuda(meg)
         if meg.dtype != torch.float32:
             raise TypeError("brainmagick_b200.SimpleConv computes in fp32, like the reference")
         assert meg.shape[1] == self.n_input_channels, "number of MEG channels differs from in_channels['meg']"

@@ -1,0 +1,48 @@
+"""The kernel-call stream of the GPU-verified configurations is pinned (tests/abi_trace.py, tests/golden/abi_trace.json):
+host-side refactors made without a GPU must not change which kernels run, in which order, with which shapes."""
+import json
+
+import pytest
+
+import abi_trace
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with open(abi_trace.GOLDEN) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("tag", list(abi_trace.CONFIGS))
+@pytest.mark.parametrize("train", [True, False])
+def test_verified_configurations_issue_the_pinned_calls(golden, tag, train):
+    key = f"{tag}.{'train' if train else 'eval'}"
+    got = abi_trace.simpleconv_step(abi_trace.CONFIGS[tag], train)
+    want = golden[key]
+    assert len(got) == len(want), (key, len(got), len(want))
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, (key, i, a, b)
+
+
+def test_full_size_step_runs_on_tensor_cores_only():
+    """At the BASELINE widths no FP32-FMA contraction is left in the step."""
+    names = {c[0] for c in abi_trace.simpleconv_step(abi_trace.CONFIGS["full"], True)}
+    assert not names & {"bm_conv1d_fwd", "bm_conv1d_bwd_data", "bm_conv1d_bwd_weight", "bm_conv1d_glu_fwd", "bm_head_fwd",
+                        "bm_head_bwd", "bm_sensor_chain_fwd", "bm_sensor_chain_bwd", "bm_attention_weights_fwd"}
+    assert {"bm_tc_conv1d_pair", "bm_tc_wgrad", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
+
+
+@pytest.mark.parametrize("override", [dict(glu=0), dict(skip=False), dict(gelu=False)])
+def test_ablation_rows_run_through_the_host_path(override):
+    """The ablation rows SimpleConv accepts: the host path completes and differs from the default where it should."""
+    base = abi_trace.simpleconv_step(abi_trace.CONFIGS["small"], True)
+    got = abi_trace.simpleconv_step(abi_trace.CONFIGS["small"], True, **override)
+    names = [c[0] for c in got]
+    if "glu" in override:
+        assert not any("glu" in n for n in names) and len(got) < len(base)
+    if "skip" in override:
+        fwd = [c for c in got if c[0] == "bm_bn_gelu_skip_fwd"]
+        assert fwd and all(c[6] is False for c in fwd)               # x_old == NULL on every layer
+    if "gelu" in override:
+        assert "bm_bn_gelu_skip_fwd" not in names and "bm_head_fwd" not in names
+        assert names.count("bm_bn_act_skip_fwd") == 11                # 10 layers + the head's activation
