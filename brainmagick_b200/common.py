@@ -209,9 +209,9 @@ class ConvSequence(nn.Module):
         self.act_code = 0 if activation is nn.GELU else 1
         self.act_slope = 0.0 if activation is nn.ReLU else (0.01 if activation is nn.LeakyReLU else float(leakiness))
         make_act = (lambda: nn.LeakyReLU(leakiness)) if activation is None else activation
-        # what SimpleConv's fused forward/backward covers: BatchNorm + activation on every layer (skip, glu and the
-        # activation kind are free there)
-        self.clip_conv_family = batch_norm and activation_on_last
+        # what SimpleConv's fused forward/backward covers: BatchNorm wherever there is an activation (skip, glu, the
+        # activation kind and a bare last layer are free there)
+        self.clip_conv_family = bool(batch_norm)
         self.sequence = nn.ModuleList()
         self.glus = nn.ModuleList()
         self.dilations: tp.List[int] = []

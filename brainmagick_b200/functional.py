@@ -44,6 +44,8 @@ class EncoderPlan:
     skip: bool = True                      # ConvSequence(skip=...): residual where a layer keeps its width (common.py:146-147)
     act_code: int = 0                      # 0 = GELU (clip_conv); 1 = LeakyReLU(act_slope), i.e. simpleconv.gelu=False
     act_slope: float = 0.0
+    bare_last: bool = False                # simpleconv.complex_out=False: no head, the last conv maps to out_channels and
+                                           # has neither BatchNorm nor activation (simpleconv.py:190-193)
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -216,7 +218,7 @@ class _EncoderFn(torch.autograd.Function):
         IL = il_w.shape[0]
         S, _, D = subj_w.shape
         H = conv_p[0][0].shape[0]
-        F = w2.shape[1]
+        F = conv_p[-1][0].shape[0] if plan.bare_last else w2.shape[1]
         rows = B * T
         save = plan.keep_for_backward
         tc = plan.use_tensor_cores
@@ -318,6 +320,25 @@ class _EncoderFn(torch.autograd.Function):
             conv = conv0 if k == 0 else _Conv(cw, T, False, tc, want_bwd=save)
             cout = conv.cout
             y = _empty((B, T, cout), meg)
+            if plan.bare_last and k == depth - 1:
+                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, None, status)
+                skip = plan.skip and conv.cin_true == cout
+                x_new = y
+                if skip:
+                    x_new = _empty((B, T, cout), meg)
+                    call("bm_bn_act_skip_fwd", ptr(y), None, None, None, None, ptr(x), ptr(x_new), rows, cout, 2, 0.0, st)
+                rec = dict(x_in=x, y=y, mean=None, invstd=None, conv=conv, skip=skip, x_new=x_new, bare=True)
+                x = x_new
+                if plan.glu_after[k]:
+                    gw, gb = glu_p[k]
+                    gconv = _Conv(gw, T, True, tc, want_bwd=save)
+                    h = _empty((B, T, gconv.cout), meg) if save else None
+                    out = _empty((B, T, gconv.cout // 2), meg)
+                    gconv.forward_glu(x, gb.contiguous(), B, T, h, out, status)
+                    rec.update(h=h, gconv=gconv)
+                    x = out
+                saved_layers.append(rec if save else None)
+                continue
             mean = _empty((cout,), meg)
             invstd = _empty((cout,), meg)
             rm, rv = plan.bn_buffers[k]
@@ -348,6 +369,19 @@ class _EncoderFn(torch.autograd.Function):
                 rec.update(h=h, gconv=gconv)
                 x = out
             saved_layers.append(rec if save else None)
+
+        if plan.bare_last:
+            # no head: the sequence already ends on out_channels; hand it out channel-major
+            est = _empty((B, F, T), meg)
+            call("bm_transpose_nt", ptr(x), B, T, F, ptr(est), st)
+            if save:
+                ctx.plan = plan
+                ctx.dims = (B, C, T, R, O, P, IL, S, D, Dp, H, F)
+                ctx.pads = (Op, ILp)
+                ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(),
+                                 il_conv=il_conv, subj_pad=subj_pad, megT=megT, heads_tc=heads_conv is not None,
+                                 layers=saved_layers, conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape)
+            return est
 
         # K5 head
         H2 = 2 * H
@@ -407,13 +441,20 @@ class _EncoderFn(torch.autograd.Function):
 
         ctx_keep: tp.List[tp.Any] = []          # operands of side-stream kernels, released after the streams join
         # ---- head ----
-        g = _empty((B, T, H), meg)
-        dw0 = _empty((H2, H), meg)
-        db0 = _empty((H2,), meg)
-        dw2 = _empty((H2, F), meg)
-        db2 = _empty((F,), meg)
-        dq = _empty((B, T, H2), meg)
-        if s["head_generic"]:
+        if plan.bare_last:
+            g = _empty((B, T, F), meg)           # no head: the gradient of the estimate IS the sequence's output gradient
+            call("bm_transpose_nt", ptr(dest), B, F, T, ptr(g), st)
+            dw0 = db0 = dw2 = db2 = dq = None
+        else:
+            g = _empty((B, T, H), meg)
+            dw0 = _empty((H2, H), meg)
+            db0 = _empty((H2,), meg)
+            dw2 = _empty((H2, F), meg)
+            db2 = _empty((F,), meg)
+            dq = _empty((B, T, H2), meg)
+        if plan.bare_last:
+            pass
+        elif s["head_generic"]:
             head0, head2 = s["head0"], s["head2"]
             dest_t = _empty((B, T, F), meg)
             call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
@@ -501,6 +542,19 @@ class _EncoderFn(torch.autograd.Function):
                 g = _empty((B, T, gconv.cin), meg)
                 gconv.backward_data(dh, None, B, T, 1, g, status)
                 del dh
+            if rec.get("bare"):
+                # bare convolution (+ residual): dL/dy = dL/dx_new; no BatchNorm behind it, so the bias gradient is real
+                dy = g.clone() if rec["skip"] else g
+                dcw, dcb = weight_grad(conv, dy, rec["x_in"], plan.dilations[k], False)
+                if rec["skip"]:
+                    conv.backward_data(dy, g, B, T, plan.dilations[k], g, status)
+                else:
+                    g_in = _empty((B, T, conv.cin), meg)
+                    conv.backward_data(dy, None, B, T, plan.dilations[k], g_in, status)
+                    g = g_in
+                layer_grads[k] = (dcw, dcb, None, None)
+                del dy
+                continue
             dy = _empty((B, T, cout), meg)
             dgamma = _empty((cout,), meg)
             dbeta = _empty((cout,), meg)
@@ -587,8 +641,11 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_attention_weights_bwd", ptr(d_att), ptr(s["att"]), ptr(s["emb"]), R, C, O, P, ptr(dscores),
                  ptr(dheads), st)
 
-        grads = [None, None, dheads, d_il_w.reshape(s["il_shape"]), d_il_b, d_subj,
-                 dw0.reshape(s["w0_shape"]), db0, dw2.reshape(s["w2_shape"]), db2]
+        if plan.bare_last:
+            grads = [None, None, dheads, d_il_w.reshape(s["il_shape"]), d_il_b, d_subj, None, None, None, None]
+        else:
+            grads = [None, None, dheads, d_il_w.reshape(s["il_shape"]), d_il_b, d_subj,
+                     dw0.reshape(s["w0_shape"]), db0, dw2.reshape(s["w2_shape"]), db2]
         for k in range(depth):
             grads.extend(layer_grads[k])
         for k in range(depth):

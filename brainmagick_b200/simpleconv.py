@@ -6,8 +6,9 @@ semantics (BatchNorm running statistics, one spatial-dropout centre per training
 hand-written sm_100a CUDA through the C ABI (`functional.encoder_forward`); there is no PyTorch/CPU fallback.
 
 Accelerated configuration = the `clip_conv` family of conf/model/clip_conv.yaml (merger + initial_linear +
-subject_layers + ConvSequence(batch_norm) + complex_out), with or without `skip`, with any `glu` period and with
-GELU or (Leaky)ReLU (three of the paper's ablations, grids/nmi/ablation_final.py:45,47,48).  Options outside that family are accepted by the
+subject_layers + ConvSequence(batch_norm) + head), with or without `skip`, with any `glu` period, with GELU or
+(Leaky)ReLU and with or without the `complex_out` head (four of the paper's ablations,
+grids/nmi/ablation_final.py:45,47,48,49).  Options outside that family are accepted by the
 signature but raise NotImplementedError.
 """
 from __future__ import annotations
@@ -88,7 +89,7 @@ class SimpleConv(nn.Module):
                              f"({set(in_channels.keys())} and {set(hidden.keys())})")
         assert kernel_size % 2 == 1, "For padding to work, this must be verified"
         off_path = dict(
-            concatenate=concatenate, linear_out=linear_out, complex_out=not complex_out, growth=growth != 1.,
+            concatenate=concatenate, linear_out=linear_out, growth=growth != 1.,
             dual_path=bool(dual_path), subject_dim=bool(subject_dim),
             subject_layers=not subject_layers, n_fft=n_fft is not None, merger=not merger, dropout=dropout > 0.,
             initial_linear=not initial_linear, initial_depth=initial_depth != 1, initial_nonlin=initial_nonlin,
@@ -129,17 +130,24 @@ class SimpleConv(nn.Module):
             activation, make_act = nn.ReLU, nn.ReLU
         sizes = [in_channels["meg"]] + [int(round(hidden["meg"] * growth ** k)) for k in range(depth)]
         final_channels = sizes[-1]
-        self.final = nn.Sequential(
-            nn.Conv1d(final_channels, 2 * final_channels, 1),
-            make_act(),
-            nn.ConvTranspose1d(2 * final_channels, out_channels, 1, 1, 0))
+        seq_kw = {}
+        if complex_out:
+            self.final = nn.Sequential(
+                nn.Conv1d(final_channels, 2 * final_channels, 1),
+                make_act(),
+                nn.ConvTranspose1d(2 * final_channels, out_channels, 1, 1, 0))
+        else:
+            # simpleconv.py:190-193: no head; the last convolution maps to out_channels, without BatchNorm / activation
+            self.final = None
+            seq_kw["activation_on_last"] = False
+            sizes[-1] = out_channels
         self.encoders = nn.ModuleDict({"meg": ConvSequence(
             sizes, kernel=kernel_size, stride=1, leakiness=relu_leakiness, dropout=conv_dropout,
             dropout_input=dropout_input, batch_norm=batch_norm, dilation_growth=dilation_growth, groups=groups,
             dilation_period=dilation_period, skip=skip, post_skip=post_skip, scale=scale, rewrite=rewrite, glu=glu,
-            glu_context=glu_context, glu_glu=glu_glu, activation=activation)})
+            glu_context=glu_context, glu_glu=glu_glu, activation=activation, **seq_kw)})
         if not self.encoders["meg"].clip_conv_family:
-            raise NotImplementedError("SimpleConv fuses the clip_conv ConvSequence (batch_norm on every layer); "
+            raise NotImplementedError("SimpleConv's fused encoder needs batch_norm=True; "
                                       "see SURVEY.md 8(f) row 4")
         self._freq: tp.Optional[torch.Tensor] = None
         self.use_tensor_cores = True     # False forces the FP32-FMA kernels everywhere (debugging / A-B timing)
@@ -148,9 +156,12 @@ class SimpleConv(nn.Module):
     def _layer_params(self):
         seq: ConvSequence = self.encoders["meg"]
         out = []
-        for block in seq.sequence:
-            conv, bn = block[0], block[1]
-            out += [conv.weight, conv.bias, bn.weight, bn.bias]
+        for k, block in enumerate(seq.sequence):
+            conv = block[0]
+            if seq.has_act[k]:
+                out += [conv.weight, conv.bias, block[1].weight, block[1].bias]
+            else:
+                out += [conv.weight, conv.bias, None, None]          # the bare last layer of complex_out=False
         for glu in seq.glus:
             if glu is not None:
                 out += [glu[0].weight, glu[0].bias]
@@ -163,7 +174,8 @@ class SimpleConv(nn.Module):
         pos, rec_of_sample, rec_order, rec_off = self.merger.position_getter.batch_layout(batch, C, device)
         if self._freq is None or self._freq.device != device:
             self._freq = self.merger.embedding.frequencies().to(device)
-        bn_buffers = [(blk[1].running_mean, blk[1].running_var) for blk in seq.sequence]
+        bn_buffers = [(blk[1].running_mean, blk[1].running_var) if seq.has_act[k] else None
+                      for k, blk in enumerate(seq.sequence)]
         bn0 = seq.sequence[0][1]
         if bn0.momentum is None:
             raise NotImplementedError("BatchNorm cumulative-average mode (momentum=None)")
@@ -174,7 +186,8 @@ class SimpleConv(nn.Module):
             subject=batch.subject_index.to(device=device, dtype=torch.int32).contiguous(),
             freq=self._freq, ban_centre=self.merger.draw_ban_centre(device), ban_radius=float(self.merger.dropout),
             bn_buffers=bn_buffers, keep_for_backward=torch.is_grad_enabled(),
-            use_tensor_cores=self.use_tensor_cores, skip=seq.skip, act_code=seq.act_code, act_slope=seq.act_slope)
+            use_tensor_cores=self.use_tensor_cores, skip=seq.skip, act_code=seq.act_code, act_slope=seq.act_slope,
+            bare_last=not seq.has_act[-1])
 
     def forward(self, inputs, batch):
         meg = inputs["meg"]
@@ -185,12 +198,13 @@ class SimpleConv(nn.Module):
         length = meg.shape[-1]
         plan = self._plan(meg, batch)
         il = self.initial_linear[0]
-        est = BF.encoder_forward(
-            plan, meg, self.merger.heads, il.weight, il.bias, self.subject_layers.weights,
-            self.final[0].weight, self.final[0].bias, self.final[2].weight, self.final[2].bias,
-            self._layer_params())
+        head = [None] * 4 if self.final is None else \
+            [self.final[0].weight, self.final[0].bias, self.final[2].weight, self.final[2].bias]
+        est = BF.encoder_forward(plan, meg, self.merger.heads, il.weight, il.bias, self.subject_layers.weights, *head,
+                                 self._layer_params())
         if self.training:
             seq: ConvSequence = self.encoders["meg"]
-            for blk in seq.sequence:          # nn.BatchNorm1d bookkeeping (running stats were updated on device)
-                blk[1].num_batches_tracked += 1
+            for k, blk in enumerate(seq.sequence):   # nn.BatchNorm1d bookkeeping (running stats were updated on device)
+                if seq.has_act[k]:
+                    blk[1].num_batches_tracked += 1
         return est[:, :, :length]

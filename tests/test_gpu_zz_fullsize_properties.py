@@ -113,9 +113,10 @@ def test_ablation_reference_configuration():
     _ablation_step("ablation_reference")
 
 
-@pytest.mark.parametrize("name", ["ablation_no_glu", "ablation_no_skip", "ablation_relu"])
-@pytest.mark.xfail(strict=False, reason="SimpleConv(glu=0 | skip=False | gelu=False) go through the fused encoder with kernels "
-                                        "that are each verified elsewhere, but these paths have not had their first GPU run yet")
+@pytest.mark.parametrize("name", ["ablation_no_glu", "ablation_no_skip", "ablation_relu", "ablation_no_complex_out"])
+@pytest.mark.xfail(strict=False, reason="SimpleConv(glu=0 | skip=False | gelu=False | complex_out=False) go through the fused "
+                                        "encoder with kernels that are each verified elsewhere, but these paths have not had "
+                                        "their first GPU run yet")
 def test_ablation_rows_the_fused_encoder_covers(name):
-    """grids/nmi/ablation_final.py:45,47,48 -- `simpleconv.glu=0`, `simpleconv.gelu=False`, `simpleconv.skip=False`."""
+    """grids/nmi/ablation_final.py:45,47,48,49 -- `simpleconv.glu=0`, `.gelu=False`, `.skip=False`, `.complex_out=False`."""
     _ablation_step(name)
