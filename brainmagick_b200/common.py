@@ -156,6 +156,25 @@ class ChannelMerger(nn.Module):
         raise RuntimeError("ChannelMerger is fused into SimpleConv.forward in brainmagick_b200")
 
 
+class ScaledEmbedding(nn.Module):
+    """Subject embedding stored divided by `scale` and multiplied back on use, which scales its learning rate
+    (reference: bm/models/common.py:28-42).  `forward` is plain torch (a [B, E] lookup); the CUDA encoder appends the rows
+    to its channels."""
+
+    def __init__(self, num_embeddings: int, embedding_dim: int, scale: float = 10.):
+        super().__init__()
+        self.embedding = nn.Embedding(num_embeddings, embedding_dim)
+        self.embedding.weight.data /= scale
+        self.scale = scale
+
+    @property
+    def weight(self):
+        return self.embedding.weight * self.scale
+
+    def forward(self, x):
+        return self.embedding(x) * self.scale
+
+
 class SubjectLayers(nn.Module):
     """Per-subject 1x1 linear layer (reference: bm/models/common.py:45-62).  Holds `weights` [S, Cin, Cout]."""
 

@@ -46,6 +46,9 @@ class EncoderPlan:
     act_slope: float = 0.0
     bare_last: bool = False                # simpleconv.complex_out=False: no head, the last conv maps to out_channels and
                                            # has neither BatchNorm nor activation (simpleconv.py:190-193)
+    staged: bool = False                   # a sensor-chain stage is missing (merger / initial_linear / subject_layers
+                                           # ablations) or a subject embedding is appended: run the chain stage by stage
+    has_sub_emb: bool = False              # the last tensor argument is the [B, E] subject-embedding rows
 
 
 def _empty(shape, like, dtype=torch.float32):
@@ -196,6 +199,95 @@ class _Conv:
         return dw, db
 
 
+# ----------------------------------------------------------------------------------------------------
+# Sensor chain in optional stages: the ablation rows merger=False / initial_linear=0 / subject_layers=False / subject_dim
+# (grids/nmi/ablation_final.py:44,46,50,51; simpleconv.py:104-151, 207-233).  Each stage is the FP32-FMA stage kernel that
+# the fused `bm_sensor_chain_fwd/bwd` is made of (csrc/bm_api.cu), called on its own; activations are channels-last.
+# ----------------------------------------------------------------------------------------------------
+def _staged_front_forward(plan: "EncoderPlan", meg, heads, il_w, il_b, subj_w, sub_emb, status):
+    """-> (x [B,T,D_total] channels-last, saved dict).  meg [B,C,T]; missing stages have None parameters."""
+    st = stream()
+    B, C, T = meg.shape
+    R = plan.rec_positions.shape[0]
+    saved = dict(meg=meg, att=None, emb=None, u=None, v=None)
+    width = C
+    if heads is not None:                                     # ChannelMerger (common.py:334-362)
+        O, P = heads.shape
+        emb = _empty((R, C, P), meg)
+        att = _empty((R, O, C), meg)
+        call("bm_attention_weights_fwd", ptr(plan.rec_positions), ptr(plan.freq), ptr(heads.contiguous()),
+             ptr(plan.ban_centre), float(plan.ban_radius), R, C, O, P, ptr(emb), ptr(att), st)
+        u = _empty((B, T, O), meg)
+        call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, O, ptr(u), st)
+        saved.update(att=att, emb=emb)
+        width = O
+    else:                                                      # raw sensors, channels-last
+        u = _empty((B, T, C), meg)
+        call("bm_transpose_nt", ptr(meg), B, C, T, ptr(u), st)
+    saved["u"] = u
+    x = u
+    if il_w is not None:                                       # initial_linear (simpleconv.py:112-120)
+        IL = il_w.shape[0]
+        v = _empty((B, T, IL), meg)
+        call("bm_initial_linear_fwd", ptr(x), width, ptr(il_w.reshape(IL, width).contiguous()), ptr(il_b.contiguous()), B, T,
+             width, IL, IL, ptr(v), st)
+        x, width = v, IL
+    saved["v"] = x                                             # input of the subject stage
+    if subj_w is not None:                                     # SubjectLayers (common.py:45-62)
+        D = subj_w.shape[2]
+        x0 = _empty((B, T, D), meg)
+        call("bm_subject_layers_fwd", ptr(x), width, ptr(subj_w.contiguous()), ptr(plan.subject), B, T, width, D, D,
+             ptr(x0), st)
+        x, width = x0, D
+    if sub_emb is not None:                                    # ScaledEmbedding appended as channels (simpleconv.py:231-233)
+        x = torch.cat([x, sub_emb[:, None, :].expand(B, T, sub_emb.shape[1])], dim=2).contiguous()
+    saved["widths"] = (C, saved["u"].shape[2], saved["v"].shape[2], width)
+    return x, saved
+
+
+def _staged_front_backward(plan: "EncoderPlan", saved, g, heads, il_w, subj_w, sub_emb):
+    """g = dL/dx [B,T,D_total] -> (dheads, d_il_w, d_il_b, d_subj, d_sub_emb); None where the stage is absent."""
+    st = stream()
+    meg = saved["meg"]
+    B, C, T = meg.shape
+    R = plan.rec_positions.shape[0]
+    _, w_u, w_v, w_x = saved["widths"]
+    d_sub_emb = None
+    if sub_emb is not None:
+        d_sub_emb = g[:, :, w_x:].sum(dim=1)                   # the embedding is constant over time
+        g = g[:, :, :w_x].contiguous()
+    d_subj = None
+    if subj_w is not None:
+        S = subj_w.shape[0]
+        subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
+        subj_off = torch.zeros(S + 1, dtype=torch.int32, device=meg.device)
+        subj_off[1:] = torch.cumsum(torch.bincount(plan.subject, minlength=S), 0).to(torch.int32)
+        d_subj = _empty((S, w_v, w_x), meg)
+        dv = _empty((B, T, w_v), meg)
+        call("bm_subject_layers_bwd", ptr(g), w_x, ptr(saved["v"]), w_v, ptr(subj_w.contiguous()), ptr(plan.subject),
+             ptr(subj_order), ptr(subj_off), B, T, w_v, w_x, S, w_v, ptr(dv), ptr(d_subj), st)
+        g = dv
+    d_il_w = d_il_b = None
+    if il_w is not None:
+        d_il_w = _empty((w_v, w_u), meg)
+        d_il_b = _empty((w_v,), meg)
+        du = _empty((B, T, w_u), meg)
+        call("bm_initial_linear_bwd", ptr(g), w_v, ptr(saved["u"]), w_u, ptr(il_w.reshape(w_v, w_u).contiguous()), B, T, w_u,
+             w_v, w_u, ptr(du), ptr(d_il_w), ptr(d_il_b), st)
+        d_il_w = d_il_w.reshape(il_w.shape)
+        g = du
+    dheads = None
+    if heads is not None:
+        O, P = heads.shape
+        d_att = _empty((R, O, C), meg)
+        call("bm_sensor_mix_bwd", ptr(g), w_u, ptr(meg), ptr(plan.rec_order), ptr(plan.rec_off), B, C, T, O, R, ptr(d_att), st)
+        dscores = _empty((R, O, C), meg)
+        dheads = _empty((O, P), meg)
+        call("bm_attention_weights_bwd", ptr(d_att), ptr(saved["att"]), ptr(saved["emb"]), R, C, O, P, ptr(dscores),
+             ptr(dheads), st)
+    return dheads, d_il_w, d_il_b, d_subj, d_sub_emb
+
+
 class _EncoderFn(torch.autograd.Function):
     """inputs: plan, meg, heads, il_w, il_b, subj_w, w0, b0, w2, b2, then per layer k: (conv_w, conv_b, gamma, beta)
     and, appended in layer order, (glu_w, glu_b) for every layer followed by a GLU block."""
@@ -203,6 +295,9 @@ class _EncoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan: EncoderPlan, meg, heads, il_w, il_b, subj_w, w0, b0, w2, b2, *layer_params):
         depth = len(plan.dilations)
+        sub_emb = None
+        if plan.has_sub_emb:                     # [B, E] rows of the (scaled) subject embedding, appended by the caller
+            sub_emb, layer_params = layer_params[-1], layer_params[:-1]
         conv_p = [layer_params[4 * k:4 * k + 4] for k in range(depth)]
         glu_flat = layer_params[4 * depth:]
         glu_p, gi = {}, 0
@@ -214,9 +309,9 @@ class _EncoderFn(torch.autograd.Function):
         meg = meg.contiguous()
         B, C, T = meg.shape
         R = plan.rec_positions.shape[0]
-        O, P = heads.shape
-        IL = il_w.shape[0]
-        S, _, D = subj_w.shape
+        O, P = heads.shape if heads is not None else (0, 0)
+        IL = il_w.shape[0] if il_w is not None else 0
+        S, _, D = subj_w.shape if subj_w is not None else (0, 0, 0)
         H = conv_p[0][0].shape[0]
         F = conv_p[-1][0].shape[0] if plan.bare_last else w2.shape[1]
         rows = B * T
@@ -224,93 +319,102 @@ class _EncoderFn(torch.autograd.Function):
         tc = plan.use_tensor_cores
         status = tc_status_tensor(meg.device)
 
-        # K1 attention weights per recording (the score contraction on the tensor cores when the widths fit)
-        emb = _empty((R, C, P), meg)
-        lib = _lib.load()
-        Opad = _round_up(O, 64)
-        heads_conv = None
-        if tc and bool(lib.bm_tc_conv3_supported(C, P, Opad, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Opad, P)):
-            hpad = torch.zeros((Opad, P, 1), device=meg.device)
-            hpad[:O, :, 0] = heads
-            heads_conv = _Conv(hpad, C, False, True, want_bwd=False)
-            if not heads_conv.fwd_v3:
-                heads_conv = None
-        if heads_conv is not None:
-            call("bm_fourier_emb", ptr(plan.rec_positions), ptr(plan.freq), R, C, P, ptr(emb), st)
-            att_full = _empty((R, Opad, C), meg)          # scores[r][o][c] = <emb[r][c], heads[o]> written channel-major
-            call(heads_conv.fwd_fn, ptr(emb), ptr(heads_conv.f_hi), ptr(heads_conv.f_lo), None, None, R, C, P, Opad, 1, 1, 1,
-                 0, 0, 1, ptr(att_full), None, None, ptr(status), st)
-            call("bm_masked_softmax", ptr(att_full), ptr(plan.rec_positions), ptr(plan.ban_centre), float(plan.ban_radius),
-                 R, Opad, C, st)
-            att = att_full[:, :O].contiguous()
+        if plan.staged:
+            # sensor-side ablation rows: the chain as optional stages (see _staged_front_forward)
+            x, front = _staged_front_forward(plan, meg, heads, il_w, il_b, subj_w, sub_emb, status)
+            D = Dp = x.shape[2]
+            conv0 = _Conv(conv_p[0][0], T, False, tc, want_bwd=save)
+            emb = att = u = v = il_w2 = il_conv = subj_pad = megT = heads_conv = None
+            Op = ILp = 0
         else:
-            att = _empty((R, O, C), meg)
-            call("bm_attention_weights_fwd", ptr(plan.rec_positions), ptr(plan.freq), ptr(heads.contiguous()),
-                 ptr(plan.ban_centre), float(plan.ban_radius), R, C, O, P, ptr(emb), ptr(att), st)
-        # K2 sensor chain; x0 is kept zero-padded to a multiple of 64 channels when the tensor-core conv follows
-        Dp = _round_up(D, 64)
-        conv0 = _Conv(conv_p[0][0], T, False, tc, pad_cin_to=Dp, want_bwd=save)
-        if not conv0.fwd_tc:
-            Dp = D
-            conv0 = _Conv(conv_p[0][0], T, False, False, want_bwd=save)
-        il_w2 = il_w.reshape(IL, O).contiguous()
-        # `initial_linear` on the tensor cores when the (64-padded) widths fit: u and v are then kept zero-padded
-        Op, ILp = _round_up(O, 64), _round_up(IL, 64)
-        il_conv = None
-        if tc:
-            wpad = torch.zeros((ILp, Op, 1), device=meg.device)
-            wpad[:IL, :O, 0] = il_w2
-            il_conv = _Conv(wpad, T, False, True, want_bwd=save)
-            if not (il_conv.fwd_tc and il_conv.bwd_tc and il_conv.wgrad_tc):
-                il_conv = None
-        x = torch.zeros((B, T, Dp), device=meg.device) if Dp != D else _empty((B, T, D), meg)
-        if il_conv is not None:
-            u = torch.zeros((B, T, Op), device=meg.device) if Op != O else _empty((B, T, O), meg)
-            v = _empty((B, T, ILp), meg)
-            bpad = torch.zeros((ILp,), device=meg.device)
-            bpad[:IL] = il_b
+            front = None
+            # K1 attention weights per recording (the score contraction on the tensor cores when the widths fit)
+            emb = _empty((R, C, P), meg)
             lib = _lib.load()
-            # sensor mix on the tensor cores: meg transposed once to channels-last (sensor count padded to 128), then
-            # u = megT @ w[rec]^T is a pointwise contraction with a per-sample weight set (one per recording)
-            Cp = _round_up(C, 128)
-            mix_tc = bool(lib.bm_tc_conv_supported(T, Cp, Op, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Op, Cp))
-            megT = None
-            if mix_tc:
-                megT = torch.zeros((B, T, Cp), device=meg.device) if Cp != C else _empty((B, T, C), meg)
-                call("bm_transpose_nt_ld", ptr(meg), B, C, T, Cp, ptr(megT), st)
-                att_pad = torch.zeros((R, Op, Cp), device=meg.device)
-                att_pad[:, :O, :C] = att
-                aw_hi, aw_lo = _empty((R * Op, Cp), meg), _empty((R * Op, Cp), meg)
-                call("bm_tc_weight_split", ptr(att_pad), R * Op, Cp, 1, ptr(aw_hi), ptr(aw_lo), None, None, st)
-                call("bm_tc_pointwise_sel", ptr(megT), ptr(aw_hi), ptr(aw_lo), ptr(plan.rec_of_sample), R, B, T, Cp, Op,
-                     ptr(u), ptr(status), st)
+            Opad = _round_up(O, 64)
+            heads_conv = None
+            if tc and bool(lib.bm_tc_conv3_supported(C, P, Opad, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Opad, P)):
+                hpad = torch.zeros((Opad, P, 1), device=meg.device)
+                hpad[:O, :, 0] = heads
+                heads_conv = _Conv(hpad, C, False, True, want_bwd=False)
+                if not heads_conv.fwd_v3:
+                    heads_conv = None
+            if heads_conv is not None:
+                call("bm_fourier_emb", ptr(plan.rec_positions), ptr(plan.freq), R, C, P, ptr(emb), st)
+                att_full = _empty((R, Opad, C), meg)          # scores[r][o][c] = <emb[r][c], heads[o]> written channel-major
+                call(heads_conv.fwd_fn, ptr(emb), ptr(heads_conv.f_hi), ptr(heads_conv.f_lo), None, None, R, C, P, Opad, 1, 1, 1,
+                     0, 0, 1, ptr(att_full), None, None, ptr(status), st)
+                call("bm_masked_softmax", ptr(att_full), ptr(plan.rec_positions), ptr(plan.ban_centre), float(plan.ban_radius),
+                     R, Opad, C, st)
+                att = att_full[:, :O].contiguous()
             else:
-                call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, Op, ptr(u), st)
-            il_conv.forward(u, bpad, B, T, 1, v, None, status)
-            subj_tc = (Dp != D or D % 64 == 0) and bool(lib.bm_tc_conv_supported(T, ILp, Dp, 1, 0)) and \
-                bool(lib.bm_tc_conv_supported(T, Dp, ILp, 1, 0)) and bool(lib.bm_tc_wgrad_supported(ILp, Dp))
-            if subj_tc:
-                # per-subject weights, zero-padded; forward operand [s][d][p] (K-major in p), tf32-split
-                subj_pad = torch.zeros((S, ILp, Dp), device=meg.device)
-                subj_pad[:, :IL, :D] = subj_w
-                mt = subj_pad.transpose(1, 2).contiguous()
-                sf_hi, sf_lo = _empty((S * Dp, ILp), meg), _empty((S * Dp, ILp), meg)
-                call("bm_tc_weight_split", ptr(mt), S * Dp, ILp, 1, ptr(sf_hi), ptr(sf_lo), None, None, st)
-                call("bm_tc_pointwise_sel", ptr(v), ptr(sf_hi), ptr(sf_lo), ptr(plan.subject), S, B, T, ILp, Dp, ptr(x),
-                     ptr(status), st)
+                att = _empty((R, O, C), meg)
+                call("bm_attention_weights_fwd", ptr(plan.rec_positions), ptr(plan.freq), ptr(heads.contiguous()),
+                     ptr(plan.ban_centre), float(plan.ban_radius), R, C, O, P, ptr(emb), ptr(att), st)
+            # K2 sensor chain; x0 is kept zero-padded to a multiple of 64 channels when the tensor-core conv follows
+            Dp = _round_up(D, 64)
+            conv0 = _Conv(conv_p[0][0], T, False, tc, pad_cin_to=Dp, want_bwd=save)
+            if not conv0.fwd_tc:
+                Dp = D
+                conv0 = _Conv(conv_p[0][0], T, False, False, want_bwd=save)
+            il_w2 = il_w.reshape(IL, O).contiguous()
+            # `initial_linear` on the tensor cores when the (64-padded) widths fit: u and v are then kept zero-padded
+            Op, ILp = _round_up(O, 64), _round_up(IL, 64)
+            il_conv = None
+            if tc:
+                wpad = torch.zeros((ILp, Op, 1), device=meg.device)
+                wpad[:IL, :O, 0] = il_w2
+                il_conv = _Conv(wpad, T, False, True, want_bwd=save)
+                if not (il_conv.fwd_tc and il_conv.bwd_tc and il_conv.wgrad_tc):
+                    il_conv = None
+            x = torch.zeros((B, T, Dp), device=meg.device) if Dp != D else _empty((B, T, D), meg)
+            if il_conv is not None:
+                u = torch.zeros((B, T, Op), device=meg.device) if Op != O else _empty((B, T, O), meg)
+                v = _empty((B, T, ILp), meg)
+                bpad = torch.zeros((ILp,), device=meg.device)
+                bpad[:IL] = il_b
+                lib = _lib.load()
+                # sensor mix on the tensor cores: meg transposed once to channels-last (sensor count padded to 128), then
+                # u = megT @ w[rec]^T is a pointwise contraction with a per-sample weight set (one per recording)
+                Cp = _round_up(C, 128)
+                mix_tc = bool(lib.bm_tc_conv_supported(T, Cp, Op, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Op, Cp))
+                megT = None
+                if mix_tc:
+                    megT = torch.zeros((B, T, Cp), device=meg.device) if Cp != C else _empty((B, T, C), meg)
+                    call("bm_transpose_nt_ld", ptr(meg), B, C, T, Cp, ptr(megT), st)
+                    att_pad = torch.zeros((R, Op, Cp), device=meg.device)
+                    att_pad[:, :O, :C] = att
+                    aw_hi, aw_lo = _empty((R * Op, Cp), meg), _empty((R * Op, Cp), meg)
+                    call("bm_tc_weight_split", ptr(att_pad), R * Op, Cp, 1, ptr(aw_hi), ptr(aw_lo), None, None, st)
+                    call("bm_tc_pointwise_sel", ptr(megT), ptr(aw_hi), ptr(aw_lo), ptr(plan.rec_of_sample), R, B, T, Cp, Op,
+                         ptr(u), ptr(status), st)
+                else:
+                    call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, Op, ptr(u), st)
+                il_conv.forward(u, bpad, B, T, 1, v, None, status)
+                subj_tc = (Dp != D or D % 64 == 0) and bool(lib.bm_tc_conv_supported(T, ILp, Dp, 1, 0)) and \
+                    bool(lib.bm_tc_conv_supported(T, Dp, ILp, 1, 0)) and bool(lib.bm_tc_wgrad_supported(ILp, Dp))
+                if subj_tc:
+                    # per-subject weights, zero-padded; forward operand [s][d][p] (K-major in p), tf32-split
+                    subj_pad = torch.zeros((S, ILp, Dp), device=meg.device)
+                    subj_pad[:, :IL, :D] = subj_w
+                    mt = subj_pad.transpose(1, 2).contiguous()
+                    sf_hi, sf_lo = _empty((S * Dp, ILp), meg), _empty((S * Dp, ILp), meg)
+                    call("bm_tc_weight_split", ptr(mt), S * Dp, ILp, 1, ptr(sf_hi), ptr(sf_lo), None, None, st)
+                    call("bm_tc_pointwise_sel", ptr(v), ptr(sf_hi), ptr(sf_lo), ptr(plan.subject), S, B, T, ILp, Dp, ptr(x),
+                         ptr(status), st)
+                else:
+                    subj_pad = None
+                    call("bm_subject_layers_fwd", ptr(v), ILp, ptr(subj_w.contiguous()), ptr(plan.subject), B, T, IL, D, Dp,
+                         ptr(x), st)
             else:
                 subj_pad = None
-                call("bm_subject_layers_fwd", ptr(v), ILp, ptr(subj_w.contiguous()), ptr(plan.subject), B, T, IL, D, Dp,
-                     ptr(x), st)
-        else:
-            subj_pad = None
-            megT = None
-            Op, ILp = O, IL
-            u = _empty((B, T, O), meg)
-            v = _empty((B, T, IL), meg)
-            call("bm_sensor_chain_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), ptr(il_w2),
-                 ptr(il_b.contiguous()), ptr(subj_w.contiguous()), ptr(plan.subject), B, C, T, O, IL, D, Dp, ptr(u),
-                 ptr(v), ptr(x), st)
+                megT = None
+                Op, ILp = O, IL
+                u = _empty((B, T, O), meg)
+                v = _empty((B, T, IL), meg)
+                call("bm_sensor_chain_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), ptr(il_w2),
+                     ptr(il_b.contiguous()), ptr(subj_w.contiguous()), ptr(plan.subject), B, C, T, O, IL, D, Dp, ptr(u),
+                     ptr(v), ptr(x), st)
 
         # K3/K4 ConvSequence
         stats = _empty((2 * H,), meg, torch.float64)
@@ -378,9 +482,11 @@ class _EncoderFn(torch.autograd.Function):
                 ctx.plan = plan
                 ctx.dims = (B, C, T, R, O, P, IL, S, D, Dp, H, F)
                 ctx.pads = (Op, ILp)
-                ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(),
+                ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=None if subj_w is None else subj_w.contiguous(),
                                  il_conv=il_conv, subj_pad=subj_pad, megT=megT, heads_tc=heads_conv is not None,
-                                 layers=saved_layers, conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape)
+                                 layers=saved_layers, conv_p=conv_p, glu_p=glu_p,
+                                 il_shape=None if il_w is None else il_w.shape, front=front,
+                                 params=(heads, il_w, subj_w, sub_emb))
             return est
 
         # K5 head
@@ -419,11 +525,12 @@ class _EncoderFn(torch.autograd.Function):
             ctx.plan = plan
             ctx.dims = (B, C, T, R, O, P, IL, S, D, Dp, H, F)
             ctx.pads = (Op, ILp)
-            ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=subj_w.contiguous(), il_conv=il_conv,
+            ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=None if subj_w is None else subj_w.contiguous(), il_conv=il_conv,
                              subj_pad=subj_pad, megT=megT, heads_tc=heads_conv is not None,
                              layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q,
                              head0=head0, head2=head2, head_tc=head_tc, head_generic=head_generic,
-                             conv_p=conv_p, glu_p=glu_p, il_shape=il_w.shape, w0_shape=w0.shape, w2_shape=w2.shape)
+                             conv_p=conv_p, glu_p=glu_p, il_shape=None if il_w is None else il_w.shape,
+                             w0_shape=w0.shape, w2_shape=w2.shape, front=front, params=(heads, il_w, subj_w, sub_emb))
         return est
 
     @staticmethod
@@ -580,83 +687,95 @@ class _EncoderFn(torch.autograd.Function):
         if side is not None:
             main.wait_stream(side)
         keep_alive.clear()
-        # ---- sensor chain + attention ----
-        subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
-        counts = torch.bincount(plan.subject, minlength=S)
-        subj_off = torch.zeros(S + 1, dtype=torch.int32, device=meg.device)
-        subj_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
-        Op, ILp = ctx.pads
-        d_subj = _empty((S, IL, D), meg)
-        d_att = _empty((R, O, C), meg)
-        il_conv = s["il_conv"]
-        if il_conv is not None:
-            if s["subj_pad"] is not None:
-                subj_pad = s["subj_pad"]                                   # [S][ILp][Dp]: data-gradient operand as is
-                sb_hi, sb_lo = _empty((S * ILp, Dp), meg), _empty((S * ILp, Dp), meg)
-                call("bm_tc_weight_split", ptr(subj_pad), S * ILp, Dp, 1, ptr(sb_hi), ptr(sb_lo), None, None, st)
-                dv = _empty((B, T, ILp), meg)
-                call("bm_tc_pointwise_sel", ptr(g), ptr(sb_hi), ptr(sb_lo), ptr(plan.subject), S, B, T, Dp, ILp, ptr(dv),
-                     ptr(status), st)
-                mpad = _round_up(ILp, 128)
-                dm = _empty((S, mpad, Dp), meg)
-                call("bm_tc_wgrad_grouped", ptr(s["v"]), ptr(g), ptr(subj_order), ptr(subj_off), S, B, T, ILp, Dp,
-                     ptr(dm), ptr(status), st)
-                d_subj = dm[:, :IL, :D].contiguous()
-            else:
-                dv = torch.zeros((B, T, ILp), device=meg.device) if ILp != IL else _empty((B, T, IL), meg)
-                call("bm_subject_layers_bwd", ptr(g), Dp, ptr(s["v"]), ILp, ptr(s["subj_w"]), ptr(plan.subject),
-                     ptr(subj_order), ptr(subj_off), B, T, IL, D, S, ILp, ptr(dv), ptr(d_subj), st)
-            du = _empty((B, T, Op), meg)
-            il_conv.backward_data(dv, None, B, T, 1, du, status)
-            dbp = _empty((ILp,), meg)
-            d_il_w = tc_wgrad(dv, s["u"], B, T, ILp, Op, O, 1, 1, status, dbias=dbp)[:IL, :, 0].contiguous()
-            d_il_b = dbp[:IL].contiguous()
-            if s["megT"] is not None:
-                megT = s["megT"]
-                Cp = megT.shape[2]
-                dwp = _empty((R, _round_up(Op, 128), Cp), meg)
-                call("bm_tc_wgrad_grouped", ptr(du), ptr(megT), ptr(plan.rec_order), ptr(plan.rec_off), R, B, T, Op, Cp,
-                     ptr(dwp), ptr(status), st)
-                d_att = dwp[:, :O, :C].contiguous()
-            else:
-                call("bm_sensor_mix_bwd", ptr(du), Op, ptr(meg), ptr(plan.rec_order), ptr(plan.rec_off), B, C, T, O, R,
-                     ptr(d_att), st)
+        if plan.staged:
+            heads_p, il_w_p, subj_w_p, sub_emb_p = s["params"]
+            dheads, d_il_w, d_il_b, d_subj, d_sub_emb = _staged_front_backward(plan, s["front"], g, heads_p, il_w_p,
+                                                                               subj_w_p, sub_emb_p)
         else:
-            dv = _empty((B, T, IL), meg)
-            du = _empty((B, T, O), meg)
-            d_il_w = _empty((IL, O), meg)
-            d_il_b = _empty((IL,), meg)
-            call("bm_sensor_chain_bwd", ptr(g), ptr(meg), ptr(s["il_w2"]), ptr(s["subj_w"]), ptr(plan.subject),
-                 ptr(s["u"]), ptr(s["v"]), ptr(subj_order), ptr(subj_off), ptr(plan.rec_order), ptr(plan.rec_off),
-                 B, C, T, O, IL, D, Dp, S, R, ptr(dv), ptr(du), ptr(d_subj), ptr(d_il_w), ptr(d_il_b), ptr(d_att), st)
-        dscores = _empty((R, O, C), meg)
-        if s["heads_tc"]:
-            Opad = _round_up(O, 64)
-            call("bm_softmax_bwd", ptr(s["att"]), ptr(d_att), R * O, C, ptr(dscores), st)
-            ds_t = torch.zeros((R, C, Opad), device=meg.device)
-            call("bm_transpose_nt_ld", ptr(dscores), R, O, C, Opad, ptr(ds_t), st)
-            dheads = tc_wgrad(ds_t, s["emb"], R, C, Opad, P, P, 1, 1, status)[:O, :, 0].contiguous()
-        else:
-            dheads = _empty((O, P), meg)
-            call("bm_attention_weights_bwd", ptr(d_att), ptr(s["att"]), ptr(s["emb"]), R, C, O, P, ptr(dscores),
-                 ptr(dheads), st)
+            d_sub_emb = None
+            # ---- sensor chain + attention ----
+            subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
+            counts = torch.bincount(plan.subject, minlength=S)
+            subj_off = torch.zeros(S + 1, dtype=torch.int32, device=meg.device)
+            subj_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            Op, ILp = ctx.pads
+            d_subj = _empty((S, IL, D), meg)
+            d_att = _empty((R, O, C), meg)
+            il_conv = s["il_conv"]
+            if il_conv is not None:
+                if s["subj_pad"] is not None:
+                    subj_pad = s["subj_pad"]                                   # [S][ILp][Dp]: data-gradient operand as is
+                    sb_hi, sb_lo = _empty((S * ILp, Dp), meg), _empty((S * ILp, Dp), meg)
+                    call("bm_tc_weight_split", ptr(subj_pad), S * ILp, Dp, 1, ptr(sb_hi), ptr(sb_lo), None, None, st)
+                    dv = _empty((B, T, ILp), meg)
+                    call("bm_tc_pointwise_sel", ptr(g), ptr(sb_hi), ptr(sb_lo), ptr(plan.subject), S, B, T, Dp, ILp, ptr(dv),
+                         ptr(status), st)
+                    mpad = _round_up(ILp, 128)
+                    dm = _empty((S, mpad, Dp), meg)
+                    call("bm_tc_wgrad_grouped", ptr(s["v"]), ptr(g), ptr(subj_order), ptr(subj_off), S, B, T, ILp, Dp,
+                         ptr(dm), ptr(status), st)
+                    d_subj = dm[:, :IL, :D].contiguous()
+                else:
+                    dv = torch.zeros((B, T, ILp), device=meg.device) if ILp != IL else _empty((B, T, IL), meg)
+                    call("bm_subject_layers_bwd", ptr(g), Dp, ptr(s["v"]), ILp, ptr(s["subj_w"]), ptr(plan.subject),
+                         ptr(subj_order), ptr(subj_off), B, T, IL, D, S, ILp, ptr(dv), ptr(d_subj), st)
+                du = _empty((B, T, Op), meg)
+                il_conv.backward_data(dv, None, B, T, 1, du, status)
+                dbp = _empty((ILp,), meg)
+                d_il_w = tc_wgrad(dv, s["u"], B, T, ILp, Op, O, 1, 1, status, dbias=dbp)[:IL, :, 0].contiguous()
+                d_il_b = dbp[:IL].contiguous()
+                if s["megT"] is not None:
+                    megT = s["megT"]
+                    Cp = megT.shape[2]
+                    dwp = _empty((R, _round_up(Op, 128), Cp), meg)
+                    call("bm_tc_wgrad_grouped", ptr(du), ptr(megT), ptr(plan.rec_order), ptr(plan.rec_off), R, B, T, Op, Cp,
+                         ptr(dwp), ptr(status), st)
+                    d_att = dwp[:, :O, :C].contiguous()
+                else:
+                    call("bm_sensor_mix_bwd", ptr(du), Op, ptr(meg), ptr(plan.rec_order), ptr(plan.rec_off), B, C, T, O, R,
+                         ptr(d_att), st)
+            else:
+                dv = _empty((B, T, IL), meg)
+                du = _empty((B, T, O), meg)
+                d_il_w = _empty((IL, O), meg)
+                d_il_b = _empty((IL,), meg)
+                call("bm_sensor_chain_bwd", ptr(g), ptr(meg), ptr(s["il_w2"]), ptr(s["subj_w"]), ptr(plan.subject),
+                     ptr(s["u"]), ptr(s["v"]), ptr(subj_order), ptr(subj_off), ptr(plan.rec_order), ptr(plan.rec_off),
+                     B, C, T, O, IL, D, Dp, S, R, ptr(dv), ptr(du), ptr(d_subj), ptr(d_il_w), ptr(d_il_b), ptr(d_att), st)
+            dscores = _empty((R, O, C), meg)
+            if s["heads_tc"]:
+                Opad = _round_up(O, 64)
+                call("bm_softmax_bwd", ptr(s["att"]), ptr(d_att), R * O, C, ptr(dscores), st)
+                ds_t = torch.zeros((R, C, Opad), device=meg.device)
+                call("bm_transpose_nt_ld", ptr(dscores), R, O, C, Opad, ptr(ds_t), st)
+                dheads = tc_wgrad(ds_t, s["emb"], R, C, Opad, P, P, 1, 1, status)[:O, :, 0].contiguous()
+            else:
+                dheads = _empty((O, P), meg)
+                call("bm_attention_weights_bwd", ptr(d_att), ptr(s["att"]), ptr(s["emb"]), R, C, O, P, ptr(dscores),
+                     ptr(dheads), st)
 
+        if d_il_w is not None:
+            d_il_w = d_il_w.reshape(s["il_shape"])
         if plan.bare_last:
-            grads = [None, None, dheads, d_il_w.reshape(s["il_shape"]), d_il_b, d_subj, None, None, None, None]
+            grads = [None, None, dheads, d_il_w, d_il_b, d_subj, None, None, None, None]
         else:
-            grads = [None, None, dheads, d_il_w.reshape(s["il_shape"]), d_il_b, d_subj,
+            grads = [None, None, dheads, d_il_w, d_il_b, d_subj,
                      dw0.reshape(s["w0_shape"]), db0, dw2.reshape(s["w2_shape"]), db2]
         for k in range(depth):
             grads.extend(layer_grads[k])
         for k in range(depth):
             if plan.glu_after[k]:
                 grads.extend(glu_grads[k])
+        if plan.has_sub_emb:
+            grads.append(d_sub_emb)
         ctx.saved = None
         return tuple(grads)
 
 
-def encoder_forward(plan: EncoderPlan, meg, heads, il_w, il_b, subj_w, w0, b0, w2, b2, layer_params):
-    return _EncoderFn.apply(plan, meg, heads, il_w, il_b, subj_w, w0, b0, w2, b2, *layer_params)
+def encoder_forward(plan: EncoderPlan, meg, heads, il_w, il_b, subj_w, w0, b0, w2, b2, layer_params, sub_emb=None):
+    """`sub_emb` [B, E]: rows of the scaled subject embedding to append as channels (plan.has_sub_emb)."""
+    extra = [] if sub_emb is None else [sub_emb]
+    return _EncoderFn.apply(plan, meg, heads, il_w, il_b, subj_w, w0, b0, w2, b2, *layer_params, *extra)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -7,8 +7,10 @@ hand-written sm_100a CUDA through the C ABI (`functional.encoder_forward`); ther
 
 Accelerated configuration = the `clip_conv` family of conf/model/clip_conv.yaml (merger + initial_linear +
 subject_layers + ConvSequence(batch_norm) + head), with or without `skip`, with any `glu` period, with GELU or
-(Leaky)ReLU and with or without the `complex_out` head (four of the paper's ablations,
-grids/nmi/ablation_final.py:45,47,48,49).  Options outside that family are accepted by the
+(Leaky)ReLU, with or without the `complex_out` head, and with merger / initial_linear / subject_layers each optional
+or replaced by a subject embedding -- every row of the paper's ablation table (grids/nmi/ablation_final.py:42-52).
+The un-ablated configuration takes the fused tensor-core path; a missing sensor stage switches the sensor chain to
+its stage-by-stage form.  Options outside that family are accepted by the
 signature but raise NotImplementedError.
 """
 from __future__ import annotations
@@ -19,7 +21,7 @@ import torch
 from torch import nn
 
 from . import functional as BF
-from .common import ChannelMerger, ConvSequence, SubjectLayers, require_library
+from .common import ChannelMerger, ConvSequence, ScaledEmbedding, SubjectLayers, require_library
 
 
 def _require_cuda(meg: torch.Tensor) -> None:
@@ -90,9 +92,8 @@ class SimpleConv(nn.Module):
         assert kernel_size % 2 == 1, "For padding to work, this must be verified"
         off_path = dict(
             concatenate=concatenate, linear_out=linear_out, growth=growth != 1.,
-            dual_path=bool(dual_path), subject_dim=bool(subject_dim),
-            subject_layers=not subject_layers, n_fft=n_fft is not None, merger=not merger, dropout=dropout > 0.,
-            initial_linear=not initial_linear, initial_depth=initial_depth != 1, initial_nonlin=initial_nonlin,
+            dual_path=bool(dual_path), n_fft=n_fft is not None, dropout=dropout > 0.,
+            initial_depth=initial_depth != 1, initial_nonlin=initial_nonlin,
             subsample_meg_channels=bool(subsample_meg_channels), inputs=set(in_channels) != {"meg"})
         bad = [k for k, v in off_path.items() if v]
         if bad:
@@ -109,17 +110,27 @@ class SimpleConv(nn.Module):
         self.dual_path = None
         self.n_input_channels = in_channels["meg"]
 
-        # construction order == the reference's (simpleconv.py:104-196), so a seeded constructor is RNG-identical
-        self.merger = ChannelMerger(merger_channels, pos_dim=merger_pos_dim, dropout=merger_dropout,
-                                    usage_penalty=merger_penalty, n_subjects=n_subjects,
-                                    per_subject=merger_per_subject)
-        in_channels["meg"] = merger_channels
-        self.initial_linear = nn.Sequential(nn.Conv1d(in_channels["meg"], initial_linear, 1))
-        in_channels["meg"] = initial_linear
-        meg_dim = in_channels["meg"]
-        dim = {"hidden": hidden["meg"], "input": meg_dim}[subject_layers_dim]
-        self.subject_layers = SubjectLayers(meg_dim, dim, n_subjects, subject_layers_id)
-        in_channels["meg"] = dim
+        # construction order == the reference's (simpleconv.py:104-196), so a seeded constructor is RNG-identical.
+        # merger / initial_linear / subject_layers are each optional and a subject embedding may be appended (the
+        # sensor-side rows of the ablation table, grids/nmi/ablation_final.py:44,46,50,51)
+        self.merger = self.initial_linear = self.subject_layers = None
+        if merger:
+            self.merger = ChannelMerger(merger_channels, pos_dim=merger_pos_dim, dropout=merger_dropout,
+                                        usage_penalty=merger_penalty, n_subjects=n_subjects,
+                                        per_subject=merger_per_subject)
+            in_channels["meg"] = merger_channels
+        if initial_linear:
+            self.initial_linear = nn.Sequential(nn.Conv1d(in_channels["meg"], initial_linear, 1))
+            in_channels["meg"] = initial_linear
+        if subject_layers:
+            meg_dim = in_channels["meg"]
+            dim = {"hidden": hidden["meg"], "input": meg_dim}[subject_layers_dim]
+            self.subject_layers = SubjectLayers(meg_dim, dim, n_subjects, subject_layers_id)
+            in_channels["meg"] = dim
+        if subject_dim:
+            self.subject_embedding = ScaledEmbedding(n_subjects, subject_dim, embedding_scale)
+            in_channels["meg"] += subject_dim
+        self._staged = not (merger and initial_linear and subject_layers) or bool(subject_dim)
 
         # simpleconv.py:85-90: GELU, else LeakyReLU(relu_leakiness), else ReLU -- in the ConvSequence and in the head
         if gelu:
@@ -171,9 +182,14 @@ class SimpleConv(nn.Module):
         seq: ConvSequence = self.encoders["meg"]
         device = meg.device
         B, C, _ = meg.shape
-        pos, rec_of_sample, rec_order, rec_off = self.merger.position_getter.batch_layout(batch, C, device)
-        if self._freq is None or self._freq.device != device:
-            self._freq = self.merger.embedding.frequencies().to(device)
+        if self.merger is None:                 # no spatial attention: the layout tables are never read
+            pos = torch.zeros(1, C, 2, device=device)
+            rec_of_sample = rec_order = torch.zeros(B, dtype=torch.int32, device=device)
+            rec_off = torch.tensor([0, B], dtype=torch.int32, device=device)
+        else:
+            pos, rec_of_sample, rec_order, rec_off = self.merger.position_getter.batch_layout(batch, C, device)
+            if self._freq is None or self._freq.device != device:
+                self._freq = self.merger.embedding.frequencies().to(device)
         bn_buffers = [(blk[1].running_mean, blk[1].running_var) if seq.has_act[k] else None
                       for k, blk in enumerate(seq.sequence)]
         bn0 = seq.sequence[0][1]
@@ -184,10 +200,11 @@ class SimpleConv(nn.Module):
             glu_kernel=seq.glu_kernel, training=self.training, bn_eps=bn0.eps, bn_momentum=bn0.momentum,
             rec_positions=pos, rec_of_sample=rec_of_sample, rec_order=rec_order, rec_off=rec_off,
             subject=batch.subject_index.to(device=device, dtype=torch.int32).contiguous(),
-            freq=self._freq, ban_centre=self.merger.draw_ban_centre(device), ban_radius=float(self.merger.dropout),
+            freq=self._freq, ban_centre=None if self.merger is None else self.merger.draw_ban_centre(device),
+            ban_radius=0.0 if self.merger is None else float(self.merger.dropout),
             bn_buffers=bn_buffers, keep_for_backward=torch.is_grad_enabled(),
             use_tensor_cores=self.use_tensor_cores, skip=seq.skip, act_code=seq.act_code, act_slope=seq.act_slope,
-            bare_last=not seq.has_act[-1])
+            bare_last=not seq.has_act[-1], staged=self._staged, has_sub_emb=self.subject_embedding is not None)
 
     def forward(self, inputs, batch):
         meg = inputs["meg"]
@@ -197,11 +214,16 @@ class SimpleConv(nn.Module):
         assert meg.shape[1] == self.n_input_channels, "number of MEG channels differs from in_channels['meg']"
         length = meg.shape[-1]
         plan = self._plan(meg, batch)
-        il = self.initial_linear[0]
+        heads = None if self.merger is None else self.merger.heads
+        il_w, il_b = (None, None) if self.initial_linear is None else \
+            (self.initial_linear[0].weight, self.initial_linear[0].bias)
+        subj_w = None if self.subject_layers is None else self.subject_layers.weights
+        sub_emb = None
+        if self.subject_embedding is not None:           # [B, E]; its gradient returns through torch's embedding backward
+            sub_emb = self.subject_embedding(batch.subject_index.to(meg.device).long())
         head = [None] * 4 if self.final is None else \
             [self.final[0].weight, self.final[0].bias, self.final[2].weight, self.final[2].bias]
-        est = BF.encoder_forward(plan, meg, self.merger.heads, il.weight, il.bias, self.subject_layers.weights, *head,
-                                 self._layer_params())
+        est = BF.encoder_forward(plan, meg, heads, il_w, il_b, subj_w, *head, self._layer_params(), sub_emb=sub_emb)
         if self.training:
             seq: ConvSequence = self.encoders["meg"]
             for k, blk in enumerate(seq.sequence):   # nn.BatchNorm1d bookkeeping (running stats were updated on device)

@@ -32,7 +32,9 @@ def test_full_size_step_runs_on_tensor_cores_only():
     assert {"bm_tc_conv1d_pair", "bm_tc_wgrad", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
 
 
-@pytest.mark.parametrize("override", [dict(glu=0), dict(skip=False), dict(gelu=False), dict(complex_out=False)])
+@pytest.mark.parametrize("override", [dict(glu=0), dict(skip=False), dict(gelu=False), dict(complex_out=False),
+                                      dict(merger=False), dict(initial_linear=0), dict(subject_layers=False),
+                                      dict(subject_layers=False, subject_dim=5)])
 def test_ablation_rows_run_through_the_host_path(override):
     """The ablation rows SimpleConv accepts: the host path completes and differs from the default where it should."""
     base = abi_trace.simpleconv_step(abi_trace.CONFIGS["small"], True)
@@ -46,6 +48,14 @@ def test_ablation_rows_run_through_the_host_path(override):
     if "gelu" in override:
         assert "bm_bn_gelu_skip_fwd" not in names and "bm_head_fwd" not in names
         assert names.count("bm_bn_act_skip_fwd") == 11                # 10 layers + the head's activation
+    if "merger" in override:
+        assert "bm_attention_weights_fwd" not in names and "bm_sensor_mix_fwd" not in names
+        assert "bm_initial_linear_fwd" in names and "bm_subject_layers_fwd" in names and "bm_subject_layers_bwd" in names
+    if "initial_linear" in override:
+        assert "bm_initial_linear_fwd" not in names and "bm_sensor_mix_fwd" in names and "bm_sensor_mix_bwd" in names
+    if "subject_layers" in override:
+        assert "bm_subject_layers_fwd" not in names and "bm_initial_linear_bwd" in names
+        assert "bm_sensor_chain_fwd" not in names                      # the fused chain needs all three stages
     if "complex_out" in override:
         assert not any("head" in n for n in names)
         assert names.count("bm_bn_gelu_skip_fwd") == 9                # the 10th layer is a bare convolution

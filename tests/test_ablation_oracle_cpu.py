@@ -38,3 +38,28 @@ def test_ablation_oracle_matches_reference(name):
             assert got.abs().max() < 1e-5 * scale, k
         else:
             assert rel_err(got, want) < 3e-5, (k, rel_err(got, want))
+
+
+@pytest.mark.parametrize("name", list(ABLATIONS))
+def test_ablation_constructor_matches_reference_layout_and_init(name):
+    """The drop-in SimpleConv with the same constructor change: same state_dict keys/shapes as the verbatim reference and,
+    seeded alike, the same initial parameters (the fixtures perturb the BatchNorm affine parameters only)."""
+    import brainmagick_b200 as bb
+    from oracle.ref_loader import clip_conv_kwargs
+    g = load_arrays(name)
+    c = ABLATION_BASE
+    kw = clip_conv_kwargs(hidden=c["hidden"], depth=c["depth"], merger_channels=c["MC"], initial_linear=c["IL"],
+                          merger_pos_dim=c["P"])
+    kw.update(ABLATIONS[name])
+    torch.manual_seed(c["seed"])
+    model = bb.SimpleConv(in_channels=dict(meg=c["C"]), out_channels=c["F"], n_subjects=c["S"], **kw)
+    sd = model.state_dict()
+    assert sorted(sd) == sorted(k[2:] for k in g if k.startswith("p."))
+    for k, v in sd.items():
+        want = g["p." + k]
+        assert tuple(v.shape) == want.shape, k
+        is_bn_affine = k.startswith("encoders.meg.sequence.") and k.split(".")[-2] == "1" and k.endswith(("weight", "bias"))
+        if not is_bn_affine:
+            assert np.array_equal(v.numpy(), want), k
+    assert (model.merger is None) == (not kw.get("merger", True))
+    assert (model.subject_embedding is not None) == bool(kw.get("subject_dim"))

@@ -85,7 +85,7 @@ def test_constructor_errors_and_unsupported_options():
         bb.SimpleConv(in_channels=dict(meg=8), out_channels=4, hidden=dict(other=8))
     with pytest.raises(AssertionError):                   # simpleconv.py:92
         bb.SimpleConv(in_channels=dict(meg=8), out_channels=4, n_subjects=2, **_kw(kernel_size=4))
-    for bad in (dict(merger=False), dict(batch_norm=False), dict(subject_dim=64), dict(dual_path=2),
+    for bad in (dict(batch_norm=False), dict(dual_path=2), dict(initial_depth=2),
                 dict(n_fft=64), dict(dropout=0.1), dict(merger_per_subject=True)):
         with pytest.raises(NotImplementedError):
             bb.SimpleConv(in_channels=dict(meg=8), out_channels=4, n_subjects=2, **_kw(**bad))
