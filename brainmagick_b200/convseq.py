@@ -214,10 +214,14 @@ class _ConvSequenceFn(torch.autograd.Function):
         return tuple(grads)
 
 
-def conv_sequence(module, x: torch.Tensor) -> torch.Tensor:
-    """`ConvSequence.forward(x)` for a `brainmagick_b200.common.ConvSequence` (or `features.DeepMel`) module."""
+def _require_cuda(x: torch.Tensor) -> None:
     if not x.is_cuda:
         raise RuntimeError("brainmagick_b200.ConvSequence runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+
+def conv_sequence(module, x: torch.Tensor) -> torch.Tensor:
+    """`ConvSequence.forward(x)` for a `brainmagick_b200.common.ConvSequence` (or `features.DeepMel`) module."""
+    _require_cuda(x)
     if x.dtype != torch.float32:
         raise TypeError("brainmagick_b200.ConvSequence computes in fp32, like the reference")
     _lib.load()
