@@ -106,3 +106,68 @@ def test_gather_with_grad_reduce_scatters_candidate_gradients():
             assert abs(loss_r - float(parts[r])) < 1e-6
             assert torch.allclose(dc_r, world * cand.grad[r * 3:(r + 1) * 3], atol=1e-6)
             assert torch.allclose(de_r, world * est.grad[r * 3:(r + 1) * 3], atol=1e-6)
+
+
+def _module_worker(rank, world, port, ret):
+    """ClipLoss(global_negatives=True) itself on two gloo ranks, its CUDA entry points served by the CPU emulator."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import abi_emulator
+        import brainmagick_b200 as bb
+        torch.manual_seed(11)
+        est = torch.randn(world * 3, 4, 6)
+        cand = torch.randn(world * 3, 4, 6)
+        mine = slice(rank * 3, rank * 3 + 3)
+        mask = torch.ones(3, 1, 6, dtype=torch.bool)
+        out = {}
+        with abi_emulator.emulated():
+            clip = bb.ClipLoss(global_negatives=True)
+            # (1) constant candidates, gather started early (prefetch) and picked up by forward
+            e = est[mine].clone().requires_grad_(True)
+            c = cand[mine].clone()
+            clip.prefetch_candidates(c)
+            assert clip._prefetched is not None
+            loss = clip(e, c, mask)
+            loss.backward()
+            out["plain"] = (float(loss), e.grad.clone())
+            # (2) same without the prefetch
+            e2 = est[mine].clone().requires_grad_(True)
+            loss2 = clip(e2, cand[mine].clone(), mask)
+            loss2.backward()
+            assert abs(float(loss2) - float(loss)) < 1e-6 and torch.allclose(e2.grad, e.grad, atol=1e-6)
+            # (3) trainable candidates: differentiable gather, no prefetch
+            e3 = est[mine].clone().requires_grad_(True)
+            c3 = cand[mine].clone().requires_grad_(True)
+            clip.prefetch_candidates(c3)
+            assert clip._prefetched is None
+            loss3 = clip(e3, c3, mask)
+            loss3.backward()
+            out["trainable"] = (float(loss3), e3.grad.clone(), c3.grad.clone())
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def test_cliploss_module_with_global_negatives_on_two_ranks():
+    from oracle import bm_oracle
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_module_worker, args=(world, port, ret), nprocs=world, join=True)
+        torch.manual_seed(11)
+        est = torch.randn(world * 3, 4, 6).requires_grad_(True)
+        cand = torch.randn(world * 3, 4, 6).requires_grad_(True)
+        parts = [bm_oracle.clip_loss(est[r * 3:(r + 1) * 3], cand, target_offset=r * 3) for r in range(world)]
+        (sum(parts) / world).backward()
+        for r in range(world):
+            loss_r, de_r = ret[r]["plain"]
+            assert abs(loss_r - float(parts[r])) < 1e-5
+            assert torch.allclose(de_r, world * est.grad[r * 3:(r + 1) * 3], atol=1e-6)
+            loss_t, de_t, dc_t = ret[r]["trainable"]
+            assert abs(loss_t - float(parts[r])) < 1e-5
+            assert torch.allclose(de_t, world * est.grad[r * 3:(r + 1) * 3], atol=1e-6)
+            assert torch.allclose(dc_t, world * cand.grad[r * 3:(r + 1) * 3], atol=1e-6)
