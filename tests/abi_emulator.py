@@ -332,6 +332,99 @@ class Emulator:
         _v(dcand, Bc, KT).copy_(g.t() @ _v(est, Bn, KT) - cf[:, None] * _v(cand, Bc, KT))
 
 
+    # ---------------------------------------------------------------- retrieval evaluation
+    def bm_retrieval_probs(self, scores, ld, Bn, n_cols, probs, stream):
+        _v(probs, Bn, n_cols).copy_(torch.softmax(_ld(scores, Bn, ld, n_cols), dim=1))
+
+    def bm_rowdot_scaled(self, a, c, Bn, K, own, stream):
+        aa, cc = _v(a, Bn, K), _v(c, Bn, K)
+        _v(own, Bn).copy_((aa * cc).sum(1) / (1e-8 + cc.norm(dim=1)))
+
+    def bm_retrieval_topk(self, vals, ld, Bn, n_cols, own_values, own_col, is_prob, k, labels, own_labels, targets, top_idx,
+                          top_prob, hit, soft, row_max, row_sum, stream):
+        v = _ld(vals, Bn, ld, n_cols).clone()
+        if own_values is not None:
+            v[:, own_col] = _v(own_values, Bn)
+        if is_prob:
+            p = v
+            valid = v >= 0
+        else:
+            mx = v.max(dim=1).values
+            ssum = torch.exp(v - mx[:, None]).sum(1)
+            p = torch.exp(v - mx[:, None]) / ssum[:, None]
+            valid = torch.ones_like(v, dtype=torch.bool)
+            if row_max is not None:
+                _v(row_max, Bn).copy_(mx)
+            if row_sum is not None:
+                _v(row_sum, Bn).copy_(ssum)
+        lab = None
+        if labels is not None:
+            lab = _v(labels, n_cols)[None].repeat(Bn, 1)
+            if own_labels is not None:
+                lab[:, own_col] = _v(own_labels, Bn)
+        for b in range(Bn):
+            cols = [int(o) for o in torch.nonzero(valid[b]).flatten()]
+            cols.sort(key=lambda o: (-float(v[b, o]), o))            # larger first, ties -> lower column
+            first = -1
+            for j in range(k):
+                col = cols[j] if j < len(cols) else -1
+                if top_idx is not None:
+                    _v(top_idx, Bn, k)[b, j] = col
+                if top_prob is not None:
+                    _v(top_prob, Bn, k)[b, j] = float(p[b, col]) if col >= 0 else 0.0
+                if col >= 0 and lab is not None and targets is not None and first < 0 and lab[b, col] == targets[b]:
+                    first = j
+            if hit is not None:
+                _v(hit, Bn)[b] = first
+            if soft is not None:
+                m = (lab[b] == targets[b]) & valid[b]
+                _v(soft, Bn)[b] = p[b][m].sum()
+
+    def bm_retrieval_vocab_probs(self, scores, ld, Bn, own_scores, row_max, row_sum, perm, seg, V, own_word, vocab, stream):
+        s = _v(scores, Bn, ld)
+        out = _v(vocab, Bn, V + 1)
+        for b in range(Bn):
+            mx, inv = _v(row_max, Bn)[b], 1.0 / _v(row_sum, Bn)[b]
+            p_own = torch.exp(_v(own_scores, Bn)[b] - mx) * inv if own_scores is not None else 0.0
+            w_own = int(_v(own_word, Bn)[b]) if own_scores is not None else -1
+            for w in range(V):
+                cols = perm[int(seg[w]):int(seg[w + 1])].long()
+                acc = (torch.exp(s[b, cols] - mx) * inv).sum()
+                out[b, w] = acc + (p_own if w == w_own else 0.0)
+            out[b, V] = p_own if w_own == V else -1.0
+
+    # ---------------------------------------------------------------- batch preparation
+    def bm_scale_clamp_crop(self, x, slot, center, scale, B, C, T, t0, T_out, limit, clip, inverse, y, peak_bits, stream):
+        xx = _v(x, B, C, T)
+        rows = slot.long()[:B] if slot is not None else torch.zeros(B, dtype=torch.long)
+        R = center.numel() // C
+        ctr, scl = _v(center, R, C), _v(scale, R, C)
+        known = rows >= 0
+        c = torch.where(known[:, None], ctr[rows.clamp_min(0)], torch.full((B, C), float("nan")))
+        s = torch.where(known[:, None], scl[rows.clamp_min(0)], torch.ones(B, C))
+        out = (xx * s[:, :, None] + c[:, :, None]) if inverse else (xx - c[:, :, None]) / s[:, :, None]
+        if clip:
+            out = torch.where(out < -limit, torch.full_like(out, -limit), torch.where(out > limit, torch.full_like(out, limit), out))
+        _v(y, B, C, T_out).copy_(out[:, :, t0:t0 + T_out])
+        if peak_bits is not None:
+            window = out[:, :, t0:t0 + T_out] if clip else out
+            peak = torch.nan_to_num(window.abs(), nan=0.0).reshape(B, -1).max(1).values
+            _v(peak_bits, B).copy_(peak.view(torch.int32))
+
+    def bm_reject_compact(self, peak_bits, mask, mask_elems, limit, B, keep, keep_rows, n_keep, stream):
+        peak = _v(peak_bits, B).view(torch.float32)
+        k = ~(peak > limit)
+        if mask is not None:
+            k = k & _v(mask, B, mask_elems).bool().any(1)
+        _v(keep, B).copy_(k)
+        rows = torch.nonzero(k).flatten().int()
+        _v(keep_rows, B)[:len(rows)] = rows
+        _v(n_keep, 1)[0] = len(rows)
+
+    def bm_gather_rows(self, x, rows, n_rows, row_elems, y, stream):
+        _v(y, n_rows, row_elems).copy_(x.reshape(-1, row_elems)[rows.long()[:n_rows]])
+
+
 class _Stream:
     def wait_stream(self, other):
         pass
@@ -357,8 +450,13 @@ def emulated():
             raise NotImplementedError(f"{name} is not emulated (a tensor-core entry point at fixture size?)")
         fn(*args)
 
+    import brainmagick_b200.norm as NM
+    import brainmagick_b200.retrieval as RT
     patches = [(BF, "call", fake_call), (BF, "ptr", fake_ptr), (BF, "stream", lambda: None),
                (CS, "call", fake_call), (CS, "ptr", fake_ptr), (CS, "stream", lambda: None),
+               (NM, "call", fake_call), (NM, "ptr", fake_ptr), (NM, "stream", lambda: None),
+               (RT, "call", fake_call), (RT, "ptr", fake_ptr), (RT, "stream", lambda: None),
+               (RT, "_device", lambda: torch.device("cpu")),
                (BF, "OVERLAP_WGRAD", False), (SC, "_require_cuda", lambda meg: None),
                (CS, "_require_cuda", lambda x: None),
                (torch.cuda, "current_stream", lambda *a, **k: _Stream())]

@@ -125,3 +125,74 @@ def test_deepmel_on_the_emulator(case):
     assert mel.grad is not None and torch.isfinite(mel.grad).all()
     _check_grads(model, {k[2:]: v for k, v in g.items() if k.startswith("g.") and k[2:] not in ("estimate", "candidates")})
     assert rel_err(out_eval, torch.from_numpy(g["candidates_eval"])) < TOL
+
+
+def test_retrieval_host_path_on_the_emulator():
+    """builds_probs / accuracies / the batched get_wer ranking (vocabulary bookkeeping, own-candidate column) against the
+    retrieval fixture.  These run green on the GPU too; here they guard the host logic between GPU sessions."""
+    import types
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import retrieval
+    g = load_arrays("retrieval_small")
+    t = lambda k: torch.from_numpy(g[k])     # noqa: E731
+    clip = bb.ClipLoss().eval()
+    args = types.SimpleNamespace(tmin=-0.5, sample_rate=120.0)
+    with abi_emulator.emulated():
+        probs = retrieval.builds_probs(clip, t("preds"), t("trues"), args, batch_size=10)
+        pw = retrieval.builds_probs(clip, t("preds"), t("trues"), args, batch_size=7, tmin=-0.45, tmax=-0.4)
+        acc = retrieval.retrieval_accuracy(clip, t("preds"), t("trues"), t("target_labels"), t("vocab_labels"),
+                                           topk=(1, 5, 10), batch_size=9)
+        acc10 = retrieval._get_accuracy_from_probs(t("probs"), t("target_labels"), t("vocab_labels"), topk=10)
+        res = [retrieval.wer_ranking(clip, t("wer_estimates"), t("wer_word_hashes"), t("wer_outputs"), t("wer_negatives"),
+                                     t("wer_negative_hashes"), int(g["wer_topx"]), batch_size=bs) for bs in (5, 64)]
+    assert np.abs(probs.numpy() - g["probs"]).max() < 2e-6
+    assert np.abs(pw.numpy() - g["probs_window"]).max() < 2e-6
+    assert [acc[1], acc[5], acc[10]] == pytest.approx([float(a) for a in g["acc"]])
+    assert acc10 == pytest.approx(float(g["acc"][2]))
+    for r in res:
+        assert r["wer"] == pytest.approx(float(g["wer"])) and r["wer_vocab"] == pytest.approx(float(g["wer_vocab"]))
+        assert r["soft_correct"] == pytest.approx(float(g["wer_soft"]), rel=1e-4)
+
+
+@pytest.mark.parametrize("clip", [0, 1])
+@pytest.mark.parametrize("excl", [0, 1])
+def test_batch_preparation_host_path_on_the_emulator(clip, excl):
+    import types
+    from brainmagick_b200 import norm as bnorm, synthetic
+    g = load_arrays("prep_small")
+    off = int(g["offset"])
+
+    class Builder(dict):
+        dimension = 5
+
+        def __init__(self):
+            super().__init__(a=types.SimpleNamespace(normalizable=True, categorical=False, cardinality=0),
+                             b=types.SimpleNamespace(normalizable=False, categorical=False, cardinality=0))
+
+        def get_slice(self, name):
+            return dict(a=slice(0, 3), b=slice(3, 5))[name]
+
+    for tag in ("pc0.", "pc1."):
+        sc = bnorm.BatchScaler(Builder(), per_channel=(tag == "pc1."))
+        for i, r in enumerate(g["rec_ids"]):
+            s = bnorm.Scaler()
+            s.center_, s.scale_ = torch.from_numpy(g[tag + "meg_center"][i]), torch.from_numpy(g[tag + "meg_scale"][i])
+            sc.meg_scalers[int(r)] = s
+        sc.feature_scalers["a"].center_ = torch.from_numpy(g[tag + "feat_center"][:3])
+        sc.feature_scalers["a"].scale_ = torch.from_numpy(g[tag + "feat_scale"][:3])
+        batch = synthetic.SyntheticBatch(torch.from_numpy(g["meg"]), torch.zeros(len(g["meg"]), dtype=torch.long), [],
+                                         features=torch.from_numpy(g["features"]),
+                                         features_mask=torch.from_numpy(g["features_mask"]),
+                                         recording_index=torch.from_numpy(g["recording_index"]))
+        k = f"{tag}clip{clip}.excl{excl}."
+        with abi_emulator.emulated():
+            sr = bnorm.ScaleReject(sc, limit=float(g["limit"]), exclude_empty_features=bool(excl), clip=bool(clip))
+            kept, keep = sr(batch)
+            meg, feats, mask, keep2 = sr.prepare(batch, off)
+            back = sc.inverse_transform(sc.transform(batch))
+        assert np.array_equal(keep.numpy(), g[k + "keep"]) and np.array_equal(keep2.numpy(), g[k + "keep"])
+        assert np.array_equal(kept.meg[..., off:].numpy(), g[k + "meg"])
+        assert np.array_equal(meg.numpy(), g[k + "meg"])
+        assert np.array_equal(feats.numpy(), g[k + "features"])
+        assert np.array_equal(mask.numpy(), g[k + "features_mask"])
+        assert np.array_equal(back.meg.numpy(), g[tag + "inverse.meg"])
