@@ -8,8 +8,10 @@ drop-in can be run here against the verbatim-reference fixtures:
   * the fixtures the GPU path is known to pass must also pass on the emulator (that validates the emulator's reading of the
     contracts), and then
   * compositions that have not had a GPU run yet (ablation rows, ...) are checked numerically against their fixtures.
-Only the FP32-FMA entry points small models use are emulated; tensor-core entry points are not (their shapes never occur at
-fixture size).  Buffers are interpreted through the integer arguments only (flat views), exactly like the C side.
+The tensor-core entry points are emulated with the same contracts in exact fp32 (no 3xTF32 rounding), which lets the
+all-tensor-core host path (paddings, operand layouts, slices) run on the CPU as well; the shape gates (`*_supported`,
+workspace sizes) are always answered by the real library.  Buffers are interpreted through the integer arguments only
+(flat views), exactly like the C side.
 """
 from __future__ import annotations
 
@@ -331,6 +333,111 @@ class Emulator:
         cf = torch.where(norm > 0, (g * _v(scores, Bn, Bc)).sum(0) / norm, torch.zeros(Bc))
         _v(dcand, Bc, KT).copy_(g.t() @ _v(est, Bn, KT) - cf[:, None] * _v(cand, Bc, KT))
 
+
+    # ---------------------------------------------------------------- tensor-core entry points (same contracts, exact fp32)
+    _armed_stats = None
+
+    def bm_tc_pair_want_stats(self, stats):
+        self._armed_stats = stats
+
+    def bm_tc_conv1d(self, x, w_hi, w_lo, bias, addend, B, T, Cin, Ntot, Kw, dilation, sign, glu, act, out_tmajor, y, aux,
+                     glu_out, status, stream):
+        w = _v(w_hi, Kw, Ntot, Cin)
+        if w_lo is not None:
+            w = w + _v(w_lo, Kw, Ntot, Cin)
+        xx = _v(x, B, T, Cin)
+        pad = (Kw // 2) * dilation
+        xp = F.pad(xx, (0, 0, pad, pad))
+        out = torch.zeros(B, T, Ntot)
+        for tap in range(Kw):
+            shift = sign * (tap - Kw // 2) * dilation
+            out += xp[:, pad + shift:pad + shift + T] @ w[tap].t()
+        if bias is not None:
+            out = out + _v(bias, Ntot)
+        if addend is not None:
+            out = out + _v(addend, B, T, Ntot)
+        stats, self._armed_stats = self._armed_stats, None
+        if stats is not None:
+            o = out.reshape(-1, Ntot).double()
+            _v(stats, 2 * Ntot).copy_(torch.cat([o.sum(0), (o * o).sum(0)]))
+        if glu:
+            H = Ntot // 2
+            if y is not None:
+                _v(y, B, T, Ntot).copy_(out)
+            _v(glu_out, B, T, H).copy_(out[..., :H] * torch.sigmoid(out[..., H:]))
+            return
+        if act:
+            if aux is not None:
+                _v(aux, B, T, Ntot).copy_(out)
+            out = F.gelu(out)
+        if out_tmajor:
+            _v(y, B, Ntot, T).copy_(out.transpose(1, 2))
+        else:
+            _v(y, B, T, Ntot).copy_(out)
+
+    bm_tc_conv1d_pair = bm_tc_conv1d
+
+    def bm_col_stats(self, y, rows, C, stats, stream):
+        o = _v(y, rows, C).double()
+        _v(stats, 2 * C).copy_(torch.cat([o.sum(0), (o * o).sum(0)]))
+
+    def bm_col_sum(self, x, rows, C, out, stream):
+        _v(out, C).copy_(_v(x, rows, C).sum(0))
+
+    def bm_gelu_bwd(self, dq, h, n, dh, stream):
+        _v(dh, n).copy_(_v(dq, n).clone() * _gelu_grad(_v(h, n)))
+
+    def bm_tc_wgrad(self, dy, x, B, T, M, N, Ntrue, Kw, dilation, ws, dw, dbias, status, stream):
+        g, xx = _v(dy, B, T, M), _v(x, B, T, N)
+        pad = (Kw // 2) * dilation
+        xp = F.pad(xx, (0, 0, pad, pad))
+        taps = [torch.einsum("btm,btn->mn", g, xp[:, j * dilation:j * dilation + T])[:, :Ntrue] for j in range(Kw)]
+        _v(dw, M, Ntrue, Kw).copy_(torch.stack(taps, dim=2))
+        if dbias is not None:
+            _v(dbias, M).copy_(g.reshape(-1, M).sum(0))
+
+    def bm_tc_pointwise_sel(self, x, w_hi, w_lo, wsel, n_sets, B, T, Cin, Ntot, y, status, stream):
+        w = _v(w_hi, n_sets, Ntot, Cin) + _v(w_lo, n_sets, Ntot, Cin)
+        _v(y, B, T, Ntot).copy_(torch.einsum("btk,bnk->btn", _v(x, B, T, Cin), w[wsel.long()[:B]]))
+
+    def bm_tc_wgrad_grouped(self, dy, x, order, seg_off, G, B, T, M, N, out, status, stream):
+        per = torch.einsum("btm,btn->bmn", _v(dy, B, T, M), _v(x, B, T, N))
+        mpad = -(-M // 128) * 128
+        o = _v(out, G, mpad, N)
+        o.zero_()
+        order, off = order.long(), seg_off.long()
+        for gi in range(G):
+            o[gi, :M] = per[order[off[gi]:off[gi + 1]]].sum(0)
+
+    def bm_fourier_emb(self, positions, freq, R, C, P, emb, stream):
+        pos = _v(positions, R, C, 2)
+        f = freq.reshape(-1)
+        n = f.numel()
+        x, y = pos[..., 0] + 0.2, pos[..., 1] + 0.2
+        loc = (x[..., None, None] * f[:, None] + y[..., None, None] * f[None, :]).reshape(R, C, n * n)
+        _v(emb, R, C, P).copy_(torch.cat([loc.cos(), loc.sin()], dim=-1))
+
+    def bm_masked_softmax(self, weights, positions, ban_centre, radius, R, O, C, stream):
+        pos = _v(positions, R, C, 2)
+        masked = (pos == INVALID).all(-1)
+        if ban_centre is not None:
+            d = pos - ban_centre.reshape(2)
+            masked = masked | (torch.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) <= radius)
+        w = _v(weights, R, O, C)
+        w.copy_(torch.softmax(w.masked_fill(masked[:, None, :], float("-inf")), dim=2))
+
+    def bm_softmax_bwd(self, weights, dweights, rows, C, dscores, stream):
+        w, dw = _v(weights, rows, C), _v(dweights, rows, C)
+        _v(dscores, rows, C).copy_(w * (dw - (dw * w).sum(-1, keepdim=True)))
+
+    def bm_head_bwd_params(self, dest, x, h1, q, B, T, H, F_, dq, dw0, db0, dw2, db2, stream):
+        d = _v(dest, B, F_, T).transpose(1, 2).reshape(B * T, F_)
+        _v(dw2, 2 * H, F_).copy_(_v(q, B * T, 2 * H).t() @ d)
+        _v(db2, F_).copy_(d.sum(0))
+        dh1 = _v(dq, B * T, 2 * H).clone() * _gelu_grad(_v(h1, B * T, 2 * H))
+        _v(dq, B * T, 2 * H).copy_(dh1)
+        _v(dw0, 2 * H, H).copy_(dh1.t() @ _v(x, B * T, H))
+        _v(db0, 2 * H).copy_(dh1.sum(0))
 
     # ---------------------------------------------------------------- retrieval evaluation
     def bm_retrieval_probs(self, scores, ld, Bn, n_cols, probs, stream):

@@ -196,3 +196,48 @@ def test_batch_preparation_host_path_on_the_emulator(clip, excl):
         assert np.array_equal(feats.numpy(), g[k + "features"])
         assert np.array_equal(mask.numpy(), g[k + "features_mask"])
         assert np.array_equal(back.meg.numpy(), g[tag + "inverse.meg"])
+
+
+@pytest.mark.parametrize("shape", [
+    # the "tcgen05-eligible widths" case of tests/test_gpu_parity.py (mixed tensor-core / FMA kernels)
+    dict(B=8, C=40, T=130, F=128, S=3, hidden=160, MC=48, IL=24, P=128, n_valid=()),
+    # BASELINE widths (every contraction through a tensor-core entry point), short and narrow in batch/time only
+    dict(B=3, C=208, T=48, F=1024, S=4, hidden=320, MC=270, IL=270, P=2048, n_valid=(208, 150, 208, 97)),
+])
+@pytest.mark.parametrize("train", [True, False])
+def test_tensor_core_host_path_on_the_emulator(shape, train):
+    """The tensor-core host path (channel paddings, tf32 hi/lo operand layouts, per-recording / per-subject weight sets,
+    grouped weight gradients, fused statistics, in-place reduce-add) with the tensor-core entry points emulated in exact
+    fp32, against the oracle."""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic
+    from oracle import bm_oracle
+    cfg = bm_oracle.Config(in_channels=shape["C"], out_channels=shape["F"], n_subjects=shape["S"], hidden=shape["hidden"],
+                           merger_channels=shape["MC"], initial_linear=shape["IL"], merger_pos_dim=shape["P"])
+    params = bm_oracle.init_state_dict(cfg, seed=11)
+    d = bm_oracle.synthetic_batch(cfg, batch=shape["B"], T=shape["T"], seed=5, n_valid=shape["n_valid"])
+    d["rec_positions"] = synthetic.normalised_positions(cfg.n_subjects, cfg.in_channels, shape["n_valid"], seed=3)
+    ref = bm_oracle.training_step(params, cfg, d["meg"], d["rec_positions"], d["rec_of_sample"], d["subject_index"],
+                                  d["candidates"], ban_centre=d["ban_centre"], training=train)
+    model = bb.SimpleConv(
+        in_channels=dict(meg=cfg.in_channels), out_channels=cfg.out_channels, hidden=dict(meg=cfg.hidden),
+        depth=cfg.depth, dilation_period=cfg.dilation_period, kernel_size=cfg.kernel_size, skip=True, subject_layers=True,
+        subject_dim=0, complex_out=True, glu=cfg.glu, glu_context=cfg.glu_context, merger=True,
+        initial_linear=cfg.initial_linear, merger_channels=cfg.merger_channels, gelu=True, batch_norm=True,
+        merger_pos_dim=cfg.merger_pos_dim, merger_dropout=cfg.merger_dropout, n_subjects=cfg.n_subjects)
+    model.load_state_dict(params, strict=True)
+    model.train(train)
+    model.merger.ban_centre_override = d["ban_centre"]
+    batch = synthetic.make_batch(d["meg"], d["subject_index"], d["rec_positions"], d["rec_of_sample"])
+    clip = bb.ClipLoss().train(train)
+    with abi_emulator.emulated() as emu:
+        est = model(dict(meg=d["meg"]), batch)
+        loss = clip(est, d["candidates"], torch.ones(len(d["meg"]), 1, d["meg"].shape[2], dtype=torch.bool))
+        loss.backward()
+    assert rel_err(est.detach(), ref["estimate"]) < TOL
+    assert abs(loss.item() - ref["loss"].item()) < 1e-5
+    _check_grads(model, {k: v.numpy() for k, v in ref["grads"].items()}, tol=2e-4)     # fp32 summation-order noise
+    if train:
+        sd = model.state_dict()
+        for key, v in ref["bn_updates"].items():
+            assert rel_err(sd[key], v) < TOL, key
