@@ -241,3 +241,40 @@ def test_tensor_core_host_path_on_the_emulator(shape, train):
         sd = model.state_dict()
         for key, v in ref["bn_updates"].items():
             assert rel_err(sd[key], v) < TOL, key
+
+
+@pytest.mark.parametrize("activation", [None, "gelu"])
+def test_deepmel_tensor_core_widths_on_the_emulator(activation):
+    """conf/feature_model/deep_mel.yaml at its real widths (120 mel padded to 128 -> 9 x 320 -> 768), short in batch/time:
+    the stand-alone ConvSequence's tensor-core host path and the candidate-side ClipLoss gradient against the oracle."""
+    import brainmagick_b200 as bb
+    from oracle import bm_oracle, deepmel_oracle
+    kw = dict(n_hidden_channels=320, n_hidden_layers=10, n_out_channels=768, kernel=3, stride=1, dilation_growth=2,
+              dilation_period=5, batch_norm=True, activation_on_last=False, skip=True, glu_context=1, glu=2)
+    if activation == "gelu":
+        kw["activation"] = torch.nn.GELU
+    torch.manual_seed(3)
+    model = bb.DeepMel(n_in_channels=120, **kw).train()
+    params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    okw = {k: v for k, v in kw.items() if k not in ("stride", "activation", "n_hidden_channels", "n_hidden_layers",
+                                                    "n_out_channels")}
+    spec = deepmel_oracle.deep_mel_spec(120, 320, 10, 768, activation="gelu" if activation == "gelu" else "lrelu", **okw)
+    B, T = 3, 40
+    mel, est = torch.randn(B, 120, T), torch.randn(B, 768, T)
+    p = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in params.items()}
+    m_ref, e_ref = mel.clone().requires_grad_(True), est.clone().requires_grad_(True)
+    cand_ref = deepmel_oracle.conv_sequence(m_ref, p, spec, training=True)
+    cand_ref.retain_grad()
+    loss_ref = bm_oracle.clip_loss(e_ref, cand_ref)
+    loss_ref.backward()
+    m, e = mel.clone().requires_grad_(True), est.clone().requires_grad_(True)
+    with abi_emulator.emulated():
+        cand = model(m)
+        cand.retain_grad()
+        loss = bb.ClipLoss()(e, cand, torch.ones(B, 1, T, dtype=torch.bool))
+        loss.backward()
+    assert rel_err(cand.detach(), cand_ref.detach()) < TOL
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    assert rel_err(e.grad, e_ref.grad) < 5e-5 and rel_err(cand.grad, cand_ref.grad) < 5e-5
+    assert rel_err(m.grad, m_ref.grad) < 5e-4
+    _check_grads(model, {k: v.grad.numpy() for k, v in p.items() if v.grad is not None}, tol=5e-4)
