@@ -278,3 +278,46 @@ def test_deepmel_tensor_core_widths_on_the_emulator(activation):
     assert rel_err(e.grad, e_ref.grad) < 5e-5 and rel_err(cand.grad, cand_ref.grad) < 5e-5
     assert rel_err(m.grad, m_ref.grad) < 5e-4
     _check_grads(model, {k: v.grad.numpy() for k, v in p.items() if v.grad is not None}, tol=5e-4)
+
+
+@pytest.mark.parametrize("change", [dict(glu=0), dict(skip=False), dict(gelu=False), dict(complex_out=False),
+                                    dict(merger=False), dict(initial_linear=0), dict(subject_layers=False),
+                                    dict(subject_layers=False, subject_dim=64)],
+                         ids=lambda c: ",".join(f"{k}={v}" for k, v in c.items()))
+def test_ablation_rows_at_baseline_widths_on_the_emulator(change):
+    """Every row of the ablation table at the BASELINE widths (where the convolutions, weight gradients and -- for the
+    un-ablated sensor chain -- the sensor stages go through tensor-core entry points), against `oracle/ablation_oracle.py`."""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic
+    from oracle import ablation_oracle, bm_oracle
+    B, C, T, Fo, S = 3, 208, 48, 1024, 4
+    kw = dict(hidden=dict(meg=320), depth=10, dilation_period=5, kernel_size=3, skip=True, subject_layers=True,
+              subject_dim=0, complex_out=True, glu=2, glu_context=1, merger=True, initial_linear=270, merger_channels=270,
+              gelu=True, batch_norm=True, merger_pos_dim=2048, merger_dropout=0.2, n_subjects=S)
+    kw.update(change)
+    torch.manual_seed(17)
+    model = bb.SimpleConv(in_channels=dict(meg=C), out_channels=Fo, **kw).train()
+    v = ablation_oracle.Variant(in_channels=C, out_channels=Fo, n_subjects=S)._replace(
+        **{k: val for k, val in change.items()})
+    p = {k: t.detach().clone().requires_grad_(t.is_floating_point() and "running" not in k)
+         for k, t in model.state_dict().items()}
+    meg = torch.randn(B, C, T).clamp_(-20, 20)
+    cand = torch.randn(B + 2, Fo, T)
+    subj = torch.tensor([2, 0, 2])
+    pos = synthetic.normalised_positions(S, C, (208, 150, 208, 97), seed=4)
+    for b in range(B):
+        meg[b, (208, 150, 208, 97)[int(subj[b])]:] = 0
+    ban = torch.tensor([0.31, 0.64])
+    est_ref = ablation_oracle.forward(p, v, meg, pos, subj, subj, training=True, ban_centre=ban)
+    loss_ref = bm_oracle.clip_loss(est_ref, cand)
+    loss_ref.backward()
+    if model.merger is not None:
+        model.merger.ban_centre_override = ban
+    batch = synthetic.make_batch(meg, subj, pos, subj)
+    with abi_emulator.emulated():
+        est = model(dict(meg=meg), batch)
+        loss = bb.ClipLoss()(est, cand, torch.ones(B, 1, T, dtype=torch.bool))
+        loss.backward()
+    assert rel_err(est.detach(), est_ref.detach()) < TOL
+    assert abs(loss.item() - loss_ref.item()) < 1e-5
+    _check_grads(model, {k: t.grad.numpy() for k, t in p.items() if t.grad is not None}, tol=2e-4)
