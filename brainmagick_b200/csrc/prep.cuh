@@ -36,7 +36,7 @@ __global__ void scale_clamp_crop_kernel(const float* __restrict__ x, const int* 
         const float ctr = known ? center[(long long)s * C + c] : __int_as_float(0x7fc00000);
         const float scl = known ? scale[(long long)s * C + c] : 1.f;
         const float* xr = x + row * T;
-        float* yr = y + row * T_out - t0;
+        float* yr = y + row * T_out;
         float peak = 0.f;
         // 8 independent 128 B loads in flight per warp before the first use (a row is ~11 such lines)
         for (int base = t_lo; base < t_hi; base += 32 * PREP_ILP) {
@@ -53,7 +53,7 @@ __global__ void scale_clamp_crop_kernel(const float* __restrict__ x, const int* 
                 if (clip) w = w < -limit ? -limit : (w > limit ? limit : w);     // NaN stays NaN, like Tensor.clamp_
                 if (t < t_hi) {
                     peak = fmaxf(peak, fabsf(w));
-                    if (t >= t0 && t < t0 + T_out) yr[t] = w;
+                    if (t >= t0 && t < t0 + T_out) yr[t - t0] = w;
                 }
             }
         }
