@@ -249,8 +249,11 @@ def run_b200(args):
     # ---- roofline of the dominant kernel: the K3 dilated conv (320 -> 320, k=3) -------------------------
     roofline = None
     cpu_baseline = None
+    also = None
     if rank == 0:
         roofline = conv_roofline(dev, B, T)
+        if world == 1:
+            also = also_measured(model, clip, make_batch, resident, host, n_host, mask, dev, B)
         if not args.no_cpu_baseline:
             cpu_baseline = run_cpu(steps=2, warmup=1, batch=16, threads=None)
     if world > 1:
@@ -268,8 +271,72 @@ def run_b200(args):
                     subjects=S, model="clip_conv (random init)", negatives="global (all-gather)" if world > 1 else "local",
                     l2="per-step working set (inputs 454 MB + ~5 GB saved activations) >> 126 MB L2; two input batches rotate",
                     last_loss=last_loss[0]),
-        clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline)
+        clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline, also=also)
     print(json.dumps(out))
+
+
+def also_measured(model, clip, make_batch, resident, host, n_host, mask, dev, B, iters=5):
+    """What SURVEY.md 8(d) asks to report beside the headline (N=1 only, after the headline has been timed; every part is
+    optional and a failure is recorded instead of raised):
+      * forward_only: the encoder in eval mode under no_grad (the evaluation-time cost), segments/s;
+      * torch_eager_gpu: the SAME step (forward + ClipLoss + backward, no optimizer) written in plain PyTorch ops -- the
+        oracle restatement of the reference modules -- run on this GPU with cuDNN / cuBLAS: the "library-kernel" bar,
+        with TF32 off (fp32-faithful like this repo) and on."""
+    out = {}
+
+    def timed_ms(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    try:
+        model.eval()
+
+        def fwd(i=0):
+            meg_d, _, subj_d = resident[i % n_host]
+            with torch.no_grad():
+                model(dict(meg=meg_d), make_batch(meg_d, subj_d, host[i % n_host][3]))
+        ms = timed_ms(fwd, iters)
+        out["forward_only"] = dict(value=B / (ms / 1e3), unit="segments/s", ms_per_batch=ms, mode="eval, no_grad")
+    except Exception as exc:
+        out["forward_only"] = dict(error=f"{type(exc).__name__}: {exc}")
+    finally:
+        model.train()
+
+    try:
+        from oracle import bm_oracle
+        from brainmagick_b200 import synthetic
+        C, T, F, S = WORKLOAD["C"], WORKLOAD["T"], WORKLOAD["F"], WORKLOAD["S"]
+        cfg = bm_oracle.Config(in_channels=C, out_channels=F, n_subjects=S)
+        params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        meg_d, feats_d, subj_d = resident[0]
+        pos = synthetic.normalised_positions(S, C, seed=7).to(dev)
+        ban = torch.tensor([0.5, 0.5], device=dev)
+        saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        res = {}
+        try:
+            for label, tf32 in (("tf32_off", False), ("tf32_on", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+
+                def eager(i=0):
+                    bm_oracle.training_step(params, cfg, meg_d, pos, subj_d, subj_d, feats_d, ban_centre=ban, training=True)
+                ms = timed_ms(eager, 3)
+                res[label] = dict(value=B / (ms / 1e3), unit="segments/s", ms_per_step=ms)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+        res["what"] = "oracle restatement of SimpleConv + ClipLoss in PyTorch ops on this GPU: forward + loss + backward, no optimizer"
+        out["torch_eager_gpu"] = res
+    except Exception as exc:
+        out["torch_eager_gpu"] = dict(error=f"{type(exc).__name__}: {exc}")
+    torch.cuda.empty_cache()
+    return out
 
 
 def ncu_traffic_bytes():

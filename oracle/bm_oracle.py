@@ -100,7 +100,7 @@ def attention_weights(positions: torch.Tensor, heads: torch.Tensor,
     The reference evaluates this per *sample*; the weights only depend on the recording's layout and on the
     single per-forward ban centre (common.py:343), so one row per recording is the same arithmetic."""
     emb = fourier_emb(positions, heads.shape[1])                                   # [R,C,P]
-    offset = torch.zeros(positions.shape[:2], dtype=positions.dtype)
+    offset = torch.zeros(positions.shape[:2], dtype=positions.dtype, device=positions.device)
     offset[(positions.float() == INVALID).all(dim=-1)] = float("-inf")             # common.py:339-340 (fp32 compare)
     if ban_centre is not None:
         banned = (positions - ban_centre.to(positions)).norm(dim=-1) <= radius     # common.py:344-346
@@ -204,7 +204,7 @@ def clip_loss(estimate, candidate, target_offset: int = 0):
     candidates r*B_loc + arange(B_loc); 0 reproduces the reference exactly."""
     assert estimate.size(0) <= candidate.size(0)
     scores = clip_scores(estimate, candidate)
-    target = torch.arange(len(scores)) + target_offset
+    target = torch.arange(len(scores), device=scores.device) + target_offset
     return F.cross_entropy(scores, target)
 
 
@@ -221,7 +221,7 @@ def training_step(p, cfg, meg, rec_positions, rec_of_sample, subject_index, cand
                              ban_centre, bn_updates)
     cands = candidates if all_candidates is None else all_candidates
     scores = clip_scores(est, cands)
-    loss = F.cross_entropy(scores, torch.arange(len(scores)) + target_offset)
+    loss = F.cross_entropy(scores, torch.arange(len(scores), device=scores.device) + target_offset)
     names = [k for k, v in params.items() if v.requires_grad]
     grads = torch.autograd.grad(loss, [params[k] for k in names], allow_unused=True)
     return dict(estimate=est.detach(), scores=scores.detach(), loss=loss.detach(),
