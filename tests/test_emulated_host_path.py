@@ -321,3 +321,54 @@ def test_ablation_rows_at_baseline_widths_on_the_emulator(change):
     assert rel_err(est.detach(), est_ref.detach()) < TOL
     assert abs(loss.item() - loss_ref.item()) < 1e-5
     _check_grads(model, {k: t.grad.numpy() for k, t in p.items() if t.grad is not None}, tol=2e-4)
+
+
+def test_multi_step_training_state_on_the_emulator():
+    """Four Adam steps: parameters, BatchNorm running statistics and `num_batches_tracked` carried from step to step must
+    follow the oracle trainer (solver.py:297,373,384-387 restated) -- the state handling around the encoder function."""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic
+    from oracle import bm_oracle
+    cfg = bm_oracle.Config(in_channels=12, out_channels=10, n_subjects=3, hidden=16, merger_channels=12, initial_linear=12,
+                           merger_pos_dim=32)
+    params = bm_oracle.init_state_dict(cfg, seed=5)
+    trainer = bm_oracle.CpuTrainer(cfg, params, lr=2e-4)
+    model = bb.SimpleConv(
+        in_channels=dict(meg=cfg.in_channels), out_channels=cfg.out_channels, hidden=dict(meg=cfg.hidden), depth=cfg.depth,
+        dilation_period=5, kernel_size=3, skip=True, subject_layers=True, subject_dim=0, complex_out=True, glu=2,
+        glu_context=1, merger=True, initial_linear=cfg.initial_linear, merger_channels=cfg.merger_channels, gelu=True,
+        batch_norm=True, merger_pos_dim=cfg.merger_pos_dim, n_subjects=cfg.n_subjects)
+    model.load_state_dict(params)
+    model.train()
+    clip = bb.ClipLoss().train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.9, 0.999))
+    pos = synthetic.normalised_positions(cfg.n_subjects, cfg.in_channels, seed=2)
+    with abi_emulator.emulated():
+        for step in range(4):
+            d = bm_oracle.synthetic_batch(cfg, batch=6, T=30, seed=100 + step)
+            ref_loss = trainer.step(d["meg"], pos, d["rec_of_sample"], d["subject_index"], d["candidates"], d["ban_centre"])
+            model.merger.ban_centre_override = d["ban_centre"]
+            batch = synthetic.make_batch(d["meg"], d["subject_index"], pos, d["rec_of_sample"])
+            opt.zero_grad(set_to_none=True)
+            loss = clip(model(dict(meg=d["meg"]), batch), d["candidates"], torch.ones(6, 1, 30, dtype=torch.bool))
+            loss.backward()
+            opt.step()
+            assert abs(loss.item() - ref_loss) < 5e-5 * max(1.0, abs(ref_loss)), (step, loss.item(), ref_loss)
+        # Parameters whose true gradient is zero (a conv bias in front of BatchNorm, the heads' column of the constant
+        # embedding term) are moved by Adam on rounding noise alone -- lr per step, in a direction the noise decides; the
+        # CUDA path returns the exact zero for the conv biases and leaves them where they are.  So parameter tensors cannot
+        # be compared one to one, and through the lag of the BatchNorm running means even the eval-mode function differs
+        # by O(lr x steps); with a small lr the FUNCTION after training can be compared.
+        d = bm_oracle.synthetic_batch(cfg, batch=5, T=30, seed=999)
+        p_ref = {k: v.detach() for k, v in trainer.p.items()}
+        want = bm_oracle.simpleconv_forward(p_ref, cfg, d["meg"], pos, d["rec_of_sample"], d["subject_index"], False)
+        model.eval()
+        with torch.no_grad():
+            got = model(dict(meg=d["meg"]), synthetic.make_batch(d["meg"], d["subject_index"], pos, d["rec_of_sample"]))
+    assert rel_err(got, want) < 1e-3, rel_err(got, want)
+    sd = model.state_dict()
+    for k, v in trainer.p.items():
+        if "num_batches" in k:
+            assert int(sd[k]) == 4
+        elif "running" in k:          # the running mean tracks the (noise-walking) conv bias of the reference: O(lr x steps)
+            assert rel_err(sd[k], v.detach()) < 5e-3, (k, rel_err(sd[k], v.detach()))
