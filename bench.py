@@ -380,7 +380,7 @@ def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None,
-             None, ptr(status), stream())
+             None, None, ptr(status), stream())
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:

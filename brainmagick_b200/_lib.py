@@ -41,18 +41,15 @@ SIGNATURES = {
     "bm_head_fwd": [P, P, P, P, P, I, I, I, I, P, P, P, P],
     "bm_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "bm_head_bwd_params": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],
-    "bm_clip_set_workspace": [P, L, P],
-    "bm_clip_scores": [P, P, I, I, L, P, P, P, P, P],
-    "bm_clip_loss_fwd": [P, P, I, I, L, I, P, P, P, P, P, P, P],
-    "bm_clip_loss_bwd": [P, P, P, P, I, I, L, I, P, P, P],
+    "bm_clip_scores": [P, P, I, I, L, I, P, P, P, P, L, P, P],
+    "bm_clip_loss_fwd": [P, P, I, I, L, I, P, P, P, P, P, P, L, P, P],
+    "bm_clip_loss_bwd": [P, P, P, P, I, I, L, I, P, P, P, P],
     "bm_set_debug_flags": [I],
     "bm_tc_conv_supported": [I, I, I, I, I],
-    "bm_tc_conv2_supported": [I, I, I, I, I],
     "bm_tc_weight_split": [P, I, I, I, P, P, P, P, P],
-    "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P],
+    "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_tc_conv3_supported": [I, I, I, I, I],
-    "bm_tc_conv1d_pair": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P],
-    "bm_tc_pair_want_stats": [P],
+    "bm_tc_conv1d_pair": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_transpose_nt": [P, I, I, I, P, P],
     "bm_transpose_nt_ld": [P, I, I, I, I, P, P],
@@ -72,7 +69,7 @@ SIGNATURES = {
     "bm_gather_rows": [P, P, I, L, P, P],
     "bm_bn_act_skip_fwd": [P, P, P, P, P, P, P, L, I, I, F, P],
     "bm_bn_act_skip_bwd": [P, P, P, P, P, P, I, L, I, I, F, P, P, P, P, P],
-    "bm_clip_loss_bwd_cand": [P, P, P, P, P, P, I, I, L, I, P, P, P, P],
+    "bm_clip_loss_bwd_cand": [P, P, P, P, P, P, I, I, L, I, P, P, P, P, P],
 }
 
 _lib = None

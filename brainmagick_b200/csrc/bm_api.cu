@@ -5,9 +5,8 @@
 #include "gemm_simt.cuh"
 #include "tc_conv.cuh"
 #include "tc_wgrad.cuh"
-#include "tc_conv2.cuh"
 #include "tc_conv3.cuh"
-#include "tc_conv4.cuh"
+#include "tc_clip.cuh"
 #include "retrieval.cuh"
 #include "prep.cuh"
 #include "convseq.cuh"
@@ -502,34 +501,12 @@ extern "C" int bm_head_bwd(const float* dest, const float* x, const float* w0, c
 // =================================================================================================
 // K6
 // =================================================================================================
-// Optional tensor-core scratch for the two CLIP contractions (caller-owned, registered once per device/stream user):
-// `ws` holds the split-K partial score tiles ([ksplit][Bn][Bc] floats); `status` is the pipeline-timeout word.
-static float* g_clip_ws = nullptr;
-static size_t g_clip_ws_floats = 0;
-static int* g_clip_status = nullptr;
-extern "C" int bm_clip_set_workspace(float* ws, long long n_floats, int* status) {
-    g_clip_ws = ws;
-    g_clip_ws_floats = ws ? (size_t)n_floats : 0;
-    g_clip_status = status;
-    return 0;
-}
-
-namespace {
-// split-K factor of the tensor-core score GEMM: enough K slices to put one CTA on every SM
-inline int clip_tc_ksplit(int Bn, int Bc, long long KT) {
-    int mt = (Bn + 127) / 128, nt = Bc / (2 * tc::conv_tc2_pick_nh(Bc, 0));
-    int ks = num_sms() / (mt * nt);
-    if (ks < 1) ks = 1;
-    long long chunks = KT / 32;
-    if (ks > chunks) ks = (int)chunks;
-    return ks;
-}
-}  // namespace
-
+// Scratch (caller-owned, passed to every call): bm_clip_workspace() floats.  Tensor-core path: split-K partial score
+// tiles + fp64 partial sums of squares + the finalize ticket (csrc/tc_clip.cuh); FP32-FMA path: fp64 sums of squares.
 extern "C" long long bm_clip_workspace(int Bn, int Bc, long long KT) {
-    if (Bn <= 0 || Bc <= 0 || KT <= 0 || KT >= (1ll << 31)) return 0;
-    if (!tc::conv_tc2_supported(Bn, (int)KT, Bc, 1, 0)) return 0;
-    return (long long)clip_tc_ksplit(Bn, Bc, KT) * Bn * Bc;
+    if (Bn <= 0 || Bc <= 0 || KT <= 0) return 0;
+    if (tc::clip_tc_supported(Bn, Bc, KT)) return tc::clip_ws_floats(Bn, Bc, KT);
+    return 2ll * Bc + 2;
 }
 
 extern "C" int bm_candidate_inv_norms(const float* cand, int Bc, long long KT, double* ss, float* inv_norm,
@@ -546,34 +523,22 @@ extern "C" int bm_candidate_inv_norms(const float* cand, int Bc, long long KT, d
     return 0;
 }
 
-extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss,
-                              float* inv_norm, float* scores, float* probs, bm_stream_t stream) {
-    BM_CHECK_ARG(est && cand && inv_norm && scores && Bn > 0 && Bc > 0 && KT > 0);
+namespace {
+// scores (+ probs / row_loss / loss) on whichever kernel the shape allows
+int clip_forward(const float* est, const float* cand, int Bn, int Bc, long long KT, int norms_given, int target_offset,
+                 float* inv_norm, float* scores, float* probs, float* row_loss, float* loss, float* ws,
+                 long long ws_floats, int* status, cudaStream_t st) {
+    BM_CHECK_ARG(est && cand && inv_norm && scores && ws && Bn > 0 && Bc > 0 && KT > 0);
     BM_CHECK_ARG(KT < (1ll << 31));
-    cudaStream_t st = ST(stream);
-    if (ss) {       // ss == NULL: inv_norm is an INPUT (candidate norms computed once, e.g. the retrieval evaluation)
-        int rc = bm_candidate_inv_norms(cand, Bc, KT, ss, inv_norm, stream);
+    BM_CHECK_ARG(ws_floats >= bm_clip_workspace(Bn, Bc, KT));
+    BM_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 7) == 0);
+    if (tc::clip_tc_supported(Bn, Bc, KT))
+        return tc::launch_clip_scores(est, cand, Bn, Bc, KT, norms_given, target_offset, inv_norm, scores, probs, row_loss,
+                                      loss, ws, status, st);
+    // FP32-FMA GEMM (feature sizes not a multiple of 4 floats: no TMA row pitch)
+    if (!norms_given) {
+        int rc = bm_candidate_inv_norms(cand, Bc, KT, reinterpret_cast<double*>(ws), inv_norm, st);
         if (rc) return rc;
-    }
-    if (g_clip_ws && g_clip_ws_floats > 0 && tc::conv_tc2_supported(Bn, (int)KT, Bc, 1, 0)) {
-        // tensor cores: scores = E C^T as a split-K pointwise "conv" (x = E [1,Bn,KT], weights = C [Bc,KT] raw fp32)
-        int ks = clip_tc_ksplit(Bn, Bc, KT);
-        if ((size_t)ks * Bn * Bc <= g_clip_ws_floats) {
-            tc::Conv2P q;
-            q.B = 1; q.T = Bn; q.Cin = (int)KT; q.Ntot = Bc; q.taps = 1; q.dilation = 1; q.sign = 1; q.glu = 0; q.nh = 0;
-            q.act = 0; q.out_tmajor = 0; q.ksplit = ks; q.bias = nullptr; q.addend = nullptr; q.y = g_clip_ws;
-            q.aux = nullptr; q.glu_out = nullptr; q.err = g_clip_status;
-            int rc = tc::launch_conv_tc2(est, cand, q, st);
-            if (rc) return rc;
-            tc::splitk_reduce_scale_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(g_clip_ws, inv_norm, scores, ks,
-                                                                                       Bn, Bc);
-            BM_CHECK_LAUNCH();
-            if (probs) {
-                clip_ce_rows_kernel<<<Bn, 256, 0, st>>>(scores, Bn, Bc, 0, nullptr, probs);
-                BM_CHECK_LAUNCH();
-            }
-            return 0;
-        }
     }
     BM_CUDA(cudaMemsetAsync(scores, 0, sizeof(float) * (size_t)Bn * Bc, st));
     GemmP g = gemm_defaults();
@@ -589,39 +554,46 @@ extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int B
     g.D = scores; g.ldd_m = Bc; g.ldd_n = 1; g.atomic = 1;
     g.colscale = inv_norm;
     BM_CUDA(launch_gemm(g, st));
-    if (probs) {
-        clip_ce_rows_kernel<<<Bn, 256, 0, st>>>(scores, Bn, Bc, 0, nullptr, probs);
+    if (probs || row_loss) {
+        clip_ce_rows_kernel<<<Bn, 256, 0, st>>>(scores, Bn, Bc, target_offset, row_loss, probs);
+        BM_CHECK_LAUNCH();
+    }
+    if (loss) {
+        mean_kernel<<<1, 256, 0, st>>>(row_loss, Bn, loss);
         BM_CHECK_LAUNCH();
     }
     return 0;
 }
+}  // namespace
+
+extern "C" int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, int norms_given,
+                              float* inv_norm, float* scores, float* probs, float* workspace,
+                              long long workspace_floats, int* status, bm_stream_t stream) {
+    return clip_forward(est, cand, Bn, Bc, KT, norms_given, 0, inv_norm, scores, probs, nullptr, nullptr, workspace,
+                        workspace_floats, status, ST(stream));
+}
 
 extern "C" int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long long KT,
-                                int target_offset, double* ss, float* inv_norm, float* scores, float* probs,
-                                float* row_loss, float* loss, bm_stream_t stream) {
+                                int target_offset, float* inv_norm, float* scores, float* probs, float* row_loss,
+                                float* loss, float* workspace, long long workspace_floats, int* status,
+                                bm_stream_t stream) {
     BM_CHECK_ARG(probs && row_loss && loss);
     BM_CHECK_ARG(target_offset >= 0 && target_offset + Bn <= Bc);
-    int rc = bm_clip_scores(est, cand, Bn, Bc, KT, ss, inv_norm, scores, nullptr, stream);
-    if (rc) return rc;
-    cudaStream_t st = ST(stream);
-    clip_ce_rows_kernel<<<Bn, 256, 0, st>>>(scores, Bn, Bc, target_offset, row_loss, probs);
-    BM_CHECK_LAUNCH();
-    mean_kernel<<<1, 256, 0, st>>>(row_loss, Bn, loss);
-    BM_CHECK_LAUNCH();
-    return 0;
+    return clip_forward(est, cand, Bn, Bc, KT, 0, target_offset, inv_norm, scores, probs, row_loss, loss, workspace,
+                        workspace_floats, status, ST(stream));
 }
 
 extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* cand, const float* gout,
                                 int Bn, int Bc, long long KT, int target_offset, float* G, float* dest,
-                                bm_stream_t stream) {
+                                int* status, bm_stream_t stream) {
     BM_CHECK_ARG(probs && inv_norm && cand && gout && G && dest && Bn > 0 && Bc > 0 && KT > 0);
     BM_CHECK_ARG(KT < (1ll << 31));
     cudaStream_t st = ST(stream);
-    if (g_clip_ws && tc::wgrad_tc_supported(Bn, (int)KT)) {
+    if (tc::wgrad_tc_supported(Bn, (int)KT)) {
         // tensor cores: dE[b][k] = sum_o G^T[o][b] C[o][k]  == weight-gradient GEMM with "positions" = candidates
         clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 1);
         BM_CHECK_LAUNCH();
-        return tc::launch_wgrad_tc(G, cand, 1, Bc, Bn, (int)KT, (int)KT, 1, 1, g_clip_ws, dest, g_clip_status, st);
+        return tc::launch_wgrad_tc(G, cand, 1, Bc, Bn, (int)KT, (int)KT, 1, 1, dest, dest, status, st);   // direct mode: no workspace
     }
     clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 0);
     BM_CHECK_LAUNCH();
@@ -672,15 +644,16 @@ extern "C" int bm_bn_act_skip_bwd(const float* g, const float* y, const float* m
 
 extern "C" int bm_clip_loss_bwd_cand(const float* probs, const float* scores, const float* inv_norm, const float* est,
                                      const float* cand, const float* gout, int Bn, int Bc, long long KT,
-                                     int target_offset, float* G, float* coef, float* dcand, bm_stream_t stream) {
+                                     int target_offset, float* G, float* coef, float* dcand, int* status,
+                                     bm_stream_t stream) {
     BM_CHECK_ARG(probs && scores && inv_norm && est && cand && gout && G && coef && dcand);
     BM_CHECK_ARG(Bn > 0 && Bc > 0 && KT > 0 && KT < (1ll << 31));
     cudaStream_t st = ST(stream);
     clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 0);
     BM_CHECK_LAUNCH();
     // dcand[o][k] = sum_b G[b][o] est[b][k]: a weight-gradient GEMM whose "positions" are the estimates
-    if (g_clip_ws && tc::wgrad_tc_supported(Bc, (int)KT)) {
-        int rc = tc::launch_wgrad_tc(G, est, 1, Bn, Bc, (int)KT, (int)KT, 1, 1, g_clip_ws, dcand, g_clip_status, st);
+    if (tc::wgrad_tc_supported(Bc, (int)KT)) {
+        int rc = tc::launch_wgrad_tc(G, est, 1, Bn, Bc, (int)KT, (int)KT, 1, 1, dcand, dcand, status, st);   // direct mode
         if (rc) return rc;
     } else {
         GemmP g = gemm_defaults();
@@ -791,10 +764,6 @@ extern "C" int bm_tc_conv_supported(int T, int Cin, int Ntot, int Kw, int glu) {
     return tc::conv_tc_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
 }
 
-extern "C" int bm_tc_conv2_supported(int T, int Cin, int Ntot, int Kw, int glu) {
-    return tc::conv_tc2_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
-}
-
 extern "C" int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, float* f_hi, float* f_lo, float* g_hi,
                                   float* g_lo, bm_stream_t stream) {
     BM_CHECK_ARG(w && Cout > 0 && Cin > 0 && Kw > 0);
@@ -807,20 +776,13 @@ extern "C" int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, flo
 
 extern "C" int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                             const float* addend, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
-                            int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, int* status,
-                            bm_stream_t stream) {
-    BM_CHECK_ARG(x && w_hi && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
+                            int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, double* stats,
+                            int* status, bm_stream_t stream) {
+    BM_CHECK_ARG(stats == nullptr);      // only the CTA-pair kernel produces BatchNorm statistics in its epilogue
+    BM_CHECK_ARG(x && w_hi && w_lo && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
     BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
     BM_CHECK_ARG(B <= 65535);
     BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
-    if (w_lo == nullptr) {      // second-generation kernel: raw fp32 weights, split in shared memory
-        BM_CHECK_ARG(tc::conv_tc2_supported(T, Cin, Ntot, Kw, glu));
-        tc::Conv2P q;
-        q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
-        q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
-        q.glu_out = glu_out; q.err = status; q.ksplit = 1;
-        return tc::launch_conv_tc2(x, w_hi, q, ST(stream));
-    }
     BM_CHECK_ARG(tc::conv_tc_supported(T, Cin, Ntot, Kw, glu));
     tc::ConvTcP p;
     p.B = B; p.T = T; p.Cin = Cin; p.Ntot = Ntot; p.taps = Kw; p.dilation = dilation; p.sign = sign; p.glu = glu;
@@ -898,46 +860,27 @@ extern "C" int bm_gelu_bwd(const float* dq, const float* h, long long n, float* 
     return 0;
 }
 
-static double* g_pair_stats = nullptr;
-
 // third-generation conv kernel: CTA pairs (tcgen05 cta_group::2); same contract as bm_tc_conv1d with pre-split weights
 extern "C" int bm_tc_conv3_supported(int T, int Cin, int Ntot, int Kw, int glu) {
     return tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
 }
 extern "C" int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, const float* bias,
                                  const float* addend, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
-                                 int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, int* status,
-                                 bm_stream_t stream) {
+                                 int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, double* stats,
+                                 int* status, bm_stream_t stream) {
     BM_CHECK_ARG(x && w_hi && w_lo && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
     BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
     BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
-    if ((g_debug_flags & 2) && tc::conv_tc4_supported(T, Cin, Ntot, Kw, glu)) {
-        // fourth generation (persistent CTA pairs, double-buffered accumulators, half-width tiles): correct but measured
-        // slower than generation 3 (it streams every x tile twice and becomes L2->SM bound); kept behind debug bit 1<<1
-        tc::Conv4P q;
-        q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
-        q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
-        q.glu_out = glu_out; q.err = status;
-        return tc::launch_conv_tc4(x, w_hi, w_lo, q, ST(stream));
-    }
     BM_CHECK_ARG(tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu));
     tc::Conv3P q;
     q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
     q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
-    q.glu_out = glu_out; q.err = status; q.stats = g_pair_stats;
-    g_pair_stats = nullptr;
+    q.glu_out = glu_out; q.err = status; q.stats = stats;
     if (q.stats) {
         BM_CHECK_ARG(!glu && !act && !aux && !out_tmajor && !addend);
         BM_CUDA(cudaMemsetAsync(q.stats, 0, sizeof(double) * 2 * Ntot, ST(stream)));
     }
     return tc::launch_conv_tc3(x, w_hi, w_lo, q, ST(stream));
-}
-
-// Arms the NEXT bm_tc_conv1d_pair call (plain forward mode) to also accumulate the BatchNorm batch statistics
-// sum(y), sum(y^2) per output channel into stats[2*Ntot] (fp64) from its epilogue tiles.
-extern "C" int bm_tc_pair_want_stats(double* stats) {
-    g_pair_stats = stats;
-    return 0;
 }
 
 // pointwise (1x1) contraction with a per-sample weight set (SubjectLayers.forward / its data gradient, common.py:55-58):

@@ -207,4 +207,26 @@ inline bool make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint
     return r == CUDA_SUCCESS;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): the attribute is per device, so a
+// process-wide flag would leave a second device of the same process without it.
+inline int ensure_dyn_smem(const void* func, int bytes) {
+    constexpr int kMaxDev = 64, kMaxFn = 16;
+    static const void* fns[kMaxFn];
+    static bool done[kMaxFn][kMaxDev];
+    static int nfn = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int f = 0;
+    while (f < nfn && fns[f] != func) ++f;
+    if (f == nfn) {
+        if (nfn == kMaxFn) return set_error(3, "%s: too many kernels%s", __func__);
+        fns[nfn++] = func;
+    }
+    if (dev >= 0 && dev < kMaxDev && done[f][dev]) return 0;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return set_error(3, "%s: cudaFuncSetAttribute: %s", __func__, cudaGetErrorString(e));
+    if (dev >= 0 && dev < kMaxDev) done[f][dev] = true;
+    return 0;
+}
+
 }  // namespace bm

@@ -281,12 +281,7 @@ inline int launch_conv_tc(const float* x, const float* w_hi, const float* w_lo, 
         if (!make_tmap_f32(&tmBh, w_hi, 2, dims, str, box) || !make_tmap_f32(&tmBl, w_lo, 2, dims, str, box))
             return set_error(4, "%s: cuTensorMapEncodeTiled(B) failed%s", __func__);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CV_SMEM_BYTES);
-        if (e != cudaSuccess) return set_error(3, "%s: cudaFuncSetAttribute: %s", __func__, cudaGetErrorString(e));
-        attr_set = true;
-    }
+    if (int rc_ = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_kernel), CV_SMEM_BYTES)) return rc_;
     dim3 grid(p.glu ? (p.Ntot / 2) / (CV_BN / 2) : p.Ntot / p.bn, (p.T + CV_BM - 1) / CV_BM, p.B);
     conv_tc_kernel<<<grid, CV_THREADS, CV_SMEM_BYTES, st>>>(tmA, tmBh, tmBl, p);
     ++g_launches;

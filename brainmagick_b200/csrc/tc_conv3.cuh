@@ -473,12 +473,7 @@ inline int launch_conv_tc3(const float* x, const float* w_hi, const float* w_lo,
             if (!make_tmap_f32(&tmY, p.y, 3, dimh, strh, box)) return set_error(4, "%s: cuTensorMapEncodeTiled(H) failed%s", __func__);
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES);
-        if (e != cudaSuccess) return set_error(3, "%s: cudaFuncSetAttribute: %s", __func__, cudaGetErrorString(e));
-        attr_set = true;
-    }
+    if (int rc_ = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc3_kernel), C3_SMEM_BYTES)) return rc_;
     const int ntiles = p.glu ? (p.Ntot / 2) / p.nh : p.Ntot / (2 * p.nh);
     const int mtiles = (p.T + C3_BM - 1) / C3_BM;
     const int pairs = mtiles * ((p.B + 1) / 2);

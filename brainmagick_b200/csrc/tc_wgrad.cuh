@@ -309,12 +309,7 @@ inline int launch_wgrad_tc(const float* dY, const float* X, int B, int T, int M,
         uint32_t box[3] = {32, 32, 1};
         if (!make_tmap_f32(&tmX, X, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return set_error(4, "%s: cuTensorMapEncodeTiled failed%s", __func__);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
-        if (e != cudaSuccess) return set_error(3, "%s: cudaFuncSetAttribute: %s", __func__, cudaGetErrorString(e));
-        attr_set = true;
-    }
+    if (int rc_ = ensure_dyn_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), WG_SMEM_BYTES)) return rc_;
     const int Mpad = mblocks * WG_BM;
     WgradP p;
     p.B = B; p.T = T; p.M = M; p.N = N; p.nh = nh; p.taps = taps; p.dilation = dilation;
@@ -355,12 +350,7 @@ inline int launch_wgrad_tc_grouped(const float* dY, const float* X, const int* z
         if (!make_tmap_f32(&tmX, X, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return set_error(4, "%s: cuTensorMapEncodeTiled failed%s", __func__);
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES);
-        if (e != cudaSuccess) return set_error(3, "%s: cudaFuncSetAttribute: %s", __func__, cudaGetErrorString(e));
-        attr_set = true;
-    }
+    if (int rc_ = ensure_dyn_smem(reinterpret_cast<const void*>(wgrad_tc_kernel), WG_SMEM_BYTES)) return rc_;
     WgradP p;
     p.B = B; p.T = T; p.M = M; p.N = N; p.nh = nh; p.taps = 1; p.dilation = 1;
     p.ksplit = G; p.bchunk = 0; p.dY = dY; p.err = err; p.P = out; p.direct = 0;

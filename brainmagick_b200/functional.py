@@ -76,7 +76,6 @@ def check_tc_status(device=None) -> None:
 
 
 OVERLAP_WGRAD = True   # weight-gradient kernels on a side stream, concurrent with the data-gradient kernels of the layer
-USE_CONV_V2 = False    # single-CTA 128x320 kernel (tc_conv2.cuh): validated, but shared-memory-bandwidth bound
 USE_CONV_V3 = True     # CTA-pair kernel (tc_conv3.cuh, tcgen05 cta_group::2): the fastest where its tiling fits
 
 
@@ -119,27 +118,23 @@ class _Conv:
         st = stream()
         lib = _lib.load()
         g = 1 if glu else 0
-        fwd_v2 = allow_tc and USE_CONV_V2 and bool(lib.bm_tc_conv2_supported(T, self.cin, self.cout, self.kw, g))
-        bwd_v2 = allow_tc and USE_CONV_V2 and bool(lib.bm_tc_conv2_supported(T, self.cout, self.cin, self.kw, 0))
         self.fwd_v3 = allow_tc and USE_CONV_V3 and bool(lib.bm_tc_conv3_supported(T, self.cin, self.cout, self.kw, g))
         self.bwd_v3 = allow_tc and USE_CONV_V3 and bool(lib.bm_tc_conv3_supported(T, self.cout, self.cin, self.kw, 0))
-        fwd_v2 = fwd_v2 and not self.fwd_v3
-        bwd_v2 = bwd_v2 and not self.bwd_v3
-        fwd_tc = self.fwd_v3 or fwd_v2 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, g)))
-        bwd_tc = self.bwd_v3 or bwd_v2 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0)))
+        fwd_tc = self.fwd_v3 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, g)))
+        bwd_tc = self.bwd_v3 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0)))
         self.fwd_tc, self.bwd_tc = fwd_tc, bwd_tc
         self.fwd_fn = "bm_tc_conv1d_pair" if self.fwd_v3 else "bm_tc_conv1d"
         self.bwd_fn = "bm_tc_conv1d_pair" if self.bwd_v3 else "bm_tc_conv1d"
         self.wgrad_tc = allow_tc and bool(lib.bm_tc_wgrad_supported(self.cout, self.cin))
         self.f_hi = self.f_lo = self.g_hi = self.g_lo = self.wf = self.wb = None
         if fwd_tc or (bwd_tc and want_bwd):
-            # v2 kernels take the RAW re-laid weights (lo = None); v1 kernels take the pre-split tf32 hi/lo pair
+            # pre-split tf32 hi/lo operand pairs
             if fwd_tc:
                 self.f_hi = _empty((self.kw, self.cout, self.cin), w)
-                self.f_lo = None if fwd_v2 else _empty((self.kw, self.cout, self.cin), w)
+                self.f_lo = _empty((self.kw, self.cout, self.cin), w)
             if bwd_tc and want_bwd:
                 self.g_hi = _empty((self.kw, self.cin, self.cout), w)
-                self.g_lo = None if bwd_v2 else _empty((self.kw, self.cin, self.cout), w)
+                self.g_lo = _empty((self.kw, self.cin, self.cout), w)
             call("bm_tc_weight_split", ptr(w), self.cout, self.cin, self.kw, ptr(self.f_hi), ptr(self.f_lo),
                  ptr(self.g_hi), ptr(self.g_lo), st)
         if (not fwd_tc) or (want_bwd and not bwd_tc):
@@ -151,11 +146,9 @@ class _Conv:
     def forward(self, x, bias, B, T, dilation, y, stats, status):
         st = stream()
         if self.fwd_tc:
-            fused = stats is not None and self.fwd_v3
-            if fused:
-                call("bm_tc_pair_want_stats", ptr(stats))       # BatchNorm statistics out of the conv epilogue
+            fused = stats is not None and self.fwd_v3          # BatchNorm statistics out of the conv epilogue
             call(self.fwd_fn, ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
-                 self.kw, dilation, 1, 0, 0, 0, ptr(y), None, None, ptr(status), st)
+                 self.kw, dilation, 1, 0, 0, 0, ptr(y), None, None, ptr(stats) if fused else None, ptr(status), st)
             if stats is not None and not fused:
                 call("bm_col_stats", ptr(y), B * T, self.cout, ptr(stats), st)
         else:
@@ -166,7 +159,7 @@ class _Conv:
         st = stream()
         if self.fwd_tc:
             call(self.fwd_fn, ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
-                 self.kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out), ptr(status), st)
+                 self.kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out), None, ptr(status), st)
         else:
             call("bm_conv1d_glu_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout // 2, self.kw,
                  ptr(h), ptr(out), st)
@@ -175,7 +168,7 @@ class _Conv:
         st = stream()
         if self.bwd_tc:
             call(self.bwd_fn, ptr(dy), ptr(self.g_hi), ptr(self.g_lo), None, ptr(addend), B, T, self.cout,
-                 self.cin, self.kw, dilation, -1, 0, 0, 0, ptr(dx), None, None, ptr(status), st)
+                 self.cin, self.kw, dilation, -1, 0, 0, 0, ptr(dx), None, None, None, ptr(status), st)
         else:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
                  dilation, ptr(dx), st)
@@ -343,7 +336,7 @@ class _EncoderFn(torch.autograd.Function):
                 call("bm_fourier_emb", ptr(plan.rec_positions), ptr(plan.freq), R, C, P, ptr(emb), st)
                 att_full = _empty((R, Opad, C), meg)          # scores[r][o][c] = <emb[r][c], heads[o]> written channel-major
                 call(heads_conv.fwd_fn, ptr(emb), ptr(heads_conv.f_hi), ptr(heads_conv.f_lo), None, None, R, C, P, Opad, 1, 1, 1,
-                     0, 0, 1, ptr(att_full), None, None, ptr(status), st)
+                     0, 0, 1, ptr(att_full), None, None, None, ptr(status), st)
                 call("bm_masked_softmax", ptr(att_full), ptr(plan.rec_positions), ptr(plan.ban_centre), float(plan.ban_radius),
                      R, Opad, C, st)
                 att = att_full[:, :O].contiguous()
@@ -514,9 +507,9 @@ class _EncoderFn(torch.autograd.Function):
             del est_cl
         elif head_tc:
             call(head0.fwd_fn, ptr(x), ptr(head0.f_hi), ptr(head0.f_lo), ptr(b0.contiguous()), None, B, T, H, H2, 1,
-                 1, 1, 0, 1, 0, ptr(q), ptr(h1), None, ptr(status), st)
+                 1, 1, 0, 1, 0, ptr(q), ptr(h1), None, None, ptr(status), st)
             call(head2.fwd_fn, ptr(q), ptr(head2.f_hi), ptr(head2.f_lo), ptr(b2.contiguous()), None, B, T, H2, F, 1,
-                 1, 1, 0, 0, 1, ptr(est), None, None, ptr(status), st)
+                 1, 1, 0, 0, 1, ptr(est), None, None, None, ptr(status), st)
         else:
             call("bm_head_fwd", ptr(x), ptr(w0_2), ptr(b0.contiguous()), ptr(w2_2), ptr(b2.contiguous()), B, T, H, F,
                  ptr(h1), ptr(q), ptr(est), st)
@@ -580,7 +573,7 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
             # dq = dest_t @ w2^T  (w2_as_conv [F,2H,1]: its data-gradient operand is [1][2H][F])
             call(head2.bwd_fn, ptr(dest_t), ptr(head2.g_hi), ptr(head2.g_lo), None, None, B, T, F, H2, 1, 1, -1, 0, 0,
-                 0, ptr(dq), None, None, ptr(status), st)
+                 0, ptr(dq), None, None, None, ptr(status), st)
             lib = _lib.load()
             if lib.bm_tc_wgrad_supported(H2, F) and lib.bm_tc_wgrad_supported(H2, H):
                 main0 = torch.cuda.current_stream()
@@ -607,7 +600,7 @@ class _EncoderFn(torch.autograd.Function):
                 call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F,
                      ptr(dq), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)   # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
             call(head0.bwd_fn, ptr(dq), ptr(head0.g_hi), ptr(head0.g_lo), None, None, B, T, H2, H, 1, 1, -1, 0, 0, 0,
-                 ptr(g), None, None, ptr(status), st)
+                 ptr(g), None, None, None, ptr(status), st)
             del dest_t
         else:
             call("bm_head_bwd", ptr(dest), ptr(s["x_last"]), ptr(s["w0_2"]), ptr(s["w2_2"]), ptr(s["h1"]), ptr(s["q"]),
@@ -784,17 +777,24 @@ def encoder_forward(plan: EncoderPlan, meg, heads, il_w, il_b, subj_w, w0, b0, w
 _clip_ws: tp.Dict[torch.device, torch.Tensor] = {}
 
 
-def _register_clip_workspace(like: torch.Tensor, Bn: int, Bc: int, floats: tp.Optional[int] = None) -> None:
-    """Scratch for the tensor-core CLIP contractions (split-K partial score tiles); one buffer per device, grown on
-    demand, registered with the library before every CLIP call (one process drives one GPU).  `floats`: exact need when
-    the caller asked the library (`bm_clip_workspace`, forward-only retrieval shapes); default = the training bound."""
-    need = 160 * Bn * Bc if floats is None else max(int(floats), 1)
+def _clip_workspace(like: torch.Tensor, Bn: int, Bc: int, KT: int) -> torch.Tensor:
+    """Scratch of the CLIP score GEMM (split-K partial tiles, partial sums of squares, finalize ticket): one buffer per
+    device, grown on demand to what the library asks for (`bm_clip_workspace`), handed to every call explicitly."""
+    need = max(int(_lib.load().bm_clip_workspace(Bn, Bc, KT)), 2)
     dev = like.device
     ws = _clip_ws.get(dev)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, device=dev, dtype=torch.float32)
         _clip_ws[dev] = ws
-    call("bm_clip_set_workspace", ptr(ws), ws.numel(), ptr(tc_status_tensor(dev)))
+    return ws
+
+
+def _check_clip_operands(est: torch.Tensor, cand: torch.Tensor) -> None:
+    if est.dtype != torch.float32 or cand.dtype != torch.float32:
+        raise TypeError(f"ClipLoss kernels are fp32 (bm/losses.py computes in the input dtype; the reference trains in "
+                        f"fp32): got {est.dtype} / {cand.dtype}")
+    if est.device != cand.device:
+        raise ValueError(f"estimate on {est.device}, candidate on {cand.device}")
 
 
 def clip_scores(estimates: torch.Tensor, candidates: torch.Tensor, want_probs: bool = False):
@@ -804,12 +804,12 @@ def clip_scores(estimates: torch.Tensor, candidates: torch.Tensor, want_probs: b
     Bn, Bc = est.shape[0], cand.shape[0]
     KT = est[0].numel()
     assert cand[0].numel() == KT
-    ss = _empty((Bc,), est, torch.float64)
     inv = _empty((Bc,), est)
     scores = _empty((Bn, Bc), est)
     probs = _empty((Bn, Bc), est) if want_probs else None
-    _register_clip_workspace(est, Bn, Bc)
-    call("bm_clip_scores", ptr(est), ptr(cand), Bn, Bc, KT, ptr(ss), ptr(inv), ptr(scores), ptr(probs), stream())
+    ws = _clip_workspace(est, Bn, Bc, KT)
+    call("bm_clip_scores", ptr(est), ptr(cand), Bn, Bc, KT, 0, ptr(inv), ptr(scores), ptr(probs), ptr(ws), ws.numel(),
+         ptr(tc_status_tensor(est.device)), stream())
     return probs if want_probs else scores
 
 
@@ -833,27 +833,28 @@ def clip_scores_prenormed(estimates: torch.Tensor, candidates: torch.Tensor, inv
     KT = est[0].numel()
     assert cand[0].numel() == KT and inv_norms.numel() == Bc
     scores = _empty((Bn, Bc), est)
-    _register_clip_workspace(est, Bn, Bc, floats=int(_lib.load().bm_clip_workspace(Bn, Bc, KT)))
-    call("bm_clip_scores", ptr(est), ptr(cand), Bn, Bc, KT, None, ptr(inv_norms), ptr(scores), None, stream())
+    ws = _clip_workspace(est, Bn, Bc, KT)
+    call("bm_clip_scores", ptr(est), ptr(cand), Bn, Bc, KT, 1, ptr(inv_norms), ptr(scores), None, ptr(ws), ws.numel(),
+         ptr(tc_status_tensor(est.device)), stream())
     return scores
 
 
 class _ClipLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, estimate, candidate, target_offset: int):
+        _check_clip_operands(estimate, candidate)
         est = estimate.contiguous()
         cand = candidate.contiguous()
         Bn, Bc = est.shape[0], cand.shape[0]
         KT = est[0].numel()
-        ss = _empty((Bc,), est, torch.float64)
         inv = _empty((Bc,), est)
         scores = _empty((Bn, Bc), est)
         probs = _empty((Bn, Bc), est)
         row_loss = _empty((Bn,), est)
         loss = _empty((1,), est)
-        _register_clip_workspace(est, Bn, Bc)
-        call("bm_clip_loss_fwd", ptr(est), ptr(cand), Bn, Bc, KT, int(target_offset), ptr(ss), ptr(inv),
-             ptr(scores), ptr(probs), ptr(row_loss), ptr(loss), stream())
+        ws = _clip_workspace(est, Bn, Bc, KT)
+        call("bm_clip_loss_fwd", ptr(est), ptr(cand), Bn, Bc, KT, int(target_offset), ptr(inv), ptr(scores), ptr(probs),
+             ptr(row_loss), ptr(loss), ptr(ws), ws.numel(), ptr(tc_status_tensor(est.device)), stream())
         if candidate.requires_grad:      # a trainable feature model produced the candidates (solver.py:304-320)
             ctx.save_for_backward(probs, inv, cand, scores, est)
         else:
@@ -862,24 +863,25 @@ class _ClipLossFn(torch.autograd.Function):
         return loss.reshape(())
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gout):
         probs, inv, cand = ctx.saved_tensors[:3]
         Bn, Bc, KT, off, shape, cand_shape = ctx.meta
         gout = gout.reshape(1).contiguous().float()
-        _register_clip_workspace(probs, Bn, Bc)
+        status = tc_status_tensor(probs.device)
         dest = dcand = None
         if ctx.needs_input_grad[0]:
             G = _empty((Bn, Bc), probs)
             dest = _empty(shape, probs)
             call("bm_clip_loss_bwd", ptr(probs), ptr(inv), ptr(cand), ptr(gout), Bn, Bc, KT, off, ptr(G), ptr(dest),
-                 stream())
+                 ptr(status), stream())
         if ctx.needs_input_grad[1]:
             scores, est = ctx.saved_tensors[3:]
             G = _empty((Bn, Bc), probs)
             coef = _empty((Bc,), probs)
             dcand = _empty(cand_shape, probs)
             call("bm_clip_loss_bwd_cand", ptr(probs), ptr(scores), ptr(inv), ptr(est), ptr(cand), ptr(gout), Bn, Bc, KT,
-                 off, ptr(G), ptr(coef), ptr(dcand), stream())
+                 off, ptr(G), ptr(coef), ptr(dcand), ptr(status), stream())
         return dest, dcand, None
 
 

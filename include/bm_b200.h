@@ -139,27 +139,27 @@ int bm_head_bwd_params(const float* dest, const float* x, const float* h1, const
  * est [Bn,KT], cand [Bc,KT] (KT = F*T, any consistent flattening).
  * bm_clip_scores = ClipLoss.get_scores (+ get_probabilities when probs != NULL):
  *   inv_norm[o] = 1/(1e-8+||cand_o||), scores[b,o] = inv_norm[o] <est_b, cand_o>, probs = softmax_o(scores).
- * ss: fp64 [Bc] scratch (NULL: inv_norm is given, see bm_candidate_inv_norms). */
-int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, double* ss, float* inv_norm,
-                   float* scores, float* probs, bm_stream_t stream);
-/* Registers caller-owned scratch that lets bm_clip_scores / bm_clip_loss_fwd / bm_clip_loss_bwd run their two big
- * contractions on the tensor cores (3xTF32): ws >= 148*Bn*Bc floats (split-K partial score tiles), status = device int
- * set on a pipeline timeout.  Without it (or for shapes outside the tcgen05 tiling) the FP32-FMA GEMM is used. */
-int bm_clip_set_workspace(float* ws, long long n_floats, int* status);
-/* Floats of workspace the tensor-core score GEMM needs for this shape (split-K slices x Bn x Bc); 0 = the shape is
- * outside the tcgen05 tiling (Bc % 256 and % 320 != 0, or KT % 32 != 0) and the FP32-FMA GEMM will be used. */
+ *   norms_given = 1: inv_norm is an INPUT (a fixed candidate set is normed once, see bm_candidate_inv_norms).
+ * One split-K tcgen05 GEMM on CTA pairs (3xTF32; every accumulation chain is bounded to 64 K-steps and drained into an
+ * fp32 round-to-nearest running sum, because the tensor core's accumulator truncates) that also produces the candidate
+ * norms, + one finalize kernel (slice reduction in a fixed order, norm scale, row softmax / cross-entropy / batch mean).
+ * workspace: bm_clip_workspace(Bn,Bc,KT) floats of caller-owned scratch, 8-byte aligned; status: device int set on a
+ * pipeline timeout (never hangs).  KT % 4 != 0 (no TMA row pitch) falls to the FP32-FMA GEMM of this library. */
 long long bm_clip_workspace(int Bn, int Bc, long long KT);
-/* inv_norm[o] = 1/(1e-8+||cand_o||) alone (losses.py:91); ss fp64 [Bc] scratch.  bm_clip_scores with ss == NULL takes
- * inv_norm as an INPUT: a fixed candidate set (retrieval evaluation) is normed once, not once per query batch. */
+int bm_clip_scores(const float* est, const float* cand, int Bn, int Bc, long long KT, int norms_given, float* inv_norm,
+                   float* scores, float* probs, float* workspace, long long workspace_floats, int* status,
+                   bm_stream_t stream);
+/* inv_norm[o] = 1/(1e-8+||cand_o||) alone (losses.py:91); ss fp64 [Bc] scratch. */
 int bm_candidate_inv_norms(const float* cand, int Bc, long long KT, double* ss, float* inv_norm, bm_stream_t stream);
 /* ClipLoss.forward: loss = mean_b CE(scores[b,:], target_offset + b).  target_offset = 0 is the reference;
- * rank*Bn is the multi-GPU extension with all-gathered candidates.  row_loss [Bn] scratch, loss [1]. */
+ * rank*Bn is the multi-GPU extension with all-gathered candidates.  row_loss [Bn], loss [1]; inv_norm, scores, probs
+ * are outputs kept for the backward. */
 int bm_clip_loss_fwd(const float* est, const float* cand, int Bn, int Bc, long long KT, int target_offset,
-                     double* ss, float* inv_norm, float* scores, float* probs, float* row_loss, float* loss,
-                     bm_stream_t stream);
+                     float* inv_norm, float* scores, float* probs, float* row_loss, float* loss, float* workspace,
+                     long long workspace_floats, int* status, bm_stream_t stream);
 /* dL/dest [Bn,KT] = gout * ((probs - onehot)/Bn * inv_norm) @ cand ; G [Bn,Bc] scratch; gout [1] on device. */
 int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const float* cand, const float* gout, int Bn,
-                     int Bc, long long KT, int target_offset, float* G, float* dest, bm_stream_t stream);
+                     int Bc, long long KT, int target_offset, float* G, float* dest, int* status, bm_stream_t stream);
 
 /* ---- Stand-alone ConvSequence / DeepMel: bm/models/common.py:79-151, bm/models/features.py:15-35 --
  * Layer epilogue x_new = act(bn(y)) (+ x_old) over channels-last rows [rows, C] and its backward, for the cases the
@@ -178,7 +178,7 @@ int bm_bn_act_skip_bwd(const float* g, const float* y, const float* mean, const 
  * (the derivative of the 1/(1e-8+||.||) normalisation, losses.py:91).  G [Bn,Bc], coef [Bc]: scratch. */
 int bm_clip_loss_bwd_cand(const float* probs, const float* scores, const float* inv_norm, const float* est,
                           const float* cand, const float* gout, int Bn, int Bc, long long KT, int target_offset,
-                          float* G, float* coef, float* dcand, bm_stream_t stream);
+                          float* G, float* coef, float* dcand, int* status, bm_stream_t stream);
 
 /* ---- Retrieval evaluation: scripts/run_eval_probs.py:237-307, bm/wer.py:80-116 ---------
  * The score matrix comes from bm_clip_scores (queries x candidates, candidate axis optionally zero-padded to the
@@ -233,31 +233,26 @@ int bm_gather_rows(const float* x, const int* rows, int n_rows, long long row_el
  * y (nullable) receives h, glu_out [B,T,H].  status: device int (nullable) set non-zero if the kernel's pipeline
  * timed out (never hangs).  bm_tc_conv_supported: shape gate (Cin % 32, Ntot % 160 or H % 80). */
 int bm_tc_conv_supported(int T, int Cin, int Ntot, int Kw, int glu);
-/* second-generation kernel (128 x 2*NH tile, activations through tensor memory, weights split in shared memory):
- * selected by passing w_lo = NULL and w_hi = the RAW fp32 re-laid weights (bm_tc_weight_split with f_lo/g_lo = NULL).
- * Shape gate: Cin % 32 == 0 and Ntot % 320 == 0 or Ntot % 256 == 0 (GLU: H % 160 == 0 or H % 128 == 0). */
-int bm_tc_conv2_supported(int T, int Cin, int Ntot, int Kw, int glu);
 int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, float* f_hi, float* f_lo, float* g_hi,
                        float* g_lo, bm_stream_t stream);
 int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* addend,
                  int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
-                 float* y, float* aux, float* glu_out, int* status, bm_stream_t stream);
+                 float* y, float* aux, float* glu_out, double* stats /* must be NULL: see bm_tc_conv1d_pair */,
+                 int* status, bm_stream_t stream);
 /* act=1: y = GELU(.) and aux (nullable) receives the pre-activation; out_tmajor=1: y is [B,Ntot,T] (the head's
  * channel-major `estimate`).  With Kw=1 this is the pointwise (1x1) contraction of the head (K5).
  * bm_col_stats: stats[0:C] = sum_r y[r,c], stats[C:2C] = sum_r y[r,c]^2 (fp64), the BatchNorm batch statistics. */
 int bm_col_stats(const float* y, long long rows, int C, double* stats, bm_stream_t stream);
 /* third-generation kernel: CTA PAIRS (tcgen05.mma.cta_group::2, M = 256 over two SMs; each CTA holds half of every
  * weight tile, activations go through tensor memory).  Same arithmetic contract and arguments as bm_tc_conv1d with
- * the pre-split (w_hi, w_lo) weights.  Shape gate as bm_tc_conv2_supported. */
+ * the pre-split (w_hi, w_lo) weights.  Shape gate: Cin % 32 == 0 and Ntot % 320 == 0 or Ntot % 256 == 0 (GLU: H % 160 == 0
+ * or H % 128 == 0).  stats (nullable; plain forward only: no glu/act/aux/addend): BatchNorm batch statistics
+ * stats[0:Ntot] = sum(y), stats[Ntot:2Ntot] = sum(y^2) (fp64, zeroed by the call), accumulated from the epilogue tiles --
+ * replaces the separate bm_col_stats pass over y. */
 int bm_tc_conv3_supported(int T, int Cin, int Ntot, int Kw, int glu);
 int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* addend,
                       int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
-                      float* y, float* aux, float* glu_out, int* status, bm_stream_t stream);
-
-/* Arms the NEXT bm_tc_conv1d_pair call (plain forward: no glu/act/aux/addend) to accumulate the BatchNorm batch
- * statistics stats[0:Ntot] = sum(y), stats[Ntot:2Ntot] = sum(y^2) (fp64, zeroed by that call) from its epilogue tiles,
- * replacing the separate bm_col_stats pass over y. */
-int bm_tc_pair_want_stats(double* stats);
+                      float* y, float* aux, float* glu_out, double* stats, int* status, bm_stream_t stream);
 
 /* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]
  * for n < Ntrue (x may be channel-padded to N); dy [B,T,M], x [B,T,N] channels-last; dw in nn.Conv1d layout

@@ -50,17 +50,17 @@ elif which == "topk":          # -k regex:retrieval_topk_kernel     (fused softm
     for _ in range(6):
         call("bm_retrieval_topk", ptr(scores), M, Bn, M, None, 0, 0, 10, ptr(labels), None, ptr(targets), ptr(top_idx),
              ptr(top_p), ptr(hit), None, None, None, stream())
-elif which == "scores":        # -k regex:conv_tc2_kernel           (retrieval / CLIP score GEMM, K = F*T = 368 640)
+elif which == "scores":        # -k regex:clip_scores_kernel           (retrieval / CLIP score GEMM, K = F*T = 368 640)
     Bn, M, KT = 1024, 2048, 1024 * 360
     est = torch.randn(Bn, KT, device=dev)
     cand = torch.randn(M, KT, device=dev)
     inv = torch.ones(M, device=dev)
     out = torch.empty(Bn, M, device=dev)
     need = int(_lib.load().bm_clip_workspace(Bn, M, KT))
-    ws = torch.empty(max(need, 1), device=dev)
-    call("bm_clip_set_workspace", ptr(ws), ws.numel(), ptr(status))
+    ws = torch.empty(max(need, 2), device=dev)
     for _ in range(3):
-        call("bm_clip_scores", ptr(est), ptr(cand), Bn, M, KT, None, ptr(inv), ptr(out), None, stream())
+        call("bm_clip_scores", ptr(est), ptr(cand), Bn, M, KT, 1, ptr(inv), ptr(out), None, ptr(ws), ws.numel(), ptr(status),
+             stream())
 torch.cuda.synchronize()
 assert int(status.item()) == 0
 print("done", which)

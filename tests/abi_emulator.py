@@ -289,9 +289,6 @@ class Emulator:
         _v(out, Z, T, ld_out)[:, :, :N].copy_(_v(inp, Z, N, T).transpose(1, 2))
 
     # ---------------------------------------------------------------- K6
-    def bm_clip_set_workspace(self, ws, n, status):
-        pass
-
     def _scores(self, est, cand, Bn, Bc, KT, inv_norm):
         c = _v(cand, Bc, KT)
         return (_v(est, Bn, KT) @ c.t()) * _v(inv_norm, Bc)
@@ -302,16 +299,18 @@ class Emulator:
         _v(ss, Bc).copy_(s)
         _v(inv_norm, Bc).copy_(1.0 / (1e-8 + torch.sqrt(s).float()))
 
-    def bm_clip_scores(self, est, cand, Bn, Bc, KT, ss, inv_norm, scores, probs, stream):
-        if ss is not None:
-            self.bm_candidate_inv_norms(cand, Bc, KT, ss, inv_norm, stream)
+    def bm_clip_scores(self, est, cand, Bn, Bc, KT, norms_given, inv_norm, scores, probs, ws, ws_floats, status, stream):
+        if not norms_given:
+            c = _v(cand, Bc, KT).double()
+            _v(inv_norm, Bc).copy_(1.0 / (1e-8 + torch.sqrt((c * c).sum(1)).float()))
         sc = self._scores(est, cand, Bn, Bc, KT, inv_norm)
         _v(scores, Bn, Bc).copy_(sc)
         if probs is not None:
             _v(probs, Bn, Bc).copy_(torch.softmax(sc, dim=1))
 
-    def bm_clip_loss_fwd(self, est, cand, Bn, Bc, KT, target_offset, ss, inv_norm, scores, probs, row_loss, loss, stream):
-        self.bm_clip_scores(est, cand, Bn, Bc, KT, ss, inv_norm, scores, probs, stream)
+    def bm_clip_loss_fwd(self, est, cand, Bn, Bc, KT, target_offset, inv_norm, scores, probs, row_loss, loss, ws, ws_floats,
+                         status, stream):
+        self.bm_clip_scores(est, cand, Bn, Bc, KT, 0, inv_norm, scores, probs, ws, ws_floats, status, stream)
         sc = _v(scores, Bn, Bc)
         rl = torch.logsumexp(sc, dim=1) - sc[torch.arange(Bn), torch.arange(Bn) + target_offset]
         _v(row_loss, Bn).copy_(rl)
@@ -322,12 +321,12 @@ class Emulator:
         p[torch.arange(Bn), torch.arange(Bn) + target_offset] -= 1
         return p * (gout.reshape(-1)[0] / Bn) * _v(inv_norm, Bc)
 
-    def bm_clip_loss_bwd(self, probs, inv_norm, cand, gout, Bn, Bc, KT, target_offset, G, dest, stream):
+    def bm_clip_loss_bwd(self, probs, inv_norm, cand, gout, Bn, Bc, KT, target_offset, G, dest, status, stream):
         g = self._G(probs, inv_norm, gout, Bn, Bc, target_offset)
         _v(dest, Bn, KT).copy_(g @ _v(cand, Bc, KT))
 
     def bm_clip_loss_bwd_cand(self, probs, scores, inv_norm, est, cand, gout, Bn, Bc, KT, target_offset, G, coef, dcand,
-                              stream):
+                              status, stream):
         g = self._G(probs, inv_norm, gout, Bn, Bc, target_offset)
         norm = 1.0 / _v(inv_norm, Bc) - 1e-8
         cf = torch.where(norm > 0, (g * _v(scores, Bn, Bc)).sum(0) / norm, torch.zeros(Bc))
@@ -335,13 +334,8 @@ class Emulator:
 
 
     # ---------------------------------------------------------------- tensor-core entry points (same contracts, exact fp32)
-    _armed_stats = None
-
-    def bm_tc_pair_want_stats(self, stats):
-        self._armed_stats = stats
-
     def bm_tc_conv1d(self, x, w_hi, w_lo, bias, addend, B, T, Cin, Ntot, Kw, dilation, sign, glu, act, out_tmajor, y, aux,
-                     glu_out, status, stream):
+                     glu_out, stats, status, stream):
         w = _v(w_hi, Kw, Ntot, Cin)
         if w_lo is not None:
             w = w + _v(w_lo, Kw, Ntot, Cin)
@@ -356,7 +350,6 @@ class Emulator:
             out = out + _v(bias, Ntot)
         if addend is not None:
             out = out + _v(addend, B, T, Ntot)
-        stats, self._armed_stats = self._armed_stats, None
         if stats is not None:
             o = out.reshape(-1, Ntot).double()
             _v(stats, 2 * Ntot).copy_(torch.cat([o.sum(0), (o * o).sum(0)]))

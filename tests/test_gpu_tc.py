@@ -23,13 +23,13 @@ def _call():
     return _lib.call, _lib.ptr, _lib.stream
 
 
-_FN = {1: "bm_tc_conv1d", 2: "bm_tc_conv1d", 3: "bm_tc_conv1d_pair", 4: "bm_tc_conv1d_pair"}
+_FN = {1: "bm_tc_conv1d", 3: "bm_tc_conv1d_pair"}
 
 
 def _gen_flags(gen):
-    """generation 3 = the CTA-pair kernel (default), 4 = the persistent half-tile variant (debug bit 2)."""
+    """generation 1 = single-CTA kernel (still used with per-sample weight sets), 3 = the CTA-pair kernel (default)."""
     from brainmagick_b200 import _lib
-    _lib.load().bm_set_debug_flags(2 if gen == 4 else 0)
+    _lib.load().bm_set_debug_flags(0)
 
 
 def _ref_conv(x, w, bias, dilation):
@@ -39,7 +39,7 @@ def _ref_conv(x, w, bias, dilation):
     return y.permute(0, 2, 1).contiguous()
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3, 4])
+@pytest.mark.parametrize("gen", [1, 3])
 @pytest.mark.parametrize("dilation", [1, 2, 16])
 @pytest.mark.parametrize("T", [360, 343, 100])
 def test_tc_conv_forward(dilation, T, gen):
@@ -52,12 +52,12 @@ def test_tc_conv_forward(dilation, T, gen):
     w = torch.randn(Cout, Cin, Kw, device=dev) / (Cin * Kw) ** 0.5
     bias = torch.randn(Cout, device=dev)
     fh = torch.empty(Kw, Cout, Cin, device=dev)
-    fl = torch.empty(Kw, Cout, Cin, device=dev) if gen != 2 else None     # gen 2: raw weights, split in-kernel
+    fl = torch.empty(Kw, Cout, Cin, device=dev)
     call("bm_tc_weight_split", ptr(w), Cout, Cin, Kw, ptr(fh), ptr(fl), None, None, stream())
     y = torch.full((B, T, Cout), float("nan"), device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     call(_FN[gen], ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, Cin, Cout, Kw, dilation, 1, 0, 0, 0, ptr(y), None, None,
-         ptr(status), stream())
+         None, ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
     ref = _ref_conv(x, w, bias, dilation)
@@ -66,7 +66,7 @@ def test_tc_conv_forward(dilation, T, gen):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3, 4])
+@pytest.mark.parametrize("gen", [1, 3])
 def test_tc_conv_glu_and_data_gradient(gen):
     call, ptr, stream = _call()
     _gen_flags(gen)
@@ -77,14 +77,14 @@ def test_tc_conv_glu_and_data_gradient(gen):
     w = torch.randn(2 * H, H, Kw, device=dev) / (H * Kw) ** 0.5
     bias = torch.randn(2 * H, device=dev)
     fh, gh = torch.empty(Kw, 2 * H, H, device=dev), torch.empty(Kw, H, 2 * H, device=dev)
-    fl = torch.empty(Kw, 2 * H, H, device=dev) if gen != 2 else None
-    gl = torch.empty(Kw, H, 2 * H, device=dev) if gen != 2 else None
+    fl = torch.empty(Kw, 2 * H, H, device=dev)
+    gl = torch.empty(Kw, H, 2 * H, device=dev)
     call("bm_tc_weight_split", ptr(w), 2 * H, H, Kw, ptr(fh), ptr(fl), ptr(gh), ptr(gl), stream())
     h = torch.empty(B, T, 2 * H, device=dev)
     out = torch.empty(B, T, H, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     call(_FN[gen], ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out),
-         ptr(status), stream())
+         None, ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     ref_h = _ref_conv(x, w, bias, 1)
@@ -96,7 +96,7 @@ def test_tc_conv_glu_and_data_gradient(gen):
     addend = torch.randn(B, T, H, device=dev)
     dx = torch.empty(B, T, H, device=dev)
     call(_FN[gen], ptr(dy), ptr(gh), ptr(gl), None, ptr(addend), B, T, 2 * H, H, Kw, 1, -1, 0, 0, 0, ptr(dx), None, None,
-         ptr(status), stream())
+         None, ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     ref_dx = torch.nn.functional.conv_transpose1d(dy.double().permute(0, 2, 1), w.double(), padding=1).permute(0, 2, 1)
@@ -107,13 +107,13 @@ def test_tc_conv_glu_and_data_gradient(gen):
     # in-place skip-gradient accumulation (addend == output): the pair kernel uses a TMA reduce-add
     acc = addend.clone()
     call(_FN[gen], ptr(dy), ptr(gh), ptr(gl), None, ptr(acc), B, T, 2 * H, H, Kw, 1, -1, 0, 0, 0, ptr(acc), None, None,
-         ptr(status), stream())
+         None, ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0
     assert rel_err(acc.cpu(), ref_dx.cpu()) < TOL
 
 
-@pytest.mark.parametrize("gen", [1, 2, 3, 4])
+@pytest.mark.parametrize("gen", [1, 3])
 def test_tc_conv_speed_report(capsys, gen):
     """Not a pass/fail on speed: prints the per-launch time at the BASELINE shape for the log."""
     call, ptr, stream = _call()
@@ -123,16 +123,16 @@ def test_tc_conv_speed_report(capsys, gen):
     x = torch.randn(B, T, C, device=dev)
     w = torch.randn(C, C, Kw, device=dev) / (C * Kw) ** 0.5
     fh = torch.empty(Kw, C, C, device=dev)
-    fl = torch.empty(Kw, C, C, device=dev) if gen != 2 else None
+    fl = torch.empty(Kw, C, C, device=dev)
     call("bm_tc_weight_split", ptr(w), C, C, Kw, ptr(fh), ptr(fl), None, None, stream())
     y = torch.empty(B, T, C, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     for _ in range(3):
-        call(_FN[gen], ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, ptr(status), stream())
+        call(_FN[gen], ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, None, ptr(status), stream())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        call(_FN[gen], ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, ptr(status), stream())
+        call(_FN[gen], ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, None, ptr(status), stream())
     e1.record()
     torch.cuda.synchronize()
     assert int(status.item()) == 0
