@@ -21,7 +21,7 @@ if which == "conv":
     call("bm_tc_weight_split", ptr(w), H, H, Kw, ptr(fh), ptr(fl), None, None, stream())
     y = torch.empty(B, T, H, device=dev)
     for _ in range(6):
-        call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), None, None, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None,
+        call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), None, None, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
              None, ptr(status), stream())
 elif which == "wgrad":
     dy = torch.randn(B, T, H, device=dev)
