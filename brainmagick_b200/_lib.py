@@ -50,6 +50,7 @@ SIGNATURES = {
     "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_tc_conv3_supported": [I, I, I, I, I],
     "bm_tc_conv1d_pair": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
+    "bm_tc_conv1d_persistent": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_transpose_nt": [P, I, I, I, P, P],
     "bm_transpose_nt_ld": [P, I, I, I, I, P, P],

@@ -7,6 +7,7 @@
 #include "tc_wgrad.cuh"
 #include "tc_conv3.cuh"
 #include "tc_clip.cuh"
+#include "tc_convp.cuh"
 #include "retrieval.cuh"
 #include "prep.cuh"
 #include "convseq.cuh"
@@ -881,6 +882,22 @@ extern "C" int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float*
         BM_CUDA(cudaMemsetAsync(q.stats, 0, sizeof(double) * 2 * Ntot, ST(stream)));
     }
     return tc::launch_conv_tc3(x, w_hi, w_lo, q, ST(stream));
+}
+
+// persistent CTA-pair kernel (csrc/tc_convp.cuh): w_raw = the RAW fp32 weights re-laid K-major [Kw][Ntot][Cin]
+// (bm_tc_weight_split with f_lo / g_lo = NULL); accumulate=1: y += conv (in place, TMA reduce-add)
+extern "C" int bm_tc_conv1d_persistent(const float* x, const float* w_raw, const float* bias, int accumulate, int B, int T,
+                                       int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act,
+                                       int out_tmajor, float* y, float* aux, float* glu_out, double* stats, int* status,
+                                       bm_stream_t stream) {
+    BM_CHECK_ARG(x && w_raw && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
+    BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
+    BM_CHECK_ARG(tc::conv_pp_supported(T, Cin, Ntot, Kw, glu));
+    tc::ConvPPArgs a;
+    a.x = x; a.w_raw = w_raw; a.bias = bias; a.B = B; a.T = T; a.Cin = Cin; a.Ntot = Ntot; a.taps = Kw;
+    a.dilation = dilation; a.sign = sign; a.glu = glu; a.act = act; a.out_tmajor = out_tmajor; a.accumulate = accumulate;
+    a.y = y; a.aux = aux; a.glu_out = glu_out; a.stats = stats; a.err = status;
+    return tc::launch_conv_pp(a, ST(stream));
 }
 
 // pointwise (1x1) contraction with a per-sample weight set (SubjectLayers.forward / its data gradient, common.py:55-58):

@@ -254,6 +254,15 @@ int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, cons
                       int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
                       float* y, float* aux, float* glu_out, double* stats, int* status, bm_stream_t stream);
 
+/* PERSISTENT CTA-pair kernel (csrc/tc_convp.cuh): one CTA pair per SM pair loops over 256-row tiles of the flattened
+ * rows b*T + t (taps that would cross a sample edge read zeros = the conv padding), epilogue warps drain tile i while the
+ * operands of tile i+1 are staged.  w_raw: RAW fp32 weights re-laid K-major [Kw][Ntot][Cin] (bm_tc_weight_split with
+ * f_lo / g_lo = NULL) -- the tensor core's truncation of the raw operand is the tf32 `hi`, the kernel derives `lo`.
+ * accumulate=1: y += conv(x) in place (the skip-path gradient; TMA reduce-add).  Other arguments as bm_tc_conv1d_pair. */
+int bm_tc_conv1d_persistent(const float* x, const float* w_raw, const float* bias, int accumulate, int B, int T, int Cin,
+                            int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor, float* y,
+                            float* aux, float* glu_out, double* stats, int* status, bm_stream_t stream);
+
 /* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]
  * for n < Ntrue (x may be channel-padded to N); dy [B,T,M], x [B,T,N] channels-last; dw in nn.Conv1d layout
  * [M][Ntrue][Kw].  workspace: bm_tc_wgrad_workspace() floats (per-batch-slice partial tiles, reduced in a fixed

@@ -1,0 +1,180 @@
+"""GPU: the persistent CTA-pair conv kernel (csrc/tc_convp.cuh, bm_tc_conv1d_persistent) in every epilogue mode against
+torch's fp64 conv (test-only reference), at the real layer shapes, incl. the flattened-row tiling across sample edges
+(odd batch sizes, T not a multiple of anything) and the BatchNorm statistics out of the epilogue."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 3e-5
+DEV = "cuda"
+
+
+def _abi():
+    from brainmagick_b200 import _lib
+    return _lib.call, _lib.ptr, _lib.stream
+
+
+def _raw_operands(w):
+    """w [Cout,Cin,Kw] -> forward operand [Kw,Cout,Cin] and data-gradient operand [Kw,Cin,Cout], raw fp32."""
+    call, ptr, stream = _abi()
+    Cout, Cin, Kw = w.shape
+    f = torch.empty(Kw, Cout, Cin, device=DEV)
+    g = torch.empty(Kw, Cin, Cout, device=DEV)
+    call("bm_tc_weight_split", ptr(w), Cout, Cin, Kw, ptr(f), None, ptr(g), None, stream())
+    return f, g
+
+
+def _ref_conv(x, w, bias, dilation):
+    y = torch.nn.functional.conv1d(x.double().permute(0, 2, 1), w.double(), None if bias is None else bias.double(),
+                                   padding=(w.shape[2] // 2) * dilation, dilation=dilation)
+    return y.permute(0, 2, 1).contiguous()
+
+
+def _run(x, w_op, bias, accumulate, B, T, Cin, Ntot, Kw, dil, sign, glu, act, tmajor, y, aux, glu_out, stats):
+    call, ptr, stream = _abi()
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    call("bm_tc_conv1d_persistent", ptr(x), ptr(w_op), ptr(bias), accumulate, B, T, Cin, Ntot, Kw, dil, sign, glu, act,
+         tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), stream())
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
+
+
+@pytest.mark.parametrize("B,T,dilation", [(3, 360, 1), (3, 360, 16), (5, 343, 2), (2, 100, 4), (1, 40, 8), (7, 361, 16),
+                                          (160, 360, 4)])
+def test_forward_with_statistics(B, T, dilation):
+    torch.manual_seed(B * 1000 + T + dilation)
+    Cin, Cout, Kw = 320, 320, 3
+    x = torch.randn(B, T, Cin, device=DEV)
+    w = torch.randn(Cout, Cin, Kw, device=DEV) / (Cin * Kw) ** 0.5
+    bias = torch.randn(Cout, device=DEV)
+    f, _ = _raw_operands(w)
+    y = torch.full((B, T, Cout), float("nan"), device=DEV)
+    stats = torch.full((2 * Cout,), float("nan"), device=DEV, dtype=torch.float64)
+    _run(x, f, bias, 0, B, T, Cin, Cout, Kw, dilation, 1, 0, 0, 0, y, None, None, stats)
+    ref = _ref_conv(x, w, bias, dilation)
+    e = rel_err(y.cpu(), ref.cpu())
+    print(f"[convp fwd B={B} T={T} d={dilation}] rel_err vs fp64 = {e:.2e}")
+    assert e < TOL
+    yd = y.double().reshape(-1, Cout)
+    assert rel_err(stats[:Cout].cpu(), yd.sum(0).cpu()) < 1e-6
+    assert rel_err(stats[Cout:].cpu(), (yd * yd).sum(0).cpu()) < 1e-6
+
+
+@pytest.mark.parametrize("B,T", [(2, 360), (3, 343), (5, 77)])
+@pytest.mark.parametrize("save_h", [True, False])
+def test_glu_and_data_gradient(B, T, save_h):
+    torch.manual_seed(7 + B)
+    H, Kw = 320, 3
+    x = torch.randn(B, T, H, device=DEV)
+    w = torch.randn(2 * H, H, Kw, device=DEV) / (H * Kw) ** 0.5
+    bias = torch.randn(2 * H, device=DEV)
+    f, g = _raw_operands(w)
+    h = torch.full((B, T, 2 * H), float("nan"), device=DEV) if save_h else None
+    out = torch.full((B, T, H), float("nan"), device=DEV)
+    _run(x, f, bias, 0, B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0, h, None, out, None)
+    ref_h = _ref_conv(x, w, bias, 1)
+    if save_h:
+        assert rel_err(h.cpu(), ref_h.cpu()) < TOL
+    ref_out = ref_h[..., :H] * torch.sigmoid(ref_h[..., H:])
+    assert rel_err(out.cpu(), ref_out.cpu()) < TOL
+    # data gradient dx[b,t,i] = sum_{o,j} w[o,i,j] dy[b,t-(j-1)d,o], plain store and in-place accumulation (K = 1920)
+    dy = torch.randn(B, T, 2 * H, device=DEV)
+    ref_dx = torch.nn.functional.conv_transpose1d(dy.double().permute(0, 2, 1), w.double(), padding=1).permute(0, 2, 1)
+    dx = torch.full((B, T, H), float("nan"), device=DEV)
+    _run(dy, g, None, 0, B, T, 2 * H, H, Kw, 1, -1, 0, 0, 0, dx, None, None, None)
+    e = rel_err(dx.cpu(), ref_dx.cpu())
+    print(f"[convp dgrad K=1920 B={B} T={T}] rel_err vs fp64 = {e:.2e}")
+    assert e < TOL
+    acc0 = torch.randn(B, T, H, device=DEV)
+    acc = acc0.clone()
+    _run(dy, g, None, 1, B, T, 2 * H, H, Kw, 1, -1, 0, 0, 0, acc, None, None, None)
+    assert rel_err(acc.cpu(), (ref_dx + acc0.double()).cpu()) < TOL
+
+
+@pytest.mark.parametrize("B,T", [(2, 360), (3, 101)])
+def test_head_modes(B, T):
+    """K5: 1x1 320->640 with GELU + saved pre-activation, then 1x1 640->1024 stored channel-major (the estimate)."""
+    torch.manual_seed(3)
+    H, F = 320, 1024
+    x = torch.randn(B, T, H, device=DEV)
+    w0 = torch.randn(2 * H, H, 1, device=DEV) / H ** 0.5
+    b0 = torch.randn(2 * H, device=DEV)
+    f0, _ = _raw_operands(w0)
+    q = torch.full((B, T, 2 * H), float("nan"), device=DEV)
+    h1 = torch.full((B, T, 2 * H), float("nan"), device=DEV)
+    _run(x, f0, b0, 0, B, T, H, 2 * H, 1, 1, 1, 0, 1, 0, q, h1, None, None)
+    ref_h1 = _ref_conv(x, w0, b0, 1)
+    assert rel_err(h1.cpu(), ref_h1.cpu()) < TOL
+    assert rel_err(q.cpu(), torch.nn.functional.gelu(ref_h1).cpu()) < TOL
+    q2 = torch.full((B, T, 2 * H), float("nan"), device=DEV)
+    _run(x, f0, b0, 0, B, T, H, 2 * H, 1, 1, 1, 0, 1, 0, q2, None, None, None)      # pre-activation not wanted (eval)
+    assert torch.equal(q, q2)
+    w2 = torch.randn(F, 2 * H, 1, device=DEV) / (2 * H) ** 0.5
+    b2 = torch.randn(F, device=DEV)
+    f2, _ = _raw_operands(w2)
+    est = torch.full((B, F, T), float("nan"), device=DEV)
+    _run(q, f2, b2, 0, B, T, 2 * H, F, 1, 1, 1, 0, 0, 1, est, None, None, None)
+    ref = _ref_conv(q, w2, b2, 1).permute(0, 2, 1)
+    assert rel_err(est.cpu(), ref.cpu()) < TOL
+
+
+def test_speed_report(capsys):
+    """Not a pass/fail on speed: per-launch times at the BASELINE shape (B=256, T=360), L2 flushed between launches."""
+    call, ptr, stream = _abi()
+    B, T, C, Kw = 256, 360, 320, 3
+    x = torch.randn(B, T, C, device=DEV)
+    w = torch.randn(C, C, Kw, device=DEV) / (C * Kw) ** 0.5
+    wg = torch.randn(2 * C, C, Kw, device=DEV) / (C * Kw) ** 0.5
+    f, g = _raw_operands(w)
+    fg, gg = _raw_operands(wg)
+    fh, fl = torch.empty(Kw, C, C, device=DEV), torch.empty(Kw, C, C, device=DEV)
+    call("bm_tc_weight_split", ptr(w), C, C, Kw, ptr(fh), ptr(fl), None, None, stream())
+    y = torch.empty(B, T, C, device=DEV)
+    h = torch.empty(B, T, 2 * C, device=DEV)
+    stats = torch.empty(2 * C, device=DEV, dtype=torch.float64)
+    status = torch.zeros(1, dtype=torch.int32, device=DEV)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
+    st = stream()
+
+    def k3_old():
+        call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
+             ptr(stats), ptr(status), st)
+
+    def k3():
+        call("bm_tc_conv1d_persistent", ptr(x), ptr(f), None, 0, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
+             ptr(stats), ptr(status), st)
+
+    def k3_acc():
+        call("bm_tc_conv1d_persistent", ptr(x), ptr(g), None, 1, B, T, C, C, Kw, 4, -1, 0, 0, 0, ptr(y), None, None,
+             None, ptr(status), st)
+
+    def k4():
+        call("bm_tc_conv1d_persistent", ptr(x), ptr(fg), None, 0, B, T, C, 2 * C, Kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(y),
+             None, ptr(status), st)
+
+    def k4_dgrad():
+        call("bm_tc_conv1d_persistent", ptr(h), ptr(gg), None, 0, B, T, 2 * C, C, Kw, 1, -1, 0, 0, 0, ptr(y), None, None,
+             None, ptr(status), st)
+
+    lines = []
+    for name, fn, flops in [("K3 gen3 (round 1)", k3_old, 2.0 * C * C * Kw * T * B), ("K3 persistent +stats", k3, 2.0 * C * C * Kw * T * B),
+                            ("K3 dgrad accumulate", k3_acc, 2.0 * C * C * Kw * T * B),
+                            ("K4 GLU (h saved)", k4, 4.0 * C * C * Kw * T * B),
+                            ("K4 dgrad (K=1920)", k4_dgrad, 4.0 * C * C * Kw * T * B)]:
+        times = []
+        for i in range(13):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                times.append(e0.elapsed_time(e1))
+        ms = sum(times) / len(times)
+        lines.append(f"[{name}] {ms:.4f} ms/launch = {flops / ms / 1e9:.1f} algorithmic TFLOP/s (min {min(times):.4f} ms)")
+    assert int(status.item()) == 0
+    with capsys.disabled():
+        print("\n" + "\n".join(lines))
