@@ -25,17 +25,48 @@ def rank() -> int:
     return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
 
-def all_gather_candidates(candidate: torch.Tensor) -> tp.Tuple[torch.Tensor, int]:
-    """[B_loc, F, T] per rank -> ([W*B_loc, F, T], target offset of this rank's rows).  For candidates that carry no
-    gradient (no feature_model); see `all_gather_candidates_with_grad` otherwise."""
+def gather_counts(n_local: int, device) -> tp.List[int]:
+    """Rows every rank contributes.  The reference's loaders have no drop_last and ScaleReject / exclude_empty_features
+    drop samples per rank (bm/norm.py:325-341), so per-rank batch sizes can differ: they are exchanged first (one tiny
+    all-gather + a host read), unless the caller vouches for equal batches (`uniform=True`, e.g. drop_last loaders)."""
+    W = world_size()
+    if W == 1:
+        return [n_local]
+    mine = torch.tensor([n_local], dtype=torch.int64, device=device)
+    allc = torch.empty(W, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allc, mine)
+    return [int(v) for v in allc.tolist()]
+
+
+def _pad_rows(x: torch.Tensor, rows: int) -> torch.Tensor:
+    if x.shape[0] == rows:
+        return x.contiguous()
+    out = x.new_zeros((rows,) + tuple(x.shape[1:]))
+    out[:x.shape[0]] = x
+    return out
+
+
+def _compact(padded: torch.Tensor, counts: tp.List[int], block: int) -> torch.Tensor:
+    """[W*block, ...] with rank r's rows at [r*block, r*block + counts[r]) -> [sum(counts), ...]"""
+    if all(c == block for c in counts):
+        return padded
+    return torch.cat([padded[r * block:r * block + c] for r, c in enumerate(counts)], dim=0)
+
+
+def all_gather_candidates(candidate: torch.Tensor, uniform: bool = False) -> tp.Tuple[torch.Tensor, int]:
+    """[B_r, F, T] on rank r -> ([sum_r B_r, F, T], row of this rank's first candidate).  For candidates that carry no
+    gradient (no feature_model); see `all_gather_candidates_with_grad` otherwise.  Ragged per-rank batches are padded to
+    the largest for the exchange and the padding rows are dropped afterwards."""
     W = world_size()
     if W == 1:
         return candidate, 0
-    candidate = candidate.contiguous()
-    out = torch.empty((W * candidate.shape[0],) + tuple(candidate.shape[1:]), dtype=candidate.dtype,
-                      device=candidate.device)
-    dist.all_gather_into_tensor(out, candidate)
-    return out, rank() * candidate.shape[0]
+    n = candidate.shape[0]
+    counts = [n] * W if uniform else gather_counts(n, candidate.device)
+    block = max(counts)
+    src = _pad_rows(candidate, block)
+    out = torch.empty((W * block,) + tuple(candidate.shape[1:]), dtype=candidate.dtype, device=candidate.device)
+    dist.all_gather_into_tensor(out, src)
+    return _compact(out, counts, block), sum(counts[:rank()])
 
 
 class _GatherWithGrad(torch.autograd.Function):
@@ -45,55 +76,72 @@ class _GatherWithGrad(torch.autograd.Function):
     `sync_gradients` / flashy's sync_model like all others, which yields the gradient of the mean of the per-rank losses.)"""
 
     @staticmethod
-    def forward(ctx, candidate):
-        candidate = candidate.contiguous()
+    def forward(ctx, candidate, counts):
         W = world_size()
-        out = torch.empty((W * candidate.shape[0],) + tuple(candidate.shape[1:]), dtype=candidate.dtype,
-                          device=candidate.device)
-        dist.all_gather_into_tensor(out, candidate)
-        ctx.rows = candidate.shape[0]
-        return out
+        block = max(counts)
+        src = _pad_rows(candidate, block)
+        out = torch.empty((W * block,) + tuple(candidate.shape[1:]), dtype=candidate.dtype, device=candidate.device)
+        dist.all_gather_into_tensor(out, src)
+        ctx.counts, ctx.block = counts, block
+        return _compact(out, counts, block)
 
     @staticmethod
     def backward(ctx, dgathered):
+        counts, block, r = ctx.counts, ctx.block, rank()
+        n = counts[r]
+        if any(c != block for c in counts):                     # back to the padded [W*block] layout of the exchange
+            padded = dgathered.new_zeros((len(counts) * block,) + tuple(dgathered.shape[1:]))
+            off = 0
+            for i, c in enumerate(counts):
+                padded[i * block:i * block + c] = dgathered[off:off + c]
+                off += c
+            dgathered = padded
         dgathered = dgathered.contiguous()
-        n, r = ctx.rows, rank()
         if dist.get_backend() == "nccl":
-            own = torch.empty((n,) + tuple(dgathered.shape[1:]), dtype=dgathered.dtype, device=dgathered.device)
+            own = torch.empty((block,) + tuple(dgathered.shape[1:]), dtype=dgathered.dtype, device=dgathered.device)
             dist.reduce_scatter_tensor(own, dgathered, op=dist.ReduceOp.SUM)
-            return own
+            return own[:n].contiguous(), None
         total = dgathered.clone()              # gloo (CPU tests) has no reduce-scatter
         dist.all_reduce(total, op=dist.ReduceOp.SUM)
-        return total[r * n:(r + 1) * n].clone()
+        return total[r * block:r * block + n].clone(), None
 
 
-def all_gather_candidates_with_grad(candidate: torch.Tensor) -> tp.Tuple[torch.Tensor, int]:
+def all_gather_candidates_with_grad(candidate: torch.Tensor, uniform: bool = False) -> tp.Tuple[torch.Tensor, int]:
     """`all_gather_candidates` for candidates that require grad: differentiable (reduce-scatter in backward)."""
-    if world_size() == 1:
+    W = world_size()
+    if W == 1:
         return candidate, 0
-    return _GatherWithGrad.apply(candidate), rank() * candidate.shape[0]
+    n = candidate.shape[0]
+    counts = [n] * W if uniform else gather_counts(n, candidate.device)
+    return _GatherWithGrad.apply(candidate, counts), sum(counts[:rank()])
 
 
 class CandidateGather:
     """The candidate all-gather started EARLY (it does not depend on the encoder): NCCL moves the blocks over NVLink while
     the encoder's forward kernels run; `wait()` joins it on the current stream just before the contrastive matmul."""
 
-    def __init__(self, candidate: torch.Tensor):
+    def __init__(self, candidate: torch.Tensor, uniform: bool = False):
         self.source = candidate
         W = world_size()
-        self.offset = rank() * candidate.shape[0]
+        n = candidate.shape[0]
         if W == 1:
-            self.out, self.work = candidate, None
+            self.out, self.work, self.offset, self.counts, self.block = candidate, None, 0, [n], n
             return
-        candidate = candidate.contiguous()
-        self.out = torch.empty((W * candidate.shape[0],) + tuple(candidate.shape[1:]), dtype=candidate.dtype,
+        self.counts = [n] * W if uniform else gather_counts(n, candidate.device)
+        self.block = max(self.counts)
+        self.offset = sum(self.counts[:rank()])
+        src = _pad_rows(candidate, self.block)
+        self.out = torch.empty((W * self.block,) + tuple(candidate.shape[1:]), dtype=candidate.dtype,
                                device=candidate.device)
-        self.work = dist.all_gather_into_tensor(self.out, candidate, async_op=True)
+        self.work = dist.all_gather_into_tensor(self.out, src, async_op=True)
+        self._src = src                        # keep the (possibly padded) source alive until the collective is joined
 
     def wait(self) -> tp.Tuple[torch.Tensor, int]:
         if self.work is not None:
             self.work.wait()          # current stream waits for NCCL's stream; the host does not block
             self.work = None
+            self._src = None
+            self.out = _compact(self.out, self.counts, self.block)
         return self.out, self.offset
 
 

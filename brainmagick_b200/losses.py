@@ -19,7 +19,8 @@ from . import distrib
 
 class ClipLoss(torch.nn.Module):
     def __init__(self, linear=None, twin=True, pool=False, tmin=None, tmax=None,
-                 tmin_train=None, tmax_train=None, dset_args=None, center=False, global_negatives=False):
+                 tmin_train=None, tmax_train=None, dset_args=None, center=False, global_negatives=False,
+                 uniform_batches=False):
         super().__init__()
         self.linear = None                      # the reference never applies its projection (losses.py:35)
         self.pool = pool
@@ -31,6 +32,10 @@ class ClipLoss(torch.nn.Module):
         self.tmin_train, self.tmax_train = tmin_train, tmax_train
         self.dset_args = dset_args
         self.global_negatives = global_negatives
+        # global_negatives only: True = every rank holds the same number of rows each step (drop_last loaders, no
+        # rejection), which saves the per-step exchange of the per-rank counts; False = counts are exchanged and ragged
+        # batches are handled (the reference's loaders have no drop_last, and ScaleReject drops samples per rank)
+        self.uniform_batches = uniform_batches
         self._prefetched = None
 
     # -- time cropping (losses.py:50-75) ---------------------------------------------------------------
@@ -78,7 +83,7 @@ class ClipLoss(torch.nn.Module):
         if self.global_negatives and distrib.world_size() > 1 and not candidate.requires_grad \
                 and not (self.pool or self.center) \
                 and self._window(candidate.shape[-1]) == (0, candidate.shape[-1]):
-            self._prefetched = distrib.CandidateGather(candidate)
+            self._prefetched = distrib.CandidateGather(candidate, self.uniform_batches)
 
     def forward(self, estimate, candidate, mask=None):
         assert mask.all(), "mask is not supported for now"
@@ -87,7 +92,7 @@ class ClipLoss(torch.nn.Module):
         if candidate.requires_grad and torch.is_grad_enabled() and self.global_negatives and distrib.world_size() > 1:
             # a trainable feature model made the candidates: differentiable gather (reduce-scatter of dC in backward)
             estimate, candidate = self._prepare(estimate, candidate)
-            candidate, offset = distrib.all_gather_candidates_with_grad(candidate)
+            candidate, offset = distrib.all_gather_candidates_with_grad(candidate, self.uniform_batches)
             return BF.clip_loss(estimate, candidate, offset)
         if pre is not None and pre.source is candidate:
             estimate, _ = self._prepare(estimate, candidate)
@@ -96,5 +101,5 @@ class ClipLoss(torch.nn.Module):
         estimate, candidate = self._prepare(estimate, candidate)
         offset = 0
         if self.global_negatives and distrib.world_size() > 1:
-            candidate, offset = distrib.all_gather_candidates(candidate)
+            candidate, offset = distrib.all_gather_candidates(candidate, self.uniform_batches)
         return BF.clip_loss(estimate, candidate, offset)

@@ -171,3 +171,62 @@ def test_cliploss_module_with_global_negatives_on_two_ranks():
             assert abs(loss_t - float(parts[r])) < 1e-5
             assert torch.allclose(de_t, world * est.grad[r * 3:(r + 1) * 3], atol=1e-6)
             assert torch.allclose(dc_t, world * cand.grad[r * 3:(r + 1) * 3], atol=1e-6)
+
+
+def _ragged_worker(rank, world, port, ret):
+    """Per-rank batch sizes differ (no drop_last, per-rank rejection): rank r holds 3 - r rows."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import abi_emulator
+        import brainmagick_b200 as bb
+        from brainmagick_b200 import distrib
+        counts = [3 - r for r in range(world)]
+        starts = [sum(counts[:r]) for r in range(world)]
+        torch.manual_seed(13)
+        est = torch.randn(sum(counts), 4, 6)
+        cand = torch.randn(sum(counts), 4, 6)
+        mine = slice(starts[rank], starts[rank] + counts[rank])
+        assert distrib.gather_counts(counts[rank], torch.device("cpu")) == counts
+        g, off = distrib.all_gather_candidates(cand[mine].clone())
+        assert off == starts[rank] and torch.equal(g, cand)
+        pre = distrib.CandidateGather(cand[mine].clone())
+        g2, off2 = pre.wait()
+        assert off2 == off and torch.equal(g2, cand)
+        out = {}
+        mask = torch.ones(counts[rank], 1, 6, dtype=torch.bool)
+        with abi_emulator.emulated():
+            clip = bb.ClipLoss(global_negatives=True)
+            e = est[mine].clone().requires_grad_(True)
+            c = cand[mine].clone().requires_grad_(True)
+            loss = clip(e, c, mask)
+            loss.backward()
+            out = (float(loss), e.grad.clone(), c.grad.clone())
+        ret[rank] = out
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ragged_per_rank_batches():
+    """ADVICE r1 (distrib.py): the gathers must not assume equal per-rank row counts."""
+    from oracle import bm_oracle
+    world = 2
+    counts = [3 - r for r in range(world)]
+    starts = [sum(counts[:r]) for r in range(world)]
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_ragged_worker, args=(world, port, ret), nprocs=world, join=True)
+        torch.manual_seed(13)
+        est = torch.randn(sum(counts), 4, 6).requires_grad_(True)
+        cand = torch.randn(sum(counts), 4, 6).requires_grad_(True)
+        parts = [bm_oracle.clip_loss(est[starts[r]:starts[r] + counts[r]], cand, target_offset=starts[r]) for r in range(world)]
+        (sum(parts) / world).backward()
+        for r in range(world):
+            loss_r, de_r, dc_r = ret[r]
+            sl = slice(starts[r], starts[r] + counts[r])
+            assert abs(loss_r - float(parts[r])) < 1e-5
+            assert torch.allclose(de_r, world * est.grad[sl], atol=1e-6)
+            assert torch.allclose(dc_r, world * cand.grad[sl], atol=1e-6)
