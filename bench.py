@@ -368,10 +368,11 @@ def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
     peaks = load_peaks()
     x = torch.randn(B, T, H, device=dev)
     w = torch.randn(H, H, Kw, device=dev) * 0.03
-    fh, fl = torch.empty(Kw, H, H, device=dev), torch.empty(Kw, H, H, device=dev)
-    call("bm_tc_weight_split", ptr(w), H, H, Kw, ptr(fh), ptr(fl), None, None, stream())
+    f = torch.empty(Kw, H, H, device=dev)
+    call("bm_tc_weight_split", ptr(w), H, H, Kw, ptr(f), None, None, None, stream())
     bias = torch.zeros(H, device=dev)
     y = torch.empty(B, T, H, device=dev)
+    stats = torch.empty(2 * H, device=dev, dtype=torch.float64)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     times = []
@@ -379,8 +380,8 @@ def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
         flush.zero_()                                                   # L2 flush between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), ptr(bias), None, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None,
-             None, None, ptr(status), stream())
+        call("bm_tc_conv1d_persistent", ptr(x), ptr(f), ptr(bias), 0, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
+             ptr(stats), ptr(status), stream())
         e1.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -390,7 +391,7 @@ def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
     flops = 2.0 * H * H * Kw * T * B
     achieved = flops / (ms / 1e3) / 1e12
     peak = peaks["bf16_tflops"]
-    return dict(kernel="conv_tc3_kernel via bm_tc_conv1d_pair (K3: Conv1d 320->320 k3 d4, tcgen05 cta_group::2 kind::tf32, 3xTF32)",
+    return dict(kernel="conv_pp_kernel via bm_tc_conv1d_persistent (K3: Conv1d 320->320 k3 d4 + BatchNorm statistics, persistent CTA pairs, tcgen05 cta_group::2 kind::tf32, 3xTF32)",
                 bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
                 traffic=ncu_traffic_bytes(), algorithmic_bytes=2.0 * B * T * H * 4,
                 ms_per_launch=ms, peak_source=peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",

@@ -52,6 +52,7 @@ SIGNATURES = {
     "bm_tc_conv1d_pair": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_tc_conv1d_persistent": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
+    "bm_channel_mask": [P, P, I, I, I, P, P],
     "bm_transpose_nt": [P, I, I, I, P, P],
     "bm_transpose_nt_ld": [P, I, I, I, I, P, P],
     "bm_tc_wgrad_supported": [I, I],

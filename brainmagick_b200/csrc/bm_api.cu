@@ -807,6 +807,15 @@ extern "C" int bm_col_stats(const float* y, long long rows, int C, double* stats
     return 0;
 }
 
+// y = x * mask[c] over [B, C, T] (SimpleConv's subsample_meg_channels, simpleconv.py:97-102,200-203); y may alias x
+extern "C" int bm_channel_mask(const float* x, const float* mask, int B, int C, int T, float* y, bm_stream_t stream) {
+    BM_CHECK_ARG(x && mask && y && B > 0 && C > 0 && T > 0);
+    const long long total = (long long)B * C * T;
+    channel_mask_kernel<<<ew_grid(total), 256, 0, ST(stream)>>>(x, mask, y, C, T, total);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
+
 // [Z, N, T] (channel-major) -> [Z, T, N] (channels-last)
 extern "C" int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream) {
     BM_CHECK_ARG(in && out && Z > 0 && N > 0 && T > 0 && Z <= 65535);

@@ -403,6 +403,16 @@ __global__ void clip_ce_bwd_kernel(const float* __restrict__ probs, const float*
     }
 }
 
+// y[b][c][t] = x[b][c][t] * mask[c]   (simpleconv.py:200-203: `subsample_meg_channels` zeroes the sensors not drawn)
+__global__ void channel_mask_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ y,
+                                    int C, int T, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)((i / T) % C);
+        y[i] = x[i] * mask[c];
+    }
+}
+
 // in [Z][N][T] -> out [Z][T][N]   (32x32 tiles through shared memory, both sides coalesced)
 __global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int T, int ld_out) {
     __shared__ float tile[32][33];

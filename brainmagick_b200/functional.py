@@ -76,7 +76,7 @@ def check_tc_status(device=None) -> None:
 
 
 OVERLAP_WGRAD = True   # weight-gradient kernels on a side stream, concurrent with the data-gradient kernels of the layer
-USE_CONV_V3 = True     # CTA-pair kernel (tc_conv3.cuh, tcgen05 cta_group::2): the fastest where its tiling fits
+USE_CONV_PP = True     # persistent CTA-pair kernel (tc_convp.cuh, tcgen05 cta_group::2) where its tiling fits
 
 
 _side_streams: tp.Dict[torch.device, torch.cuda.Stream] = {}
@@ -118,23 +118,24 @@ class _Conv:
         st = stream()
         lib = _lib.load()
         g = 1 if glu else 0
-        self.fwd_v3 = allow_tc and USE_CONV_V3 and bool(lib.bm_tc_conv3_supported(T, self.cin, self.cout, self.kw, g))
-        self.bwd_v3 = allow_tc and USE_CONV_V3 and bool(lib.bm_tc_conv3_supported(T, self.cout, self.cin, self.kw, 0))
-        fwd_tc = self.fwd_v3 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, g)))
-        bwd_tc = self.bwd_v3 or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0)))
+        # persistent CTA-pair kernel (csrc/tc_convp.cuh) where its tiling fits, else the single-CTA tensor-core kernel,
+        # else FP32 FMA
+        self.fwd_pp = allow_tc and USE_CONV_PP and bool(lib.bm_tc_conv3_supported(T, self.cin, self.cout, self.kw, g))
+        self.bwd_pp = allow_tc and USE_CONV_PP and bool(lib.bm_tc_conv3_supported(T, self.cout, self.cin, self.kw, 0))
+        fwd_tc = self.fwd_pp or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, g)))
+        bwd_tc = self.bwd_pp or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0)))
         self.fwd_tc, self.bwd_tc = fwd_tc, bwd_tc
-        self.fwd_fn = "bm_tc_conv1d_pair" if self.fwd_v3 else "bm_tc_conv1d"
-        self.bwd_fn = "bm_tc_conv1d_pair" if self.bwd_v3 else "bm_tc_conv1d"
         self.wgrad_tc = allow_tc and bool(lib.bm_tc_wgrad_supported(self.cout, self.cin))
         self.f_hi = self.f_lo = self.g_hi = self.g_lo = self.wf = self.wb = None
         if fwd_tc or (bwd_tc and want_bwd):
-            # pre-split tf32 hi/lo operand pairs
+            # K-major operands: RAW fp32 for the persistent kernel (it derives the tf32 lo part itself), a pre-split tf32
+            # hi/lo pair for the single-CTA kernel
             if fwd_tc:
                 self.f_hi = _empty((self.kw, self.cout, self.cin), w)
-                self.f_lo = _empty((self.kw, self.cout, self.cin), w)
+                self.f_lo = None if self.fwd_pp else _empty((self.kw, self.cout, self.cin), w)
             if bwd_tc and want_bwd:
                 self.g_hi = _empty((self.kw, self.cin, self.cout), w)
-                self.g_lo = _empty((self.kw, self.cin, self.cout), w)
+                self.g_lo = None if self.bwd_pp else _empty((self.kw, self.cin, self.cout), w)
             call("bm_tc_weight_split", ptr(w), self.cout, self.cin, self.kw, ptr(self.f_hi), ptr(self.f_lo),
                  ptr(self.g_hi), ptr(self.g_lo), st)
         if (not fwd_tc) or (want_bwd and not bwd_tc):
@@ -142,13 +143,31 @@ class _Conv:
             self.wb = _empty((self.kw, self.cout, self.cin), w) if (want_bwd and not bwd_tc) else None
             call("bm_conv_weight_prep", ptr(w), self.cout, self.cin, self.kw, ptr(self.wf), ptr(self.wb), st)
 
+    def run_tc(self, fwd: bool, x, bias, addend, B, T, dilation, glu, act, tmajor, y, aux, glu_out, stats, status):
+        """One tensor-core conv launch: forward taps (fwd) or the data gradient; `addend` must be None or `y` itself
+        (in-place accumulation) on the persistent kernel."""
+        st = stream()
+        if fwd:
+            pp, hi, lo, cin, ntot, sign = self.fwd_pp, self.f_hi, self.f_lo, self.cin, self.cout, 1
+        else:
+            pp, hi, lo, cin, ntot, sign = self.bwd_pp, self.g_hi, self.g_lo, self.cout, self.cin, -1
+        if pp:
+            assert addend is None or addend.data_ptr() == y.data_ptr(), "the persistent kernel accumulates in place only"
+            call("bm_tc_conv1d_persistent", ptr(x), ptr(hi), ptr(bias), 0 if addend is None else 1, B, T, cin, ntot,
+                 self.kw, dilation, sign, glu, act, tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), st)
+        else:
+            assert stats is None
+            call("bm_tc_conv1d", ptr(x), ptr(hi), ptr(lo), ptr(bias), ptr(addend), B, T, cin, ntot, self.kw, dilation,
+                 sign, glu, act, tmajor, ptr(y), ptr(aux), ptr(glu_out), None, ptr(status), st)
+
     # y = conv(x) (+bias); optionally BatchNorm statistics into `stats`
     def forward(self, x, bias, B, T, dilation, y, stats, status):
         st = stream()
         if self.fwd_tc:
-            fused = stats is not None and self.fwd_v3          # BatchNorm statistics out of the conv epilogue
-            call(self.fwd_fn, ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
-                 self.kw, dilation, 1, 0, 0, 0, ptr(y), None, None, ptr(stats) if fused else None, ptr(status), st)
+            fused = stats is not None and self.fwd_pp          # BatchNorm statistics out of the conv epilogue
+            if self.cout > 320:
+                fused = False                                   # the kernel keeps the statistics of ONE N tile in smem
+            self.run_tc(True, x, bias, None, B, T, dilation, 0, 0, 0, y, None, None, stats if fused else None, status)
             if stats is not None and not fused:
                 call("bm_col_stats", ptr(y), B * T, self.cout, ptr(stats), st)
         else:
@@ -158,8 +177,7 @@ class _Conv:
     def forward_glu(self, x, bias, B, T, h, out, status):
         st = stream()
         if self.fwd_tc:
-            call(self.fwd_fn, ptr(x), ptr(self.f_hi), ptr(self.f_lo), ptr(bias), None, B, T, self.cin, self.cout,
-                 self.kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(out), None, ptr(status), st)
+            self.run_tc(True, x, bias, None, B, T, 1, 1, 0, 0, h, None, out, None, status)
         else:
             call("bm_conv1d_glu_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout // 2, self.kw,
                  ptr(h), ptr(out), st)
@@ -167,8 +185,7 @@ class _Conv:
     def backward_data(self, dy, addend, B, T, dilation, dx, status):
         st = stream()
         if self.bwd_tc:
-            call(self.bwd_fn, ptr(dy), ptr(self.g_hi), ptr(self.g_lo), None, ptr(addend), B, T, self.cout,
-                 self.cin, self.kw, dilation, -1, 0, 0, 0, ptr(dx), None, None, None, ptr(status), st)
+            self.run_tc(False, dy, None, addend, B, T, dilation, 0, 0, 0, dx, None, None, None, status)
         else:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
                  dilation, ptr(dx), st)
@@ -330,13 +347,12 @@ class _EncoderFn(torch.autograd.Function):
                 hpad = torch.zeros((Opad, P, 1), device=meg.device)
                 hpad[:O, :, 0] = heads
                 heads_conv = _Conv(hpad, C, False, True, want_bwd=False)
-                if not heads_conv.fwd_v3:
+                if not heads_conv.fwd_pp:
                     heads_conv = None
             if heads_conv is not None:
                 call("bm_fourier_emb", ptr(plan.rec_positions), ptr(plan.freq), R, C, P, ptr(emb), st)
                 att_full = _empty((R, Opad, C), meg)          # scores[r][o][c] = <emb[r][c], heads[o]> written channel-major
-                call(heads_conv.fwd_fn, ptr(emb), ptr(heads_conv.f_hi), ptr(heads_conv.f_lo), None, None, R, C, P, Opad, 1, 1, 1,
-                     0, 0, 1, ptr(att_full), None, None, None, ptr(status), st)
+                heads_conv.run_tc(True, emb, None, None, R, C, 1, 0, 0, 1, att_full, None, None, None, status)
                 call("bm_masked_softmax", ptr(att_full), ptr(plan.rec_positions), ptr(plan.ban_centre), float(plan.ban_radius),
                      R, Opad, C, st)
                 att = att_full[:, :O].contiguous()
@@ -506,10 +522,8 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_transpose_nt", ptr(est_cl), B, T, F, ptr(est), st)
             del est_cl
         elif head_tc:
-            call(head0.fwd_fn, ptr(x), ptr(head0.f_hi), ptr(head0.f_lo), ptr(b0.contiguous()), None, B, T, H, H2, 1,
-                 1, 1, 0, 1, 0, ptr(q), ptr(h1), None, None, ptr(status), st)
-            call(head2.fwd_fn, ptr(q), ptr(head2.f_hi), ptr(head2.f_lo), ptr(b2.contiguous()), None, B, T, H2, F, 1,
-                 1, 1, 0, 0, 1, ptr(est), None, None, None, ptr(status), st)
+            head0.run_tc(True, x, b0.contiguous(), None, B, T, 1, 0, 1, 0, q, h1 if save else None, None, None, status)
+            head2.run_tc(True, q, b2.contiguous(), None, B, T, 1, 0, 0, 1, est, None, None, None, status)
         else:
             call("bm_head_fwd", ptr(x), ptr(w0_2), ptr(b0.contiguous()), ptr(w2_2), ptr(b2.contiguous()), B, T, H, F,
                  ptr(h1), ptr(q), ptr(est), st)
@@ -572,8 +586,7 @@ class _EncoderFn(torch.autograd.Function):
             dest_t = _empty((B, T, F), meg)
             call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
             # dq = dest_t @ w2^T  (w2_as_conv [F,2H,1]: its data-gradient operand is [1][2H][F])
-            call(head2.bwd_fn, ptr(dest_t), ptr(head2.g_hi), ptr(head2.g_lo), None, None, B, T, F, H2, 1, 1, -1, 0, 0,
-                 0, ptr(dq), None, None, None, ptr(status), st)
+            head2.run_tc(False, dest_t, None, None, B, T, 1, 0, 0, 0, dq, None, None, None, status)
             lib = _lib.load()
             if lib.bm_tc_wgrad_supported(H2, F) and lib.bm_tc_wgrad_supported(H2, H):
                 main0 = torch.cuda.current_stream()
@@ -599,8 +612,7 @@ class _EncoderFn(torch.autograd.Function):
             else:
                 call("bm_head_bwd_params", ptr(dest), ptr(s["x_last"]), ptr(s["h1"]), ptr(s["q"]), B, T, H, F,
                      ptr(dq), ptr(dw0), ptr(db0), ptr(dw2), ptr(db2), st)   # dq <- dq*GELU'(h1); dW0, db0, dW2, db2
-            call(head0.bwd_fn, ptr(dq), ptr(head0.g_hi), ptr(head0.g_lo), None, None, B, T, H2, H, 1, 1, -1, 0, 0, 0,
-                 ptr(g), None, None, None, ptr(status), st)
+            head0.run_tc(False, dq, None, None, B, T, 1, 0, 0, 0, g, None, None, None, status)
             del dest_t
         else:
             call("bm_head_bwd", ptr(dest), ptr(s["x_last"]), ptr(s["w0_2"]), ptr(s["w2_2"]), ptr(s["h1"]), ptr(s["q"]),

@@ -15,6 +15,7 @@ signature but raise NotImplementedError.
 """
 from __future__ import annotations
 
+import random
 import typing as tp
 
 import torch
@@ -94,7 +95,7 @@ class SimpleConv(nn.Module):
             concatenate=concatenate, linear_out=linear_out, growth=growth != 1.,
             dual_path=bool(dual_path), n_fft=n_fft is not None, dropout=dropout > 0.,
             initial_depth=initial_depth != 1, initial_nonlin=initial_nonlin,
-            subsample_meg_channels=bool(subsample_meg_channels), inputs=set(in_channels) != {"meg"})
+            inputs=set(in_channels) != {"meg"})
         bad = [k for k, v in off_path.items() if v]
         if bad:
             raise NotImplementedError(
@@ -104,6 +105,11 @@ class SimpleConv(nn.Module):
         self._concatenate = concatenate
         self.out_channels = out_channels
         self.subsampled_meg_channels: tp.Optional[list] = None
+        if subsample_meg_channels:               # simpleconv.py:97-102: the same draw as the reference
+            indexes = list(range(in_channels["meg"]))
+            random.Random(1234).shuffle(indexes)
+            self.subsampled_meg_channels = indexes[:subsample_meg_channels]
+        self._channel_mask: tp.Optional[torch.Tensor] = None
         self.dropout = None
         self.stft = None
         self.subject_embedding = None
@@ -213,6 +219,16 @@ class SimpleConv(nn.Module):
             raise TypeError("brainmagick_b200.SimpleConv computes in fp32, like the reference")
         assert meg.shape[1] == self.n_input_channels, "number of MEG channels differs from in_channels['meg']"
         length = meg.shape[-1]
+        if self.subsampled_meg_channels is not None:         # simpleconv.py:200-203
+            if self._channel_mask is None or self._channel_mask.device != meg.device:
+                mask = torch.zeros(self.n_input_channels)
+                mask[self.subsampled_meg_channels] = 1.
+                self._channel_mask = mask.to(meg.device)
+            meg = meg.contiguous()
+            masked = torch.empty_like(meg)
+            BF.call("bm_channel_mask", BF.ptr(meg), BF.ptr(self._channel_mask), meg.shape[0], meg.shape[1], meg.shape[2],
+                    BF.ptr(masked), BF.stream())
+            meg = inputs["meg"] = masked
         plan = self._plan(meg, batch)
         heads = None if self.merger is None else self.merger.heads
         il_w, il_b = (None, None) if self.initial_linear is None else \

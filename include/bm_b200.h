@@ -283,6 +283,9 @@ int bm_tc_wgrad_grouped(const float* dy, const float* x, const int* order, const
                         int N, float* out, int* status, bm_stream_t stream);
 /* dh = dq * GELU'(h), elementwise over n values (dh may alias dq): the head's activation backward. */
 int bm_gelu_bwd(const float* dq, const float* h, long long n, float* dh, bm_stream_t stream);
+/* y[b,c,t] = x[b,c,t] * mask[c]: SimpleConv(subsample_meg_channels=n) keeps n sensors drawn with random.Random(1234)
+ * and zeroes the others before the merger (bm/models/simpleconv.py:97-102, 200-203).  y may alias x. */
+int bm_channel_mask(const float* x, const float* mask, int B, int C, int T, float* y, bm_stream_t stream);
 /* in [Z,N,T] (channel-major) -> out [Z,T,N] (channels-last): the gradient of `estimate` enters the head backward. */
 int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream);
 /* same with an output row stride ld_out >= N (pad columns untouched): meg [B,C,T] -> channels-last, channel-padded. */

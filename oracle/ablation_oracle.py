@@ -8,6 +8,7 @@
     glu=0, skip=False       ConvSequence without GLU blocks / residuals              common.py:79-151
     gelu=False              ReLU in the ConvSequence AND in the head                 simpleconv.py:85-90, 187
     complex_out=False       no head: the last conv maps to out_channels, no BN/act   simpleconv.py:190-193
+    subsample_meg_channels  only n sensors (drawn with random.Random(1234)) are kept  simpleconv.py:97-102, 200-203
 This is step (a) -- the oracle -- of that row: it is pinned against the verbatim reference (`tests/golden/ablation_*.npz`,
 made by `oracle/make_golden.py`) so that the CUDA variants can be built against it.  The CUDA SimpleConv still accepts only
 the `clip_conv` family.
@@ -45,6 +46,7 @@ class Variant(tp.NamedTuple):
     complex_out: bool = True
     kernel_size: int = 3
     dilation_period: int = 5
+    subsample_meg_channels: int = 0
 
     def sequence_spec(self) -> deepmel_oracle.SequenceSpec:
         c = self.in_channels
@@ -67,6 +69,13 @@ def forward(p: tp.Dict[str, torch.Tensor], v: Variant, meg, rec_positions, rec_o
     """simpleconv.py:198-249 for one variant; parameters under the reference's state_dict names."""
     length = meg.shape[-1]
     x = meg
+    if v.subsample_meg_channels:                                                                 # simpleconv.py:97-102,200-203
+        import random
+        indexes = list(range(v.in_channels))
+        random.Random(1234).shuffle(indexes)
+        mask = torch.zeros(1, v.in_channels, 1, dtype=x.dtype)
+        mask[:, indexes[:v.subsample_meg_channels]] = 1.
+        x = x * mask
     if v.merger:
         centre = ban_centre if (training and v.merger_dropout) else None
         w = bm_oracle.attention_weights(rec_positions, p["merger.heads"], centre, v.merger_dropout)

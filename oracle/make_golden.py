@@ -274,6 +274,7 @@ ABLATIONS = {
     "ablation_no_complex_out": dict(complex_out=False),
     "ablation_no_subject_layers": dict(subject_layers=False),
     "ablation_subject_embedding": dict(subject_layers=False, subject_dim=5),
+    "ablation_subsample_channels": dict(subsample_meg_channels=6),
 }
 
 

@@ -1,5 +1,5 @@
 """Runs each hot kernel a few times at the BASELINE shape (B=256, T=360, H=320) so that one `ncu --set full`
-capture per kernel is short (which = conv | wgrad | prep | topk | scores):   ncu --set full --clock-control none --import-source on -k regex:<name> -s 3 -c 2 \
+capture per kernel is short (which = conv | conv_glu | conv_acc | wgrad | prep | topk | scores | scores_train):   ncu --set full --clock-control none --import-source on -k regex:<name> -s 3 -c 2 \
                                -o gpurun_out/prof_<name> python profiles/profile_kernels.py <which>"""
 import os
 import sys
@@ -14,15 +14,26 @@ which = sys.argv[1] if len(sys.argv) > 1 else "conv"
 dev = "cuda"
 B, T, H, Kw = 256, 360, 320, 3
 status = torch.zeros(1, dtype=torch.int32, device=dev)
-if which == "conv":
+if which in ("conv", "conv_glu", "conv_acc"):
+    # -k regex:conv_pp_kernel: K3 forward with BatchNorm statistics | K4 GLU forward (h saved) | K3 data gradient, y += tile
     x = torch.randn(B, T, H, device=dev)
-    w = torch.randn(H, H, Kw, device=dev) * 0.03
-    fh, fl = torch.empty(Kw, H, H, device=dev), torch.empty(Kw, H, H, device=dev)
-    call("bm_tc_weight_split", ptr(w), H, H, Kw, ptr(fh), ptr(fl), None, None, stream())
-    y = torch.empty(B, T, H, device=dev)
+    N = 2 * H if which == "conv_glu" else H
+    w = torch.randn(N, H, Kw, device=dev) * 0.03
+    f, g = torch.empty(Kw, N, H, device=dev), torch.empty(Kw, H, N, device=dev)
+    call("bm_tc_weight_split", ptr(w), N, H, Kw, ptr(f), None, ptr(g), None, stream())
+    y = torch.zeros(B, T, H, device=dev)
+    h = torch.empty(B, T, 2 * H, device=dev) if which == "conv_glu" else None
+    stats = torch.empty(2 * H, device=dev, dtype=torch.float64)
     for _ in range(6):
-        call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), None, None, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
-             None, ptr(status), stream())
+        if which == "conv":
+            call("bm_tc_conv1d_persistent", ptr(x), ptr(f), None, 0, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
+                 ptr(stats), ptr(status), stream())
+        elif which == "conv_glu":
+            call("bm_tc_conv1d_persistent", ptr(x), ptr(f), None, 0, B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(y),
+                 None, ptr(status), stream())
+        else:
+            call("bm_tc_conv1d_persistent", ptr(x), ptr(g), None, 1, B, T, H, H, Kw, 4, -1, 0, 0, 0, ptr(y), None, None,
+                 None, ptr(status), stream())
 elif which == "wgrad":
     dy = torch.randn(B, T, H, device=dev)
     x = torch.randn(B, T, H, device=dev)
@@ -50,6 +61,16 @@ elif which == "topk":          # -k regex:retrieval_topk_kernel     (fused softm
     for _ in range(6):
         call("bm_retrieval_topk", ptr(scores), M, Bn, M, None, 0, 0, 10, ptr(labels), None, ptr(targets), ptr(top_idx),
              ptr(top_p), ptr(hit), None, None, None, stream())
+elif which == "scores_train":  # -k regex:clip_scores_kernel          (training shape: 256 x 256 x 368 640, norms + CE fused)
+    Bn, M, KT = 256, 256, 1024 * 360
+    est = torch.randn(Bn, KT, device=dev) * 0.01
+    cand = torch.randn(M, KT, device=dev)
+    inv, sc, pr = torch.empty(M, device=dev), torch.empty(Bn, M, device=dev), torch.empty(Bn, M, device=dev)
+    rl, loss = torch.empty(Bn, device=dev), torch.empty(1, device=dev)
+    ws = torch.empty(max(int(_lib.load().bm_clip_workspace(Bn, M, KT)), 2), device=dev)
+    for _ in range(4):
+        call("bm_clip_loss_fwd", ptr(est), ptr(cand), Bn, M, KT, 0, ptr(inv), ptr(sc), ptr(pr), ptr(rl), ptr(loss), ptr(ws),
+             ws.numel(), ptr(status), stream())
 elif which == "scores":        # -k regex:clip_scores_kernel           (retrieval / CLIP score GEMM, K = F*T = 368 640)
     Bn, M, KT = 1024, 2048, 1024 * 360
     est = torch.randn(Bn, KT, device=dev)

@@ -282,6 +282,9 @@ class Emulator:
         _v(db0, 2 * H).copy_(dh1.sum(0))
         _v(dx, B * T, H).copy_(dh1 @ _v(w0, 2 * H, H))
 
+    def bm_channel_mask(self, x, mask, B, C, T, y, stream):
+        _v(y, B, C, T).copy_(_v(x, B, C, T) * _v(mask, C)[None, :, None])
+
     def bm_transpose_nt(self, inp, Z, N, T, out, stream):
         _v(out, Z, T, N).copy_(_v(inp, Z, N, T).transpose(1, 2))
 
@@ -369,6 +372,11 @@ class Emulator:
             _v(y, B, T, Ntot).copy_(out)
 
     bm_tc_conv1d_pair = bm_tc_conv1d
+
+    def bm_tc_conv1d_persistent(self, x, w_raw, bias, accumulate, B, T, Cin, Ntot, Kw, dilation, sign, glu, act, out_tmajor,
+                                y, aux, glu_out, stats, status, stream):
+        self.bm_tc_conv1d(x, w_raw, None, bias, y if accumulate else None, B, T, Cin, Ntot, Kw, dilation, sign, glu, act,
+                          out_tmajor, y, aux, glu_out, stats, status, stream)
 
     def bm_col_stats(self, y, rows, C, stats, stream):
         o = _v(y, rows, C).double()

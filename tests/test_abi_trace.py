@@ -10,7 +10,7 @@ def test_full_size_step_runs_on_tensor_cores_only():
     names = {c[0] for c in abi_trace.simpleconv_step(abi_trace.CONFIGS["full"], True)}
     assert not names & {"bm_conv1d_fwd", "bm_conv1d_bwd_data", "bm_conv1d_bwd_weight", "bm_conv1d_glu_fwd", "bm_head_fwd",
                         "bm_head_bwd", "bm_sensor_chain_fwd", "bm_sensor_chain_bwd", "bm_attention_weights_fwd"}
-    assert {"bm_tc_conv1d_pair", "bm_tc_wgrad", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
+    assert {"bm_tc_conv1d_persistent", "bm_tc_wgrad", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
 
 
 @pytest.mark.parametrize("override", [dict(glu=0), dict(skip=False), dict(gelu=False), dict(complex_out=False),

@@ -175,6 +175,29 @@ def test_speed_report(capsys):
                 times.append(e0.elapsed_time(e1))
         ms = sum(times) / len(times)
         lines.append(f"[{name}] {ms:.4f} ms/launch = {flops / ms / 1e9:.1f} algorithmic TFLOP/s (min {min(times):.4f} ms)")
+    # time = fixed + rounds * per-tile: T = 256 makes one 256-row tile per sample, so B = 74 k gives k tiles per CTA pair
+    Tt = 256
+    xs = torch.randn(370, Tt, C, device=DEV)
+    ys = torch.empty(370, Tt, C, device=DEV)
+    fit = []
+    for k in (1, 2, 3, 4, 5):
+        Bk = 74 * k
+        times = []
+        for i in range(9):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            call("bm_tc_conv1d_persistent", ptr(xs), ptr(f), None, 0, Bk, Tt, C, C, Kw, 4, 1, 0, 0, 0, ptr(ys), None, None,
+                 None, ptr(status), st)
+            e1.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                times.append(e0.elapsed_time(e1))
+        fit.append((k, min(times) * 1e3))
+    per_tile = (fit[-1][1] - fit[0][1]) / 4
+    lines.append("[K3 persistent, k tiles per pair -> us] " + ", ".join(f"{k}: {t:.1f}" for k, t in fit) +
+                 f"  => per tile {per_tile:.2f} us, fixed {fit[0][1] - per_tile:.1f} us "
+                 f"(57 600 MMA cycles per tile: {57600 / per_tile / 1e3:.2f} GHz-equivalent)")
     assert int(status.item()) == 0
     with capsys.disabled():
         print("\n" + "\n".join(lines))

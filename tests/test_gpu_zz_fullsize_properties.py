@@ -116,7 +116,7 @@ def test_ablation_reference_configuration():
 
 @pytest.mark.parametrize("name", ["ablation_no_glu", "ablation_no_skip", "ablation_relu", "ablation_no_complex_out",
                                   "ablation_no_merger", "ablation_no_initial_linear", "ablation_no_subject_layers",
-                                  "ablation_subject_embedding"])
+                                  "ablation_subject_embedding", "ablation_subsample_channels"])
 def test_ablation_rows(name):
     """grids/nmi/ablation_final.py:42-52, each against the fixture the verbatim reference produced with the same change."""
     _ablation_step(name)
