@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """Benchmark of the contrastive training step (BASELINE.json metric: 3 s-segments/sec).
 
-    python bench.py --gpus N --steps K --warmup W                 # B200 arm (this repo's CUDA path)
-    python bench.py --impl reference --gpus N --steps K --warmup W  # reference arm: the CPU path on host cores
+    python bench.py --gpus N --steps K --warmup W [--config cfg2|cfg3|cfg4|cfg5]   # B200 arm (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K --warmup W                 # reference arm: the reference's OWN
+                                                                                   # modules on the host cores
 
-One "step" = SimpleConv forward + ClipLoss forward + backward of both + Adam(lr 3e-4) update on one synthetic
-batch (bm/solver.py:297,373,384-387; bm/train.py:119); for N > 1 the candidates are all-gathered before the
-contrastive matmul and the gradients all-reduced.  Workload at N=1 = BASELINE.json configs[1]:
-synthetic gwilliams2022-like MEG (208 sensors, 3 s @ 120 Hz = 360 samples, 1024-d wav2vec-like features, 27
-subjects), B = 256 per GPU.  Prints ONE JSON line on rank 0.
+One "step" = SimpleConv forward + ClipLoss forward + backward of both + Adam(lr 3e-4) update on one synthetic batch
+(bm/solver.py:297,373,384-387; bm/train.py:119); for N > 1 the candidates are all-gathered before the contrastive matmul
+and the gradients all-reduced.  Default workload = BASELINE.json configs[1] (cfg2): synthetic
+gwilliams2022-like MEG (208 sensors, 3 s @ 120 Hz = 360 samples, 1024-d wav2vec-like features, 27 subjects), B = 256 per
+GPU, weak scaling.  The other BASELINE configurations are behind --config: cfg3 (273 sensors, 96 subjects, GLOBAL batch
+512, strong scaling), cfg4 (128 sensors, 120 mel features, 19 subjects, 256 per GPU), cfg5 (4 mixed studies padded to 273
+sensors, 175 subjects, GLOBAL batch 1024, strong scaling).  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -26,10 +29,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(name="cfg2 synthetic gwilliams2022 (208 sensors, 3s@120Hz, F=1024, S=27)", C=208, T=360, F=1024, S=27)
+CONFIGS = {
+    "cfg2": dict(name="cfg2 synthetic gwilliams2022 (208 sensors, 3s@120Hz, F=1024, S=27)", C=208, T=360, F=1024, S=27,
+                 n_valid=(), batch_per_gpu=256, global_batch=None),
+    "cfg3": dict(name="cfg3 synthetic audio_mous (273 sensors, 3s@120Hz, F=1024, S=96), global batch 512", C=273, T=360,
+                 F=1024, S=96, n_valid=(), batch_per_gpu=None, global_batch=512),
+    "cfg4": dict(name="cfg4 synthetic broderick2019 EEG (128 sensors, 3s@120Hz, 120 mel features, S=19)", C=128, T=360, F=120,
+                 S=19, n_valid=(), batch_per_gpu=256, global_batch=None),
+    "cfg5": dict(name="cfg5 mixed 4-study synthetic (273/208/128/60 valid sensors padded to 273, F=1024, S=175), global batch 1024",
+                 C=273, T=360, F=1024, S=175, n_valid=(273, 208, 128, 60), batch_per_gpu=None, global_batch=1024),
+}
 CLIP_CONV = dict(hidden=dict(meg=320), batch_norm=True, depth=10, dilation_period=5, kernel_size=3, skip=True,
                  subject_layers=True, subject_dim=0, complex_out=True, glu=2, glu_context=1, merger=True,
                  initial_linear=270, gelu=True, merger_pos_dim=2048)       # conf/model/clip_conv.yaml:6-22
+METRIC = "3s-segments/sec (training step: SimpleConv fwd + ClipLoss + bwd + Adam)"
 
 
 def load_peaks():
@@ -40,6 +53,16 @@ def load_peaks():
         return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
                     bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def host_threads() -> int:
+    """Threads for the CPU arm: BM_CPU_THREADS, else one per physical core (logical / 2 on these SMT-2 hosts).  Set
+    EXPLICITLY with torch.set_num_threads: torchrun exports OMP_NUM_THREADS=1, which starved round 1's N>1 reference arm."""
+    env = os.environ.get("BM_CPU_THREADS")
+    if env:
+        return max(1, int(env))
+    n = os.cpu_count() or 1
+    return max(1, n // 2) if n >= 4 else n
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -92,13 +115,24 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------
 # synthetic workload: generated on CPU, pinned, shared by the e2e and resident runs
 # ------------------------------------------------------------------------------------------------------
-def make_host_batch(B, seed):
+def make_host_batch(cfg, B, seed):
     g = torch.Generator().manual_seed(seed)
-    C, T, F, S = WORKLOAD["C"], WORKLOAD["T"], WORKLOAD["F"], WORKLOAD["S"]
+    C, T, F, S = cfg["C"], cfg["T"], cfg["F"], cfg["S"]
     meg = torch.randn(B, C, T, generator=g).clamp_(-20, 20)
     feats = torch.randn(B, F, T, generator=g)
     subj = torch.randint(0, S, (B,), generator=g)
+    if cfg["n_valid"]:                                  # mixed studies: sensors beyond a study's own count are zero padding
+        nv = cfg["n_valid"]                             # (bm/dataset.py:353-354, 471)
+        for b in range(B):
+            meg[b, nv[int(subj[b]) % len(nv)]:] = 0
     return meg, feats, subj
+
+
+def local_batch(cfg, world):
+    if cfg["global_batch"] is not None:
+        assert cfg["global_batch"] % world == 0
+        return cfg["global_batch"] // world, "strong"
+    return cfg["batch_per_gpu"], "weak"
 
 
 def run_b200(args):
@@ -117,22 +151,25 @@ def run_b200(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     _lib.load()
 
-    B = args.batch
-    C, T, F, S = WORKLOAD["C"], WORKLOAD["T"], WORKLOAD["F"], WORKLOAD["S"]
+    cfg = CONFIGS[args.config]
+    B, scaling = local_batch(cfg, world)
+    if args.batch:
+        B, scaling = args.batch, "weak"
+    C, T, F, S = cfg["C"], cfg["T"], cfg["F"], cfg["S"]
     torch.manual_seed(2036)                                             # conf/config.yaml:33
     model = bb.SimpleConv(in_channels=dict(meg=C), out_channels=F, n_subjects=S,
                           **{k: (dict(v) if isinstance(v, dict) else v) for k, v in CLIP_CONV.items()}).to(dev)
-    clip = bb.ClipLoss(global_negatives=world > 1).to(dev)
+    clip = bb.ClipLoss(global_negatives=world > 1, uniform_batches=True).to(dev)
     model.train()
     clip.train()
     opt = torch.optim.Adam(model.parameters(), lr=3e-4, betas=(0.9, 0.999), fused=True)   # bm/train.py:119
-    positions = synthetic.normalised_positions(S, C, seed=7)
+    positions = synthetic.normalised_positions(S, C, n_valid=cfg["n_valid"], seed=7)
     mask = torch.ones(B, 1, T, dtype=torch.bool, device=dev)
 
     n_host = 2                                                          # rotate two different host batches
     host = []
     for i in range(n_host):
-        meg, feats, subj = make_host_batch(B, 2036 + 1000 * rank + i)
+        meg, feats, subj = make_host_batch(cfg, B, 2036 + 1000 * rank + i)
         host.append((meg.pin_memory(), feats.pin_memory(), subj.pin_memory(), subj.tolist()))
     resident = [tuple(t.to(dev) for t in hb[:3]) for hb in host]
     recs = [synthetic.SyntheticRecording(s, positions[s]) for s in range(S)]
@@ -246,16 +283,17 @@ def run_b200(args):
     e2e = dict(value=world * B / (ms_e2e / 1e3), unit="segments/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                ms_per_step=ms_e2e, note="inputs copied from pinned host memory on a copy stream one step ahead; one loss.item() per step, read one step behind")
 
-    # ---- roofline of the dominant kernel: the K3 dilated conv (320 -> 320, k=3) -------------------------
+    # ---- rooflines: the dominant kernel (K3 dilated conv) + the other kernels the north star names --------
     roofline = None
     cpu_baseline = None
     also = None
     if rank == 0:
-        roofline = conv_roofline(dev, B, T)
-        if world == 1:
-            also = also_measured(model, clip, make_batch, resident, host, n_host, mask, dev, B)
-        if not args.no_cpu_baseline:
-            cpu_baseline = run_cpu(steps=2, warmup=1, batch=16, threads=None)
+        roofline, others = kernel_rooflines(dev, B, T, F, B * world)
+        roofline["other_kernels"] = others
+        if world == 1 and not args.lean:
+            also = also_measured(cfg, model, clip, make_batch, resident, host, n_host, mask, dev, B)
+        if not args.no_cpu_baseline and world == 1:
+            cpu_baseline = run_cpu(cfg, steps=2, warmup=1, batch=32, threads=host_threads())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -263,19 +301,20 @@ def run_b200(args):
     BF.check_tc_status()
     if rank != 0:
         return
+    act_gb = 5.0 * B / 256
     out = dict(
-        metric="3s-segments/sec (training step: SimpleConv fwd + ClipLoss + bwd + Adam)", value=value,
-        unit="segments/s", n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
-        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=WORKLOAD["name"], batch_per_gpu=B, global_batch=B * world, sensors=C, T=T, F=F,
+        metric=METRIC, value=value, unit="segments/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms_per_step, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=cfg["name"], batch_per_gpu=B, global_batch=B * world, sensors=C, T=T, F=F,
                     subjects=S, model="clip_conv (random init)", negatives="global (all-gather)" if world > 1 else "local",
-                    l2="per-step working set (inputs 454 MB + ~5 GB saved activations) >> 126 MB L2; two input batches rotate",
+                    l2=f"per-step working set (inputs {h2d / 1e6:.0f} MB + ~{act_gb:.1f} GB saved activations) >> 126 MB L2; "
+                       "two input batches rotate",
                     last_loss=last_loss[0]),
         clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline, also=also)
     print(json.dumps(out))
 
 
-def also_measured(model, clip, make_batch, resident, host, n_host, mask, dev, B, iters=5):
+def also_measured(cfg, model, clip, make_batch, resident, host, n_host, mask, dev, B, iters=5):
     """What SURVEY.md 8(d) asks to report beside the headline (N=1 only, after the headline has been timed; every part is
     optional and a failure is recorded instead of raised):
       * forward_only: the encoder in eval mode under no_grad (the evaluation-time cost), segments/s;
@@ -312,11 +351,11 @@ def also_measured(model, clip, make_batch, resident, host, n_host, mask, dev, B,
     try:
         from oracle import bm_oracle
         from brainmagick_b200 import synthetic
-        C, T, F, S = WORKLOAD["C"], WORKLOAD["T"], WORKLOAD["F"], WORKLOAD["S"]
-        cfg = bm_oracle.Config(in_channels=C, out_channels=F, n_subjects=S)
+        C, T, F, S = cfg["C"], cfg["T"], cfg["F"], cfg["S"]
+        ocfg = bm_oracle.Config(in_channels=C, out_channels=F, n_subjects=S)
         params = {k: v.detach().clone() for k, v in model.state_dict().items()}
         meg_d, feats_d, subj_d = resident[0]
-        pos = synthetic.normalised_positions(S, C, seed=7).to(dev)
+        pos = synthetic.normalised_positions(S, C, n_valid=cfg["n_valid"], seed=7).to(dev)
         ban = torch.tensor([0.5, 0.5], device=dev)
         saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
         res = {}
@@ -326,7 +365,7 @@ def also_measured(model, clip, make_batch, resident, host, n_host, mask, dev, B,
                 torch.backends.cuda.matmul.allow_tf32 = tf32
 
                 def eager(i=0):
-                    bm_oracle.training_step(params, cfg, meg_d, pos, subj_d, subj_d, feats_d, ban_centre=ban, training=True)
+                    bm_oracle.training_step(params, ocfg, meg_d, pos, subj_d, subj_d, feats_d, ban_centre=ban, training=True)
                 ms = timed_ms(eager, 3)
                 res[label] = dict(value=B / (ms / 1e3), unit="segments/s", ms_per_step=ms)
         finally:
@@ -339,12 +378,15 @@ def also_measured(model, clip, make_batch, resident, host, n_host, mask, dev, B,
     return out
 
 
-def ncu_traffic_bytes():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu capture
-    (profiles/*_ncu_conv3_summary.csv, `ncu --set full` of profiles/profile_kernels.py conv); None if absent."""
+# ------------------------------------------------------------------------------------------------------
+# kernel rooflines: each kernel alone, CUDA events on the launching stream, L2 flushed between launches
+# ------------------------------------------------------------------------------------------------------
+def ncu_traffic_bytes(pattern):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's committed `ncu --set full` summary
+    (profiles/r2*_ncu_<pattern>_summary.csv, made from the .ncu-rep with `ncu -i ... --page raw --csv`); None if absent."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_conv3_summary.csv")))
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r2*_ncu_{pattern}_summary.csv")))
     if not files:
         return None
     try:
@@ -360,87 +402,192 @@ def ncu_traffic_bytes():
         return None
 
 
-def conv_roofline(dev, B, T, H=320, Kw=3, iters=20):
-    """Times the dominant kernel alone -- bm_tc_conv1d_pair, the tcgen05 3xTF32 implicit-GEMM conv (K3: 320->320, k=3) --
-    with CUDA events on the launching stream, L2 flushed between launches.  Algorithmic work: 2*H*H*Kw*T FLOP per
-    segment (221.2 MFLOP/seg); the tensor pipe executes 3x that (hi*hi + lo*hi + hi*lo)."""
-    from brainmagick_b200._lib import call, ptr, stream
-    peaks = load_peaks()
-    x = torch.randn(B, T, H, device=dev)
-    w = torch.randn(H, H, Kw, device=dev) * 0.03
-    f = torch.empty(Kw, H, H, device=dev)
-    call("bm_tc_weight_split", ptr(w), H, H, Kw, ptr(f), None, None, None, stream())
-    bias = torch.zeros(H, device=dev)
-    y = torch.empty(B, T, H, device=dev)
-    stats = torch.empty(2 * H, device=dev, dtype=torch.float64)
-    status = torch.zeros(1, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+def _time_kernel(fn, flush, iters=12, skip=3):
     times = []
-    for i in range(iters + 3):
+    for i in range(iters + skip):
         flush.zero_()                                                   # L2 flush between timed launches
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call("bm_tc_conv1d_persistent", ptr(x), ptr(f), ptr(bias), 0, B, T, H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
-             ptr(stats), ptr(status), stream())
+        fn()
         e1.record()
         torch.cuda.synchronize()
-        if i >= 3:
+        if i >= skip:
             times.append(e0.elapsed_time(e1))
-    assert int(status.item()) == 0, "tcgen05 conv reported a pipeline timeout"
-    ms = statistics.mean(times)
-    flops = 2.0 * H * H * Kw * T * B
-    achieved = flops / (ms / 1e3) / 1e12
-    peak = peaks["bf16_tflops"]
-    return dict(kernel="conv_pp_kernel via bm_tc_conv1d_persistent (K3: Conv1d 320->320 k3 d4 + BatchNorm statistics, persistent CTA pairs, tcgen05 cta_group::2 kind::tf32, 3xTF32)",
-                bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                traffic=ncu_traffic_bytes(), algorithmic_bytes=2.0 * B * T * H * 4,
-                ms_per_launch=ms, peak_source=peaks["source"] + " cuBLAS bf16 burst (MEASURED_PEAKS.json)",
-                executed_tflops=3 * achieved, tf32_pipe_peak=peak / 2, frac_of_tf32_pipe_executed=3 * achieved / (peak / 2),
-                frac_of_3xtf32_ceiling=achieved / (peak / 6),
-                note="achieved = ALGORITHMIC fp32 FLOPs (2*320*320*3*T*B per launch) / time. fp32-faithful parity (1e-4) "
-                     "needs 3 tf32 MMAs per product, and kind::tf32 runs at half the bf16 rate, so the ceiling of "
-                     "`frac` for this scheme is 1/6; frac_of_tf32_pipe_executed is the tensor-pipe view")
+    return statistics.mean(times)
+
+
+def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
+    """The dominant kernel first (K3: Conv1d 320->320 k3 + BatchNorm statistics, half of the step with its data-gradient
+    twin), then K4 (Conv1d 320->640 + GLU), K6 (CLIP scores + norms + softmax/CE), the weight-gradient kernel and the
+    HBM-bound BatchNorm/GELU kernels.  Algorithmic work per SURVEY.md 8(d); the tensor pipe executes 3x the algorithmic
+    FLOPs (hi*hi + lo*hi + hi*lo) at the tf32 rate (= bf16 / 2), so a tensor-bound `frac` against the measured bf16 peak
+    tops out at 1/6: `frac_of_3xtf32_ceiling` is the same number against peak/6."""
+    from brainmagick_b200._lib import call, ptr, stream, load
+    lib = load()
+    peaks = load_peaks()
+    peak_tf, peak_gb = peaks["bf16_tflops"], peaks["hbm_gbs"]
+    src = peaks["source"]
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    st = stream()
+    x = torch.randn(B, T, H, device=dev)
+    w = torch.randn(H, H, Kw, device=dev) * 0.03
+    wg = torch.randn(2 * H, H, Kw, device=dev) * 0.03
+    f, g = torch.empty(Kw, H, H, device=dev), torch.empty(Kw, H, H, device=dev)
+    fg = torch.empty(Kw, 2 * H, H, device=dev)
+    call("bm_tc_weight_split", ptr(w), H, H, Kw, ptr(f), None, ptr(g), None, st)
+    call("bm_tc_weight_split", ptr(wg), 2 * H, H, Kw, ptr(fg), None, None, None, st)
+    bias = torch.zeros(H, device=dev)
+    y = torch.empty(B, T, H, device=dev)
+    h = torch.empty(B, T, 2 * H, device=dev)
+    stats = torch.empty(2 * H, device=dev, dtype=torch.float64)
+
+    def tensor_entry(kernel, ms, flops, alg_bytes, traffic):
+        ach = flops / (ms / 1e3) / 1e12
+        return dict(kernel=kernel, bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf,
+                    traffic=traffic, algorithmic_bytes=alg_bytes, ms_per_launch=ms,
+                    peak_source=src + " cuBLAS bf16 burst (MEASURED_PEAKS.json)", executed_tflops=3 * ach,
+                    frac_of_3xtf32_ceiling=ach / (peak_tf / 6))
+
+    def hbm_entry(kernel, ms, alg_bytes, traffic):
+        ach = alg_bytes / (ms / 1e3) / 1e9
+        return dict(kernel=kernel, bound="hbm", achieved=ach, peak=peak_gb, unit="GB/s", frac=ach / peak_gb,
+                    traffic=traffic, algorithmic_bytes=alg_bytes, ms_per_launch=ms,
+                    peak_source=src + " copy bandwidth (MEASURED_PEAKS.json)")
+
+    ms = _time_kernel(lambda: call("bm_tc_conv1d_persistent", ptr(x), ptr(f), ptr(bias), 0, B, T, H, H, Kw, 4, 1, 0, 0, 0,
+                                   ptr(y), None, None, ptr(stats), ptr(status), st), flush)
+    main = tensor_entry("conv_pp_kernel via bm_tc_conv1d_persistent (K3: Conv1d 320->320 k3 d4 + BatchNorm statistics; "
+                        "persistent CTA pairs, tcgen05 cta_group::2 kind::tf32, 3xTF32)", ms, 2.0 * H * H * Kw * T * B,
+                        2.0 * B * T * H * 4, ncu_traffic_bytes("convp"))
+    main["note"] = ("achieved = ALGORITHMIC fp32 FLOPs (2*320*320*3*T*B per launch) / time. fp32-faithful parity (1e-4) needs 3 "
+                    "tf32 MMAs per product and kind::tf32 runs at half the bf16 rate, so the ceiling of `frac` for this scheme "
+                    "is 1/6 (frac_of_3xtf32_ceiling = achieved / (peak/6))")
+    others = []
+    try:
+        ms = _time_kernel(lambda: call("bm_tc_conv1d_persistent", ptr(x), ptr(fg), None, 0, B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0,
+                                       ptr(h), None, ptr(y), None, ptr(status), st), flush)
+        others.append(tensor_entry("conv_pp_kernel GLU mode (K4: Conv1d 320->640 k3 + GLU, h saved)", ms,
+                                   4.0 * H * H * Kw * T * B, 4.0 * B * T * H * 4, ncu_traffic_bytes("convp_glu")))
+        ms = _time_kernel(lambda: call("bm_tc_conv1d_persistent", ptr(x), ptr(g), None, 1, B, T, H, H, Kw, 4, -1, 0, 0, 0,
+                                       ptr(y), None, None, None, ptr(status), st), flush)
+        others.append(tensor_entry("conv_pp_kernel data gradient, y += tile (TMA reduce-add)", ms, 2.0 * H * H * Kw * T * B,
+                                   3.0 * B * T * H * 4, ncu_traffic_bytes("convp_acc")))
+        # K6: CLIP scores + candidate norms + softmax / CE / mean at the training shape (Bn = local rows, Bc = global rows)
+        KT = F * T
+        est = torch.randn(B, KT, device=dev) * 0.01
+        cand = torch.randn(Bc, KT, device=dev)
+        inv, sc, pr = torch.empty(Bc, device=dev), torch.empty(B, Bc, device=dev), torch.empty(B, Bc, device=dev)
+        rl, loss = torch.empty(B, device=dev), torch.empty(1, device=dev)
+        ws = torch.empty(max(int(lib.bm_clip_workspace(B, Bc, KT)), 2), device=dev)
+        ms = _time_kernel(lambda: call("bm_clip_loss_fwd", ptr(est), ptr(cand), B, Bc, KT, 0, ptr(inv), ptr(sc), ptr(pr),
+                                       ptr(rl), ptr(loss), ptr(ws), ws.numel(), ptr(status), st), flush)
+        e = tensor_entry(f"clip_scores_kernel + clip_finalize_kernel via bm_clip_loss_fwd (K6: {B} x {Bc} x {KT}, norms and "
+                         "softmax/CE fused; split-K CTA pairs, bounded accumulation chains)", ms, 2.0 * B * Bc * KT,
+                         4.0 * KT * (B + Bc), ncu_traffic_bytes("clip"))
+        hbm = 4.0 * KT * (B + Bc) / (ms / 1e3) / 1e9
+        e["hbm_view"] = dict(achieved=hbm, peak=peak_gb, unit="GB/s", frac=hbm / peak_gb,
+                             note="arithmetic intensity B*Bc/(2(B+Bc)) FLOP/B: at 256 x 256 the kernel sits near the ridge "
+                                  "of 3xTF32 (SURVEY 8d), so both views are given")
+        others.append(e)
+        del est, cand
+        # weight gradient (K3 shape)
+        dy = torch.randn(B, T, H, device=dev)
+        wsg = torch.empty(int(lib.bm_tc_wgrad_workspace(B, H, H, Kw)), device=dev)
+        dw = torch.empty(H, H, Kw, device=dev)
+        ms = _time_kernel(lambda: call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(wsg), ptr(dw), None,
+                                       ptr(status), st), flush)
+        others.append(tensor_entry("wgrad_tc_kernel (+reduce) via bm_tc_wgrad (weight gradient of K3)", ms,
+                                   2.0 * H * H * Kw * T * B, 2.0 * B * T * H * 4, ncu_traffic_bytes("wgrad")))
+        # HBM-bound: BatchNorm + GELU (+skip) backward and forward
+        gam, bet = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+        mean, invstd = torch.zeros(H, device=dev), torch.ones(H, device=dev)
+        sums = torch.empty(2 * H, device=dev, dtype=torch.float64)
+        dgam, dbet = torch.empty(H, device=dev), torch.empty(H, device=dev)
+        gy = torch.empty(B, T, H, device=dev)
+        rows = B * T
+        ms = _time_kernel(lambda: call("bm_bn_gelu_skip_bwd", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), 1,
+                                       rows, H, ptr(sums), ptr(gy), ptr(dgam), ptr(dbet), st), flush)
+        others.append(hbm_entry("bm_bn_gelu_skip_bwd (BatchNorm + GELU backward)", ms, 3.0 * rows * H * 4,
+                                ncu_traffic_bytes("bn_bwd")))
+        ms = _time_kernel(lambda: call("bm_bn_gelu_skip_fwd", ptr(dy), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), ptr(x),
+                                       ptr(gy), rows, H, st), flush)
+        others.append(hbm_entry("bm_bn_gelu_skip_fwd (BatchNorm apply + GELU + skip)", ms, 3.0 * rows * H * 4,
+                                ncu_traffic_bytes("bn_fwd")))
+    except Exception as exc:
+        others.append(dict(error=f"{type(exc).__name__}: {exc}"))
+    assert int(status.item()) == 0, "a tcgen05 kernel reported a pipeline timeout"
+    return main, others
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's CPU path on the host cores
+# CPU arm: the reference's own modules (staged under baseline/_ref by oracle/stage_reference.py) on the host cores
 # ------------------------------------------------------------------------------------------------------
-def run_cpu(steps, warmup, batch, threads):
-    from oracle import bm_oracle
-    if threads:
-        torch.set_num_threads(threads)
-    cfg = bm_oracle.Config(in_channels=WORKLOAD["C"], out_channels=WORKLOAD["F"], n_subjects=WORKLOAD["S"])
-    params = bm_oracle.init_state_dict(cfg, seed=0)
-    tr = bm_oracle.CpuTrainer(cfg, params)
-    d = bm_oracle.synthetic_batch(cfg, batch=batch, T=WORKLOAD["T"], seed=2036)
-    a = (d["meg"], d["rec_positions"], d["rec_of_sample"], d["subject_index"], d["candidates"], d["ban_centre"])
+def run_cpu(cfg, steps, warmup, batch, threads):
+    """A bounded sample of the workload on the host: `steps` training steps of `batch` segments at the configuration's
+    shapes.  kind "reference" = the VERBATIM bm.models.SimpleConv + bm.losses.ClipLoss under the step harness of
+    oracle/ref_trainer.py; kind "port" (only if the staged reference is missing) = the oracle restatement."""
+    from oracle import ref_loader
+    torch.set_num_threads(threads)
+    meg, feats, subj = make_host_batch(cfg, batch, 2036)
+    if ref_loader.reference_available():
+        from oracle import ref_trainer
+        tr = ref_trainer.VerbatimTrainer(cfg["C"], cfg["F"], cfg["S"], n_valid=cfg["n_valid"])
+
+        def one():
+            return tr.step(meg, feats, subj)
+        kind = "reference"
+        what = f"verbatim bm.models.SimpleConv + bm.losses.ClipLoss ({ref_loader.REF_KIND}), fwd+loss+bwd+Adam"
+    else:
+        from oracle import bm_oracle
+        ocfg = bm_oracle.Config(in_channels=cfg["C"], out_channels=cfg["F"], n_subjects=cfg["S"])
+        tr = bm_oracle.CpuTrainer(ocfg, bm_oracle.init_state_dict(ocfg, seed=0))
+        d = bm_oracle.synthetic_batch(ocfg, batch=batch, T=cfg["T"], seed=2036, n_valid=cfg["n_valid"])
+
+        def one():
+            return tr.step(d["meg"], d["rec_positions"], d["rec_of_sample"], d["subject_index"], d["candidates"], d["ban_centre"])
+        kind = "port"
+        what = "oracle/bm_oracle.py CpuTrainer (baseline/_ref not staged), fwd+loss+bwd+Adam"
     for _ in range(warmup):
-        tr.step(*a)
-    t0 = time.perf_counter()
+        one()
+    per = []
     for _ in range(steps):
-        tr.step(*a)
-    dt = (time.perf_counter() - t0) / steps
-    return dict(value=batch / dt, unit="segments/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"{steps} steps of B={batch} at the cfg2 shapes (oracle/bm_oracle.py CpuTrainer: torch CPU ops "
-                       f"fwd+loss+bwd+Adam), host has {os.cpu_count()} logical cores", s_per_step=dt)
+        t0 = time.perf_counter()
+        one()
+        per.append(time.perf_counter() - t0)
+    dt = statistics.mean(per)
+    return dict(value=batch / dt, unit="segments/s", cores=torch.get_num_threads(), kind=kind,
+                sample=f"{steps} steps of B={batch} at the {cfg['name'].split()[0]} shapes ({what}); host has "
+                       f"{os.cpu_count()} logical cores", s_per_step=dt, s_per_step_min=min(per), s_per_step_max=max(per))
 
 
 def run_reference(args):
+    """Reference arm: rank 0 alone (the other ranks exit 0 without work), threads set explicitly."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 32
-    res = run_cpu(steps=args.steps, warmup=min(args.warmup, 2), batch=batch, threads=None)
+    cfg = CONFIGS[args.config]
+    threads = host_threads()
+    batch = 64                                   # bounded sample per step; CPU seg/s is batch-insensitive (SURVEY 8d)
+    res = run_cpu(cfg, steps=args.steps, warmup=min(args.warmup, 2), batch=batch, threads=threads)
+    also = {}
+    try:                                         # what bm/train.py:182 actually sets: ONE thread
+        also["one_thread"] = run_cpu(cfg, steps=1, warmup=0, batch=8, threads=1)
+        torch.set_num_threads(threads)
+        if not args.lean:                        # one step at the full B=256 of the metric
+            also["full_batch"] = run_cpu(cfg, steps=1, warmup=0, batch=256, threads=threads)
+    except Exception as exc:
+        also["error"] = f"{type(exc).__name__}: {exc}"
     out = dict(
-        impl="reference",
-        metric="3s-segments/sec (training step: SimpleConv fwd + ClipLoss + bwd + Adam)", value=res["value"],
-        unit="segments/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=res["s_per_step"] * 1e3,
-        higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-        config=dict(workload=WORKLOAD["name"], batch_per_step=batch, sensors=WORKLOAD["C"], T=WORKLOAD["T"],
-                    F=WORKLOAD["F"], subjects=WORKLOAD["S"], model="clip_conv (random init)",
-                    note="reference is pure Python/PyTorch and its deps (mne, flashy, dora) are absent, so its CPU path "
-                         "is timed through the oracle port (same torch CPU ops), all host threads, bounded sample"),
-        cpu_baseline=res,
+        impl="reference", metric=METRIC, value=res["value"], unit="segments/s", n_gpus=args.gpus, steps=args.steps,
+        warmup=args.warmup, ms_per_step=res["s_per_step"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f32", data="synthetic",
+        config=dict(workload=cfg["name"], batch_per_step=batch, sensors=cfg["C"], T=cfg["T"], F=cfg["F"],
+                    subjects=cfg["S"], model="clip_conv (random init)",
+                    note="the reference's own SimpleConv + ClipLoss (unmodified files staged under baseline/_ref by "
+                         "oracle/stage_reference.py) under the restated Solver step; bounded sample of B=64 per step, "
+                         f"{threads} threads set with torch.set_num_threads (also under torchrun)"),
+        cpu_baseline=res, also=also,
         e2e=dict(value=res["value"], unit="segments/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out))
 
@@ -451,8 +598,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="batch per GPU (256 = BASELINE.json configs[1])")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the batch per GPU (default: the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="skip the `also` extras (forward-only, eager-PyTorch bar, B=256 CPU step)")
     ap.add_argument("--next-rows", action="store_true",
                     help="instead of the headline step: the SURVEY 8(f) rows (batch preparation, retrieval evaluation, "
                          "DeepMel), each beside a bounded CPU sample of its oracle; one GPU")

@@ -37,6 +37,7 @@ class ClipLoss(torch.nn.Module):
         # batches are handled (the reference's loaders have no drop_last, and ScaleReject drops samples per rank)
         self.uniform_batches = uniform_batches
         self._prefetched = None
+        self._mask_ok = None
 
     # -- time cropping (losses.py:50-75) ---------------------------------------------------------------
     def _window(self, n_samples: int):
@@ -85,8 +86,17 @@ class ClipLoss(torch.nn.Module):
                 and self._window(candidate.shape[-1]) == (0, candidate.shape[-1]):
             self._prefetched = distrib.CandidateGather(candidate, self.uniform_batches)
 
+    def _check_mask(self, mask) -> None:
+        """losses.py:110 `assert mask.all()`: on a CUDA mask that is a device->host sync per call.  The verdict is kept per
+        mask tensor (same storage, same version counter), so a caller that reuses one all-true mask pays it once; a fresh
+        mask per batch (what bm/solver.py passes) is checked every time, exactly like the reference."""
+        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.device)
+        if key != self._mask_ok:
+            assert mask.all(), "mask is not supported for now"
+            self._mask_ok = key
+
     def forward(self, estimate, candidate, mask=None):
-        assert mask.all(), "mask is not supported for now"
+        self._check_mask(mask)
         assert estimate.size(0) <= candidate.size(0), "need at least as many targets as estimates"
         pre, self._prefetched = self._prefetched, None
         if candidate.requires_grad and torch.is_grad_enabled() and self.global_negatives and distrib.world_size() > 1:

@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE ONLY -- loads the *verbatim* brainmagick hot-path modules from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- loads the *verbatim* brainmagick hot-path modules from /root/reference (build container) or
+from the unmodified copy staged under baseline/_ref/ by oracle/stage_reference.py (GPU box; `bench.py --impl reference`).
 
 Used by `oracle/make_golden.py` (fixture generation) and by `tests/test_oracle_vs_reference.py`
 (which skips when /root/reference is absent, i.e. on the GPU box).  `load_reference_norm()` adds the verbatim
@@ -18,8 +19,22 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("BM_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _find_root() -> str:
+    """/root/reference in the build container; on the GPU box the copy staged by oracle/stage_reference.py."""
+    env = os.environ.get("BM_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/bm/models/simpleconv.py"):
+        return "/root/reference"
+    return _STAGED
+
+
+REF_ROOT = _find_root()
 REF = os.path.join(REF_ROOT, "bm")
+REF_KIND = "source tree" if REF_ROOT == "/root/reference" else "staged copy (baseline/_ref)"
 
 
 def reference_available() -> bool:
