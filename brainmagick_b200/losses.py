@@ -11,6 +11,8 @@ grad (a trainable feature model) the gather is differentiable (reduce-scatter of
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import functional as BF
@@ -88,12 +90,13 @@ class ClipLoss(torch.nn.Module):
 
     def _check_mask(self, mask) -> None:
         """losses.py:110 `assert mask.all()`: on a CUDA mask that is a device->host sync per call.  The verdict is kept per
-        mask tensor (same storage, same version counter), so a caller that reuses one all-true mask pays it once; a fresh
+        mask tensor OBJECT (weak reference + version counter), so a caller that reuses one all-true mask pays it once; a fresh
         mask per batch (what bm/solver.py passes) is checked every time, exactly like the reference."""
-        key = (mask.data_ptr(), mask._version, tuple(mask.shape), mask.device)
-        if key != self._mask_ok:
-            assert mask.all(), "mask is not supported for now"
-            self._mask_ok = key
+        seen = self._mask_ok
+        if seen is not None and seen[0]() is mask and seen[1] == mask._version:
+            return
+        assert mask.all(), "mask is not supported for now"
+        self._mask_ok = (weakref.ref(mask), mask._version)
 
     def forward(self, estimate, candidate, mask=None):
         self._check_mask(mask)
