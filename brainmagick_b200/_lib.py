@@ -57,6 +57,8 @@ SIGNATURES = {
     "bm_transpose_nt_ld": [P, I, I, I, I, P, P],
     "bm_tc_wgrad_supported": [I, I],
     "bm_tc_wgrad": [P, P, I, I, I, I, I, I, I, P, P, P, P, P],
+    "bm_tc_wgrad_conv_supported": [I, I, I, I],
+    "bm_tc_wgrad_conv": [P, P, I, I, I, I, I, I, I, P, P, P, P],
     "bm_col_sum": [P, L, I, P, P],
     "bm_tc_pointwise_sel": [P, P, P, P, I, I, I, I, I, P, P, P],
     "bm_tc_wgrad_grouped": [P, P, P, P, I, I, I, I, I, P, P, P],
@@ -99,6 +101,8 @@ def load():
     lib.bm_launch_count.argtypes = []
     lib.bm_tc_wgrad_workspace.restype = c_longlong
     lib.bm_tc_wgrad_workspace.argtypes = [I, I, I, I]
+    lib.bm_tc_wgrad_conv_workspace.restype = c_longlong
+    lib.bm_tc_wgrad_conv_workspace.argtypes = [I, I, I, I, I]
     lib.bm_clip_workspace.restype = c_longlong
     lib.bm_clip_workspace.argtypes = [I, I, L]
     for name, argtypes in SIGNATURES.items():

@@ -8,6 +8,7 @@
 #include "tc_conv3.cuh"
 #include "tc_clip.cuh"
 #include "tc_convp.cuh"
+#include "tc_wgradp.cuh"
 #include "retrieval.cuh"
 #include "prep.cuh"
 #include "convseq.cuh"
@@ -844,6 +845,21 @@ extern "C" int bm_tc_wgrad(const float* dy, const float* x, int B, int T, int M,
     BM_CHECK_ARG(dy && x && workspace && dw && B > 0 && T > 0 && Kw >= 1 && Kw <= 3 && dilation >= 1);
     BM_CHECK_ARG(tc::wgrad_tc_supported(M, N) && Ntrue > 0 && Ntrue <= N);
     return tc::launch_wgrad_tc(dy, x, B, T, M, N, Ntrue, Kw, dilation, workspace, dw, status, ST(stream), dbias);
+}
+
+// CTA-pair weight gradient of a k-tap conv (csrc/tc_wgradp.cuh): output rows = (tap, x channel), reduction over the
+// flattened rows; no bias gradient (use bm_col_sum on dy where the layer's bias gradient is not exactly zero)
+extern "C" int bm_tc_wgrad_conv_supported(int T, int M, int N, int Kw) {
+    return tc::wgradp_supported(T, M, N, Kw) ? 1 : 0;
+}
+extern "C" long long bm_tc_wgrad_conv_workspace(int B, int T, int M, int N, int Kw) {
+    return (long long)tc::wgradp_workspace_floats(B, T, M, N, Kw);
+}
+extern "C" int bm_tc_wgrad_conv(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw,
+                                int dilation, float* workspace, float* dw, int* status, bm_stream_t stream) {
+    BM_CHECK_ARG(dy && x && workspace && dw && B > 0 && T > 0 && dilation >= 1);
+    BM_CHECK_ARG(tc::wgradp_supported(T, M, N, Kw) && Ntrue > 0 && Ntrue <= N);
+    return tc::launch_wgrad_pp(dy, x, B, T, M, N, Ntrue, Kw, dilation, workspace, dw, status, ST(stream));
 }
 
 extern "C" int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream) {

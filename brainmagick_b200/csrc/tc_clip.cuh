@@ -80,12 +80,12 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
     if (threadIdx.x == 0) {
         for (int s = 0; s < CL_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&conv_bar[s], 2 * (128 + 64));              // both CTAs' converters arrive on the LEADER's copy
+            mbar_init(&conv_bar[s], 2 * (4 + 2));                 // one elected lane per converter warp of both CTAs (LEADER's copy)
             mbar_init(&empty_bar[s], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&part_full[i], 1);
-            mbar_init(&part_empty[i], 2 * 128);                   // both CTAs' drain warps, on the LEADER's copy
+            mbar_init(&part_empty[i], 2 * 4);                     // one elected lane per drain warp of both CTAs
         }
         fence_barrier_init();
     }
@@ -165,7 +165,8 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                 bl[idx] = l;
             }
             fence_proxy_async();
-            mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
         }
     } else if (warp < 8) {
         // ------------------------------------------------ candidate rows -> TMEM (hi | lo), sum of squares -------------
@@ -198,7 +199,8 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             tmem_st32(tq + CL_A_COL + (it & 1) * CL_A_COLS + CL_BK, lo);
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
         }
         const int o = m0 + row;
         if (p.ssp && n_tile == 0 && o < p.Bc) p.ssp[(long long)ksl * p.Bc + o] = ssq;
@@ -240,7 +242,8 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             if (!last) {
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive_cluster(mapa_u32(smem_u32(&part_empty[pp]), 0));
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&part_empty[pp]), 0));
             }
         }
         tc_fence_before();

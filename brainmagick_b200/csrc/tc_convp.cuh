@@ -115,11 +115,11 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < PP_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&conv_bar[s], 2 * (128 + 64));            // A and B converters of both CTAs, on the LEADER's copy
+            mbar_init(&conv_bar[s], 2 * (4 + 2));               // one elected lane per converter warp of both CTAs (LEADER's copy)
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&acc_full, 1);
-        mbar_init(&acc_empty, 2 * PP_EPI_WARPS * 32);           // epilogue threads of both CTAs, on the LEADER's copy
+        mbar_init(&acc_empty, 2 * PP_EPI_WARPS);                // one elected lane per epilogue warp of both CTAs
         fence_barrier_init();
     }
     if (p.stats)
@@ -226,7 +226,8 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_st32(tq + PP_ACC_COLS + s * PP_A_COLS + PP_BK, lo);
                 tmem_st_wait();
                 tc_fence_before();
-                mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
             }
         }
     } else if (warp < 8) {
@@ -257,7 +258,8 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
                 fence_proxy_async();
-                mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
             }
         }
     } else {
@@ -288,7 +290,8 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld32(tq + nh + c * 32, g);
                     if (c + 1 == ch_end) {                            // last TMEM read of this thread: release the accumulator
                         tc_fence_before();
-                        mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
                     }
                     if (p.bias) {
 #pragma unroll
@@ -318,7 +321,8 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tmem_ld32(tq + ncol0 + c * 32, v);
                     if (c + 1 == nch) {
                         tc_fence_before();
-                        mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
                     }
                     if (p.bias) {
 #pragma unroll

@@ -93,11 +93,21 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
+USE_WGRAD_PP = True    # CTA-pair weight-gradient kernel (tc_wgradp.cuh) for the k = 3 convolutions
+
+
 def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None):
     """dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-kw//2)*dilation,n] on the tensor cores -> [M, Ntrue, kw];
-    `dbias` [M] (optional) receives sum_{b,t} dy[b,t,m] from the same kernel."""
-    ws = _empty((int(_lib.load().bm_tc_wgrad_workspace(B, M, N, kw)),), dy)
+    `dbias` [M] (optional) receives sum_{b,t} dy[b,t,m]."""
+    lib = _lib.load()
     dw = _empty((M, Ntrue, kw), dy)
+    if USE_WGRAD_PP and kw == 3 and bool(lib.bm_tc_wgrad_conv_supported(T, M, N, kw)):
+        ws = _empty((int(lib.bm_tc_wgrad_conv_workspace(B, T, M, N, kw)),), dy)
+        call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(status), stream())
+        if dbias is not None:
+            call("bm_col_sum", ptr(dy), B * T, M, ptr(dbias), stream())
+        return dw
+    ws = _empty((int(lib.bm_tc_wgrad_workspace(B, M, N, kw)),), dy)
     call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(dbias), ptr(status),
          stream())
     return dw

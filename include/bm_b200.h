@@ -272,6 +272,14 @@ int bm_tc_wgrad_supported(int M, int N);
 long long bm_tc_wgrad_workspace(int B, int M, int N, int Kw);
 int bm_tc_wgrad(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw, int dilation,
                 float* workspace, float* dw, float* dbias, int* status, bm_stream_t stream);
+/* bm_tc_wgrad_conv: the same weight gradient on CTA PAIRS (csrc/tc_wgradp.cuh): ONE GEMM whose output rows are the
+ * (tap, x-channel) pairs (3 x 320 = 960 rows in 4 pair-tiles instead of 3 x 384 padded rows), reduced over the flattened
+ * rows b*T + t in exact chunks of 32 (the tap shift is applied to the x side; a shifted row across a sample edge reads 0),
+ * each CTA holding half of the dy tile.  No dbias output.  T >= 32; M % 64 == 0; N % 4 == 0. */
+int bm_tc_wgrad_conv_supported(int T, int M, int N, int Kw);
+long long bm_tc_wgrad_conv_workspace(int B, int T, int M, int N, int Kw);
+int bm_tc_wgrad_conv(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw, int dilation,
+                     float* workspace, float* dw, int* status, bm_stream_t stream);
 int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream);
 /* SubjectLayers (common.py:55-58) on the tensor cores.
  * bm_tc_pointwise_sel: y[b,t,n] = sum_k x[b,t,k] W[wsel[b]][n][k] with tf32-split weight sets w_hi/w_lo [S][Ntot][Cin].

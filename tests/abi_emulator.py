@@ -397,6 +397,9 @@ class Emulator:
         if dbias is not None:
             _v(dbias, M).copy_(g.reshape(-1, M).sum(0))
 
+    def bm_tc_wgrad_conv(self, dy, x, B, T, M, N, Ntrue, Kw, dilation, ws, dw, status, stream):
+        self.bm_tc_wgrad(dy, x, B, T, M, N, Ntrue, Kw, dilation, ws, dw, None, status, stream)
+
     def bm_tc_pointwise_sel(self, x, w_hi, w_lo, wsel, n_sets, B, T, Cin, Ntot, y, status, stream):
         w = _v(w_hi, n_sets, Ntot, Cin) + _v(w_lo, n_sets, Ntot, Cin)
         _v(y, B, T, Ntot).copy_(torch.einsum("btk,bnk->btn", _v(x, B, T, Cin), w[wsel.long()[:B]]))

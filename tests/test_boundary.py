@@ -33,7 +33,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/bm_b200.h but not exported"
     bound = set(_lib.SIGNATURES) | {"bm_last_error", "bm_abi_version", "bm_launch_count", "bm_tc_wgrad_workspace",
-             "bm_clip_workspace"}
+             "bm_clip_workspace", "bm_tc_wgrad_conv_workspace"}
     assert declared == bound, (declared ^ bound)
     _lib.load()
     assert _lib.load().bm_abi_version() == 1

@@ -205,3 +205,79 @@ def test_tc_wgrad_speed_report(capsys, trunc):
     with capsys.disabled():
         _lib.load().bm_set_debug_flags(0)
         print(f"\n[tc wgrad rna_split={trunc} 320x320 k3 B=256 T=360] {ms:.3f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
+
+
+@pytest.mark.parametrize("case", [
+    dict(B=5, T=360, M=320, N=320, Kw=3, dil=1),
+    dict(B=3, T=343, M=320, N=320, Kw=3, dil=16),
+    dict(B=4, T=100, M=640, N=320, Kw=3, dil=2),
+    dict(B=7, T=77, M=320, N=320, Kw=3, dil=4),
+    dict(B=3, T=360, M=1024, N=640, Kw=1, dil=1),
+    dict(B=2, T=64, M=192, N=96, Kw=3, dil=1),
+    dict(B=40, T=360, M=320, N=320, Kw=3, dil=8),
+])
+def test_tc_wgrad_pair_kernel(case):
+    """bm_tc_wgrad_conv (csrc/tc_wgradp.cuh): rows = (tap, x channel), flattened reduction, CTA pairs."""
+    call, ptr, stream = _call()
+    from brainmagick_b200 import _lib
+    torch.manual_seed(11)
+    B, T, M, N, Kw, dil = (case[k] for k in ("B", "T", "M", "N", "Kw", "dil"))
+    dev = "cuda"
+    assert _lib.load().bm_tc_wgrad_conv_supported(T, M, N, Kw)
+    dy = torch.randn(B, T, M, device=dev)
+    x = torch.randn(B, T, N, device=dev)
+    ws = torch.full((int(_lib.load().bm_tc_wgrad_conv_workspace(B, T, M, N, Kw)),), float("nan"), device=dev)
+    dw = torch.full((M, N, Kw), float("nan"), device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw), ptr(status), stream())
+    torch.cuda.synchronize()
+    assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
+    ref = torch.zeros(M, N, Kw, dtype=torch.float64, device=dev)
+    xd, dyd = x.double(), dy.double()
+    for j in range(Kw):
+        s = (j - Kw // 2) * dil
+        lo, hi = max(0, -s), min(T, T - s)
+        ref[:, :, j] = torch.einsum("btm,btn->mn", dyd[:, lo:hi], xd[:, lo + s:hi + s])
+    e = rel_err(dw.cpu(), ref.cpu())
+    print(f"[tc wgrad pair {case}] rel_err vs fp64 = {e:.2e}")
+    assert e < TOL
+    dw2 = torch.empty_like(dw)
+    call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw2), ptr(status), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)                                   # fixed-order reduction
+
+
+def test_tc_wgrad_pair_speed_report(capsys):
+    call, ptr, stream = _call()
+    from brainmagick_b200 import _lib
+    dev = "cuda"
+    B, T, Kw = 256, 360, 3
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    lines = []
+    for M, N in ((320, 320), (640, 320)):
+        dy = torch.randn(B, T, M, device=dev)
+        x = torch.randn(B, T, N, device=dev)
+        dw = torch.empty(M, N, Kw, device=dev)
+        ws_new = torch.empty(int(_lib.load().bm_tc_wgrad_conv_workspace(B, T, M, N, Kw)), device=dev)
+        ws_old = torch.empty(int(_lib.load().bm_tc_wgrad_workspace(B, M, N, Kw)), device=dev)
+        for name, fn in (("pair kernel", lambda: call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws_new),
+                                                       ptr(dw), ptr(status), stream())),
+                         ("round-1 kernel", lambda: call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws_old),
+                                                          ptr(dw), None, ptr(status), stream()))):
+            times = []
+            for i in range(13):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= 3:
+                    times.append(e0.elapsed_time(e1))
+            ms = sum(times) / len(times)
+            tf = 2.0 * M * N * Kw * T * B / (ms * 1e-3) / 1e12
+            lines.append(f"[wgrad {M}x{N} k3 B=256 T=360, {name}] {ms:.4f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
+    assert int(status.item()) == 0
+    with capsys.disabled():
+        print("\n" + "\n".join(lines))
