@@ -45,6 +45,7 @@ SIGNATURES = {
     "bm_clip_loss_fwd": [P, P, I, I, L, I, P, P, P, P, P, P, L, P, P],
     "bm_clip_loss_bwd": [P, P, P, P, I, I, L, I, P, P, P, P],
     "bm_set_debug_flags": [I],
+    "bm_set_debug_buffer": [P],
     "bm_tc_conv_supported": [I, I, I, I, I],
     "bm_tc_weight_split": [P, I, I, I, P, P, P, P, P],
     "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],

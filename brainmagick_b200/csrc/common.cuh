@@ -10,6 +10,7 @@ namespace bm {
 // ---- error plumbing (C-ABI returns an int, message kept for bm_last_error()) -------------------
 extern thread_local char g_last_error[512];
 extern int g_debug_flags;               // bm_set_debug_flags(): experiment switches (bit 0: wgrad keeps X raw as hi)
+extern long long* g_debug_buf;           // bm_set_debug_buffer(): device scratch some kernels fill with cycle counters
 extern unsigned long long g_launches;   // kernels launched by this library since load (bm_launch_count())
 inline int set_error(int code, const char* fmt, const char* a = "", const char* b = "") {
     snprintf(g_last_error, sizeof(g_last_error), fmt, a, b);

@@ -46,6 +46,7 @@ struct WgradPP {
     const float* X;
     float* P;                   // [ks][mtiles*256][Mdy]
     int* err;
+    long long* dbg;             // debug only (bm_set_debug_buffer): per CTA 8 cycle counters, see the kernel
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 1)
@@ -116,10 +117,13 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             const uint32_t idesc0 = umma_idesc_tf32_bmn(256, p.h0);
             const uint32_t idesc1 = p.h1 ? umma_idesc_tf32_bmn(256, p.h1) : 0u;
             bool ok = true;
+            long long t_wait = 0, t_begin = clock64();
             for (int it = 0; it < total && ok; ++it) {
                 const int s = it % WP_STAGES;
                 const uint32_t ph = (it / WP_STAGES) & 1;
+                const long long c0 = clock64();
                 ok = mbar_wait(&conv_bar[s], ph, p.err, 83);
+                t_wait += clock64() - c0;
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t b_hi = smem_base + s * WP_STAGE_BYTES, b_lo = b_hi + WP_B_BYTES;
@@ -147,6 +151,7 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
                 umma_commit_2sm(&empty_bar[s]);
             }
             umma_commit_2sm(&tmem_full_bar);
+            if (p.dbg) { p.dbg[blockIdx.x * 8 + 0] = t_wait; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; }
         }
     } else if (warp < 6) {
         // ------------------------------------------------ A: shifted X rows -> TMEM; then the epilogue ------------------
@@ -157,8 +162,10 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
         const int tap = row_ok ? grow / p.Nx : 0;
         const int n = row_ok ? grow - tap * p.Nx : 0;
         const int shift = (tap - p.taps / 2) * p.dilation;
-        float nxt[WP_BK];
-        auto load_a = [&](int it) {
+        // The X column of a chunk is loaded TWO chunks ahead into alternating register buffers: the operand comes from HBM
+        // (an activation saved by the forward pass), and one chunk of MMA time (~1.4 us) does not cover that latency.
+        float bufA[WP_BK], bufB[WP_BK];
+        auto load_a = [&](int it, float* dst) {
             const int p0 = (it_begin + it) * WP_BK;
             int t = p0 % p.T;                                                // time of the chunk's first row in its sample
             const float* src = p.X + ((long long)p0 + shift) * p.Nx + n;
@@ -166,20 +173,24 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             for (int j = 0; j < WP_BK; ++j) {
                 const int ts = t + shift;
                 const bool ok = row_ok && ts >= 0 && ts < p.T && p0 + j < p.R;
-                nxt[j] = ok ? __ldg(src + (long long)j * p.Nx) : 0.f;
+                dst[j] = ok ? __ldg(src + (long long)j * p.Nx) : 0.f;
                 if (++t == p.T) t = 0;
             }
         };
-        if (total > 0) load_a(0);
         bool ok = true;
-        for (int it = 0; it < total && ok; ++it) {
+        long long t_split = 0, t_empty = 0, t_st = 0;
+        auto convert = [&](int it, float* buf) {
             const int s = it % WP_STAGES;
             const uint32_t ph = (it / WP_STAGES) & 1;
             float hi[WP_BK], lo[WP_BK];
+            const long long c0 = clock64();
 #pragma unroll
-            for (int j = 0; j < WP_BK; ++j) tf32_split(nxt[j], hi[j], lo[j]);
-            if (it + 1 < total) load_a(it + 1);                          // prefetch the next chunk's column
+            for (int j = 0; j < WP_BK; ++j) tf32_split(buf[j], hi[j], lo[j]);
+            if (it + 2 < total) load_a(it + 2, buf);                     // refill this buffer for the chunk after next
+            const long long c1 = clock64();
             ok = mbar_wait(&empty_bar[s], ph ^ 1, p.err, 84);            // the MMAs of chunk it-STAGES have left this slot
+            const long long c2 = clock64();
+            t_split += c1 - c0; t_empty += c2 - c1;
             tc_fence_after();
             tmem_st32(tq + WP_ACC_COLS + s * WP_A_COLS, hi);
             tmem_st32(tq + WP_ACC_COLS + s * WP_A_COLS + WP_BK, lo);
@@ -187,6 +198,16 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
+            t_st += clock64() - c2;
+        };
+        if (total > 0) load_a(0, bufA);
+        if (total > 1) load_a(1, bufB);
+        for (int it = 0; it < total && ok; it += 2) {
+            convert(it, bufA);
+            if (it + 1 < total && ok) convert(it + 1, bufB);
+        }
+        if (p.dbg && warp == 2 && lane == 0) {
+            p.dbg[blockIdx.x * 8 + 2] = t_split; p.dbg[blockIdx.x * 8 + 3] = t_empty; p.dbg[blockIdx.x * 8 + 4] = t_st;
         }
         // ---- epilogue: partial tile -> workspace [ks][mtiles*256][Mdy] ----
         if (!skip) {
@@ -213,10 +234,13 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
         const int ct = (warp - 6) * 32 + lane;                           // 0..63
         const int nvec = (int)(b_bytes / 16);
         bool ok = true;
+        long long t_full = 0;
         for (int it = 0; it < total && ok; ++it) {
             const int s = it % WP_STAGES;
             const uint32_t ph = (it / WP_STAGES) & 1;
+            const long long c0 = clock64();
             ok = mbar_wait(&full_bar[s], ph, p.err, 85);
+            t_full += clock64() - c0;
             const float4* bh = reinterpret_cast<const float4*>(smem + s * WP_STAGE_BYTES);
             float4* bl = reinterpret_cast<float4*>(smem + s * WP_STAGE_BYTES + WP_B_BYTES);
 #pragma unroll 4
@@ -233,6 +257,7 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
         }
+        if (p.dbg && warp == 6 && lane == 0) p.dbg[blockIdx.x * 8 + 5] = t_full;
     }
     __syncthreads();
     cluster_sync_all();
@@ -313,7 +338,7 @@ inline int launch_wgrad_pp(const float* dY, const float* X, int B, int T, int Md
     WgradPP p;
     p.R = (int)R; p.T = T; p.Mdy = Mdy; p.Nx = Nx; p.taps = taps; p.dilation = dilation; p.rows = g.rows;
     p.mtiles = g.mtiles; p.ntiles = g.ntiles; p.ks = g.ks; p.nt = g.nt; p.h0 = g.h0; p.h1 = g.h1;
-    p.chunks = g.chunks; p.per_split = g.per_split; p.X = X; p.P = ws; p.err = err;
+    p.chunks = g.chunks; p.per_split = g.per_split; p.X = X; p.P = ws; p.err = err; p.dbg = g_debug_buf;
     wgrad_pp_kernel<<<2 * g.mtiles * g.ntiles * g.ks, WP_THREADS, WP_SMEM_BYTES, st>>>(tmDY, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();

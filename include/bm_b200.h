@@ -32,6 +32,9 @@ unsigned long long bm_launch_count(void);
  * `hi` operand (the tensor core ignores the 13 low mantissa bits) and only writes `lo = x - trunc(x)`; bit 0 restores
  * the explicit round-to-nearest hi/lo split (one third more shared-memory traffic). */
 int bm_set_debug_flags(int flags);
+/* profiling aid (process-wide, NOT part of the product path): device buffer of >= 8 * gridDim long longs that the CTA-pair
+ * weight-gradient kernel fills with per-CTA cycle counters (barrier waits per warp role); NULL (default) disables it. */
+int bm_set_debug_buffer(long long* buf);
 
 /* ---- K1: spatial-attention weights, once per recording ------------------------------------------------
  * replaces FourierEmb.forward (bm/models/common.py:254-271) + the score/softmax half of ChannelMerger.forward

@@ -278,6 +278,27 @@ def test_tc_wgrad_pair_speed_report(capsys):
             ms = sum(times) / len(times)
             tf = 2.0 * M * N * Kw * T * B / (ms * 1e-3) / 1e12
             lines.append(f"[wgrad {M}x{N} k3 B=256 T=360, {name}] {ms:.4f} ms/launch = {tf:.1f} algorithmic TFLOP/s")
+    # where the pair kernel's warp roles wait (cycle counters of the debug buffer, averaged over the leader CTAs)
+    M, N = 320, 320
+    dy = torch.randn(B, T, M, device=dev)
+    x = torch.randn(B, T, N, device=dev)
+    dw = torch.empty(M, N, Kw, device=dev)
+    ws_new = torch.empty(int(_lib.load().bm_tc_wgrad_conv_workspace(B, T, M, N, Kw)), device=dev)
+    dbg = torch.zeros(8 * 148, device=dev, dtype=torch.int64)
+    call("bm_set_debug_buffer", ptr(dbg))
+    try:
+        flush.zero_()
+        call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws_new), ptr(dw), ptr(status), stream())
+        torch.cuda.synchronize()
+    finally:
+        call("bm_set_debug_buffer", None)
+    d = dbg.reshape(148, 8).double()
+    lead, foll = d[0::2], d[1::2]
+    lines.append("[wgrad pair kernel cycles, mean over CTAs] MMA thread: waiting for converters %.0f of %.0f total; "
+                 "A converter: split+issue loads %.0f, wait slot free %.0f, tmem store+arrive %.0f; B converter: wait TMA %.0f "
+                 "(follower CTA: A %.0f / %.0f / %.0f, B %.0f)" % (
+                     lead[:, 0].mean(), lead[:, 1].mean(), lead[:, 2].mean(), lead[:, 3].mean(), lead[:, 4].mean(),
+                     lead[:, 5].mean(), foll[:, 2].mean(), foll[:, 3].mean(), foll[:, 4].mean(), foll[:, 5].mean()))
     assert int(status.item()) == 0
     with capsys.disabled():
         print("\n" + "\n".join(lines))
