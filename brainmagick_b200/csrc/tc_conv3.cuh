@@ -75,8 +75,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster.  Default semantics (.release.cta), NOT .release.cluster: ptxas lowers
+// a cluster-scope release to MEMBAR.ALL.GPU + ERRBAR, which cost the converter warps ~1 300 cycles per K chunk (measured
+// with the cycle counters of tc_wgradp.cuh: the MMA thread waited for the converters 53 % of the time).  What the consumer
+// reads is ordered by other means: tensor memory by the tcgen05.fence::before/after_thread_sync pair around this arrive,
+// shared memory written through the generic proxy by the fence.proxy.async before it (the pattern of CUTLASS's
+// ClusterBarrier::arrive(cta_id)).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
