@@ -14,9 +14,11 @@
 //   * one CTA multiplied a 128-row block against all 320 columns: every B byte was read from shared memory three times by
 //     the MMAs plus once by the splitter -- 125 B/cycle of the SM's 128.  A CTA pair (cta_group::2, M = 256) holds HALF of
 //     the dY tile per CTA: 62 B/cycle.
-// Operands:  A = Xs^T through REGISTERS into TENSOR MEMORY: thread r of the 4 converter warps owns row (tap, n) and loads
-//            X[p + shift, n] for the chunk's 32 positions (each warp-load is one coalesced 128-byte row piece; rows whose
-//            shifted time falls outside [0, T) are zeros = the conv padding), splits hi/lo, tcgen05.st;
+// Operands:  A = Xs^T: per converter warp one TMA box [32 positions][32 x-channels] at row p + shift(tap) (un-swizzled: the
+//            warp reads it column-wise, lane = channel, conflict-free) in a SIX-deep ring -- X is an activation saved by the
+//            forward pass and comes from HBM; per-thread loads one or two chunks ahead left the MMA thread waiting 47-53 %
+//            of the time (cycle counters, bm_set_debug_buffer).  Thread r owns row (tap, n): positions whose shifted time
+//            falls outside [0, T) are zeros (the conv padding); split hi/lo, tcgen05.st into tensor memory;
 //            B = dY tile by TMA as MN-major SWIZZLE_128B_ATOM_32B blocks ([32 positions] x [32 channels], 4 KB), raw =
 //            the tensor core's `hi`; two warps write lo = x - trunc(x) beside it.
 // One CTA pair = one (256-row tile, N tile, K slice); partial tiles go to the workspace and `wgradp_reduce_kernel` sums the
@@ -28,12 +30,13 @@
 namespace bm {
 namespace tc {
 
-constexpr int WP_BK = 32, WP_STAGES = 3, WP_THREADS = 256;
+constexpr int WP_BK = 32, WP_STAGES = 3, WP_ASTAGES = 6, WP_THREADS = 288;
 constexpr int WP_BLK_BYTES = 32 * 32 * 4;                    // one [32 positions][32 channels] block
 constexpr int WP_MAX_BLKS = 5;                               // per CTA: half of an N tile of <= 320 channels
 constexpr int WP_B_BYTES = WP_MAX_BLKS * WP_BLK_BYTES;       // 20 KB
 constexpr int WP_STAGE_BYTES = 2 * WP_B_BYTES;               // raw + lo
-constexpr int WP_SMEM_BYTES = WP_STAGES * WP_STAGE_BYTES + 1024;
+constexpr int WP_ATILE_BYTES = 4 * WP_BLK_BYTES;             // X tile of one chunk: per converter warp [32 positions][32 rows]
+constexpr int WP_SMEM_BYTES = WP_STAGES * WP_STAGE_BYTES + WP_ASTAGES * WP_ATILE_BYTES + 1024;
 constexpr int WP_ACC_COLS = 320, WP_A_COLS = 2 * WP_BK;
 
 struct WgradPP {
@@ -43,16 +46,16 @@ struct WgradPP {
     int mtiles, ntiles, ks;     // 256-row tiles, N tiles, K slices
     int nt, h0, h1;             // N tile and its two MMA halves (h1 may be 0); each a multiple of 64
     int chunks, per_split;
-    const float* X;
     float* P;                   // [ks][mtiles*256][Mdy]
     int* err;
     long long* dbg;             // debug only (bm_set_debug_buffer): per CTA 8 cycle counters, see the kernel
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WP_THREADS, 1)
-wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
+wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradPP p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[WP_STAGES], conv_bar[WP_STAGES], empty_bar[WP_STAGES], tmem_full_bar;
+    __shared__ __align__(8) uint64_t afull_bar[WP_ASTAGES], aempty_bar[WP_ASTAGES];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int prior_error;
 
@@ -82,6 +85,10 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&conv_bar[s], 2 * (4 + 2));                   // one elected lane per converter warp of both CTAs (LEADER's copy)
             mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < WP_ASTAGES; ++s) {
+            mbar_init(&afull_bar[s], 1);
+            mbar_init(&aempty_bar[s], 4);                           // one elected lane per converter warp (this CTA)
         }
         mbar_init(&tmem_full_bar, 1);
         fence_barrier_init();
@@ -160,35 +167,31 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
         const int grow = m_tile * 256 + (int)rank * 128 + q * 32 + lane;      // output row (tap, n)
         const bool row_ok = grow < p.rows;
         const int tap = row_ok ? grow / p.Nx : 0;
-        const int n = row_ok ? grow - tap * p.Nx : 0;
         const int shift = (tap - p.taps / 2) * p.dilation;
-        // The X column of a chunk is loaded TWO chunks ahead into alternating register buffers: the operand comes from HBM
-        // (an activation saved by the forward pass), and one chunk of MMA time (~1.4 us) does not cover that latency.
-        float bufA[WP_BK], bufB[WP_BK];
-        auto load_a = [&](int it, float* dst) {
+        uint8_t* a_ring = smem + WP_STAGES * WP_STAGE_BYTES;
+        bool ok = true;
+        long long t_split = 0, t_empty = 0, t_st = 0;
+        for (int it = 0; it < total && ok; ++it) {
+            const int s = it % WP_STAGES, sa = it % WP_ASTAGES;
+            const uint32_t ph = (it / WP_STAGES) & 1, pha = (it / WP_ASTAGES) & 1;
+            const long long c0 = clock64();
+            ok = mbar_wait(&afull_bar[sa], pha, p.err, 87);              // this chunk's X boxes have landed
+            const float* col = reinterpret_cast<const float*>(a_ring + sa * WP_ATILE_BYTES + q * WP_BLK_BYTES) + lane;
             const int p0 = (it_begin + it) * WP_BK;
-            int t = p0 % p.T;                                                // time of the chunk's first row in its sample
-            const float* src = p.X + ((long long)p0 + shift) * p.Nx + n;
+            int t = p0 % p.T;                                            // time of the chunk's first row in its sample
+            float hi[WP_BK], lo[WP_BK];
 #pragma unroll
             for (int j = 0; j < WP_BK; ++j) {
                 const int ts = t + shift;
-                const bool ok = row_ok && ts >= 0 && ts < p.T && p0 + j < p.R;
-                dst[j] = ok ? __ldg(src + (long long)j * p.Nx) : 0.f;
+                float v = col[j * 32];
+                if (!(row_ok && ts >= 0 && ts < p.T)) v = 0.f;           // across a sample edge: the conv's zero padding
+                tf32_split(v, hi[j], lo[j]);
                 if (++t == p.T) t = 0;
             }
-        };
-        bool ok = true;
-        long long t_split = 0, t_empty = 0, t_st = 0;
-        auto convert = [&](int it, float* buf) {
-            const int s = it % WP_STAGES;
-            const uint32_t ph = (it / WP_STAGES) & 1;
-            float hi[WP_BK], lo[WP_BK];
-            const long long c0 = clock64();
-#pragma unroll
-            for (int j = 0; j < WP_BK; ++j) tf32_split(buf[j], hi[j], lo[j]);
-            if (it + 2 < total) load_a(it + 2, buf);                     // refill this buffer for the chunk after next
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aempty_bar[sa]);                 // the ring slot can be refilled
             const long long c1 = clock64();
-            ok = mbar_wait(&empty_bar[s], ph ^ 1, p.err, 84);            // the MMAs of chunk it-STAGES have left this slot
+            ok = ok && mbar_wait(&empty_bar[s], ph ^ 1, p.err, 84);      // the MMAs of chunk it-STAGES have left this slot
             const long long c2 = clock64();
             t_split += c1 - c0; t_empty += c2 - c1;
             tc_fence_after();
@@ -199,12 +202,6 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
             t_st += clock64() - c2;
-        };
-        if (total > 0) load_a(0, bufA);
-        if (total > 1) load_a(1, bufB);
-        for (int it = 0; it < total && ok; it += 2) {
-            convert(it, bufA);
-            if (it + 1 < total && ok) convert(it + 1, bufB);
         }
         if (p.dbg && warp == 2 && lane == 0) {
             p.dbg[blockIdx.x * 8 + 2] = t_split; p.dbg[blockIdx.x * 8 + 3] = t_empty; p.dbg[blockIdx.x * 8 + 4] = t_st;
@@ -229,7 +226,7 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             }
             tc_fence_before();
         }
-    } else {
+    } else if (warp < 8) {
         // ------------------------------------------------ B: lo = dy - trunc_tf32(dy) ---------------------------------
         const int ct = (warp - 6) * 32 + lane;                           // 0..63
         const int nvec = (int)(b_bytes / 16);
@@ -258,6 +255,32 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const WgradPP p) {
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
         }
         if (p.dbg && warp == 6 && lane == 0) p.dbg[blockIdx.x * 8 + 5] = t_full;
+    } else {
+        // ------------------------------------------------ TMA producer of the X ring: 4 boxes (one per converter warp) ---
+        if (lane == 0) {
+            prefetch_tmap(&tmX);
+            uint8_t* a_ring = smem + WP_STAGES * WP_STAGE_BYTES;
+            int nq[4], sh[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int wrow = m_tile * 256 + (int)rank * 128 + w * 32;   // first (tap, n) row of converter quarter w
+                const bool okw = wrow < p.rows;                             // Nx % 32 == 0: a quarter never straddles a tap
+                const int tapw = okw ? wrow / p.Nx : 0;
+                nq[w] = okw ? wrow - tapw * p.Nx : -1;
+                sh[w] = (tapw - p.taps / 2) * p.dilation;
+            }
+            for (int it = 0; it < total; ++it) {
+                const int sa = it % WP_ASTAGES;
+                const uint32_t pha = (it / WP_ASTAGES) & 1;
+                if (!mbar_wait(&aempty_bar[sa], pha ^ 1, p.err, 88)) break;
+                const int p0 = (it_begin + it) * WP_BK;
+                uint8_t* dst = a_ring + sa * WP_ATILE_BYTES;
+                mbar_expect_tx(&afull_bar[sa], WP_ATILE_BYTES);
+#pragma unroll
+                for (int w = 0; w < 4; ++w)        // padding quarters read past the end of the tensor: zero-filled
+                    tma_load_2d(dst + w * WP_BLK_BYTES, &tmX, &afull_bar[sa], nq[w] < 0 ? 0 : nq[w], nq[w] < 0 ? p.R : p0 + sh[w]);
+            }
+        }
     }
     __syncthreads();
     cluster_sync_all();
@@ -297,7 +320,7 @@ inline bool wgradp_pick_nt(int Mdy, int* nt, int* h0, int* h1) {
 }
 inline bool wgradp_supported(int T, int Mdy, int Nx, int taps) {
     int nt, h0, h1;
-    return T >= WP_BK && Nx % 4 == 0 && Nx >= 32 && taps >= 1 && taps <= 3 && wgradp_pick_nt(Mdy, &nt, &h0, &h1);
+    return T >= WP_BK && Nx % 32 == 0 && Nx >= 32 && taps >= 1 && taps <= 3 && wgradp_pick_nt(Mdy, &nt, &h0, &h1);
 }
 inline WgradPPGeom wgradp_geometry(int B, int T, int Mdy, int Nx, int taps) {
     WgradPPGeom g;
@@ -334,12 +357,20 @@ inline int launch_wgrad_pp(const float* dY, const float* X, int B, int T, int Md
         if (!make_tmap_f32(&tmDY, dY, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return set_error(4, "%s: cuTensorMapEncodeTiled failed%s", __func__);
     }
+    CUtensorMap tmX;
+    {
+        uint64_t dims[2] = {(uint64_t)Nx, (uint64_t)R};
+        uint64_t str[1] = {(uint64_t)Nx * 4};
+        uint32_t box[2] = {32, 32};
+        if (!make_tmap_f32(&tmX, X, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return set_error(4, "%s: cuTensorMapEncodeTiled(X) failed%s", __func__);
+    }
     if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(wgrad_pp_kernel), WP_SMEM_BYTES)) return rc;
     WgradPP p;
     p.R = (int)R; p.T = T; p.Mdy = Mdy; p.Nx = Nx; p.taps = taps; p.dilation = dilation; p.rows = g.rows;
     p.mtiles = g.mtiles; p.ntiles = g.ntiles; p.ks = g.ks; p.nt = g.nt; p.h0 = g.h0; p.h1 = g.h1;
-    p.chunks = g.chunks; p.per_split = g.per_split; p.X = X; p.P = ws; p.err = err; p.dbg = g_debug_buf;
-    wgrad_pp_kernel<<<2 * g.mtiles * g.ntiles * g.ks, WP_THREADS, WP_SMEM_BYTES, st>>>(tmDY, p);
+    p.chunks = g.chunks; p.per_split = g.per_split; p.P = ws; p.err = err; p.dbg = g_debug_buf;
+    wgrad_pp_kernel<<<2 * g.mtiles * g.ntiles * g.ks, WP_THREADS, WP_SMEM_BYTES, st>>>(tmDY, tmX, p);
     ++g_launches;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(3, "%s: launch failed: %s", __func__, cudaGetErrorString(e));
