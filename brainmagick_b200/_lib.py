@@ -37,7 +37,7 @@ SIGNATURES = {
     "bm_conv1d_bwd_data": [P, P, P, I, I, I, I, I, I, P, P],
     "bm_conv1d_bwd_weight": [P, P, I, I, I, I, I, I, P, P, P],
     "bm_conv1d_glu_fwd": [P, P, P, I, I, I, I, I, P, P, P],
-    "bm_glu_bwd": [P, P, L, I, P, P],
+    "bm_glu_bwd": [P, P, L, I, P, P, P],
     "bm_head_fwd": [P, P, P, P, P, I, I, I, I, P, P, P, P],
     "bm_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "bm_head_bwd_params": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],

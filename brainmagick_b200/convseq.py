@@ -157,8 +157,9 @@ class _ConvSequenceFn(torch.autograd.Function):
             if plan.glu_after[k]:
                 gconv: _Conv = rec["gconv"]
                 dh = _empty((B, T, gconv.cout), dout)
-                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), st)
-                glu_grads[k] = gconv.backward_weight(dh, rec["x_new"], B, T, 1, dout, status)
+                dgb = torch.empty((gconv.cout,), device=dout.device, dtype=torch.float32)
+                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), ptr(dgb), st)
+                glu_grads[k] = gconv.backward_weight(dh, rec["x_new"], B, T, 1, dout, status, known_dbias=dgb)
                 g = _empty((B, T, gconv.cin), dout)
                 gconv.backward_data(dh, None, B, T, 1, g, status)
                 del dh

@@ -1,4 +1,5 @@
 // C-ABI entry points of libbm_b200.so (see include/bm_b200.h for the contract and the reference citations).
+#include <algorithm>
 #include "../../include/bm_b200.h"
 #include "common.cuh"
 #include "elementwise.cuh"
@@ -305,6 +306,13 @@ extern "C" int bm_bn_gelu_skip_fwd(const float* y, const float* mean, const floa
     long long total = rows * C;
     bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x_new) |
                                  reinterpret_cast<uintptr_t>(x_old)) % 16 == 0);
+    if (vec && C / 4 <= 256 && aligned16(mean, invstd, gamma) && aligned16(beta)) {
+        const int cx = C / 4, ry = std::max(1, 320 / cx);
+        const unsigned nblk = (unsigned)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
+        bn_gelu_skip_fwd_cs_kernel<<<nblk, dim3(cx, ry), 0, ST(stream)>>>(y, mean, invstd, gamma, beta, x_old, x_new, rows, C);
+        BM_CHECK_LAUNCH();
+        return 0;
+    }
     if (vec)
         bn_gelu_skip_fwd_kernel<4><<<ew_grid(total, 256, 4), 256, 0, ST(stream)>>>(y, mean, invstd, gamma, beta,
                                                                                  x_old, x_new, total, C);
@@ -323,7 +331,20 @@ extern "C" int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* 
     BM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const long long total = rows * C;
     const bool vec = (C % 4 == 0) && aligned16(g, y, dy) && aligned16(mean, invstd, gamma) && aligned16(beta);
-    {   // (a float4-per-thread variant of this reduction measured slower: 4x fewer threads in flight)
+    if (vec && C / 4 <= 256 && aligned16(dgamma, dbeta)) {
+        const int cx = C / 4, ry = std::max(1, 320 / cx);
+        const unsigned nblk = (unsigned)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
+        bn_gelu_bwd_reduce_cs_kernel<<<nblk, dim3(cx, ry), sizeof(float) * 2 * C * ry, st>>>(g, y, mean, invstd, gamma, beta,
+                                                                                          sums, rows, C);
+        BM_CHECK_LAUNCH();
+        bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, C);
+        BM_CHECK_LAUNCH();
+        bn_gelu_bwd_apply_cs_kernel<<<nblk, dim3(cx, ry), 0, st>>>(g, y, mean, invstd, gamma, beta, dgamma, dbeta,
+                                                                   (float)(1.0 / (double)rows), batch_stats, dy, rows, C);
+        BM_CHECK_LAUNCH();
+        return 0;
+    }
+    {   // generic shapes: one thread per column, 128 rows per block
         const int rpb = 128;
         dim3 grid((unsigned)((rows + rpb - 1) / rpb), (C + 127) / 128);
         bn_gelu_bwd_reduce_kernel<<<grid, 128, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, rows, C, rpb);
@@ -385,14 +406,29 @@ extern "C" int bm_conv1d_glu_fwd(const float* x, const float* wf, const float* b
     return conv_gemm(x, wf, bias, nullptr, B, T, Cin, 2 * H, Kw, 1, +1, h, nullptr, 1, out, ST(stream));
 }
 
-extern "C" int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh, bm_stream_t stream) {
+extern "C" int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh, float* dbias,
+                          bm_stream_t stream) {
     BM_CHECK_ARG(g && h && dh && rows > 0 && H > 0);
+    cudaStream_t st = ST(stream);
+    if (dbias) BM_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 2 * H, st));
+    if (H % 4 == 0 && H / 4 <= 256 && aligned16(g, h, dh)) {
+        const int cx = H / 4, ry = std::max(1, 320 / cx);
+        const unsigned nblk = (unsigned)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
+        glu_bwd_cs_kernel<<<nblk, dim3(cx, ry), dbias ? sizeof(float) * 2 * H * ry : 0, st>>>(g, h, dh, dbias, rows, H);
+        BM_CHECK_LAUNCH();
+        return 0;
+    }
     if (H % 4 == 0 && aligned16(g, h, dh))
-        glu_bwd_v4_kernel<<<ew_grid(rows * H / 4), 256, 0, ST(stream)>>>(
+        glu_bwd_v4_kernel<<<ew_grid(rows * H / 4), 256, 0, st>>>(
             reinterpret_cast<const float4*>(g), reinterpret_cast<const float4*>(h), reinterpret_cast<float4*>(dh), rows, H);
     else
-        glu_bwd_kernel<<<ew_grid(rows * H), 256, 0, ST(stream)>>>(g, h, dh, rows, H);
+        glu_bwd_kernel<<<ew_grid(rows * H), 256, 0, st>>>(g, h, dh, rows, H);
     BM_CHECK_LAUNCH();
+    if (dbias) {
+        dim3 grid((unsigned)((rows + 255) / 256), (2 * H + 127) / 128);
+        colsum_cl_kernel<<<grid, 128, 0, st>>>(dh, dbias, rows, 2 * H, 256);
+        BM_CHECK_LAUNCH();
+    }
     return 0;
 }
 

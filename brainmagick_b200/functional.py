@@ -93,7 +93,7 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
-USE_WGRAD_PP = True    # CTA-pair weight-gradient kernel (tc_wgradp.cuh) for the k = 3 convolutions
+USE_WGRAD_PP = True    # CTA-pair weight-gradient kernel (tc_wgradp.cuh) where its 256-row tiling wastes < 10 %
 
 
 def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None):
@@ -101,7 +101,10 @@ def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None):
     `dbias` [M] (optional) receives sum_{b,t} dy[b,t,m]."""
     lib = _lib.load()
     dw = _empty((M, Ntrue, kw), dy)
-    if USE_WGRAD_PP and kw == 3 and bool(lib.bm_tc_wgrad_conv_supported(T, M, N, kw)):
+    rows = kw * N                                       # output rows of the pair kernel, tiled in blocks of 256
+    pair_ok = USE_WGRAD_PP and bool(lib.bm_tc_wgrad_conv_supported(T, M, N, kw)) and \
+        rows / (-(-rows // 256) * 256) >= 0.9            # else the single-CTA kernel wastes less on padding rows
+    if pair_ok:
         ws = _empty((int(lib.bm_tc_wgrad_conv_workspace(B, T, M, N, kw)),), dy)
         call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(status), stream())
         if dbias is not None:
@@ -200,10 +203,13 @@ class _Conv:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
                  dilation, ptr(dx), st)
 
-    def backward_weight(self, dy, x, B, T, dilation, like, status, bias_grad_is_zero=False):
+    def backward_weight(self, dy, x, B, T, dilation, like, status, bias_grad_is_zero=False, known_dbias=None):
         """`bias_grad_is_zero`: the conv feeds a training-mode BatchNorm, whose backward makes sum(dy) == 0 exactly
-        (the reference's value there is rounding noise around 0); skip the reduction."""
+        (the reference's value there is rounding noise around 0); skip the reduction.  `known_dbias`: the producer of dy
+        already summed it over the rows."""
         if self.wgrad_tc:
+            if known_dbias is not None:
+                return tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status), known_dbias
             if bias_grad_is_zero:
                 dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status)
                 return dw, torch.zeros((self.cout,), device=like.device)
@@ -638,12 +644,14 @@ class _EncoderFn(torch.autograd.Function):
         side = _side_stream(meg.device) if (OVERLAP_WGRAD and plan.use_tensor_cores) else None
         keep_alive: tp.List[tp.Any] = ctx_keep
 
-        def weight_grad(conv_obj, dy_t, x_t, dil, bias_zero):
+        def weight_grad(conv_obj, dy_t, x_t, dil, bias_zero, known_dbias=None):
             if side is None:
-                return conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero)
+                return conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero,
+                                                known_dbias=known_dbias)
             side.wait_stream(main)
             with torch.cuda.stream(side):
-                out = conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero)
+                out = conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero,
+                                               known_dbias=known_dbias)
             # the big operands are kept alive until the streams join (no record_stream: with the host running steps ahead
             # it would block the allocator from reusing ~3 GB of blocks and force cudaMallocs in the timed loop)
             keep_alive.append((dy_t, x_t))
@@ -659,8 +667,9 @@ class _EncoderFn(torch.autograd.Function):
             if plan.glu_after[k]:
                 gconv: _Conv = rec["gconv"]
                 dh = _empty((B, T, gconv.cout), meg)
-                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), st)
-                glu_grads[k] = weight_grad(gconv, dh, rec["x_new"], 1, False)
+                dgb = _empty((gconv.cout,), meg)          # the GLU conv's bias gradient, summed while dh is produced
+                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), ptr(dgb), st)
+                glu_grads[k] = weight_grad(gconv, dh, rec["x_new"], 1, False, dgb)
                 g = _empty((B, T, gconv.cin), meg)
                 gconv.backward_data(dh, None, B, T, 1, g, status)
                 del dh

@@ -122,7 +122,9 @@ int bm_conv1d_bwd_weight(const float* dy, const float* x, int B, int T, int Cin,
  * wf [Kw,Cin,2H]; h (nullable, saved for backward) [B,T,2H]; out [B,T,H] = h[:, :H] * sigmoid(h[:, H:]). */
 int bm_conv1d_glu_fwd(const float* x, const float* wf, const float* bias, int B, int T, int Cin, int H, int Kw,
                       float* h, float* out, bm_stream_t stream);
-int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh, bm_stream_t stream);
+int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh,
+               float* dbias /* nullable [2H]: sum over rows of dh = the GLU conv's bias gradient, from the same pass */,
+               bm_stream_t stream);
 
 /* ---- K5: head Conv1d(H,2H,1) -> GELU -> ConvTranspose1d(2H,F,1) (simpleconv.py:185-189,246-249) --------
  * x [B,T,H]; w0 [2H,H]; w2 [2H,F] (ConvTranspose1d weight is input-major); out h1,q [B,T,2H], est [B,F,T]. */

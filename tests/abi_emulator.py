@@ -255,11 +255,13 @@ class Emulator:
             _v(h, B, T, 2 * H).copy_(hh)
         _v(out, B, T, H).copy_(hh[..., :H] * torch.sigmoid(hh[..., H:]))
 
-    def bm_glu_bwd(self, g, h, rows, H, dh, stream):
+    def bm_glu_bwd(self, g, h, rows, H, dh, dbias, stream):
         gg, hh = _v(g, rows, H), _v(h, rows, 2 * H)
         a, b = hh[:, :H], hh[:, H:]
         s = torch.sigmoid(b)
         _v(dh, rows, 2 * H).copy_(torch.cat([gg * s, gg * a * s * (1 - s)], dim=1))
+        if dbias is not None:
+            _v(dbias, 2 * H).copy_(_v(dh, rows, 2 * H).sum(0))
 
     # ---------------------------------------------------------------- K5
     def bm_head_fwd(self, x, w0, b0, w2, b2, B, T, H, F_, h1, q, est, stream):
