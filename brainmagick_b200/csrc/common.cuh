@@ -38,9 +38,14 @@ inline int set_error(int code, const char* fmt, const char* a = "", const char* 
 //     erfc(x) = t exp(-x^2 + P(t)),  t = 1/(1 + x/2),  x >= 0        fractional error < 1.2e-7 EVERYWHERE, so the tails keep
 // their relative accuracy (measured in fp32 over [-9, 9]: <= 7e-6 relative at |z| > 8, ~1e-7 elsewhere).  erff() + expf()
 // cost about twice the instructions and made the HBM-bound BatchNorm/GELU kernels ALU-bound.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void gelu_parts(float z, float& cdf, float& pdf) {
     const float ax = fabsf(z) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.5f, ax, 1.0f));
+    const float t = rcp_approx(fmaf(0.5f, ax, 1.0f));            // MUFU.RCP (1 ulp); __frcp_rn branches on special cases
     float poly = fmaf(t, 0.17087277f, -0.82215223f);
     poly = fmaf(t, poly, 1.48851587f);
     poly = fmaf(t, poly, -1.13520398f);
@@ -66,6 +71,8 @@ __device__ __forceinline__ float gelu_grad_f(float z) {
     return fmaf(z, pdf, cdf);
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// ~2 ulp version for the HBM-bound GLU backward (MUFU.EX2 + MUFU.RCP instead of the IEEE division and expf)
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -499,61 +499,77 @@ __global__ void gelu_bwd_v4_kernel(const float4* __restrict__ dq, const float4* 
 // the per-column parameters live in registers (no i % C, no parameter reloads, no fp64 divisions per element) and every
 // warp-level access is a contiguous row piece.  Rows are unrolled by 4 for memory-level parallelism.
 // ------------------------------------------------------------------------------------------------
-constexpr int CS_ROWS_PER_BLOCK = 96;
+constexpr int CS_ROWS_PER_BLOCK = 96, CS_U = 4;       // rows per block; rows per thread whose loads are issued together
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }   // streamed once
 
 // x_new = GELU((y - mean) * invstd * gamma + beta) (+ x_old)
-__global__ void bn_gelu_skip_fwd_cs_kernel(const float* __restrict__ y, const float* __restrict__ mean,
-                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, const float* __restrict__ x_old,
-                                           float* __restrict__ x_new, long long rows, int C) {
-    const int c = threadIdx.x * 4;
+__global__ void __launch_bounds__(320, 2)
+bn_gelu_skip_fwd_cs_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
+                           const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ x_old,
+                           float* __restrict__ x_new, long long rows, int C) {
+    const int c = threadIdx.x * 4, RY = blockDim.y;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c), be = ld4(beta + c);
-    // z = y * sc + sh
-    const float4 sc = make_float4(is.x * ga.x, is.y * ga.y, is.z * ga.z, is.w * ga.w);
     const long long r0 = (long long)blockIdx.x * CS_ROWS_PER_BLOCK;
     const long long r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
-#pragma unroll 4
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        const long long off = r * C + c;
-        const float4 v = ld4(y + off);
-        float4 o;
-        // same operation order as the reference BatchNorm: ((y - mean) * invstd) * gamma + beta
-        o.x = gelu_f(fmaf((v.x - mu.x) * is.x, ga.x, be.x));
-        o.y = gelu_f(fmaf((v.y - mu.y) * is.y, ga.y, be.y));
-        o.z = gelu_f(fmaf((v.z - mu.z) * is.z, ga.z, be.z));
-        o.w = gelu_f(fmaf((v.w - mu.w) * is.w, ga.w, be.w));
-        if (x_old) {
-            const float4 u = ld4(x_old + off);
-            o.x += u.x; o.y += u.y; o.z += u.z; o.w += u.w;
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)CS_U * RY) {
+        float4 v[CS_U], u[CS_U];
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) {
+                v[k] = ld4s(y + rr * C + c);
+                if (x_old) u[k] = ld4(x_old + rr * C + c);
+            }
         }
-        *reinterpret_cast<float4*>(x_new + off) = o;
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) {
+                float4 o;
+                // same operation order as the reference BatchNorm: ((y - mean) * invstd) * gamma + beta
+                o.x = gelu_f(fmaf((v[k].x - mu.x) * is.x, ga.x, be.x));
+                o.y = gelu_f(fmaf((v[k].y - mu.y) * is.y, ga.y, be.y));
+                o.z = gelu_f(fmaf((v[k].z - mu.z) * is.z, ga.z, be.z));
+                o.w = gelu_f(fmaf((v[k].w - mu.w) * is.w, ga.w, be.w));
+                if (x_old) { o.x += u[k].x; o.y += u[k].y; o.z += u[k].z; o.w += u[k].w; }
+                *reinterpret_cast<float4*>(x_new + rr * C + c) = o;
+            }
+        }
     }
-    (void)sc;
 }
 
 // backward pass 1: sums[c] += sum dz, sums[C+c] += sum dz*yhat  with dz = g * GELU'(z); fp32 per thread, combined over the
 // block's RY row lanes in shared memory, ONE fp64 atomic pair per column per block
-__global__ void bn_gelu_bwd_reduce_cs_kernel(const float* __restrict__ g, const float* __restrict__ y,
-                                             const float* __restrict__ mean, const float* __restrict__ invstd,
-                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                             double* __restrict__ sums, long long rows, int C) {
+__global__ void __launch_bounds__(320, 2)
+bn_gelu_bwd_reduce_cs_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ mean,
+                             const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                             double* __restrict__ sums, long long rows, int C) {
     extern __shared__ float red[];                       // [RY][2][C]
-    const int c = threadIdx.x * 4;
+    const int c = threadIdx.x * 4, RY = blockDim.y;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c), be = ld4(beta + c);
     const long long r0 = (long long)blockIdx.x * CS_ROWS_PER_BLOCK;
     const long long r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
     float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-#pragma unroll 4
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        const long long off = r * C + c;
-        const float4 yv = ld4(y + off), gv = ld4(g + off);
-        float yh, dz;
-        yh = (yv.x - mu.x) * is.x; dz = gv.x * gelu_grad_f(fmaf(yh, ga.x, be.x)); s1.x += dz; s2.x = fmaf(dz, yh, s2.x);
-        yh = (yv.y - mu.y) * is.y; dz = gv.y * gelu_grad_f(fmaf(yh, ga.y, be.y)); s1.y += dz; s2.y = fmaf(dz, yh, s2.y);
-        yh = (yv.z - mu.z) * is.z; dz = gv.z * gelu_grad_f(fmaf(yh, ga.z, be.z)); s1.z += dz; s2.z = fmaf(dz, yh, s2.z);
-        yh = (yv.w - mu.w) * is.w; dz = gv.w * gelu_grad_f(fmaf(yh, ga.w, be.w)); s1.w += dz; s2.w = fmaf(dz, yh, s2.w);
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)CS_U * RY) {
+        float4 yv[CS_U], gv[CS_U];
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) { yv[k] = ld4(y + rr * C + c); gv[k] = ld4(g + rr * C + c); }
+        }
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) {
+                float yh, dz;
+                yh = (yv[k].x - mu.x) * is.x; dz = gv[k].x * gelu_grad_f(fmaf(yh, ga.x, be.x)); s1.x += dz; s2.x = fmaf(dz, yh, s2.x);
+                yh = (yv[k].y - mu.y) * is.y; dz = gv[k].y * gelu_grad_f(fmaf(yh, ga.y, be.y)); s1.y += dz; s2.y = fmaf(dz, yh, s2.y);
+                yh = (yv[k].z - mu.z) * is.z; dz = gv[k].z * gelu_grad_f(fmaf(yh, ga.z, be.z)); s1.z += dz; s2.z = fmaf(dz, yh, s2.z);
+                yh = (yv[k].w - mu.w) * is.w; dz = gv[k].w * gelu_grad_f(fmaf(yh, ga.w, be.w)); s1.w += dz; s2.w = fmaf(dz, yh, s2.w);
+            }
+        }
     }
     float* mine = red + (size_t)threadIdx.y * 2 * C;
     *reinterpret_cast<float4*>(mine + c) = s1;
@@ -562,19 +578,19 @@ __global__ void bn_gelu_bwd_reduce_cs_kernel(const float* __restrict__ g, const 
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     for (int i = tid; i < 2 * C; i += nthr) {
         double acc = 0.0;
-        for (int ry = 0; ry < (int)blockDim.y; ++ry) acc += (double)red[(size_t)ry * 2 * C + i];
+        for (int ry = 0; ry < RY; ++ry) acc += (double)red[(size_t)ry * 2 * C + i];
         atomicAdd(sums + i, acc);
     }
 }
 
 // backward pass 2: dy = gamma*invstd*(dz - mean(dz) - yhat*mean(dz*yhat)); the two means come as dbeta/n and dgamma/n
 // (written by bn_param_grad_kernel from the fp64 sums); eval mode (use_batch_stats = 0): dy = gamma*invstd*dz
-__global__ void bn_gelu_bwd_apply_cs_kernel(const float* __restrict__ g, const float* __restrict__ y,
-                                            const float* __restrict__ mean, const float* __restrict__ invstd,
-                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            const float* __restrict__ dgamma, const float* __restrict__ dbeta, float rn,
-                                            int use_batch_stats, float* __restrict__ dy, long long rows, int C) {
-    const int c = threadIdx.x * 4;
+__global__ void __launch_bounds__(320, 2)
+bn_gelu_bwd_apply_cs_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ mean,
+                            const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            const float* __restrict__ dgamma, const float* __restrict__ dbeta, float rn, int use_batch_stats,
+                            float* __restrict__ dy, long long rows, int C) {
+    const int c = threadIdx.x * 4, RY = blockDim.y;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c), be = ld4(beta + c);
     float4 m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
     if (use_batch_stats) {
@@ -582,46 +598,67 @@ __global__ void bn_gelu_bwd_apply_cs_kernel(const float* __restrict__ g, const f
         m1 = make_float4(db.x * rn, db.y * rn, db.z * rn, db.w * rn);
         m2 = make_float4(dg.x * rn, dg.y * rn, dg.z * rn, dg.w * rn);
     }
-    const float4 k = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
+    const float4 kk = make_float4(ga.x * is.x, ga.y * is.y, ga.z * is.z, ga.w * is.w);
     const long long r0 = (long long)blockIdx.x * CS_ROWS_PER_BLOCK;
     const long long r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
-#pragma unroll 4
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        const long long off = r * C + c;
-        const float4 yv = ld4(y + off), gv = ld4(g + off);
-        float4 o;
-        float yh, dz;
-        yh = (yv.x - mu.x) * is.x; dz = gv.x * gelu_grad_f(fmaf(yh, ga.x, be.x)); o.x = k.x * (dz - m1.x - yh * m2.x);
-        yh = (yv.y - mu.y) * is.y; dz = gv.y * gelu_grad_f(fmaf(yh, ga.y, be.y)); o.y = k.y * (dz - m1.y - yh * m2.y);
-        yh = (yv.z - mu.z) * is.z; dz = gv.z * gelu_grad_f(fmaf(yh, ga.z, be.z)); o.z = k.z * (dz - m1.z - yh * m2.z);
-        yh = (yv.w - mu.w) * is.w; dz = gv.w * gelu_grad_f(fmaf(yh, ga.w, be.w)); o.w = k.w * (dz - m1.w - yh * m2.w);
-        *reinterpret_cast<float4*>(dy + off) = o;
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)CS_U * RY) {
+        float4 yv[CS_U], gv[CS_U];
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) { yv[k] = ld4s(y + rr * C + c); gv[k] = ld4s(g + rr * C + c); }
+        }
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) {
+                float4 o;
+                float yh, dz;
+                yh = (yv[k].x - mu.x) * is.x; dz = gv[k].x * gelu_grad_f(fmaf(yh, ga.x, be.x)); o.x = kk.x * (dz - m1.x - yh * m2.x);
+                yh = (yv[k].y - mu.y) * is.y; dz = gv[k].y * gelu_grad_f(fmaf(yh, ga.y, be.y)); o.y = kk.y * (dz - m1.y - yh * m2.y);
+                yh = (yv[k].z - mu.z) * is.z; dz = gv[k].z * gelu_grad_f(fmaf(yh, ga.z, be.z)); o.z = kk.z * (dz - m1.z - yh * m2.z);
+                yh = (yv[k].w - mu.w) * is.w; dz = gv[k].w * gelu_grad_f(fmaf(yh, ga.w, be.w)); o.w = kk.w * (dz - m1.w - yh * m2.w);
+                *reinterpret_cast<float4*>(dy + rr * C + c) = o;
+            }
+        }
     }
 }
 
 // GLU backward, column-stationary (H % 4 == 0, H/4 <= 256): thread (cx, ry) owns a-columns 4cx.. and the matching gate columns;
 // optionally accumulates the bias gradient of the GLU convolution, dbias[c] = sum_rows dh[row][c] (2H columns), from the values
 // it has just produced (shared-memory combine over the row lanes, one fp32 atomic per column per block; zeroed by the caller).
-__global__ void glu_bwd_cs_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ dh,
-                                  float* __restrict__ dbias, long long rows, int H) {
+__global__ void __launch_bounds__(320, 2)
+glu_bwd_cs_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ dh, float* __restrict__ dbias,
+                  long long rows, int H) {
     extern __shared__ float red[];                       // [RY][2H]
-    const int c = threadIdx.x * 4;
+    const int c = threadIdx.x * 4, RY = blockDim.y;
     const long long r0 = (long long)blockIdx.x * CS_ROWS_PER_BLOCK;
     const long long r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
     float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
-#pragma unroll 4
-    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
-        const float4 a = ld4(h + r * 2 * H + c), b = ld4(h + r * 2 * H + H + c), gg = ld4(g + r * H + c);
-        float4 da, db;
-        float s;
-        s = sigmoid_f(b.x); da.x = gg.x * s; db.x = gg.x * a.x * s * (1.f - s);
-        s = sigmoid_f(b.y); da.y = gg.y * s; db.y = gg.y * a.y * s * (1.f - s);
-        s = sigmoid_f(b.z); da.z = gg.z * s; db.z = gg.z * a.z * s * (1.f - s);
-        s = sigmoid_f(b.w); da.w = gg.w * s; db.w = gg.w * a.w * s * (1.f - s);
-        *reinterpret_cast<float4*>(dh + r * 2 * H + c) = da;
-        *reinterpret_cast<float4*>(dh + r * 2 * H + H + c) = db;
-        sa.x += da.x; sa.y += da.y; sa.z += da.z; sa.w += da.w;
-        sb.x += db.x; sb.y += db.y; sb.z += db.z; sb.w += db.w;
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)CS_U * RY) {
+        float4 av[CS_U], bv[CS_U], gv[CS_U];
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) { av[k] = ld4s(h + rr * 2 * H + c); bv[k] = ld4s(h + rr * 2 * H + H + c); gv[k] = ld4s(g + rr * H + c); }
+        }
+#pragma unroll
+        for (int k = 0; k < CS_U; ++k) {
+            const long long rr = r + (long long)k * RY;
+            if (rr < r1) {
+                const float4 a = av[k], b = bv[k], gg = gv[k];
+                float4 da, db;
+                float s;
+                s = sigmoid_fast(b.x); da.x = gg.x * s; db.x = gg.x * a.x * s * (1.f - s);
+                s = sigmoid_fast(b.y); da.y = gg.y * s; db.y = gg.y * a.y * s * (1.f - s);
+                s = sigmoid_fast(b.z); da.z = gg.z * s; db.z = gg.z * a.z * s * (1.f - s);
+                s = sigmoid_fast(b.w); da.w = gg.w * s; db.w = gg.w * a.w * s * (1.f - s);
+                *reinterpret_cast<float4*>(dh + rr * 2 * H + c) = da;
+                *reinterpret_cast<float4*>(dh + rr * 2 * H + H + c) = db;
+                sa.x += da.x; sa.y += da.y; sa.z += da.z; sa.w += da.w;
+                sb.x += db.x; sb.y += db.y; sb.z += db.z; sb.w += db.w;
+            }
+        }
     }
     if (!dbias) return;
     float* mine = red + (size_t)threadIdx.y * 2 * H;
@@ -631,7 +668,7 @@ __global__ void glu_bwd_cs_kernel(const float* __restrict__ g, const float* __re
     const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
     for (int i = tid; i < 2 * H; i += nthr) {
         float acc = 0.f;
-        for (int ry = 0; ry < (int)blockDim.y; ++ry) acc += red[(size_t)ry * 2 * H + i];
+        for (int ry = 0; ry < RY; ++ry) acc += red[(size_t)ry * 2 * H + i];
         atomicAdd(dbias + i, acc);
     }
 }
