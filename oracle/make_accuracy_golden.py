@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import accuracy_task as at, bm_oracle  # noqa: E402
 
-SPEC = dict(C=208, F=1024, S=27, T=360, n_train=4096, n_eval=1024, batch=32, epochs=2, lr=1e-3, noise=5.0, latent=8,
+SPEC = dict(C=208, F=1024, S=27, T=360, n_train=4096, n_eval=1024, batch=32, epochs=2, lr=1e-3, noise=8.0, latent=8,
             init_seed=3, task_seed=0, sched_seed=1)
 OUT = os.path.join(ROOT, "tests", "golden", "accuracy_full_width.json")
 

@@ -82,3 +82,70 @@ def test_top10_accuracy_parity_on_synthetic_task():
     assert abs(losses[0] - loss_ref[0]) < 1e-4 * max(1.0, abs(loss_ref[0]))
     assert acc_ref > 0.3, "the task must be learnt for the comparison to mean anything"
     assert abs(acc - acc_ref) <= 0.005, (acc, acc_ref)          # +-0.5 pt
+
+
+def test_top10_accuracy_parity_at_baseline_widths():
+    """The same comparison at the BASELINE widths (208 sensors, hidden 320, F = 1024, T = 360, 27 subjects).
+    The reference side (the CPU oracle trained for the same schedule from the same state) takes ~20 minutes and was
+    computed once in the build container: tests/golden/accuracy_full_width.json, made by oracle/make_accuracy_golden.py.
+    Here the task, the schedule and the initial state are regenerated from the same seeds, the CUDA drop-in is trained, and
+    the held-out top-10 / top-1 accuracies -- through brainmagick_b200.retrieval.retrieval_accuracy, the batched evaluation
+    path -- must be within +-0.5 pt / +-2 pt of the stored reference (north star: top-10 within +-0.5 pt)."""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import functional as BF, retrieval, synthetic
+    from oracle import make_accuracy_golden as mg
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "accuracy_full_width.json")
+    with open(path) as f:
+        gold = json.load(f)
+    spec = gold["spec"]
+    cfg, task, sched, p0 = mg.build(spec)
+    assert len(sched) == gold["steps"]
+    model = bb.SimpleConv(
+        in_channels=dict(meg=cfg.in_channels), out_channels=cfg.out_channels, hidden=dict(meg=cfg.hidden), depth=cfg.depth,
+        dilation_period=5, kernel_size=3, skip=True, subject_layers=True, subject_dim=0, complex_out=True, glu=2,
+        glu_context=1, merger=True, initial_linear=cfg.initial_linear, merger_channels=cfg.merger_channels, gelu=True,
+        batch_norm=True, merger_pos_dim=cfg.merger_pos_dim, n_subjects=cfg.n_subjects)
+    model.load_state_dict(p0)
+    model = model.cuda().train()
+    clip = bb.ClipLoss().cuda().train()
+    opt = torch.optim.Adam(model.parameters(), lr=spec["lr"], betas=(0.9, 0.999))
+    recs = [synthetic.SyntheticRecording(s, task["positions"][s]) for s in range(cfg.n_subjects)]
+    d = task["train"]
+    mask = torch.ones(spec["batch"], 1, spec["T"], dtype=torch.bool, device="cuda")
+    losses = []
+    for idx, ban in sched:
+        meg, feats, subj = d["meg"][idx].cuda(), d["feats"][idx].cuda(), d["subj"][idx].cuda()
+        batch = synthetic.SyntheticBatch(meg, subj, [recs[int(s)] for s in d["subj"][idx]])
+        model.merger.ban_centre_override = ban
+        opt.zero_grad(set_to_none=True)
+        loss = clip(model(dict(meg=meg), batch), feats, mask)
+        loss.backward()
+        opt.step()
+        losses.append(loss.detach())
+    losses = [float(v) for v in torch.stack(losses).cpu()]
+    BF.check_tc_status()
+    model.eval()
+    clip.eval()
+    e = task["eval"]
+    ests = []
+    with torch.no_grad():
+        for i in range(0, len(e["meg"]), 256):
+            sl = slice(i, i + 256)
+            meg = e["meg"][sl].cuda()
+            batch = synthetic.SyntheticBatch(meg, e["subj"][sl].cuda(), [recs[int(s)] for s in e["subj"][sl]])
+            ests.append(model(dict(meg=meg), batch))
+    est = torch.cat(ests)
+    labels = torch.arange(len(est))
+    acc = retrieval.retrieval_accuracy(clip, est, e["feats"], labels, labels, topk=(1, 10), batch_size=256)
+    result = dict(task=gold["what"], spec=spec, top10_reference_cpu_oracle=gold["top10"], top10_cuda=acc[10],
+                  top1_reference_cpu_oracle=gold["top1"], top1_cuda=acc[1], first_loss_reference=gold["losses"][0],
+                  first_loss_cuda=losses[0], final_loss_reference=gold["losses"][-1], final_loss_cuda=losses[-1])
+    print("\n[accuracy parity, BASELINE widths]", json.dumps(result))
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "accuracy_parity_full_width.json"), "w") as f:
+            json.dump(result, f, indent=1)
+    assert abs(losses[0] - gold["losses"][0]) < 1e-4 * max(1.0, abs(gold["losses"][0]))
+    assert abs(acc[10] - gold["top10"]) <= 0.005, (acc, gold["top10"])          # +-0.5 pt
+    assert abs(acc[1] - gold["top1"]) <= 0.02, (acc, gold["top1"])

@@ -56,7 +56,7 @@ def _check_grads(model, ref_grads, train, tol):
         if train and "sequence" in name and name.endswith(".0.bias"):
             assert g.abs().max().item() < 1e-4 * wscale + 1e-6, name      # true gradient is 0 (BN follows)
             continue
-        assert rel_err(g, ref) < 5 * tol, (name, rel_err(g, ref))
+        assert rel_err(g, ref) < tol, (name, rel_err(g, ref))
 
 
 @pytest.mark.parametrize("name", GOLDEN_CASES)
@@ -130,104 +130,60 @@ def test_extra_negatives_and_target_offset():
         assert rel_err(e.grad.cpu(), e_ref.grad) < TOL
 
 
-@pytest.mark.parametrize("case", [
-    dict(name="cfg3 audio_mous-like", B=6, C=273, T=360, F=1024, S=8, n_valid=()),
-    dict(name="cfg4 broderick mel", B=6, C=128, T=360, F=120, S=5, n_valid=()),
-    dict(name="cfg5 mixed studies, real T", B=9, C=273, T=343, F=1024, S=6, n_valid=(273, 208, 128, 60)),
-])
-def test_other_baseline_configs_tensor_core_vs_fma(case):
-    """BASELINE.json configs 3-5 at small batch (odd batch, ragged T=343, padded sensors, F=120): tcgen05 path vs the
-    FP32-FMA path of the same library on identical inputs and parameters."""
-    import brainmagick_b200 as bb
-    from brainmagick_b200 import synthetic, functional as BF
-    torch.manual_seed(5)
-    B, C, T, F, S = case["B"], case["C"], case["T"], case["F"], case["S"]
-    kw = dict(hidden=dict(meg=320), batch_norm=True, depth=10, dilation_period=5, kernel_size=3, skip=True,
-              subject_layers=True, subject_dim=0, complex_out=True, glu=2, glu_context=1, merger=True,
-              initial_linear=270, gelu=True, merger_pos_dim=2048)
-    model = bb.SimpleConv(in_channels=dict(meg=C), out_channels=F, n_subjects=S, **kw).cuda().train()
-    clip = bb.ClipLoss().cuda().train()
-    pos = synthetic.normalised_positions(S, C, case["n_valid"], seed=2)
-    subj = torch.randint(0, S, (B,))
-    meg = torch.randn(B, C, T).clamp_(-20, 20)
-    if case["n_valid"]:
-        for b in range(B):
-            meg[b, case["n_valid"][int(subj[b]) % len(case["n_valid"])]:] = 0
-    meg = meg.cuda()
-    cand = torch.randn(B, F, T).cuda()
-    batch = synthetic.make_batch(meg, subj.cuda(), pos, subj.tolist())
-    mask = torch.ones(B, 1, T, dtype=torch.bool, device="cuda")
-    model.merger.ban_centre_override = torch.tensor([0.7, 0.2])
-    state = {k: v.clone() for k, v in model.state_dict().items()}
-    res = []
-    for use_tc in (True, False):
-        model.load_state_dict(state)
-        model.zero_grad(set_to_none=True)
-        model.use_tensor_cores = use_tc
-        est = model(dict(meg=meg), batch)
-        loss = clip(est, cand, mask)
-        loss.backward()
-        torch.cuda.synchronize()
-        BF.check_tc_status()
-        res.append((est.detach().clone(), loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()}))
-    (e1, l1, g1), (e0, l0, g0) = res
-    assert torch.isfinite(e1).all()
-    assert rel_err(e1.cpu(), e0.cpu()) < TOL, case["name"]
-    assert abs(l1 - l0) < TOL * max(1.0, abs(l0))
-    wscale = max(v.norm().item() for k, v in g0.items() if k.endswith("weight"))
-    for name in g0:
-        if "sequence" in name and name.endswith(".0.bias"):
-            assert g1[name].abs().max().item() < 1e-4 * wscale + 1e-6
-            continue
-        assert rel_err(g1[name].cpu(), g0[name].cpu()) < 5 * TOL, (case["name"], name)
+BASELINE_SHAPES = [
+    dict(name="cfg2 gwilliams2022", B=16, C=208, T=360, F=1024, S=27, n_valid=()),
+    dict(name="cfg3 audio_mous", B=12, C=273, T=360, F=1024, S=96, n_valid=()),
+    dict(name="cfg4 broderick2019 mel", B=16, C=128, T=360, F=120, S=19, n_valid=()),
+    dict(name="cfg5 mixed studies, real T", B=13, C=273, T=343, F=1024, S=175, n_valid=(273, 208, 128, 60)),
+]
 
 
-def test_full_size_tensor_core_path_agrees_with_fp32_fma_path():
-    """BASELINE.json configs[1] shapes (208 sensors, T=360, F=1024, hidden 320) at B=32: the tcgen05 (3xTF32) kernels
-    and the FP32-FMA kernels are two independent implementations; estimate, loss and every gradient must agree to
-    the parity bar.  (The oracle cannot run this size in seconds; this is the size-independent cross-check.)"""
-    import brainmagick_b200 as bb
-    from brainmagick_b200 import synthetic, functional as BF
-    torch.manual_seed(3)
-    B, C, T, F, S = 32, 208, 360, 1024, 27
-    kw = dict(hidden=dict(meg=320), batch_norm=True, depth=10, dilation_period=5, kernel_size=3, skip=True,
-              subject_layers=True, subject_dim=0, complex_out=True, glu=2, glu_context=1, merger=True,
-              initial_linear=270, gelu=True, merger_pos_dim=2048)
-    model = bb.SimpleConv(in_channels=dict(meg=C), out_channels=F, n_subjects=S, **kw).cuda().train()
-    clip = bb.ClipLoss().cuda().train()
-    meg = torch.randn(B, C, T).clamp_(-20, 20).cuda()
-    cand = torch.randn(B, F, T).cuda()
-    subj = torch.randint(0, S, (B,))
-    pos = synthetic.normalised_positions(S, C, seed=1)
-    batch = synthetic.make_batch(meg, subj.cuda(), pos, subj.tolist())
-    mask = torch.ones(B, 1, T, dtype=torch.bool, device="cuda")
-    model.merger.ban_centre_override = torch.tensor([0.3, 0.6])
-    state = {k: v.clone() for k, v in model.state_dict().items()}
-    results = []
-    for use_tc in (True, False):
-        model.load_state_dict(state)
-        model.zero_grad(set_to_none=True)
-        model.use_tensor_cores = use_tc
-        est = model(dict(meg=meg), batch)
-        loss = clip(est, cand, mask)
-        loss.backward()
-        torch.cuda.synchronize()
-        BF.check_tc_status()
-        results.append((est.detach().clone(), loss.item(), {n: p.grad.clone() for n, p in model.named_parameters()}))
-    (e1, l1, g1), (e0, l0, g0) = results
-    print(f"estimate rel_err(tc vs fma) = {rel_err(e1.cpu(), e0.cpu()):.2e}; loss {l1:.6f} vs {l0:.6f}")
-    assert rel_err(e1.cpu(), e0.cpu()) < TOL
-    assert abs(l1 - l0) < TOL * max(1.0, abs(l0))
-    wscale = max(v.norm().item() for k, v in g0.items() if k.endswith("weight"))
-    worst = 0.0
-    for name in g0:
+@pytest.mark.parametrize("case", BASELINE_SHAPES, ids=[c["name"].split()[0] for c in BASELINE_SHAPES])
+def test_baseline_shapes_match_oracle(case):
+    """BASELINE.json configs 2-5 at their REAL widths (hidden 320, merger 270, 2048-d positional embedding, F = 1024 / 120,
+    sensors 208 / 273 / 128 / padded mixed studies, T = 360 and the real-training 343) against the oracle restatement of the
+    reference (oracle/bm_oracle.training_step) on the same seeded inputs: estimate, scores, loss, BatchNorm running
+    statistics and EVERY parameter gradient.  The truth is the oracle in fp64; the oracle in fp32 (= what the reference
+    computes) is run beside it to show its own distance from that truth.  Bar: 1e-4 relative on everything (north star),
+    gradients included; the conv biases in front of a training-mode BatchNorm have an exactly-zero true gradient (rounding
+    noise in the reference) and are compared in absolute terms.  Only the batch is small (the CPU oracle needs ~1 s per
+    8 segments); every tensor-core tiling of the full-size model is exercised (all widths are the full ones)."""
+    from oracle import bm_oracle
+    from brainmagick_b200 import synthetic
+    cfg = bm_oracle.Config(in_channels=case["C"], out_channels=case["F"], n_subjects=case["S"])
+    params = bm_oracle.init_state_dict(cfg, seed=21)
+    d = bm_oracle.synthetic_batch(cfg, batch=case["B"], T=case["T"], seed=9, n_valid=case["n_valid"])
+    d["rec_positions"] = synthetic.normalised_positions(cfg.n_subjects, cfg.in_channels, case["n_valid"], seed=4)
+
+    def oracle(dtype):
+        cast = lambda t: t.to(dtype) if t.is_floating_point() else t          # noqa: E731
+        return bm_oracle.training_step({k: cast(v) for k, v in params.items()}, cfg, cast(d["meg"]), cast(d["rec_positions"]),
+                                       d["rec_of_sample"], d["subject_index"], cast(d["candidates"]),
+                                       ban_centre=cast(d["ban_centre"]), training=True)
+    ref64, ref32 = oracle(torch.float64), oracle(torch.float32)
+    model = _build_model(cfg, params)
+    est, loss, scores, probs = _run_step(model, cfg, d, True)
+    e_est, e_sc = rel_err(est, ref64["estimate"]), rel_err(scores, ref64["scores"])
+    print(f"[{case['name']}] estimate {e_est:.2e} (oracle fp32: {rel_err(ref32['estimate'], ref64['estimate']):.2e}), "
+          f"scores {e_sc:.2e}, loss {loss.item():.6f} vs {ref64['loss'].item():.6f}")
+    assert e_est < TOL and e_sc < TOL
+    assert abs(loss.item() - ref64["loss"].item()) < TOL * max(1.0, abs(ref64["loss"].item()))
+    sd = model.state_dict()
+    for key, v in ref64["bn_updates"].items():
+        assert rel_err(sd[key].cpu(), v) < TOL, key
+    wscale = max(v.norm().item() for k, v in ref64["grads"].items() if k.endswith("weight") and v.numel())
+    worst, worst32 = ("", 0.0), 0.0
+    for name, p in model.named_parameters():
+        g, r64, r32 = p.grad.detach().cpu(), ref64["grads"][name], ref32["grads"][name]
         if "sequence" in name and name.endswith(".0.bias"):
-            assert g1[name].abs().max().item() < 1e-4 * wscale + 1e-6
+            assert g.abs().max().item() < 1e-4 * wscale + 1e-6, name                 # true gradient is 0 (BatchNorm follows)
             continue
-        e = rel_err(g1[name].cpu(), g0[name].cpu())
-        worst = max(worst, e)
-        assert e < 5 * TOL, (name, e)
-    print(f"worst gradient rel_err(tc vs fma) = {worst:.2e}")
+        e = rel_err(g, r64)
+        worst32 = max(worst32, rel_err(r32, r64))
+        if e > worst[1]:
+            worst = (name, e)
+        assert e < TOL, (case["name"], name, e)
+    print(f"[{case['name']}] worst gradient {worst[1]:.2e} ({worst[0]}); the fp32 oracle's own worst: {worst32:.2e}")
 
 
 @pytest.mark.parametrize("Bn,Bc", [(256, 256), (64, 512), (100, 256)])
