@@ -49,8 +49,7 @@ SIGNATURES = {
     "bm_tc_conv_supported": [I, I, I, I, I],
     "bm_tc_weight_split": [P, I, I, I, P, P, P, P, P],
     "bm_tc_conv1d": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
-    "bm_tc_conv3_supported": [I, I, I, I, I],
-    "bm_tc_conv1d_pair": [P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
+    "bm_tc_conv1d_persistent_supported": [I, I, I, I, I],
     "bm_tc_conv1d_persistent": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_channel_mask": [P, P, I, I, I, P, P],

@@ -6,7 +6,6 @@
 #include "gemm_simt.cuh"
 #include "tc_conv.cuh"
 #include "tc_wgrad.cuh"
-#include "tc_conv3.cuh"
 #include "tc_clip.cuh"
 #include "tc_convp.cuh"
 #include "tc_wgradp.cuh"
@@ -924,29 +923,9 @@ extern "C" int bm_gelu_bwd(const float* dq, const float* h, long long n, float* 
     return 0;
 }
 
-// third-generation conv kernel: CTA pairs (tcgen05 cta_group::2); same contract as bm_tc_conv1d with pre-split weights
-extern "C" int bm_tc_conv3_supported(int T, int Cin, int Ntot, int Kw, int glu) {
-    return tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
+extern "C" int bm_tc_conv1d_persistent_supported(int T, int Cin, int Ntot, int Kw, int glu) {
+    return tc::conv_pp_supported(T, Cin, Ntot, Kw, glu) ? 1 : 0;
 }
-extern "C" int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, const float* bias,
-                                 const float* addend, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
-                                 int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, double* stats,
-                                 int* status, bm_stream_t stream) {
-    BM_CHECK_ARG(x && w_hi && w_lo && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
-    BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
-    BM_CHECK_ARG(!(glu && (act || out_tmajor || aux)));
-    BM_CHECK_ARG(tc::conv_tc3_supported(T, Cin, Ntot, Kw, glu));
-    tc::Conv3P q;
-    q.B = B; q.T = T; q.Cin = Cin; q.Ntot = Ntot; q.taps = Kw; q.dilation = dilation; q.sign = sign; q.glu = glu;
-    q.nh = 0; q.act = act; q.out_tmajor = out_tmajor; q.bias = bias; q.addend = addend; q.y = y; q.aux = aux;
-    q.glu_out = glu_out; q.err = status; q.stats = stats;
-    if (q.stats) {
-        BM_CHECK_ARG(!glu && !act && !aux && !out_tmajor && !addend);
-        BM_CUDA(cudaMemsetAsync(q.stats, 0, sizeof(double) * 2 * Ntot, ST(stream)));
-    }
-    return tc::launch_conv_tc3(x, w_hi, w_lo, q, ST(stream));
-}
-
 // persistent CTA-pair kernel (csrc/tc_convp.cuh): w_raw = the RAW fp32 weights re-laid K-major [Kw][Ntot][Cin]
 // (bm_tc_weight_split with f_lo / g_lo = NULL); accumulate=1: y += conv (in place, TMA reduce-add)
 extern "C" int bm_tc_conv1d_persistent(const float* x, const float* w_raw, const float* bias, int accumulate, int B, int T,

@@ -20,7 +20,7 @@
 //   outputs: partial scores [ks][Bn][Bc] (transposed store is the coalesced one: lane = candidate) and [ks][Bc] fp64
 //   partial sums of squares; `clip_finalize_kernel` reduces both in a fixed order (deterministic).
 #pragma once
-#include "tc_conv3.cuh"
+#include "tc_pair.cuh"
 
 namespace bm {
 namespace tc {
@@ -221,10 +221,13 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             ok = mbar_wait(&part_full[pp], (uint32_t)(c >> 1) & 1, p.err, 67);
             tc_fence_after();
             const bool last = c + 1 == nchains;
+            const float comp = acc_trunc_comp(min(CL_CHAIN, total - c * CL_CHAIN) * (CL_BK / 8) * 3);
 #pragma unroll 1
             for (int j = 0; j < nt / 32; ++j) {
                 float a[32];
                 tmem_ld32(tq + pp * CL_PART_COLS + j * 32, a);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) a[i] *= comp;
                 if (c > 0) {
                     float r[32];
                     tmem_ld32(tq + CL_RUN_COL + j * 32, r);

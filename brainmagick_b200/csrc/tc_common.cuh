@@ -156,6 +156,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// The tensor core's fp32 accumulator TRUNCATES toward zero on every tcgen05.mma addition.  Measured on B200
+// (profiles/accumulator_gain_probe.py, kind::tf32, 3xTF32 chains of 120 ... 720 additions, random-sign and all-positive
+// data alike): the result is the true sum times (1 - 1.66e-8 * n_additions) plus a residual half that size -- a systematic
+// GAIN, which compounds through the ~25 chained contractions of a backward pass (8.7e-5 on the deepest gradients).  Every
+// epilogue multiplies the accumulator it drains by acc_trunc_comp(n_additions), the inverse of that expected gain.
+constexpr float TC_ACC_TRUNC_PER_ADD = 1.66e-8f;
+__host__ __device__ __forceinline__ float acc_trunc_comp(int n_additions) { return 1.0f + TC_ACC_TRUNC_PER_ADD * (float)n_additions; }
+
 // fp32 -> (hi, lo) with hi = rna_tf32(x) and lo = rna_tf32(x - hi): x*y ~= hi*hi' + lo*hi' + hi*lo' to ~2^-21
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;

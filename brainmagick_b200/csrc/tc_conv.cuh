@@ -162,6 +162,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int t = t0 + q * 32 + lane;
         const bool valid = t < p.T;
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        const float comp = acc_trunc_comp(total * (CV_BK / 8) * 3);          // additions chained into the accumulator
         if (!p.glu) {
             const int n0 = n_tile * p.bn;
             const long long off = ((long long)b * p.T + t) * p.Ntot + n0;
@@ -169,6 +170,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = 0; c < p.bn / 16; ++c) {
                 float v[16];
                 tmem_ld16(tq + c * 16, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= comp;
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
@@ -200,6 +203,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float a[16], g[16];
                 tmem_ld16(tq + c * 16, a);
                 tmem_ld16(tq + CV_BN / 2 + c * 16, g);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { a[j] *= comp; g[j] *= comp; }
                 if (valid) {
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {

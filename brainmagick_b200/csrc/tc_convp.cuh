@@ -2,7 +2,7 @@
 //
 //   y[p, n] = bias[n] + sum_tap sum_k x[p + shift(tap), k] * W[tap][n][k]        p = b*T + t (channels-last rows)
 //
-// What round 1's pair kernel (tc_conv3.cuh) lost, and what changes here:
+// What round 1's pair kernel (one CTA pair per tile; removed) lost, and what changes here:
 //   * one CTA pair per 256-row tile, 384 tiles on 74 SM pairs = 5.19 waves (13 % idle) and every tile paid the launch,
 //     TMEM allocation, pipeline fill and a fully exposed epilogue        -> the grid is ONE CTA pair per SM pair; each loops
 //     over its tiles with the pipeline (TMA producer, converters) running ahead across tile boundaries, and dedicated
@@ -24,7 +24,7 @@
 //   TMEM: [0, 320) accumulator (two column halves of nh), [320 + 64 s, +64) x stage s (hi | lo).
 //   Accumulation chain per tile: taps * Cin/8 * 3 MMAs (360 at K = 960): the accumulator's truncation stays < 1e-5.
 #pragma once
-#include "tc_conv3.cuh"
+#include "tc_pair.cuh"
 
 namespace bm {
 namespace tc {
@@ -270,6 +270,7 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         uint8_t* buf = epi_smem + ew * PP_EPI_BUF;
         if (lane == 0) { prefetch_tmap(&tmY); prefetch_tmap(&tmO); }
+        const float comp = acc_trunc_comp(per_tile * (PP_BK / 8) * 3);       // additions chained into this accumulator
         int tcount = 0;
         bool ok = true;
         for (int tile = pair; tile < ntiles && ok; tile += npairs, ++tcount) {
@@ -293,6 +294,8 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
                     }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { a[j] *= comp; g[j] *= comp; }
                     if (p.bias) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -324,6 +327,8 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
                     }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= comp;
                     if (p.bias) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -387,8 +392,8 @@ conv_pp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
-inline int conv_pp_pick_nh(int Ntot, int glu) { return conv_tc3_pick_nh(Ntot, glu); }
-inline bool conv_pp_supported(int T, int Cin, int Ntot, int Kw, int glu) { return conv_tc3_supported(T, Cin, Ntot, Kw, glu); }
+inline int conv_pp_pick_nh(int Ntot, int glu) { return pair_pick_nh(Ntot, glu); }
+inline bool conv_pp_supported(int T, int Cin, int Ntot, int Kw, int glu) { return pair_conv_supported(T, Cin, Ntot, Kw, glu); }
 
 // x [R = B*T, Cin] channels-last rows; w_raw [Kw][Ntot][Cin] (fp32, K-major re-layout of the nn.Conv1d weight)
 struct ConvPPArgs {

@@ -238,6 +238,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const WgradP p) {
         for (int c = 0; c < 2 * p.nh / 32; ++c) {
             float v[32];
             tmem_ld32(tq + c * 32, v);
+            {
+                const float comp = acc_trunc_comp(total * (WG_BK / 8) * 3);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= comp;
+            }
             if (total == 0) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0.f;

@@ -25,7 +25,7 @@
 // K slices in a fixed order (deterministic) while scattering into the nn.Conv1d layout [m][n][tap].
 #pragma once
 #include "tc_wgrad.cuh"
-#include "tc_conv3.cuh"
+#include "tc_pair.cuh"
 
 namespace bm {
 namespace tc {
@@ -216,6 +216,9 @@ wgrad_pp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                 float v[32];
                 if (total > 0) {
                     tmem_ld32(tq + c * 32, v);
+                    const float comp = acc_trunc_comp(total * (WP_BK / 8) * 3);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= comp;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0.f;

@@ -133,8 +133,8 @@ class _Conv:
         g = 1 if glu else 0
         # persistent CTA-pair kernel (csrc/tc_convp.cuh) where its tiling fits, else the single-CTA tensor-core kernel,
         # else FP32 FMA
-        self.fwd_pp = allow_tc and USE_CONV_PP and bool(lib.bm_tc_conv3_supported(T, self.cin, self.cout, self.kw, g))
-        self.bwd_pp = allow_tc and USE_CONV_PP and bool(lib.bm_tc_conv3_supported(T, self.cout, self.cin, self.kw, 0))
+        self.fwd_pp = allow_tc and USE_CONV_PP and bool(lib.bm_tc_conv1d_persistent_supported(T, self.cin, self.cout, self.kw, g))
+        self.bwd_pp = allow_tc and USE_CONV_PP and bool(lib.bm_tc_conv1d_persistent_supported(T, self.cout, self.cin, self.kw, 0))
         fwd_tc = self.fwd_pp or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cin, self.cout, self.kw, g)))
         bwd_tc = self.bwd_pp or (allow_tc and bool(lib.bm_tc_conv_supported(T, self.cout, self.cin, self.kw, 0)))
         self.fwd_tc, self.bwd_tc = fwd_tc, bwd_tc
@@ -359,7 +359,7 @@ class _EncoderFn(torch.autograd.Function):
             lib = _lib.load()
             Opad = _round_up(O, 64)
             heads_conv = None
-            if tc and bool(lib.bm_tc_conv3_supported(C, P, Opad, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Opad, P)):
+            if tc and bool(lib.bm_tc_conv1d_persistent_supported(C, P, Opad, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Opad, P)):
                 hpad = torch.zeros((Opad, P, 1), device=meg.device)
                 hpad[:O, :, 0] = heads
                 heads_conv = _Conv(hpad, C, False, True, want_bwd=False)

@@ -49,7 +49,7 @@ int bm_attention_weights_bwd(const float* dweights, const float* weights, const 
                              int P, float* dscores, float* dheads, bm_stream_t stream);
 
 /* K1 in pieces (the two contractions -- scores = emb heads^T and dheads = dscores^T emb -- then run on the tensor-core
- * kernels bm_tc_conv1d_pair(out_tmajor) / bm_tc_wgrad): Fourier embedding, in-place masked softmax, softmax backward. */
+ * kernels bm_tc_conv1d_persistent(out_tmajor) / bm_tc_wgrad): Fourier embedding, in-place masked softmax, softmax backward. */
 int bm_fourier_emb(const float* positions, const float* freq, int R, int C, int P, float* emb, bm_stream_t stream);
 int bm_masked_softmax(float* weights, const float* positions, const float* ban_centre, float radius, int R, int O, int C,
                       bm_stream_t stream);
@@ -75,7 +75,7 @@ int bm_sensor_chain_bwd(const float* dx0, const float* meg, const float* il_w, c
                         float* d_il_b, float* d_weights, bm_stream_t stream);
 
 /* The same chain as separate stages with explicit leading dimensions (u / v / dv / du / x0 may be kept zero-padded to a
- * multiple of 64 channels so that `initial_linear` runs on the tensor-core pointwise kernel, bm_tc_conv1d_pair Kw=1). */
+ * multiple of 64 channels so that `initial_linear` runs on the tensor-core pointwise kernel, bm_tc_conv1d_persistent Kw=1). */
 int bm_sensor_mix_fwd(const float* meg, const float* weights, const int* rec_of_sample, int B, int C, int T, int O,
                       int ld_u, float* u, bm_stream_t stream);
 int bm_initial_linear_fwd(const float* u, int ld_u, const float* il_w, const float* il_b, int B, int T, int O, int IL,
@@ -242,28 +242,21 @@ int bm_tc_weight_split(const float* w, int Cout, int Cin, int Kw, float* f_hi, f
                        float* g_lo, bm_stream_t stream);
 int bm_tc_conv1d(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* addend,
                  int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
-                 float* y, float* aux, float* glu_out, double* stats /* must be NULL: see bm_tc_conv1d_pair */,
+                 float* y, float* aux, float* glu_out, double* stats /* must be NULL: see bm_tc_conv1d_persistent */,
                  int* status, bm_stream_t stream);
 /* act=1: y = GELU(.) and aux (nullable) receives the pre-activation; out_tmajor=1: y is [B,Ntot,T] (the head's
  * channel-major `estimate`).  With Kw=1 this is the pointwise (1x1) contraction of the head (K5).
  * bm_col_stats: stats[0:C] = sum_r y[r,c], stats[C:2C] = sum_r y[r,c]^2 (fp64), the BatchNorm batch statistics. */
 int bm_col_stats(const float* y, long long rows, int C, double* stats, bm_stream_t stream);
-/* third-generation kernel: CTA PAIRS (tcgen05.mma.cta_group::2, M = 256 over two SMs; each CTA holds half of every
- * weight tile, activations go through tensor memory).  Same arithmetic contract and arguments as bm_tc_conv1d with
- * the pre-split (w_hi, w_lo) weights.  Shape gate: Cin % 32 == 0 and Ntot % 320 == 0 or Ntot % 256 == 0 (GLU: H % 160 == 0
- * or H % 128 == 0).  stats (nullable; plain forward only: no glu/act/aux/addend): BatchNorm batch statistics
- * stats[0:Ntot] = sum(y), stats[Ntot:2Ntot] = sum(y^2) (fp64, zeroed by the call), accumulated from the epilogue tiles --
- * replaces the separate bm_col_stats pass over y. */
-int bm_tc_conv3_supported(int T, int Cin, int Ntot, int Kw, int glu);
-int bm_tc_conv1d_pair(const float* x, const float* w_hi, const float* w_lo, const float* bias, const float* addend,
-                      int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor,
-                      float* y, float* aux, float* glu_out, double* stats, int* status, bm_stream_t stream);
-
 /* PERSISTENT CTA-pair kernel (csrc/tc_convp.cuh): one CTA pair per SM pair loops over 256-row tiles of the flattened
  * rows b*T + t (taps that would cross a sample edge read zeros = the conv padding), epilogue warps drain tile i while the
  * operands of tile i+1 are staged.  w_raw: RAW fp32 weights re-laid K-major [Kw][Ntot][Cin] (bm_tc_weight_split with
  * f_lo / g_lo = NULL) -- the tensor core's truncation of the raw operand is the tf32 `hi`, the kernel derives `lo`.
- * accumulate=1: y += conv(x) in place (the skip-path gradient; TMA reduce-add).  Other arguments as bm_tc_conv1d_pair. */
+ * accumulate=1: y += conv(x) in place (the skip-path gradient; TMA reduce-add).  glu / act / out_tmajor / aux / glu_out as
+ * bm_tc_conv1d.  stats (nullable; plain forward only): BatchNorm batch statistics stats[0:Ntot] = sum(y), stats[Ntot:2Ntot]
+ * = sum(y^2) (fp64, zeroed by the call) accumulated in shared memory across the CTA's tiles -- replaces bm_col_stats.
+ * Shape gate (bm_tc_conv1d_persistent_supported): Cin % 32 == 0 and Ntot % 320 == 0 or Ntot % 256 == 0 (GLU: halves). */
+int bm_tc_conv1d_persistent_supported(int T, int Cin, int Ntot, int Kw, int glu);
 int bm_tc_conv1d_persistent(const float* x, const float* w_raw, const float* bias, int accumulate, int B, int T, int Cin,
                             int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor, float* y,
                             float* aux, float* glu_out, double* stats, int* status, bm_stream_t stream);

@@ -373,7 +373,6 @@ class Emulator:
         else:
             _v(y, B, T, Ntot).copy_(out)
 
-    bm_tc_conv1d_pair = bm_tc_conv1d
 
     def bm_tc_conv1d_persistent(self, x, w_raw, bias, accumulate, B, T, Cin, Ntot, Kw, dilation, sign, glu, act, out_tmajor,
                                 y, aux, glu_out, stats, status, stream):

@@ -129,18 +129,12 @@ def test_speed_report(capsys):
     wg = torch.randn(2 * C, C, Kw, device=DEV) / (C * Kw) ** 0.5
     f, g = _raw_operands(w)
     fg, gg = _raw_operands(wg)
-    fh, fl = torch.empty(Kw, C, C, device=DEV), torch.empty(Kw, C, C, device=DEV)
-    call("bm_tc_weight_split", ptr(w), C, C, Kw, ptr(fh), ptr(fl), None, None, stream())
     y = torch.empty(B, T, C, device=DEV)
     h = torch.empty(B, T, 2 * C, device=DEV)
     stats = torch.empty(2 * C, device=DEV, dtype=torch.float64)
     status = torch.zeros(1, dtype=torch.int32, device=DEV)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
     st = stream()
-
-    def k3_old():
-        call("bm_tc_conv1d_pair", ptr(x), ptr(fh), ptr(fl), None, None, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
-             ptr(stats), ptr(status), st)
 
     def k3():
         call("bm_tc_conv1d_persistent", ptr(x), ptr(f), None, 0, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
@@ -159,7 +153,7 @@ def test_speed_report(capsys):
              None, ptr(status), st)
 
     lines = []
-    for name, fn, flops in [("K3 gen3 (round 1)", k3_old, 2.0 * C * C * Kw * T * B), ("K3 persistent +stats", k3, 2.0 * C * C * Kw * T * B),
+    for name, fn, flops in [("K3 persistent +stats", k3, 2.0 * C * C * Kw * T * B),
                             ("K3 dgrad accumulate", k3_acc, 2.0 * C * C * Kw * T * B),
                             ("K4 GLU (h saved)", k4, 4.0 * C * C * Kw * T * B),
                             ("K4 dgrad (K=1920)", k4_dgrad, 4.0 * C * C * Kw * T * B)]:

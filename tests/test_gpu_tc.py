@@ -23,11 +23,12 @@ def _call():
     return _lib.call, _lib.ptr, _lib.stream
 
 
-_FN = {1: "bm_tc_conv1d", 3: "bm_tc_conv1d_pair"}
+_FN = {1: "bm_tc_conv1d"}
 
 
 def _gen_flags(gen):
-    """generation 1 = single-CTA kernel (still used with per-sample weight sets), 3 = the CTA-pair kernel (default)."""
+    """generation 1 = single-CTA kernel (still used with per-sample weight sets); the persistent CTA-pair kernel has its own
+    file, tests/test_gpu_convp.py."""
     from brainmagick_b200 import _lib
     _lib.load().bm_set_debug_flags(0)
 
@@ -39,7 +40,7 @@ def _ref_conv(x, w, bias, dilation):
     return y.permute(0, 2, 1).contiguous()
 
 
-@pytest.mark.parametrize("gen", [1, 3])
+@pytest.mark.parametrize("gen", [1])
 @pytest.mark.parametrize("dilation", [1, 2, 16])
 @pytest.mark.parametrize("T", [360, 343, 100])
 def test_tc_conv_forward(dilation, T, gen):
@@ -66,7 +67,7 @@ def test_tc_conv_forward(dilation, T, gen):
     assert err < TOL, err
 
 
-@pytest.mark.parametrize("gen", [1, 3])
+@pytest.mark.parametrize("gen", [1])
 def test_tc_conv_glu_and_data_gradient(gen):
     call, ptr, stream = _call()
     _gen_flags(gen)
@@ -113,7 +114,7 @@ def test_tc_conv_glu_and_data_gradient(gen):
     assert rel_err(acc.cpu(), ref_dx.cpu()) < TOL
 
 
-@pytest.mark.parametrize("gen", [1, 3])
+@pytest.mark.parametrize("gen", [1])
 def test_tc_conv_speed_report(capsys, gen):
     """Not a pass/fail on speed: prints the per-launch time at the BASELINE shape for the log."""
     call, ptr, stream = _call()
