@@ -9,6 +9,7 @@
 #include "tc_clip.cuh"
 #include "tc_convp.cuh"
 #include "tc_wgradp.cuh"
+#include "tc_gemm_nt.cuh"
 #include "retrieval.cuh"
 #include "prep.cuh"
 #include "convseq.cuh"
@@ -628,6 +629,12 @@ extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const
     BM_CHECK_ARG(probs && inv_norm && cand && gout && G && dest && Bn > 0 && Bc > 0 && KT > 0);
     BM_CHECK_ARG(KT < (1ll << 31));
     cudaStream_t st = ST(stream);
+    if (tc::gemm_nt_pp_supported(Bn, (int)KT, Bc)) {
+        // persistent CTA pairs (csrc/tc_gemm_nt.cuh): dE = G C with G [Bn][Bc], C [Bc][KT]
+        clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 0);
+        BM_CHECK_LAUNCH();
+        return tc::launch_gemm_nt_pp(G, cand, dest, Bn, (int)KT, Bc, status, st);
+    }
     if (tc::wgrad_tc_supported(Bn, (int)KT)) {
         // tensor cores: dE[b][k] = sum_o G^T[o][b] C[o][k]  == weight-gradient GEMM with "positions" = candidates
         clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 1);
@@ -690,8 +697,16 @@ extern "C" int bm_clip_loss_bwd_cand(const float* probs, const float* scores, co
     cudaStream_t st = ST(stream);
     clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 0);
     BM_CHECK_LAUNCH();
-    // dcand[o][k] = sum_b G[b][o] est[b][k]: a weight-gradient GEMM whose "positions" are the estimates
-    if (tc::wgrad_tc_supported(Bc, (int)KT)) {
+    clip_cand_coef_kernel<<<(Bc + 127) / 128, 128, 0, st>>>(G, scores, inv_norm, Bn, Bc, coef);     // needs G as [Bn][Bc]
+    BM_CHECK_LAUNCH();
+    // dcand[o][k] = sum_b G[b][o] est[b][k]
+    if (tc::gemm_nt_pp_supported(Bc, (int)KT, Bn)) {
+        // persistent CTA pairs (csrc/tc_gemm_nt.cuh): A = G^T [Bc][Bn] (rewritten into the same scratch), B = est [Bn][KT]
+        clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 1);
+        BM_CHECK_LAUNCH();
+        int rc = tc::launch_gemm_nt_pp(G, est, dcand, Bc, (int)KT, Bn, status, st);
+        if (rc) return rc;
+    } else if (tc::wgrad_tc_supported(Bc, (int)KT)) {
         int rc = tc::launch_wgrad_tc(G, est, 1, Bn, Bc, (int)KT, (int)KT, 1, 1, dcand, dcand, status, st);   // direct mode
         if (rc) return rc;
     } else {
@@ -702,8 +717,6 @@ extern "C" int bm_clip_loss_bwd_cand(const float* probs, const float* scores, co
         g.D = dcand; g.ldd_m = KT; g.ldd_n = 1;
         BM_CUDA(launch_gemm(g, st));
     }
-    clip_cand_coef_kernel<<<(Bc + 127) / 128, 128, 0, st>>>(G, scores, inv_norm, Bn, Bc, coef);
-    BM_CHECK_LAUNCH();
     clip_cand_correct_kernel<<<ew_grid((long long)Bc * KT), 256, 0, st>>>(cand, coef, KT, (long long)Bc * KT, dcand);
     BM_CHECK_LAUNCH();
     return 0;

@@ -7,9 +7,11 @@
 // Why a kernel of its own (round 1 ran this on the conv kernel with 37-74 K slices): the tensor core's fp32 accumulator
 // TRUNCATES.  One accumulator that chains ~3 700 tcgen05.mma additions of same-signed products (a self dot product, or any
 // well-trained estimate/candidate pair) comes out 1.1e-4 low -- measured: 2.9e-8 relative per addition.  Here a chain is
-// at most CL_CHAIN chunks (64 K-steps, 192 additions, <= 6e-6); chains alternate between two TMEM accumulators and four
-// "drain" warps add each finished chain into an fp32 running sum (round-to-nearest, kept in TMEM as well) while the next
-// chain runs, so the bound costs no tensor-core time.
+// at most CL_CHAIN chunks (128 K-steps, 384 additions; the expected truncation gain is compensated, tc_common.cuh, which
+// leaves <= 5e-6); four "drain" warps add each finished chain into an fp32 running sum (round-to-nearest, kept in tensor
+// memory as well) -- a ~3 % pause of the MMA stream per chain.  (A first version alternated two chain accumulators and left
+// only two tensor-memory slots for the A operand: the converter <-> MMA hand-shake latency was then exposed on every chunk
+// and the MMA thread waited 31 % of the time; four slots and two alternating converter warp sets hide it.)
 //
 //   cluster = 2 CTAs = 256 candidate rows (M side, through TMEM) x NT (64 or 128) estimate rows (N side, smem)
 //   per K chunk of 32, per CTA:  candidates 128 x 32 (16 KB) by TMA -> 4 converter warps: tf32 hi/lo -> TMEM, and the
@@ -25,15 +27,15 @@
 namespace bm {
 namespace tc {
 
-constexpr int CL_BM = 128, CL_BK = 32, CL_STAGES = 4, CL_THREADS = 384;
-constexpr int CL_CHAIN = 16;                                      // chunks per accumulation chain
+constexpr int CL_BM = 128, CL_BK = 32, CL_STAGES = 4, CL_THREADS = 512;
+constexpr int CL_CHAIN = 32;                                      // chunks per accumulation chain
 constexpr int CL_A_BYTES = CL_BM * CL_BK * 4;                     // 16 KB
 constexpr int CL_BH_BYTES = 64 * CL_BK * 4;                       // 8 KB: NT/2 <= 64 estimate rows
 constexpr int CL_STAGE_BYTES = CL_A_BYTES + 2 * CL_BH_BYTES;      // 32 KB
 constexpr int CL_SMEM_BYTES = CL_STAGES * CL_STAGE_BYTES + 1024;
-constexpr int CL_PART_COLS = 128;                                 // TMEM: partial0 | partial1 | running | A slot 0 | A slot 1
-constexpr int CL_RUN_COL = 2 * CL_PART_COLS;
-constexpr int CL_A_COL = 3 * CL_PART_COLS, CL_A_COLS = 2 * CL_BK;
+constexpr int CL_PART_COLS = 128;                                 // TMEM: chain accumulator | running sum | A slots 0..3
+constexpr int CL_RUN_COL = CL_PART_COLS;
+constexpr int CL_A_COL = 2 * CL_PART_COLS, CL_A_COLS = 2 * CL_BK;
 
 struct ClipP {
     int Bn, Bc;               // estimates, candidates
@@ -50,7 +52,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CL_THREADS, 1)
 clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmE, const ClipP p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[CL_STAGES], conv_bar[CL_STAGES], empty_bar[CL_STAGES];
-    __shared__ __align__(8) uint64_t part_full[2], part_empty[2];
+    __shared__ __align__(8) uint64_t part_full, part_empty;
+    __shared__ double ssq_sh[CL_BM];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int prior_error;
 
@@ -84,10 +87,8 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             mbar_init(&conv_bar[s], 2 * (4 + 2));                 // one elected lane per converter warp of both CTAs (LEADER's copy)
             mbar_init(&empty_bar[s], 1);
         }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&part_full[i], 1);
-            mbar_init(&part_empty[i], 2 * 4);                     // one elected lane per drain warp of both CTAs
-        }
+        mbar_init(&part_full, 1);
+        mbar_init(&part_empty, 2 * 4);                            // one elected lane per drain warp of both CTAs
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2sm<512>(&tmem_base_smem);
@@ -122,11 +123,11 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             for (int it = 0; it < total && ok; ++it) {
                 const int s = it % CL_STAGES;
                 const uint32_t ph = (it / CL_STAGES) & 1;
-                const int c = it / CL_CHAIN, pp = c & 1;
+                const int c = it / CL_CHAIN;
                 const bool first = (it - c * CL_CHAIN) == 0;
                 long long c0 = clock64();
-                if (first && c >= 2) {                            // the drain of chain c-2 has left this accumulator
-                    ok = mbar_wait(&part_empty[pp], (uint32_t)((c >> 1) - 1) & 1, p.err, 62);
+                if (first && c >= 1) {                            // the drain of the previous chain has read the accumulator
+                    ok = mbar_wait(&part_empty, (uint32_t)(c - 1) & 1, p.err, 62);
                     if (!ok) break;
                     t_drain += clock64() - c0;
                     c0 = clock64();
@@ -136,8 +137,8 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t b_hi = smem_base + s * CL_STAGE_BYTES + CL_A_BYTES, b_lo = b_hi + CL_BH_BYTES;
-                const uint32_t a_hi = tmem + CL_A_COL + (it & 1) * CL_A_COLS, a_lo = a_hi + CL_BK;
-                const uint32_t d = tmem + pp * CL_PART_COLS;
+                const uint32_t a_hi = tmem + CL_A_COL + s * CL_A_COLS, a_lo = a_hi + CL_BK;
+                const uint32_t d = tmem;
 #pragma unroll
                 for (int kk = 0; kk < CL_BK / 8; ++kk) {
                     const uint64_t dbh = umma_desc_k_sw128(b_hi + kk * 32), dbl = umma_desc_k_sw128(b_lo + kk * 32);
@@ -146,7 +147,7 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                     umma_tf32_ts_2sm(d, a_hi + kk * 8, dbh, idesc, 1);
                 }
                 umma_commit_2sm(&empty_bar[s]);
-                if (it + 1 == total || (it + 1) % CL_CHAIN == 0) umma_commit_2sm(&part_full[pp]);
+                if (it + 1 == total || (it + 1) % CL_CHAIN == 0) umma_commit_2sm(&part_full);
             }
             if (p.dbg) {
                 p.dbg[blockIdx.x * 8 + 0] = t_conv; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_drain;
@@ -177,19 +178,21 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
         }
-    } else if (warp < 8) {
+    } else if (warp < 12) {
         // ------------------------------------------------ candidate rows -> TMEM (hi | lo), sum of squares -------------
+        // two sets of four warps take alternate chunks (a set's ~780 cycles per chunk would otherwise equal the MMA time)
+        const int set = (warp - 4) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         double ssq = 0.0;
         bool ok = true;
         long long t_full = 0, t_slot = 0, t_work = 0;
-        for (int it = 0; it < total && ok; ++it) {
+        for (int it = set; it < total && ok; it += 2) {
             const int s = it % CL_STAGES;
             const uint32_t ph = (it / CL_STAGES) & 1;
             const long long c0 = clock64();
-            ok = mbar_wait(&full_bar[s], ph, p.err, 65);
+            ok = mbar_wait(&full_bar[s], ph, p.err, 65);      // the stage is loaded => the MMAs that read TMEM slot s are done
             const long long c1 = clock64();
             t_full += c1 - c0;
             const uint8_t* arow = smem + s * CL_STAGE_BYTES + row * 128;
@@ -204,15 +207,11 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             }
             ssq += (double)sq;
             const long long c2 = clock64();
-            if (it >= 2) {                                        // TMEM slot it&1 is free once the MMAs of chunk it-2 are done
-                const int s2 = (it - 2) % CL_STAGES;
-                ok = ok && mbar_wait(&empty_bar[s2], (uint32_t)((it - 2) / CL_STAGES) & 1, p.err, 66);
-                tc_fence_after();
-            }
+            tc_fence_after();
             const long long c3 = clock64();
             t_slot += c3 - c2;
-            tmem_st32(tq + CL_A_COL + (it & 1) * CL_A_COLS, hi);
-            tmem_st32(tq + CL_A_COL + (it & 1) * CL_A_COLS + CL_BK, lo);
+            tmem_st32(tq + CL_A_COL + s * CL_A_COLS, hi);
+            tmem_st32(tq + CL_A_COL + s * CL_A_COLS + CL_BK, lo);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -222,8 +221,11 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
         if (p.dbg && warp == 4 && lane == 0) {
             p.dbg[blockIdx.x * 8 + 2] = t_full; p.dbg[blockIdx.x * 8 + 3] = t_slot; p.dbg[blockIdx.x * 8 + 4] = t_work;
         }
+        // the two sets each hold half of the row's sum of squares: set 1 hands its half over through shared memory
+        if (set == 1) ssq_sh[row] = ssq;
+        asm volatile("bar.sync 1, 256;" ::: "memory");           // the eight converter warps
         const int o = m0 + row;
-        if (p.ssp && n_tile == 0 && o < p.Bc) p.ssp[(long long)ksl * p.Bc + o] = ssq;
+        if (set == 0 && p.ssp && n_tile == 0 && o < p.Bc) p.ssp[(long long)ksl * p.Bc + o] = ssq + ssq_sh[row];
     } else {
         // ------------------------------------------------ drain: running += finished chain (fp32, RN); final store -----
         const int q = warp & 3;
@@ -237,15 +239,14 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
         }
         bool ok = true;
         for (int c = 0; c < nchains && ok; ++c) {
-            const int pp = c & 1;
-            ok = mbar_wait(&part_full[pp], (uint32_t)(c >> 1) & 1, p.err, 67);
+            ok = mbar_wait(&part_full, (uint32_t)c & 1, p.err, 67);
             tc_fence_after();
             const bool last = c + 1 == nchains;
             const float comp = acc_trunc_comp(min(CL_CHAIN, total - c * CL_CHAIN) * (CL_BK / 8) * 3);
 #pragma unroll 1
             for (int j = 0; j < nt / 32; ++j) {
                 float a[32];
-                tmem_ld32(tq + pp * CL_PART_COLS + j * 32, a);
+                tmem_ld32(tq + j * 32, a);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) a[i] *= comp;
                 if (c > 0) {
@@ -266,7 +267,7 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&part_empty[pp]), 0));
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&part_empty), 0));
             }
         }
         tc_fence_before();
