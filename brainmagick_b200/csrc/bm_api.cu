@@ -629,8 +629,10 @@ extern "C" int bm_clip_loss_bwd(const float* probs, const float* inv_norm, const
     BM_CHECK_ARG(probs && inv_norm && cand && gout && G && dest && Bn > 0 && Bc > 0 && KT > 0);
     BM_CHECK_ARG(KT < (1ll << 31));
     cudaStream_t st = ST(stream);
-    if (tc::gemm_nt_pp_supported(Bn, (int)KT, Bc)) {
-        // persistent CTA pairs (csrc/tc_gemm_nt.cuh): dE = G C with G [Bn][Bc], C [Bc][KT]
+    if (tc::gemm_nt_pp_supported(Bn, (int)KT, Bc) && Bn >= 192) {
+        // persistent CTA pairs (csrc/tc_gemm_nt.cuh): dE = G C with G [Bn][Bc], C [Bc][KT].  Its M tile is 256 rows: with
+        // fewer than 192 estimates (cfg3 / cfg5 per-rank batches of 64 / 128) the padding costs more than the single-CTA
+        // kernel below loses (measured 0.47 vs 0.32 ms at 64 x 512, 0.75 vs 0.59 ms at 128 x 1024)
         clip_ce_bwd_kernel<<<ew_grid((long long)Bn * Bc), 256, 0, st>>>(probs, inv_norm, gout, Bn, Bc, target_offset, G, 0);
         BM_CHECK_LAUNCH();
         return tc::launch_gemm_nt_pp(G, cand, dest, Bn, (int)KT, Bc, status, st);
