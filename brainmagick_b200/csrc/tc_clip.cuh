@@ -27,14 +27,14 @@
 namespace bm {
 namespace tc {
 
-constexpr int CL_BM = 128, CL_BK = 32, CL_STAGES = 4, CL_THREADS = 512;
+constexpr int CL_BM = 128, CL_BK = 32, CL_STAGES = 6, CL_TSLOTS = 4, CL_THREADS = 512;
 constexpr int CL_CHAIN = 32;                                      // chunks per accumulation chain
 constexpr int CL_PF_CHUNKS = 8;                                   // K chunks covered by one L2 prefetch box (256 floats = 1 KB per row)
 constexpr int CL_A_BYTES = CL_BM * CL_BK * 4;                     // 16 KB
 constexpr int CL_BH_BYTES = 64 * CL_BK * 4;                       // 8 KB: NT/2 <= 64 estimate rows
 constexpr int CL_STAGE_BYTES = CL_A_BYTES + 2 * CL_BH_BYTES;      // 32 KB
 constexpr int CL_SMEM_BYTES = CL_STAGES * CL_STAGE_BYTES + 1024;
-constexpr int CL_PART_COLS = 128;                                 // TMEM: chain accumulator | running sum | A slots 0..3
+constexpr int CL_PART_COLS = 128;                                 // TMEM: chain accumulator | running sum | A slots 0..3 (six smem stages)
 constexpr int CL_RUN_COL = CL_PART_COLS;
 constexpr int CL_A_COL = 2 * CL_PART_COLS, CL_A_COLS = 2 * CL_BK;
 
@@ -155,7 +155,7 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                 if (!ok) break;
                 tc_fence_after();
                 const uint32_t b_hi = smem_base + s * CL_STAGE_BYTES + CL_A_BYTES, b_lo = b_hi + CL_BH_BYTES;
-                const uint32_t a_hi = tmem + CL_A_COL + s * CL_A_COLS, a_lo = a_hi + CL_BK;
+                const uint32_t a_hi = tmem + CL_A_COL + (it % CL_TSLOTS) * CL_A_COLS, a_lo = a_hi + CL_BK;
                 const uint32_t d = tmem;
 #pragma unroll
                 for (int kk = 0; kk < CL_BK / 8; ++kk) {
@@ -210,7 +210,7 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             const int s = it % CL_STAGES;
             const uint32_t ph = (it / CL_STAGES) & 1;
             const long long c0 = clock64();
-            ok = mbar_wait(&full_bar[s], ph, p.err, 65);      // the stage is loaded => the MMAs that read TMEM slot s are done
+            ok = mbar_wait(&full_bar[s], ph, p.err, 65);
             const long long c1 = clock64();
             t_full += c1 - c0;
             const uint8_t* arow = smem + s * CL_STAGE_BYTES + row * 128;
@@ -225,11 +225,15 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             }
             ssq += (double)sq;
             const long long c2 = clock64();
+            if (it >= CL_TSLOTS) {            // tensor-memory slot it % 4 is free once the MMAs of chunk it-4 have completed
+                const int i4 = it - CL_TSLOTS;
+                ok = ok && mbar_wait(&empty_bar[i4 % CL_STAGES], (uint32_t)(i4 / CL_STAGES) & 1, p.err, 66);
+            }
             tc_fence_after();
             const long long c3 = clock64();
             t_slot += c3 - c2;
-            tmem_st32(tq + CL_A_COL + s * CL_A_COLS, hi);
-            tmem_st32(tq + CL_A_COL + s * CL_A_COLS + CL_BK, lo);
+            tmem_st32(tq + CL_A_COL + (it % CL_TSLOTS) * CL_A_COLS, hi);
+            tmem_st32(tq + CL_A_COL + (it % CL_TSLOTS) * CL_A_COLS + CL_BK, lo);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
