@@ -133,8 +133,9 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer (leader) -----------------------------------------
-        if (leader && lane == 0) {
+        // ------------------------------------------------ MMA issuer (leader): the whole warp walks the loop, one elected
+        // lane issues (see elect_one) ------------------------------------------------------------------------------------
+        if (leader) {
             const uint32_t idesc = umma_idesc_tf32(2 * CL_BM, nt);
             bool ok = true;
             long long t_conv = 0, t_drain = 0, t_begin = clock64();
@@ -146,28 +147,31 @@ clip_scores_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constan
                 long long c0 = clock64();
                 if (first && c >= 1) {                            // the drain of the previous chain has read the accumulator
                     ok = mbar_wait(&part_empty, (uint32_t)(c - 1) & 1, p.err, 62);
-                    if (!ok) break;
                     t_drain += clock64() - c0;
                     c0 = clock64();
                 }
-                ok = mbar_wait(&conv_bar[s], ph, p.err, 63);
+                ok = ok && mbar_wait(&conv_bar[s], ph, p.err, 63);
+                ok = __all_sync(0xffffffffu, ok);
                 t_conv += clock64() - c0;
                 if (!ok) break;
                 tc_fence_after();
-                const uint32_t b_hi = smem_base + s * CL_STAGE_BYTES + CL_A_BYTES, b_lo = b_hi + CL_BH_BYTES;
-                const uint32_t a_hi = tmem + CL_A_COL + (it % CL_TSLOTS) * CL_A_COLS, a_lo = a_hi + CL_BK;
-                const uint32_t d = tmem;
+                if (elect_one()) {
+                    const uint32_t b_hi = smem_base + s * CL_STAGE_BYTES + CL_A_BYTES, b_lo = b_hi + CL_BH_BYTES;
+                    const uint32_t a_hi = tmem + CL_A_COL + (it % CL_TSLOTS) * CL_A_COLS, a_lo = a_hi + CL_BK;
+                    const uint64_t dbh0 = umma_desc_k_sw128(b_hi), dbl0 = umma_desc_k_sw128(b_lo);
 #pragma unroll
-                for (int kk = 0; kk < CL_BK / 8; ++kk) {
-                    const uint64_t dbh = umma_desc_k_sw128(b_hi + kk * 32), dbl = umma_desc_k_sw128(b_lo + kk * 32);
-                    umma_tf32_ts_2sm(d, a_lo + kk * 8, dbh, idesc, (first && kk == 0) ? 0u : 1u);
-                    umma_tf32_ts_2sm(d, a_hi + kk * 8, dbl, idesc, 1);
-                    umma_tf32_ts_2sm(d, a_hi + kk * 8, dbh, idesc, 1);
+                    for (int kk = 0; kk < CL_BK / 8; ++kk) {
+                        const uint64_t dbh = dbh0 + (uint64_t)(kk * 2), dbl = dbl0 + (uint64_t)(kk * 2);   // +32 bytes >> 4
+                        umma_tf32_ts_2sm(tmem, a_lo + kk * 8, dbh, idesc, (first && kk == 0) ? 0u : 1u);
+                        umma_tf32_ts_2sm(tmem, a_hi + kk * 8, dbl, idesc, 1);
+                        umma_tf32_ts_2sm(tmem, a_hi + kk * 8, dbh, idesc, 1);
+                    }
+                    umma_commit_2sm(&empty_bar[s]);
+                    if (it + 1 == total || (it + 1) % CL_CHAIN == 0) umma_commit_2sm(&part_full);
                 }
-                umma_commit_2sm(&empty_bar[s]);
-                if (it + 1 == total || (it + 1) % CL_CHAIN == 0) umma_commit_2sm(&part_full);
+                __syncwarp();
             }
-            if (p.dbg) {
+            if (p.dbg && lane == 0) {
                 p.dbg[blockIdx.x * 8 + 0] = t_conv; p.dbg[blockIdx.x * 8 + 1] = clock64() - t_begin; p.dbg[blockIdx.x * 8 + 6] = t_drain;
             }
         }

@@ -86,6 +86,20 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// One lane of a CONVERGED warp (elect.sync).  Issuing tcgen05.mma from `if (lane == 0)` code makes ptxas wrap every MMA in
+// an ELECT / BRA.U.ANY loop over the active lanes (~45 cycles per instruction: the 12 MMAs of a 768-cycle K chunk of the
+// CLIP kernel then cost 1 000 cycles to issue); with the whole warp in the loop and only the issue under this predicate the
+// MMAs are plainly predicated instructions.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred)::"memory");
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, tf32 inputs, fp32 accumulate; issued by ONE thread.
 __device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
