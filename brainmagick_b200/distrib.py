@@ -7,10 +7,13 @@ like the reference which never converts to SyncBatchNorm), then
   * `all_gather_candidates_with_grad`: the same exchange when a trainable feature model produced the candidates --
     its backward is the reduce-scatter(sum) of the candidate gradients;
   * `sync_gradients`: the reference's gradient all-reduce(avg) (flashy.distrib.sync_model, bm/solver.py:386),
-    done on one flat bucket.
+    done on one flat bucket AFTER the backward pass: the backward's kernels are persistent and own every SM, so an NCCL
+    kernel overlapped with them would push CTA pairs into a second round (see the candidate gather below), costing more
+    than the ~0.3 ms the 36-80 MB all-reduce takes on its own.
 """
 from __future__ import annotations
 
+import os
 import typing as tp
 
 import torch
@@ -116,20 +119,86 @@ def all_gather_candidates_with_grad(candidate: torch.Tensor, uniform: bool = Fal
     return _GatherWithGrad.apply(candidate, counts), sum(counts[:rank()])
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Candidate all-gather over NVLink peer memory, driven by the COPY ENGINES (no SMs)
+# ---------------------------------------------------------------------------------------------------------------------
+# The conv / weight-gradient / CLIP kernels are persistent: one CTA (pair) per SM, all registers and shared memory of the
+# SM.  An NCCL all-gather kernel that runs beside them for milliseconds (3 GB at N = 8) takes a handful of SMs for that
+# whole time, and every persistent launch in that window finds fewer SMs than CTA pairs: the leftover pairs wait for a
+# whole pair to finish its tiles -- a second round, up to 2x per kernel.  So the gather is done without SMs: every rank
+# copies its block into a symmetric-memory buffer (torch.distributed._symmetric_memory: cuMem allocations mapped into
+# every peer), and after a barrier PULLS the other ranks' blocks with cudaMemcpyAsync device-to-device copies, which the
+# copy engines execute over NVLink.  A second barrier tells the owners that their buffer may be overwritten by the next
+# step.  Anything missing (torch without symmetric memory, peers without P2P) falls back to the NCCL all-gather.
+_symm_state: tp.Dict[tp.Any, tp.Any] = {}
+USE_SYMMETRIC_GATHER = os.environ.get("BM_SYMM_GATHER", "1") != "0"      # BM_SYMM_GATHER=0: NCCL all-gather (A/B timing)
+
+
+def _symm_buffers(shape: tp.Tuple[int, ...], device: torch.device):
+    """One symmetric buffer + handle per (shape, device), created collectively on first use (None if unavailable)."""
+    key = (tuple(shape), device)
+    if key in _symm_state:
+        return _symm_state[key]
+    out = None
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD
+        buf = symm_mem.empty(*shape, dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(buf, group.group_name)
+        out = (buf, hdl, torch.cuda.Stream(device=device))
+    except Exception as exc:                                   # pragma: no cover - depends on the installation
+        import warnings
+        warnings.warn(f"symmetric-memory candidate gather unavailable ({type(exc).__name__}: {exc}); using NCCL all-gather")
+    # every rank must take the same branch: agree on availability
+    flag = torch.tensor([1 if out is not None else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        out = None
+    _symm_state[key] = out
+    return out
+
+
 class CandidateGather:
-    """The candidate all-gather started EARLY (it does not depend on the encoder): NCCL moves the blocks over NVLink while
-    the encoder's forward kernels run; `wait()` joins it on the current stream just before the contrastive matmul."""
+    """The candidate all-gather started EARLY (it does not depend on the encoder): the blocks move over NVLink while the
+    encoder's forward kernels run; `wait()` joins it on the current stream just before the contrastive matmul.
+    Uniform per-rank batches on NCCL devices go through symmetric memory and the copy engines (above); ragged batches and
+    other backends through the (padded) NCCL / gloo all-gather."""
 
     def __init__(self, candidate: torch.Tensor, uniform: bool = False):
         self.source = candidate
         W = world_size()
         n = candidate.shape[0]
+        self.work = self.event = None
         if W == 1:
-            self.out, self.work, self.offset, self.counts, self.block = candidate, None, 0, [n], n
+            self.out, self.offset, self.counts, self.block = candidate, 0, [n], n
             return
         self.counts = [n] * W if uniform else gather_counts(n, candidate.device)
         self.block = max(self.counts)
         self.offset = sum(self.counts[:rank()])
+        ragged = any(c != self.block for c in self.counts)
+        symm = None
+        if USE_SYMMETRIC_GATHER and not ragged and candidate.is_cuda and candidate.dtype == torch.float32 \
+                and dist.get_backend() == "nccl":
+            symm = _symm_buffers(tuple(candidate.shape), candidate.device)
+        if symm is not None:
+            buf, hdl, side = symm
+            r = rank()
+            main = torch.cuda.current_stream()
+            self.out = torch.empty((W * n,) + tuple(candidate.shape[1:]), dtype=candidate.dtype, device=candidate.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                buf.copy_(candidate)                                   # my block, where the peers can read it
+                hdl.barrier(channel=0)                                 # every rank's block is in place
+                for step in range(1, W):
+                    peer = (r - step) % W
+                    self.out[peer * n:(peer + 1) * n].copy_(hdl.get_buffer(peer, candidate.shape, candidate.dtype))
+                self.out[r * n:(r + 1) * n].copy_(candidate)
+                hdl.barrier(channel=1)                                 # every rank has read my block: it may be reused
+                self.event = torch.cuda.Event()
+                self.event.record(side)
+            self.out.record_stream(side)
+            self._src = candidate
+            return
         src = _pad_rows(candidate, self.block)
         self.out = torch.empty((W * self.block,) + tuple(candidate.shape[1:]), dtype=candidate.dtype,
                                device=candidate.device)
@@ -137,6 +206,10 @@ class CandidateGather:
         self._src = src                        # keep the (possibly padded) source alive until the collective is joined
 
     def wait(self) -> tp.Tuple[torch.Tensor, int]:
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
+            self.event = None
+            self._src = None
         if self.work is not None:
             self.work.wait()          # current stream waits for NCCL's stream; the host does not block
             self.work = None
