@@ -78,7 +78,7 @@ class _ConvSequenceFn(torch.autograd.Function):
         if not conv0.fwd_tc and Cp != C0:
             Cp = C0
             conv0 = _Conv(conv_p[0][0], T, False, False, want_bwd=save)
-        x = torch.zeros((B, T, Cp), device=x_in.device) if Cp != C0 else _empty((B, T, C0), x_in)
+        x = _empty((B, T, Cp), x_in)                               # the transpose writes the pad columns as zeros
         call("bm_transpose_nt_ld", ptr(x_in), B, C0, T, Cp, ptr(x), st)
 
         max_c = max(w.shape[0] for w, _, _, _ in conv_p)

@@ -873,16 +873,16 @@ extern "C" int bm_channel_mask(const float* x, const float* mask, int B, int C, 
 extern "C" int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream) {
     BM_CHECK_ARG(in && out && Z > 0 && N > 0 && T > 0 && Z <= 65535);
     dim3 grid((T + 31) / 32, (N + 31) / 32, Z);
-    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T, N);
+    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T, N, N);
     BM_CHECK_LAUNCH();
     return 0;
 }
 
-// same with an output row stride ld_out >= N (columns N..ld_out-1 are left untouched: zero them once for padding)
+// same with an output row stride ld_out >= N; the pad columns N..ld_out-1 are written as zeros
 extern "C" int bm_transpose_nt_ld(const float* in, int Z, int N, int T, int ld_out, float* out, bm_stream_t stream) {
     BM_CHECK_ARG(in && out && Z > 0 && N > 0 && T > 0 && Z <= 65535 && ld_out >= N);
-    dim3 grid((T + 31) / 32, (N + 31) / 32, Z);
-    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T, ld_out);
+    dim3 grid((T + 31) / 32, (ld_out + 31) / 32, Z);
+    transpose_nt_kernel<<<grid, dim3(32, 8), 0, ST(stream)>>>(in, out, N, T, ld_out, ld_out);
     BM_CHECK_LAUNCH();
     return 0;
 }

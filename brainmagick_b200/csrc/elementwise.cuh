@@ -414,7 +414,9 @@ __global__ void channel_mask_kernel(const float* __restrict__ x, const float* __
 }
 
 // in [Z][N][T] -> out [Z][T][N]   (32x32 tiles through shared memory, both sides coalesced)
-__global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int T, int ld_out) {
+__global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int T, int ld_out,
+                                    int n_store) {
+    // n_store = N: plain transpose; n_store = ld_out > N: the pad columns [N, ld_out) are written as zeros
     __shared__ float tile[32][33];
     const long long zoff = (long long)blockIdx.z * N * T;
     const long long zout = (long long)blockIdx.z * T * ld_out;
@@ -429,7 +431,7 @@ __global__ void transpose_nt_kernel(const float* __restrict__ in, float* __restr
 #pragma unroll
     for (int i = threadIdx.y; i < 32; i += 8) {
         int tt = blockIdx.x * 32 + i;
-        if (n < N && tt < T) out[zout + (long long)tt * ld_out + n] = tile[threadIdx.x][i];
+        if (n < n_store && tt < T) out[zout + (long long)tt * ld_out + n] = tile[threadIdx.x][i];
     }
 }
 

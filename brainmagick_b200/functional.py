@@ -392,20 +392,30 @@ class _EncoderFn(torch.autograd.Function):
                 il_conv = _Conv(wpad, T, False, True, want_bwd=save)
                 if not (il_conv.fwd_tc and il_conv.bwd_tc and il_conv.wgrad_tc):
                     il_conv = None
-            x = torch.zeros((B, T, Dp), device=meg.device) if Dp != D else _empty((B, T, D), meg)
+            # u [B,T,Op] and x [B,T,Dp] carry zero pad columns.  The tensor-core contractions write every column (their padded
+            # weight rows are zero), so the buffers only need a fill when an FP32-FMA stage kernel (valid columns only) runs.
+            def _padded(width_pad, width, written_in_full):
+                if width_pad == width or written_in_full:
+                    return _empty((B, T, width_pad), meg)
+                return torch.zeros((B, T, width_pad), device=meg.device)
+
+            lib = _lib.load()
+            Cp = _round_up(C, 128)
+            mix_tc = il_conv is not None and bool(lib.bm_tc_conv_supported(T, Cp, Op, 1, 0)) and \
+                bool(lib.bm_tc_wgrad_supported(Op, Cp))
+            subj_tc = il_conv is not None and (Dp != D or D % 64 == 0) and bool(lib.bm_tc_conv_supported(T, ILp, Dp, 1, 0)) and \
+                bool(lib.bm_tc_conv_supported(T, Dp, ILp, 1, 0)) and bool(lib.bm_tc_wgrad_supported(ILp, Dp))
+            x = _padded(Dp, D, subj_tc)
             if il_conv is not None:
-                u = torch.zeros((B, T, Op), device=meg.device) if Op != O else _empty((B, T, O), meg)
+                u = _padded(Op, O, mix_tc)
                 v = _empty((B, T, ILp), meg)
                 bpad = torch.zeros((ILp,), device=meg.device)
                 bpad[:IL] = il_b
-                lib = _lib.load()
                 # sensor mix on the tensor cores: meg transposed once to channels-last (sensor count padded to 128), then
                 # u = megT @ w[rec]^T is a pointwise contraction with a per-sample weight set (one per recording)
-                Cp = _round_up(C, 128)
-                mix_tc = bool(lib.bm_tc_conv_supported(T, Cp, Op, 1, 0)) and bool(lib.bm_tc_wgrad_supported(Op, Cp))
                 megT = None
                 if mix_tc:
-                    megT = torch.zeros((B, T, Cp), device=meg.device) if Cp != C else _empty((B, T, C), meg)
+                    megT = _empty((B, T, Cp), meg)                 # the transpose writes the pad columns as zeros
                     call("bm_transpose_nt_ld", ptr(meg), B, C, T, Cp, ptr(megT), st)
                     att_pad = torch.zeros((R, Op, Cp), device=meg.device)
                     att_pad[:, :O, :C] = att
@@ -416,8 +426,6 @@ class _EncoderFn(torch.autograd.Function):
                 else:
                     call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(plan.rec_of_sample), B, C, T, O, Op, ptr(u), st)
                 il_conv.forward(u, bpad, B, T, 1, v, None, status)
-                subj_tc = (Dp != D or D % 64 == 0) and bool(lib.bm_tc_conv_supported(T, ILp, Dp, 1, 0)) and \
-                    bool(lib.bm_tc_conv_supported(T, Dp, ILp, 1, 0)) and bool(lib.bm_tc_wgrad_supported(ILp, Dp))
                 if subj_tc:
                     # per-subject weights, zero-padded; forward operand [s][d][p] (K-major in p), tf32-split
                     subj_pad = torch.zeros((S, ILp, Dp), device=meg.device)
@@ -770,7 +778,7 @@ class _EncoderFn(torch.autograd.Function):
             if s["heads_tc"]:
                 Opad = _round_up(O, 64)
                 call("bm_softmax_bwd", ptr(s["att"]), ptr(d_att), R * O, C, ptr(dscores), st)
-                ds_t = torch.zeros((R, C, Opad), device=meg.device)
+                ds_t = _empty((R, C, Opad), meg)                   # pad columns zeroed by the transpose
                 call("bm_transpose_nt_ld", ptr(dscores), R, O, C, Opad, ptr(ds_t), st)
                 dheads = tc_wgrad(ds_t, s["emb"], R, C, Opad, P, P, 1, 1, status)[:O, :, 0].contiguous()
             else:

@@ -294,7 +294,7 @@ int bm_gelu_bwd(const float* dq, const float* h, long long n, float* dh, bm_stre
 int bm_channel_mask(const float* x, const float* mask, int B, int C, int T, float* y, bm_stream_t stream);
 /* in [Z,N,T] (channel-major) -> out [Z,T,N] (channels-last): the gradient of `estimate` enters the head backward. */
 int bm_transpose_nt(const float* in, int Z, int N, int T, float* out, bm_stream_t stream);
-/* same with an output row stride ld_out >= N (pad columns untouched): meg [B,C,T] -> channels-last, channel-padded. */
+/* same with an output row stride ld_out >= N (pad columns written as zeros): meg [B,C,T] -> channels-last, channel-padded. */
 int bm_transpose_nt_ld(const float* in, int Z, int N, int T, int ld_out, float* out, bm_stream_t stream);
 
 #ifdef __cplusplus

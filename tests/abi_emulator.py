@@ -291,7 +291,9 @@ class Emulator:
         _v(out, Z, T, N).copy_(_v(inp, Z, N, T).transpose(1, 2))
 
     def bm_transpose_nt_ld(self, inp, Z, N, T, ld_out, out, stream):
-        _v(out, Z, T, ld_out)[:, :, :N].copy_(_v(inp, Z, N, T).transpose(1, 2))
+        o = _v(out, Z, T, ld_out)
+        o[:, :, :N].copy_(_v(inp, Z, N, T).transpose(1, 2))
+        o[:, :, N:].zero_()
 
     # ---------------------------------------------------------------- K6
     def _scores(self, est, cand, Bn, Bc, KT, inv_norm):
