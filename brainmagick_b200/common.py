@@ -24,6 +24,13 @@ def _find_layout(info):
     return mne.find_layout(info)
 
 
+def _require_cuda_fp32(x: torch.Tensor, who: str) -> None:
+    if x.dtype != torch.float32:
+        raise TypeError(f"brainmagick_b200.{who} computes in fp32, got {x.dtype}")
+    if not x.is_cuda:
+        raise RuntimeError(f"brainmagick_b200.{who} runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+
 class PositionGetter:
     """2-D sensor positions per recording, min-max normalised to [0,1]; INVALID for sensors missing from the
     layout or padded (reference: bm/models/common.py:183-236)."""
@@ -153,7 +160,15 @@ class ChannelMerger(nn.Module):
         return torch.rand(2, device=device)
 
     def forward(self, meg, batch):
-        raise RuntimeError("ChannelMerger is fused into SimpleConv.forward in brainmagick_b200")
+        """Stand-alone call (bm/models/common.py:334-362): [B, C, T] -> [B, chout, T].  Inside SimpleConv the merger is
+        fused into the encoder; this runs the same stage kernels for callers that use the module on its own."""
+        from . import functional as BF
+        _require_cuda_fp32(meg, "ChannelMerger")
+        B, C, T = meg.shape
+        pos, rec_of_sample, rec_order, rec_off = self.position_getter.batch_layout(batch, C, meg.device)
+        freq = self.embedding.frequencies().to(meg.device)
+        return BF.channel_merger_forward(meg, self.heads, pos, rec_of_sample, rec_order, rec_off, freq,
+                                         self.draw_ban_centre(meg.device), float(self.dropout))
 
 
 class ScaledEmbedding(nn.Module):
@@ -187,7 +202,14 @@ class SubjectLayers(nn.Module):
         self.weights.data *= 1 / in_channels ** 0.5
 
     def forward(self, x, subjects):
-        raise RuntimeError("SubjectLayers is fused into SimpleConv.forward in brainmagick_b200")
+        """Stand-alone call (bm/models/common.py:55-58): einsum("bct,bcd->bdt", x, weights[subjects]); inside SimpleConv the
+        layer is fused into the encoder."""
+        from . import functional as BF
+        _require_cuda_fp32(x, "SubjectLayers")
+        n_subjects = self.weights.shape[0]
+        if subjects.numel() and (int(subjects.max()) >= n_subjects or int(subjects.min()) < 0):
+            raise IndexError(f"subject index out of range for {n_subjects} subjects")      # the reference's gather raises too
+        return BF.subject_layers_forward(x, self.weights, subjects.to(device=x.device, dtype=torch.int32).contiguous())
 
     def __repr__(self):
         S, C, D = self.weights.shape

@@ -928,5 +928,88 @@ def clip_loss(estimate, candidate, target_offset: int = 0):
     return _ClipLossFn.apply(estimate, candidate, target_offset)
 
 
+# ----------------------------------------------------------------------------------------------------
+# Stand-alone ChannelMerger.forward / SubjectLayers.forward (bm/models/common.py:334-362, 55-58): inside SimpleConv both are
+# fused into the encoder; called on their own (analysis notebooks, user code) they run the same stage kernels.  Channel-major
+# tensors in and out, like the reference; gradients flow to the parameters (and to `x` for SubjectLayers), not to `meg`.
+# ----------------------------------------------------------------------------------------------------
+class _MergerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, meg, heads, positions, rec_of_sample, rec_order, rec_off, freq, ban_centre, radius: float):
+        meg = meg.contiguous()
+        B, C, T = meg.shape
+        R = positions.shape[0]
+        O, P = heads.shape
+        st = stream()
+        emb, att = _empty((R, C, P), meg), _empty((R, O, C), meg)
+        call("bm_attention_weights_fwd", ptr(positions), ptr(freq), ptr(heads.contiguous()), ptr(ban_centre), float(radius),
+             R, C, O, P, ptr(emb), ptr(att), st)
+        u = _empty((B, T, O), meg)
+        call("bm_sensor_mix_fwd", ptr(meg), ptr(att), ptr(rec_of_sample), B, C, T, O, O, ptr(u), st)
+        out = _empty((B, O, T), meg)
+        call("bm_transpose_nt", ptr(u), B, T, O, ptr(out), st)
+        ctx.save_for_backward(meg, emb, att, rec_order, rec_off)
+        ctx.dims = (B, C, T, R, O, P)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        meg, emb, att, rec_order, rec_off = ctx.saved_tensors
+        B, C, T, R, O, P = ctx.dims
+        st = stream()
+        g = _empty((B, T, O), meg)
+        call("bm_transpose_nt", ptr(gout.contiguous()), B, O, T, ptr(g), st)
+        d_att, dscores, dheads = _empty((R, O, C), meg), _empty((R, O, C), meg), _empty((O, P), meg)
+        call("bm_sensor_mix_bwd", ptr(g), O, ptr(meg), ptr(rec_order), ptr(rec_off), B, C, T, O, R, ptr(d_att), st)
+        call("bm_attention_weights_bwd", ptr(d_att), ptr(att), ptr(emb), R, C, O, P, ptr(dscores), ptr(dheads), st)
+        return None, dheads, None, None, None, None, None, None, None
+
+
+def channel_merger_forward(meg, heads, positions, rec_of_sample, rec_order, rec_off, freq, ban_centre, radius):
+    return _MergerFn.apply(meg, heads, positions, rec_of_sample, rec_order, rec_off, freq, ban_centre, radius)
+
+
+class _SubjectLayersFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weights, subject):
+        x = x.contiguous()
+        B, Cin, T = x.shape
+        S, _, D = weights.shape
+        st = stream()
+        xl = _empty((B, T, Cin), x)
+        call("bm_transpose_nt", ptr(x), B, Cin, T, ptr(xl), st)
+        yl = _empty((B, T, D), x)
+        w = weights.contiguous()
+        call("bm_subject_layers_fwd", ptr(xl), Cin, ptr(w), ptr(subject), B, T, Cin, D, D, ptr(yl), st)
+        out = _empty((B, D, T), x)
+        call("bm_transpose_nt", ptr(yl), B, T, D, ptr(out), st)
+        ctx.save_for_backward(xl, w, subject)
+        ctx.dims = (B, Cin, T, S, D)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        xl, w, subject = ctx.saved_tensors
+        B, Cin, T, S, D = ctx.dims
+        st = stream()
+        g = _empty((B, T, D), xl)
+        call("bm_transpose_nt", ptr(gout.contiguous()), B, D, T, ptr(g), st)
+        order = torch.argsort(subject, stable=True).to(torch.int32)
+        off = torch.zeros(S + 1, dtype=torch.int32, device=xl.device)
+        off[1:] = torch.cumsum(torch.bincount(subject, minlength=S), 0).to(torch.int32)
+        dxl, dw = _empty((B, T, Cin), xl), _empty((S, Cin, D), xl)
+        call("bm_subject_layers_bwd", ptr(g), D, ptr(xl), Cin, ptr(w), ptr(subject), ptr(order), ptr(off), B, T, Cin, D, S,
+             Cin, ptr(dxl), ptr(dw), st)
+        dx = _empty((B, Cin, T), xl)
+        call("bm_transpose_nt", ptr(dxl), B, T, Cin, ptr(dx), st)
+        return dx, dw, None
+
+
+def subject_layers_forward(x, weights, subject):
+    return _SubjectLayersFn.apply(x, weights, subject)
+
+
 def library_loaded() -> bool:
     return _lib._lib is not None

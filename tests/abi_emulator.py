@@ -547,6 +547,7 @@ class _Stream:
 @contextlib.contextmanager
 def emulated():
     """Inside this context the drop-in modules run on CPU tensors through the emulator above."""
+    import brainmagick_b200.common as CM
     import brainmagick_b200.convseq as CS
     import brainmagick_b200.functional as BF
     import brainmagick_b200.simpleconv as SC
@@ -572,7 +573,7 @@ def emulated():
                (RT, "call", fake_call), (RT, "ptr", fake_ptr), (RT, "stream", lambda: None),
                (RT, "_device", lambda: torch.device("cpu")),
                (BF, "OVERLAP_WGRAD", False), (SC, "_require_cuda", lambda meg: None),
-               (CS, "_require_cuda", lambda x: None),
+               (CS, "_require_cuda", lambda x: None), (CM, "_require_cuda_fp32", lambda x, who: None),
                (torch.cuda, "current_stream", lambda *a, **k: _Stream())]
     saved = [(mod, name, getattr(mod, name)) for mod, name, _ in patches if hasattr(mod, name)]
     for mod, name, val in patches:

@@ -372,3 +372,45 @@ def test_multi_step_training_state_on_the_emulator():
             assert int(sd[k]) == 4
         elif "running" in k:          # the running mean tracks the (noise-walking) conv bias of the reference: O(lr x steps)
             assert rel_err(sd[k], v.detach()) < 5e-3, (k, rel_err(sd[k], v.detach()))
+
+
+def _standalone_modules_case(device):
+    """ChannelMerger.forward / SubjectLayers.forward called on their own (bm/models/common.py:334-362, 55-58) against the
+    oracle's restatement: values and gradients."""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic
+    from oracle import bm_oracle
+    g = torch.Generator().manual_seed(5)
+    B, C, T, O, P, S, D = 6, 19, 40, 12, 32, 3, 10
+    meg = torch.randn(B, C, T, generator=g)
+    subj = torch.tensor([0, 2, 1, 2, 0, 1])
+    rec_of_sample = torch.tensor([1, 0, 1, 1, 0, 0])
+    pos = synthetic.normalised_positions(2, C, n_valid=(C, C - 3), seed=3)
+    merger = bb.ChannelMerger(O, pos_dim=P, dropout=0.2).train()
+    merger.ban_centre_override = torch.tensor([0.4, 0.6])
+    layer = bb.SubjectLayers(O, D, S)
+    batch = synthetic.make_batch(meg, subj, pos, rec_of_sample)
+    gout = torch.randn(B, D, T, generator=g)
+
+    heads = merger.heads.detach().double().requires_grad_()
+    w = layer.weights.detach().double().requires_grad_()
+    att = bm_oracle.attention_weights(pos.double(), heads, merger.ban_centre_override.double(), 0.2)
+    u = torch.einsum("bct,boc->bot", meg.double(), att[rec_of_sample])
+    want = torch.einsum("bct,bcd->bdt", u, w[subj])
+    want.backward(gout.double())
+
+    merger, layer = merger.to(device), layer.to(device)
+    u_got = merger(meg.to(device), batch)
+    got = layer(u_got, subj.to(device))
+    got.backward(gout.to(device))
+    assert rel_err(u_got.detach().cpu(), u.detach()) < TOL
+    assert rel_err(got.detach().cpu(), want.detach()) < TOL
+    assert rel_err(merger.heads.grad.cpu(), heads.grad) < 5e-5
+    assert rel_err(layer.weights.grad.cpu(), w.grad) < 5e-5
+    with pytest.raises(IndexError):
+        layer(u_got.detach(), torch.full((B,), S, device=device))
+
+
+def test_standalone_merger_and_subject_layers_on_the_emulator():
+    with abi_emulator.emulated():
+        _standalone_modules_case(torch.device("cpu"))

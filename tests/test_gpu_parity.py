@@ -209,3 +209,10 @@ def test_clip_tensor_core_shapes_match_oracle(Bn, Bc):
     assert rel_err(scores.cpu(), bm_oracle.clip_scores(est, cand)) < TOL
     assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
     assert rel_err(e.grad.cpu(), e_ref.grad) < TOL
+
+
+@pytest.mark.gpu
+def test_standalone_merger_and_subject_layers_match_oracle():
+    """ChannelMerger.forward / SubjectLayers.forward on their own (bm/models/common.py:334-362, 55-58) run the stage kernels."""
+    from test_emulated_host_path import _standalone_modules_case
+    _standalone_modules_case(torch.device("cuda"))
