@@ -379,7 +379,7 @@ def also_measured(cfg, model, clip, make_batch, resident, host, n_host, mask, de
 
 
 # ------------------------------------------------------------------------------------------------------
-# kernel rooflines: each kernel alone, CUDA events on the launching stream, L2 flushed between launches
+# kernel rooflines: each kernel alone, back to back over rotating operand sets larger than L2, CUDA events on the launching stream
 # ------------------------------------------------------------------------------------------------------
 def ncu_traffic_bytes(pattern):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from this round's committed `ncu --set full` summary
@@ -402,18 +402,22 @@ def ncu_traffic_bytes(pattern):
         return None
 
 
-def _time_kernel(fn, flush, iters=12, skip=3):
-    times = []
-    for i in range(iters + skip):
-        flush.zero_()                                                   # L2 flush between timed launches
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        torch.cuda.synchronize()
-        if i >= skip:
-            times.append(e0.elapsed_time(e1))
-    return statistics.mean(times)
+def _time_kernel(fns, flush=None, iters=24, skip=4):
+    """Mean duration of one launch, the way the training step runs it: back to back on the launching stream, CUDA events
+    around `iters` launches.  `fns` = the same launch over ROTATING operand sets whose combined footprint is several times
+    the 126 MB L2 (timing rule: inputs larger than L2), so no launch finds its operands cached by the previous one."""
+    if callable(fns):
+        fns = [fns]
+    for i in range(skip):
+        fns[i % len(fns)]()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fns[i % len(fns)]()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
 
 
 def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
@@ -428,9 +432,11 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
     peak_tf, peak_gb = peaks["bf16_tflops"], peaks["hbm_gbs"]
     src = peaks["source"]
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    flush = None
     st = stream()
-    x = torch.randn(B, T, H, device=dev)
+    NSETS = 3                                               # 3 x (118 MB in + >= 118 MB out) per conv launch >> L2
+    xs = [torch.randn(B, T, H, device=dev) for _ in range(NSETS)]
+    x = xs[0]
     w = torch.randn(H, H, Kw, device=dev) * 0.03
     wg = torch.randn(2 * H, H, Kw, device=dev) * 0.03
     f, g = torch.empty(Kw, H, H, device=dev), torch.empty(Kw, H, H, device=dev)
@@ -438,7 +444,8 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
     call("bm_tc_weight_split", ptr(w), H, H, Kw, ptr(f), None, ptr(g), None, st)
     call("bm_tc_weight_split", ptr(wg), 2 * H, H, Kw, ptr(fg), None, None, None, st)
     bias = torch.zeros(H, device=dev)
-    y = torch.empty(B, T, H, device=dev)
+    ys = [torch.empty(B, T, H, device=dev) for _ in range(NSETS)]
+    y = ys[0]
     h = torch.empty(B, T, 2 * H, device=dev)
     stats = torch.empty(2 * H, device=dev, dtype=torch.float64)
 
@@ -455,8 +462,8 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
                     traffic=traffic, algorithmic_bytes=alg_bytes, ms_per_launch=ms,
                     peak_source=src + " copy bandwidth (MEASURED_PEAKS.json)")
 
-    ms = _time_kernel(lambda: call("bm_tc_conv1d_persistent", ptr(x), ptr(f), ptr(bias), 0, B, T, H, H, Kw, 4, 1, 0, 0, 0,
-                                   ptr(y), None, None, ptr(stats), ptr(status), st), flush)
+    ms = _time_kernel([lambda x=x, y=y: call("bm_tc_conv1d_persistent", ptr(x), ptr(f), ptr(bias), 0, B, T, H, H, Kw, 4, 1, 0,
+                                             0, 0, ptr(y), None, None, ptr(stats), ptr(status), st) for x, y in zip(xs, ys)])
     main = tensor_entry("conv_pp_kernel via bm_tc_conv1d_persistent (K3: Conv1d 320->320 k3 d4 + BatchNorm statistics; "
                         "persistent CTA pairs, tcgen05 cta_group::2 kind::tf32, 3xTF32)", ms, 2.0 * H * H * Kw * T * B,
                         2.0 * B * T * H * 4, ncu_traffic_bytes("convp"))
@@ -465,12 +472,12 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
                     "is 1/6 (frac_of_3xtf32_ceiling = achieved / (peak/6))")
     others = []
     try:
-        ms = _time_kernel(lambda: call("bm_tc_conv1d_persistent", ptr(x), ptr(fg), None, 0, B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0,
-                                       ptr(h), None, ptr(y), None, ptr(status), st), flush)
+        ms = _time_kernel([lambda x=x, y=y: call("bm_tc_conv1d_persistent", ptr(x), ptr(fg), None, 0, B, T, H, 2 * H, Kw, 1, 1,
+                                                 1, 0, 0, ptr(h), None, ptr(y), None, ptr(status), st) for x, y in zip(xs, ys)])
         others.append(tensor_entry("conv_pp_kernel GLU mode (K4: Conv1d 320->640 k3 + GLU, h saved)", ms,
                                    4.0 * H * H * Kw * T * B, 4.0 * B * T * H * 4, ncu_traffic_bytes("convp_glu")))
-        ms = _time_kernel(lambda: call("bm_tc_conv1d_persistent", ptr(x), ptr(g), None, 1, B, T, H, H, Kw, 4, -1, 0, 0, 0,
-                                       ptr(y), None, None, None, ptr(status), st), flush)
+        ms = _time_kernel([lambda x=x, y=y: call("bm_tc_conv1d_persistent", ptr(x), ptr(g), None, 1, B, T, H, H, Kw, 4, -1, 0,
+                                                 0, 0, ptr(y), None, None, None, ptr(status), st) for x, y in zip(xs, ys)])
         others.append(tensor_entry("conv_pp_kernel data gradient, y += tile (TMA reduce-add)", ms, 2.0 * H * H * Kw * T * B,
                                    3.0 * B * T * H * 4, ncu_traffic_bytes("convp_acc")))
         # K6: CLIP scores + candidate norms + softmax / CE / mean at the training shape (Bn = local rows, Bc = global rows)
@@ -481,7 +488,7 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
         rl, loss = torch.empty(B, device=dev), torch.empty(1, device=dev)
         ws = torch.empty(max(int(lib.bm_clip_workspace(B, Bc, KT)), 2), device=dev)
         ms = _time_kernel(lambda: call("bm_clip_loss_fwd", ptr(est), ptr(cand), B, Bc, KT, 0, ptr(inv), ptr(sc), ptr(pr),
-                                       ptr(rl), ptr(loss), ptr(ws), ws.numel(), ptr(status), st), flush)
+                                       ptr(rl), ptr(loss), ptr(ws), ws.numel(), ptr(status), st))
         e = tensor_entry(f"clip_scores_kernel + clip_finalize_kernel via bm_clip_loss_fwd (K6: {B} x {Bc} x {KT}, norms and "
                          "softmax/CE fused; split-K CTA pairs, bounded accumulation chains)", ms, 2.0 * B * Bc * KT,
                          4.0 * KT * (B + Bc), ncu_traffic_bytes("clip"))
@@ -492,26 +499,46 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
         others.append(e)
         del est, cand
         # weight gradient (K3 shape)
-        dy = torch.randn(B, T, H, device=dev)
-        wsg = torch.empty(int(lib.bm_tc_wgrad_workspace(B, H, H, Kw)), device=dev)
+        dys = [torch.randn(B, T, H, device=dev) for _ in range(NSETS)]
+        dy = dys[0]
         dw = torch.empty(H, H, Kw, device=dev)
-        ms = _time_kernel(lambda: call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(wsg), ptr(dw), None,
-                                       ptr(status), st), flush)
-        others.append(tensor_entry("wgrad_tc_kernel (+reduce) via bm_tc_wgrad (weight gradient of K3)", ms,
+        # the kernel the training step uses for this layer (functional.tc_wgrad's choice): CTA pairs, rows = (tap, x channel)
+        assert lib.bm_tc_wgrad_conv_supported(T, H, H, Kw)
+        wsg = torch.empty(int(lib.bm_tc_wgrad_conv_workspace(B, T, H, H, Kw)), device=dev)
+        ms = _time_kernel([lambda x=x, dy=dy: call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(wsg), ptr(dw),
+                                                   ptr(status), st) for x, dy in zip(xs, dys)])
+        others.append(tensor_entry("wgrad_pp_kernel (+reduce) via bm_tc_wgrad_conv (weight gradient of K3)", ms,
                                    2.0 * H * H * Kw * T * B, 2.0 * B * T * H * 4, ncu_traffic_bytes("wgrad")))
+        del wsg
+        # ... and of the GLU conv (640 x 320 x 3): the second-largest share of the step after conv_pp
+        dy2 = torch.randn(B, T, 2 * H, device=dev)
+        dw2 = torch.empty(2 * H, H, Kw, device=dev)
+        wsg = torch.empty(int(lib.bm_tc_wgrad_conv_workspace(B, T, 2 * H, H, Kw)), device=dev)
+        ms = _time_kernel([lambda x=x: call("bm_tc_wgrad_conv", ptr(dy2), ptr(x), B, T, 2 * H, H, H, Kw, 1, ptr(wsg), ptr(dw2),
+                                            ptr(status), st) for x in xs])
+        others.append(tensor_entry("wgrad_pp_kernel (+reduce) via bm_tc_wgrad_conv (weight gradient of K4)", ms,
+                                   2.0 * 2 * H * H * Kw * T * B, 3.0 * B * T * H * 4, None))
+        del wsg, dy2, dw2
         # HBM-bound: BatchNorm + GELU (+skip) backward and forward
         gam, bet = torch.ones(H, device=dev), torch.zeros(H, device=dev)
         mean, invstd = torch.zeros(H, device=dev), torch.ones(H, device=dev)
         sums = torch.empty(2 * H, device=dev, dtype=torch.float64)
         dgam, dbet = torch.empty(H, device=dev), torch.empty(H, device=dev)
-        gy = torch.empty(B, T, H, device=dev)
         rows = B * T
-        ms = _time_kernel(lambda: call("bm_bn_gelu_skip_bwd", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), 1,
-                                       rows, H, ptr(sums), ptr(gy), ptr(dgam), ptr(dbet), st), flush)
-        others.append(hbm_entry("bm_bn_gelu_skip_bwd (BatchNorm + GELU backward)", ms, 3.0 * rows * H * 4,
-                                ncu_traffic_bytes("bn_bwd")))
-        ms = _time_kernel(lambda: call("bm_bn_gelu_skip_fwd", ptr(dy), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), ptr(x),
-                                       ptr(gy), rows, H, st), flush)
+        ms = _time_kernel([lambda x=x, dy=dy, gy=gy: call("bm_bn_gelu_skip_bwd", ptr(dy), ptr(x), ptr(mean), ptr(invstd),
+                                                          ptr(gam), ptr(bet), 1, rows, H, ptr(sums), ptr(gy), ptr(dgam),
+                                                          ptr(dbet), st) for x, dy, gy in zip(xs, dys, ys)])
+        e = hbm_entry("bm_bn_gelu_skip_bwd (BatchNorm + GELU backward: reduce pass + apply pass)", ms, 3.0 * rows * H * 4,
+                      ncu_traffic_bytes("bn_bwd"))
+        two = 5.0 * rows * H * 4 / (ms / 1e3) / 1e9
+        e["two_pass_view"] = dict(achieved=two, peak=peak_gb, unit="GB/s", frac=two / peak_gb,
+                                  note="algorithmic = read dy, read x, write dx once (3 arrays); the batch statistics of the "
+                                       "gradient must be complete before any dx is written and 236 MB does not stay in L2, "
+                                       "so the kernel pair necessarily moves 5 arrays (2 reads for the sums, 2 reads + 1 write)")
+        others.append(e)
+        ms = _time_kernel([lambda x=x, dy=dy, gy=gy: call("bm_bn_gelu_skip_fwd", ptr(dy), ptr(mean), ptr(invstd), ptr(gam),
+                                                          ptr(bet), ptr(x), ptr(gy), rows, H, st)
+                           for x, dy, gy in zip(xs, dys, ys)])
         others.append(hbm_entry("bm_bn_gelu_skip_fwd (BatchNorm apply + GELU + skip)", ms, 3.0 * rows * H * 4,
                                 ncu_traffic_bytes("bn_fwd")))
     except Exception as exc:

@@ -231,13 +231,30 @@ def training_step(p, cfg, meg, rec_positions, rec_of_sample, subject_index, cand
 # ------------------------------------------------------------------------------------------------
 # retrieval accuracy (scripts/run_eval_probs.py:237-264 semantics on unique candidates)
 # ------------------------------------------------------------------------------------------------
-def topk_accuracy(estimates, candidates, true_index, k=10, chunk=256):
+def topk_accuracy(estimates, candidates, true_index, k=10, chunk=256, on="probs"):
+    """Top-k segment retrieval (scripts/run_eval_probs.py:237-264: `probs.topk(k)` holds the true segment).
+
+    on="probs" is the reference's literal arithmetic: the fp32 softmax of losses.py:97-102, then topk.  When score gaps
+    exceed ~87 the softmax underflows to exact zeros and topk's choice among the tied zeros is unspecified (see
+    `degenerate_rows`); on="scores" ranks the scores themselves -- the same order wherever the probabilities are distinct."""
     hits = 0
     for i in range(0, len(estimates), chunk):
-        probs = clip_probabilities(estimates[i:i + chunk], candidates)
-        top = probs.topk(k, dim=1).indices
+        vals = clip_scores(estimates[i:i + chunk], candidates)
+        if on == "probs":
+            vals = torch.softmax(vals, dim=1)
+        top = vals.topk(k, dim=1).indices
         hits += (top == true_index[i:i + chunk, None]).any(dim=1).sum().item()
     return hits / len(estimates)
+
+
+def degenerate_rows(estimates, candidates, k=10, chunk=256) -> int:
+    """Rows whose fp32 softmax has fewer than k distinct non-zero probabilities among its k+1 best: there the reference's
+    `probs.topk(k)` is decided by tie-breaking, not by the model."""
+    n = 0
+    for i in range(0, len(estimates), chunk):
+        top = clip_probabilities(estimates[i:i + chunk], candidates).topk(k + 1, dim=1).values
+        n += int((top[:, 1:] == top[:, :-1]).any(dim=1).sum().item())
+    return n
 
 
 # ------------------------------------------------------------------------------------------------

@@ -154,7 +154,11 @@ def test_top10_accuracy_parity_at_baseline_widths():
                 ests_ref.append(bm_oracle.simpleconv_forward(params, cfg, meg, pos_g, subj, subj, False))
         est, est_ref = torch.cat(ests), torch.cat(ests_ref)
         feats_g = e["feats"].cuda()
-        acc_ref = {k: bm_oracle.topk_accuracy(est_ref, feats_g, torch.arange(n_eval, device="cuda"), k=k) for k in (1, 10)}
+        ar = torch.arange(n_eval, device="cuda")
+        acc_ref = {k: bm_oracle.topk_accuracy(est_ref, feats_g, ar, k=k, on="scores") for k in (1, 10)}
+        acc_ref_probs = {k: bm_oracle.topk_accuracy(est_ref, feats_g, ar, k=k, on="probs") for k in (1, 10)}
+        acc_cuda_est_oracle_metric = {k: bm_oracle.topk_accuracy(est, feats_g, ar, k=k, on="scores") for k in (1, 10)}
+        tied = bm_oracle.degenerate_rows(est_ref, feats_g, k=10)
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
     labels = torch.arange(n_eval)
@@ -162,7 +166,12 @@ def test_top10_accuracy_parity_at_baseline_widths():
     e_est = rel_err(est.cpu(), est_ref.cpu())
     result = dict(task=gold["what"], spec=spec, steps=len(sched),
                   same_weights=dict(top10_cuda=acc[10], top10_oracle_ops=acc_ref[10], top1_cuda=acc[1],
-                                    top1_oracle_ops=acc_ref[1], estimate_rel_err=e_est),
+                                    top1_oracle_ops=acc_ref[1], estimate_rel_err=e_est,
+                                    top10_oracle_ops_via_fp32_softmax=acc_ref_probs[10],
+                                    top10_cuda_estimates_oracle_metric=acc_cuda_est_oracle_metric[10],
+                                    rows_decided_by_softmax_ties=tied,
+                                    note="ranking on scores; where the fp32 softmax underflows to tied zeros the reference's "
+                                         "probs.topk is decided by tie-breaking (rows counted above)"),
                   same_recipe=dict(top10_cuda_trained=acc[10], top10_cpu_oracle_trained=gold["top10"], top1_cuda_trained=acc[1],
                                    top1_cpu_oracle_trained=gold["top1"], first_loss_cuda=losses[0],
                                    first_loss_cpu_oracle=gold["losses"][0], final_loss_cuda=losses[-1],
