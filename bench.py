@@ -391,13 +391,14 @@ def ncu_traffic_bytes(pattern):
         return None
     try:
         rows = list(csv.reader(open(files[-1])))
-        hdr, units, vals = rows[0], rows[1], rows[-1]
+        hdr, units, data = rows[0], rows[1], rows[2:]
         tot = 0.0
         for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(name)
             scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[units[i]]
-            tot += float(vals[i]) * scale
-        return tot
+            tot += sum(float(v[i]) for v in data) * scale
+        # one captured launch per row; the BatchNorm backward is a kernel PAIR (reduce + apply) captured once each
+        return tot / (len(data) / 2.0 if pattern == "bn_bwd" else len(data))
     except Exception:
         return None
 

@@ -1,5 +1,5 @@
 """Runs each hot kernel a few times at the BASELINE shape (B=256, T=360, H=320) so that one `ncu --set full`
-capture per kernel is short (which = conv | conv_glu | conv_acc | wgrad | prep | topk | scores | scores_train):   ncu --set full --clock-control none --import-source on -k regex:<name> -s 3 -c 2 \
+capture per kernel is short (which = conv | conv_glu | conv_acc | wgrad | prep | topk | scores | scores_train | bn_bwd | bn_fwd):   ncu --set full --clock-control none --import-source on -k regex:<name> -s 3 -c 2 \
                                -o gpurun_out/prof_<name> python profiles/profile_kernels.py <which>"""
 import os
 import sys
@@ -37,10 +37,10 @@ if which in ("conv", "conv_glu", "conv_acc"):
 elif which == "wgrad":
     dy = torch.randn(B, T, H, device=dev)
     x = torch.randn(B, T, H, device=dev)
-    ws = torch.empty(_lib.load().bm_tc_wgrad_workspace(B, H, H, Kw), device=dev)
+    ws = torch.empty(_lib.load().bm_tc_wgrad_conv_workspace(B, T, H, H, Kw), device=dev)      # -k regex:wgrad_pp_kernel
     dw = torch.empty(H, H, Kw, device=dev)
     for _ in range(6):
-        call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(ws), ptr(dw), None, ptr(status), stream())
+        call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(ws), ptr(dw), ptr(status), stream())
 elif which == "prep":          # -k regex:scale_clamp_crop_kernel   (batch preparation, HBM-bound)
     C, Tm, off, R = 273, 361, 18, 27
     x = torch.randn(B, C, Tm, device=dev)
@@ -82,6 +82,19 @@ elif which == "scores":        # -k regex:clip_scores_kernel           (retrieva
     for _ in range(3):
         call("bm_clip_scores", ptr(est), ptr(cand), Bn, M, KT, 1, ptr(inv), ptr(out), None, ptr(ws), ws.numel(), ptr(status),
              stream())
+elif which in ("bn_bwd", "bn_fwd"):   # -k regex:bn_gelu_bwd_(reduce|apply)_cs_kernel | -k regex:bn_gelu_skip_fwd_cs_kernel
+    rows = B * T
+    dy, x, gy = (torch.randn(B, T, H, device=dev) for _ in range(3))
+    gam, bet = torch.ones(H, device=dev), torch.zeros(H, device=dev)
+    mean, invstd = torch.zeros(H, device=dev), torch.ones(H, device=dev)
+    sums = torch.empty(2 * H, device=dev, dtype=torch.float64)
+    dgam, dbet = torch.empty(H, device=dev), torch.empty(H, device=dev)
+    for _ in range(6):
+        if which == "bn_bwd":
+            call("bm_bn_gelu_skip_bwd", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), 1, rows, H, ptr(sums),
+                 ptr(gy), ptr(dgam), ptr(dbet), stream())
+        else:
+            call("bm_bn_gelu_skip_fwd", ptr(dy), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), ptr(x), ptr(gy), rows, H, stream())
 torch.cuda.synchronize()
 assert int(status.item()) == 0
 print("done", which)
