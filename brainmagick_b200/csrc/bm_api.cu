@@ -8,6 +8,7 @@
 #include "tc_wgrad.cuh"
 #include "tc_clip.cuh"
 #include "tc_convp.cuh"
+#include "tc_convh.cuh"
 #include "tc_wgradp.cuh"
 #include "tc_gemm_nt.cuh"
 #include "retrieval.cuh"
@@ -955,6 +956,33 @@ extern "C" int bm_tc_conv1d_persistent(const float* x, const float* w_raw, const
     a.dilation = dilation; a.sign = sign; a.glu = glu; a.act = act; a.out_tmajor = out_tmajor; a.accumulate = accumulate;
     a.y = y; a.aux = aux; a.glu_out = glu_out; a.stats = stats; a.err = status;
     return tc::launch_conv_pp(a, ST(stream));
+}
+
+// ---- the same conv on the F16 tensor pipe (csrc/tc_convh.cuh): fp32 operands as two fp16 pieces of a power-of-two-scaled
+// tensor.  bm_amax writes the largest magnitude of a tensor into a device float; bm_f16_split prepares the weights
+// (w_raw [Kw][Ntot][Cin] -> fp16 hi / lo copies of w_raw * scale(amax)); the kernel scales x itself.
+extern "C" int bm_amax(const float* x, long long n, float* amax, bm_stream_t stream) {
+    BM_CHECK_ARG(x && amax && n > 0);
+    return tc::launch_amax(x, n, amax, ST(stream));
+}
+extern "C" int bm_f16_split(const float* src, long long n, const float* amax, void* hi, void* lo, bm_stream_t stream) {
+    BM_CHECK_ARG(src && amax && hi && lo && n > 0);
+    return tc::launch_f16_split(src, n, amax, hi, lo, ST(stream));
+}
+extern "C" int bm_tc_conv1d_f16(const float* x, const float* x_amax, const void* w_hi, const void* w_lo, const float* w_amax,
+                                const float* bias, int accumulate, int B, int T, int Cin, int Ntot, int Kw, int dilation,
+                                int sign, int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out,
+                                double* stats, int* status, bm_stream_t stream) {
+    BM_CHECK_ARG(x && x_amax && w_hi && w_lo && w_amax && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
+    BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
+    BM_CHECK_ARG(tc::conv_pp_supported(T, Cin, Ntot, Kw, glu));
+    tc::ConvHPArgs h;
+    tc::ConvPPArgs& a = h.c;
+    a.x = x; a.w_raw = nullptr; a.bias = bias; a.B = B; a.T = T; a.Cin = Cin; a.Ntot = Ntot; a.taps = Kw;
+    a.dilation = dilation; a.sign = sign; a.glu = glu; a.act = act; a.out_tmajor = out_tmajor; a.accumulate = accumulate;
+    a.y = y; a.aux = aux; a.glu_out = glu_out; a.stats = stats; a.err = status;
+    h.x_amax = x_amax; h.w_hi = w_hi; h.w_lo = w_lo; h.w_amax = w_amax;
+    return tc::launch_conv_hp(h, ST(stream));
 }
 
 // pointwise (1x1) contraction with a per-sample weight set (SubjectLayers.forward / its data gradient, common.py:55-58):

@@ -261,6 +261,21 @@ int bm_tc_conv1d_persistent(const float* x, const float* w_raw, const float* bia
                             int Ntot, int Kw, int dilation, int sign, int glu, int act, int out_tmajor, float* y,
                             float* aux, float* glu_out, double* stats, int* status, bm_stream_t stream);
 
+/* The same conv on the F16 tensor pipe (csrc/tc_convh.cuh; replaces the same reference lines as bm_tc_conv1d_persistent:
+ * nn.Conv1d / GLU in bm/models/common.py:107-151, the head's 1x1 convs simpleconv.py:153-168).  Each fp32 operand is
+ * carried as two fp16 pieces (11 + 11 significant bits, like the two tf32 pieces) of the tensor times a power of two that
+ * puts its largest magnitude in [2^14, 2^15): three kind::f16 MMAs per product cost half the tensor-pipe time of three
+ * kind::tf32 MMAs.  bm_amax: amax[0] = max |x[i]| (device float; one HBM pass).  bm_f16_split: hi/lo = fp16 pieces of
+ * src * scale(amax[0]) in the same element order (the weights, once per step, from bm_tc_weight_split's raw K-major
+ * re-layout).  bm_tc_conv1d_f16: arguments as bm_tc_conv1d_persistent with (w_hi, w_lo, w_amax) in place of w_raw and
+ * x_amax = the device float bm_amax wrote for x; same shape gate. */
+int bm_amax(const float* x, long long n, float* amax, bm_stream_t stream);
+int bm_f16_split(const float* src, long long n, const float* amax, void* hi, void* lo, bm_stream_t stream);
+int bm_tc_conv1d_f16(const float* x, const float* x_amax, const void* w_hi, const void* w_lo, const float* w_amax,
+                     const float* bias, int accumulate, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
+                     int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, double* stats, int* status,
+                     bm_stream_t stream);
+
 /* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]
  * for n < Ntrue (x may be channel-padded to N); dy [B,T,M], x [B,T,N] channels-last; dw in nn.Conv1d layout
  * [M][Ntrue][Kw].  workspace: bm_tc_wgrad_workspace() floats (per-batch-slice partial tiles, reduced in a fixed

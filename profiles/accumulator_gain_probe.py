@@ -27,6 +27,28 @@ for (B,T,Cin,Cout,Kw,label) in [(8,360,320,320,3,"K3 fwd n_adds=360"),(8,360,640
         torch.cuda.synchronize()
         ref=torch.nn.functional.conv1d(x.double().permute(0,2,1), w.double(), None, padding=Kw//2).permute(0,2,1)
         probe(label+" "+dist, y, ref)
+# the same conv on the F16 pipe (fp16 pieces), compensation switched off (debug flag 2): gain per tcgen05.mma addition
+lib=_lib.load()
+def f16_ops(x, f):
+    amax=torch.empty(2,device=dev)
+    call("bm_amax", ptr(x), x.numel(), ptr(amax[0:1]), stream()); call("bm_amax", ptr(f), f.numel(), ptr(amax[1:2]), stream())
+    hi=torch.empty(f.shape,device=dev,dtype=torch.float16); lo=torch.empty(f.shape,device=dev,dtype=torch.float16)
+    call("bm_f16_split", ptr(f), f.numel(), ptr(amax[1:2]), ptr(hi), ptr(lo), stream()); return amax,hi,lo
+for flags,tag in ((2,"uncompensated"),(0,"compensated")):
+    lib.bm_set_debug_flags(flags)
+    for (B,T,Cin,Cout,Kw,label) in [(8,360,320,320,3,"f16 K=960 n_adds=180"),(8,360,640,320,3,"f16 K=1920 n_adds=360"),(8,360,320,640,1,"f16 1x1 K=320 n_adds=60"),(8,360,1024,640,1,"f16 1x1 K=1024 n_adds=192")]:
+        for dist in ("randn","gelu-like"):
+            x=torch.randn(B,T,Cin,device=dev)
+            if dist=="gelu-like": x=torch.nn.functional.gelu(x)+x.abs()*0.3
+            w=torch.randn(Cout,Cin,Kw,device=dev)/(Cin*Kw)**0.5
+            f,_=raw(w)
+            amax,hi,lo=f16_ops(x,f)
+            y=torch.empty(B,T,Cout,device=dev)
+            call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, 0, B,T,Cin,Cout,Kw,1,1,0,0,0, ptr(y),None,None,None,ptr(status),stream())
+            torch.cuda.synchronize()
+            ref=torch.nn.functional.conv1d(x.double().permute(0,2,1), w.double(), None, padding=Kw//2).permute(0,2,1)
+            probe(tag+" "+label+" "+dist, y, ref)
+lib.bm_set_debug_flags(0)
 # wgrad pair
 B,T,M,N,Kw=64,360,320,320,3
 dy=torch.randn(B,T,M,device=dev); x=torch.randn(B,T,N,device=dev)

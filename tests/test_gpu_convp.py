@@ -1,6 +1,7 @@
-"""GPU: the persistent CTA-pair conv kernel (csrc/tc_convp.cuh, bm_tc_conv1d_persistent) in every epilogue mode against
-torch's fp64 conv (test-only reference), at the real layer shapes, incl. the flattened-row tiling across sample edges
-(odd batch sizes, T not a multiple of anything) and the BatchNorm statistics out of the epilogue."""
+"""GPU: the persistent CTA-pair conv kernels -- 3xTF32 (csrc/tc_convp.cuh, bm_tc_conv1d_persistent) and the fp16-pieces
+variant on the F16 pipe (csrc/tc_convh.cuh, bm_tc_conv1d_f16) -- in every epilogue mode against torch's fp64 conv (test-only
+reference), at the real layer shapes, incl. the flattened-row tiling across sample edges (odd batch sizes, T not a multiple
+of anything) and the BatchNorm statistics out of the epilogue."""
 import pytest
 import torch
 
@@ -32,13 +33,59 @@ def _ref_conv(x, w, bias, dilation):
     return y.permute(0, 2, 1).contiguous()
 
 
+PIPE = "tf32"
+
+
+@pytest.fixture(params=["tf32", "f16"], autouse=True)
+def pipe(request):
+    global PIPE
+    PIPE = request.param
+    yield request.param
+    PIPE = "tf32"
+
+
+def _f16_operands(x, w_op):
+    """What the host path prepares for bm_tc_conv1d_f16: amax of x, amax + fp16 pieces of the (re-laid) weights."""
+    call, ptr, stream = _abi()
+    amax = torch.empty(2, device=DEV)
+    call("bm_amax", ptr(x), x.numel(), ptr(amax[0:1]), stream())
+    call("bm_amax", ptr(w_op), w_op.numel(), ptr(amax[1:2]), stream())
+    hi = torch.empty(w_op.shape, device=DEV, dtype=torch.float16)
+    lo = torch.empty(w_op.shape, device=DEV, dtype=torch.float16)
+    call("bm_f16_split", ptr(w_op), w_op.numel(), ptr(amax[1:2]), ptr(hi), ptr(lo), stream())
+    return amax, hi, lo
+
+
 def _run(x, w_op, bias, accumulate, B, T, Cin, Ntot, Kw, dil, sign, glu, act, tmajor, y, aux, glu_out, stats):
     call, ptr, stream = _abi()
     status = torch.zeros(1, dtype=torch.int32, device=DEV)
-    call("bm_tc_conv1d_persistent", ptr(x), ptr(w_op), ptr(bias), accumulate, B, T, Cin, Ntot, Kw, dil, sign, glu, act,
-         tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), stream())
+    if PIPE == "f16":
+        amax, hi, lo = _f16_operands(x, w_op)
+        call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), ptr(bias), accumulate, B, T, Cin,
+             Ntot, Kw, dil, sign, glu, act, tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), stream())
+    else:
+        call("bm_tc_conv1d_persistent", ptr(x), ptr(w_op), ptr(bias), accumulate, B, T, Cin, Ntot, Kw, dil, sign, glu, act,
+             tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), stream())
     torch.cuda.synchronize()
     assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
+
+
+@pytest.mark.parametrize("xs,ws,spread", [(1e-6, 1e-3, 0), (3e4, 50.0, 0), (1.0, 1.0, 12), (1e-30, 1e30, 6)])
+def test_operand_ranges(xs, ws, spread):
+    """Operand magnitudes far from 1 and a wide dynamic range inside one tensor (per-channel factors 2^-spread .. 2^spread):
+    the fp16 pieces rely on the per-tensor power-of-two scale, the tf32 pieces on nothing."""
+    torch.manual_seed(11)
+    B, T, Cin, Cout, Kw = 3, 200, 320, 320, 3
+    fac = torch.exp2((torch.rand(Cin, device=DEV) * 2 - 1) * spread)
+    x = torch.randn(B, T, Cin, device=DEV) * fac * xs
+    w = torch.randn(Cout, Cin, Kw, device=DEV) / (Cin * Kw) ** 0.5 * ws
+    f, _ = _raw_operands(w)
+    y = torch.full((B, T, Cout), float("nan"), device=DEV)
+    _run(x, f, None, 0, B, T, Cin, Cout, Kw, 2, 1, 0, 0, 0, y, None, None, None)
+    ref = _ref_conv(x, w, None, 2)
+    e = rel_err(y.cpu(), ref.cpu())
+    print(f"[conv {PIPE} x*{xs:g} w*{ws:g} spread 2^+-{spread}] rel_err vs fp64 = {e:.2e}")
+    assert e < TOL
 
 
 @pytest.mark.parametrize("B,T,dilation", [(3, 360, 1), (3, 360, 16), (5, 343, 2), (2, 100, 4), (1, 40, 8), (7, 361, 16),
@@ -136,27 +183,31 @@ def test_speed_report(capsys):
     flush = torch.empty(256 * 1024 * 1024 // 4, device=DEV)
     st = stream()
 
-    def k3():
-        call("bm_tc_conv1d_persistent", ptr(x), ptr(f), None, 0, B, T, C, C, Kw, 4, 1, 0, 0, 0, ptr(y), None, None,
-             ptr(stats), ptr(status), st)
+    def launcher(xt, w_op, acc, Cin, Ntot, dil, sign, glu, yt, glu_out, stats_t, Bn=B, Tn=T):
+        """A closure that launches ONLY the conv kernel (f16: the operand preparation is done here, once)."""
+        if PIPE == "f16":
+            amax, hi, lo = _f16_operands(xt, w_op)
+            return lambda: call("bm_tc_conv1d_f16", ptr(xt), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, acc, Bn,
+                                Tn, Cin, Ntot, Kw, dil, sign, glu, 0, 0, ptr(yt), None, ptr(glu_out), ptr(stats_t),
+                                ptr(status), st)
+        return lambda: call("bm_tc_conv1d_persistent", ptr(xt), ptr(w_op), None, acc, Bn, Tn, Cin, Ntot, Kw, dil, sign, glu,
+                            0, 0, ptr(yt), None, ptr(glu_out), ptr(stats_t), ptr(status), st)
 
-    def k3_acc():
-        call("bm_tc_conv1d_persistent", ptr(x), ptr(g), None, 1, B, T, C, C, Kw, 4, -1, 0, 0, 0, ptr(y), None, None,
-             None, ptr(status), st)
+    k3 = launcher(x, f, 0, C, C, 4, 1, 0, y, None, stats)
+    k3_acc = launcher(x, g, 1, C, C, 4, -1, 0, y, None, None)
+    k4 = launcher(x, fg, 0, C, 2 * C, 1, 1, 1, h, y, None)
+    k4_dgrad = launcher(h, gg, 0, 2 * C, C, 1, -1, 0, y, None, None)
+    amax_cell = torch.empty(1, device=DEV)
 
-    def k4():
-        call("bm_tc_conv1d_persistent", ptr(x), ptr(fg), None, 0, B, T, C, 2 * C, Kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(y),
-             None, ptr(status), st)
-
-    def k4_dgrad():
-        call("bm_tc_conv1d_persistent", ptr(h), ptr(gg), None, 0, B, T, 2 * C, C, Kw, 1, -1, 0, 0, 0, ptr(y), None, None,
-             None, ptr(status), st)
+    def amax_pass():
+        call("bm_amax", ptr(x), x.numel(), ptr(amax_cell), st)
 
     lines = []
-    for name, fn, flops in [("K3 persistent +stats", k3, 2.0 * C * C * Kw * T * B),
+    for name, fn, flops in [(f"{PIPE} K3 persistent +stats", k3, 2.0 * C * C * Kw * T * B),
                             ("K3 dgrad accumulate", k3_acc, 2.0 * C * C * Kw * T * B),
                             ("K4 GLU (h saved)", k4, 4.0 * C * C * Kw * T * B),
-                            ("K4 dgrad (K=1920)", k4_dgrad, 4.0 * C * C * Kw * T * B)]:
+                            ("K4 dgrad (K=1920)", k4_dgrad, 4.0 * C * C * Kw * T * B),
+                            ("bm_amax over one activation tensor (118 MB)", amax_pass, 0.0)]:
         times = []
         for i in range(13):
             flush.zero_()
@@ -176,13 +227,13 @@ def test_speed_report(capsys):
     fit = []
     for k in (1, 2, 3, 4, 5):
         Bk = 74 * k
+        fn_k = launcher(xs, f, 0, C, C, 4, 1, 0, ys, None, None, Bn=Bk, Tn=Tt)
         times = []
         for i in range(9):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            call("bm_tc_conv1d_persistent", ptr(xs), ptr(f), None, 0, Bk, Tt, C, C, Kw, 4, 1, 0, 0, 0, ptr(ys), None, None,
-                 None, ptr(status), st)
+            fn_k()
             e1.record()
             torch.cuda.synchronize()
             if i >= 3:
