@@ -93,6 +93,7 @@ def _round_up(n, m):
     return (n + m - 1) // m * m
 
 
+USE_CONV_F16 = True    # the persistent conv on the F16 tensor pipe (tc_convh.cuh: fp16 hi/lo pieces, twice the MMA rate of 3xTF32)
 USE_WGRAD_PP = True    # CTA-pair weight-gradient kernel (tc_wgradp.cuh) where its 256-row tiling wastes < 10 %
 
 
@@ -114,6 +115,13 @@ def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None):
     call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(dbias), ptr(status),
          stream())
     return dw
+
+
+def tensor_amax(x: torch.Tensor) -> torch.Tensor:
+    """max |x| as a device float [1] (bm_amax: one pass over x): the F16 pipe's per-tensor scale comes from it."""
+    cell = _empty((1,), x)
+    call("bm_amax", ptr(x), x.numel(), ptr(cell), stream())
+    return cell
 
 
 class _Conv:
@@ -151,20 +159,42 @@ class _Conv:
                 self.g_lo = None if self.bwd_pp else _empty((self.kw, self.cin, self.cout), w)
             call("bm_tc_weight_split", ptr(w), self.cout, self.cin, self.kw, ptr(self.f_hi), ptr(self.f_lo),
                  ptr(self.g_hi), ptr(self.g_lo), st)
+        # F16 pipe: the raw K-major weights once more as fp16 hi/lo pieces of w * 2^k (k from the weights' largest magnitude)
+        self.f_h16 = self.g_h16 = self.w_amax = None
+        if USE_CONV_F16 and (self.fwd_pp or (self.bwd_pp and want_bwd)):
+            src = self.f_hi if self.fwd_pp else self.g_hi
+            self.w_amax = _empty((1,), w)
+            call("bm_amax", ptr(src), src.numel(), ptr(self.w_amax), st)
+            for name, raw_w, on in (("f_h16", self.f_hi, self.fwd_pp), ("g_h16", self.g_hi, self.bwd_pp and want_bwd)):
+                if on:
+                    hi = torch.empty(raw_w.shape, device=w.device, dtype=torch.float16)
+                    lo = torch.empty(raw_w.shape, device=w.device, dtype=torch.float16)
+                    call("bm_f16_split", ptr(raw_w), raw_w.numel(), ptr(self.w_amax), ptr(hi), ptr(lo), st)
+                    setattr(self, name, (hi, lo))
         if (not fwd_tc) or (want_bwd and not bwd_tc):
             self.wf = _empty((self.kw, self.cin, self.cout), w) if not fwd_tc else None
             self.wb = _empty((self.kw, self.cout, self.cin), w) if (want_bwd and not bwd_tc) else None
             call("bm_conv_weight_prep", ptr(w), self.cout, self.cin, self.kw, ptr(self.wf), ptr(self.wb), st)
 
-    def run_tc(self, fwd: bool, x, bias, addend, B, T, dilation, glu, act, tmajor, y, aux, glu_out, stats, status):
+    def run_tc(self, fwd: bool, x, bias, addend, B, T, dilation, glu, act, tmajor, y, aux, glu_out, stats, status,
+               x_amax=None):
         """One tensor-core conv launch: forward taps (fwd) or the data gradient; `addend` must be None or `y` itself
-        (in-place accumulation) on the persistent kernel."""
+        (in-place accumulation) on the persistent kernel.  `x_amax` (F16 pipe): the device float holding max |x| when the
+        producer of x already knows it, else one bm_amax pass here."""
         st = stream()
         if fwd:
             pp, hi, lo, cin, ntot, sign = self.fwd_pp, self.f_hi, self.f_lo, self.cin, self.cout, 1
         else:
             pp, hi, lo, cin, ntot, sign = self.bwd_pp, self.g_hi, self.g_lo, self.cout, self.cin, -1
-        if pp:
+        h16 = self.f_h16 if fwd else self.g_h16
+        if pp and h16 is not None:
+            assert addend is None or addend.data_ptr() == y.data_ptr(), "the persistent kernel accumulates in place only"
+            if x_amax is None:
+                x_amax = tensor_amax(x)
+            call("bm_tc_conv1d_f16", ptr(x), ptr(x_amax), ptr(h16[0]), ptr(h16[1]), ptr(self.w_amax), ptr(bias),
+                 0 if addend is None else 1, B, T, cin, ntot, self.kw, dilation, sign, glu, act, tmajor, ptr(y), ptr(aux),
+                 ptr(glu_out), ptr(stats), ptr(status), st)
+        elif pp:
             assert addend is None or addend.data_ptr() == y.data_ptr(), "the persistent kernel accumulates in place only"
             call("bm_tc_conv1d_persistent", ptr(x), ptr(hi), ptr(bias), 0 if addend is None else 1, B, T, cin, ntot,
                  self.kw, dilation, sign, glu, act, tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), st)

@@ -381,6 +381,39 @@ class Emulator:
         self.bm_tc_conv1d(x, w_raw, None, bias, y if accumulate else None, B, T, Cin, Ntot, Kw, dilation, sign, glu, act,
                           out_tmajor, y, aux, glu_out, stats, status, stream)
 
+    # ---- F16 pipe (csrc/tc_convh.cuh): power-of-two scale from the tensor's amax, operands as fp16 hi + lo pieces ----
+    @staticmethod
+    def _f16_scale(amax: float) -> float:
+        import math
+        if not (amax > 0.0) or math.isinf(amax) or math.isnan(amax):
+            return 1.0
+        e = math.frexp(amax)[1] - 1                       # amax in [2^e, 2^(e+1))
+        if e < -126:                                      # fp32 subnormal: exponent field 0 -> scale 1 (f16_scale_of)
+            return 1.0
+        return 2.0 ** max(-126, min(127, 14 - e))
+
+    def bm_amax(self, x, n, amax, stream):
+        v = _v(x, n).abs()
+        v = v[~torch.isnan(v)]
+        _v(amax, 1).fill_(float(v.max()) if v.numel() else 0.0)
+
+    def bm_f16_split(self, src, n, amax, hi, lo, stream):
+        v = _v(src, n) * self._f16_scale(float(_v(amax, 1)))
+        h = v.to(torch.float16)
+        _v(hi, n).copy_(h)
+        _v(lo, n).copy_((v - h.float()).to(torch.float16))
+
+    def bm_tc_conv1d_f16(self, x, x_amax, w_hi, w_lo, w_amax, bias, accumulate, B, T, Cin, Ntot, Kw, dilation, sign, glu, act,
+                         out_tmajor, y, aux, glu_out, stats, status, stream):
+        sx, sw = self._f16_scale(float(_v(x_amax, 1))), self._f16_scale(float(_v(w_amax, 1)))
+        n = Kw * Ntot * Cin
+        w = (_v(w_hi, n).float() + _v(w_lo, n).float()) / sw            # what the tensor core multiplies by, unscaled
+        xv = _v(x, B * T * Cin) * sx
+        xh = xv.to(torch.float16)
+        xq = (xh.float() + (xv - xh.float()).to(torch.float16).float()) / sx
+        self.bm_tc_conv1d(xq.contiguous(), w.contiguous(), None, bias, y if accumulate else None, B, T, Cin, Ntot, Kw,
+                          dilation, sign, glu, act, out_tmajor, y, aux, glu_out, stats, status, stream)
+
     def bm_col_stats(self, y, rows, C, stats, stream):
         o = _v(y, rows, C).double()
         _v(stats, 2 * C).copy_(torch.cat([o.sum(0), (o * o).sum(0)]))
