@@ -194,12 +194,16 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(n_steps, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for i in range(n_steps):
             fn(i)
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / n_steps      # host time to ENQUEUE a step (no sync inside the loop)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -222,6 +226,7 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     ms_total = timed(args.steps, resident_step)
     launches = _lib.launch_count() - launches0
+    host_ms_value = host_ms[0]        # ~= ms_per_step means the host, not the GPU, paces the step
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step / 1e3)
@@ -310,6 +315,7 @@ def run_b200(args):
                     l2=f"per-step working set (inputs {h2d / 1e6:.0f} MB + ~{act_gb:.1f} GB saved activations) >> 126 MB L2; "
                        "two input batches rotate",
                     last_loss=last_loss[0]),
+        host_enqueue_ms_per_step=host_ms_value,
         clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline, also=also)
     print(json.dumps(out))
 
@@ -526,9 +532,10 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
         sums = torch.empty(2 * H, device=dev, dtype=torch.float64)
         dgam, dbet = torch.empty(H, device=dev), torch.empty(H, device=dev)
         rows = B * T
+        amax = torch.empty(1, device=dev)                     # max |output| for the F16-pipe conv downstream, as in the step
         ms = _time_kernel([lambda x=x, dy=dy, gy=gy: call("bm_bn_gelu_skip_bwd", ptr(dy), ptr(x), ptr(mean), ptr(invstd),
                                                           ptr(gam), ptr(bet), 1, rows, H, ptr(sums), ptr(gy), ptr(dgam),
-                                                          ptr(dbet), st) for x, dy, gy in zip(xs, dys, ys)])
+                                                          ptr(dbet), ptr(amax), st) for x, dy, gy in zip(xs, dys, ys)])
         e = hbm_entry("bm_bn_gelu_skip_bwd (BatchNorm + GELU backward: reduce pass + apply pass)", ms, 3.0 * rows * H * 4,
                       ncu_traffic_bytes("bn_bwd"))
         two = 5.0 * rows * H * 4 / (ms / 1e3) / 1e9
@@ -538,7 +545,7 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
                                        "so the kernel pair necessarily moves 5 arrays (2 reads for the sums, 2 reads + 1 write)")
         others.append(e)
         ms = _time_kernel([lambda x=x, dy=dy, gy=gy: call("bm_bn_gelu_skip_fwd", ptr(dy), ptr(mean), ptr(invstd), ptr(gam),
-                                                          ptr(bet), ptr(x), ptr(gy), rows, H, st)
+                                                          ptr(bet), ptr(x), ptr(gy), rows, H, ptr(amax), st)
                            for x, dy, gy in zip(xs, dys, ys)])
         others.append(hbm_entry("bm_bn_gelu_skip_fwd (BatchNorm apply + GELU + skip)", ms, 3.0 * rows * H * 4,
                                 ncu_traffic_bytes("bn_fwd")))

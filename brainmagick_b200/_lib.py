@@ -32,12 +32,12 @@ SIGNATURES = {
     "bm_conv1d_fwd": [P, P, P, I, I, I, I, I, I, P, P, P],
     "bm_bn_stats_finalize": [P, L, F, F, P, P, P, P, I, P],
     "bm_bn_eval_stats": [P, P, F, P, P, I, P],
-    "bm_bn_gelu_skip_fwd": [P, P, P, P, P, P, P, L, I, P],
-    "bm_bn_gelu_skip_bwd": [P, P, P, P, P, P, I, L, I, P, P, P, P, P],
+    "bm_bn_gelu_skip_fwd": [P, P, P, P, P, P, P, L, I, P, P],
+    "bm_bn_gelu_skip_bwd": [P, P, P, P, P, P, I, L, I, P, P, P, P, P, P],
     "bm_conv1d_bwd_data": [P, P, P, I, I, I, I, I, I, P, P],
     "bm_conv1d_bwd_weight": [P, P, I, I, I, I, I, I, P, P, P],
     "bm_conv1d_glu_fwd": [P, P, P, I, I, I, I, I, P, P, P],
-    "bm_glu_bwd": [P, P, L, I, P, P, P],
+    "bm_glu_bwd": [P, P, L, I, P, P, P, P],
     "bm_head_fwd": [P, P, P, P, P, I, I, I, I, P, P, P, P],
     "bm_head_bwd": [P, P, P, P, P, P, I, I, I, I, P, P, P, P, P, P, P],
     "bm_head_bwd_params": [P, P, P, P, I, I, I, I, P, P, P, P, P, P],
@@ -53,7 +53,7 @@ SIGNATURES = {
     "bm_tc_conv1d_persistent": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_amax": [P, L, P, P],
     "bm_f16_split": [P, L, P, P, P, P],
-    "bm_tc_conv1d_f16": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
+    "bm_tc_conv1d_f16": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_channel_mask": [P, P, I, I, I, P, P],
     "bm_transpose_nt": [P, I, I, I, P, P],

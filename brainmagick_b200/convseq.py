@@ -41,7 +41,7 @@ class SequencePlan(tp.NamedTuple):
 def _epilogue_fwd(plan: SequencePlan, y, mean, invstd, gamma, beta, x_old, x_new, rows, C, act):
     if plan.batch_norm and act == ACT_GELU:       # the encoder's tuned BatchNorm+GELU(+skip) kernel
         call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(x_old), ptr(x_new), rows, C,
-             stream())
+             None, stream())
     else:
         call("bm_bn_act_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(x_old), ptr(x_new), rows, C,
              act, float(plan.act_slope), stream())
@@ -158,7 +158,7 @@ class _ConvSequenceFn(torch.autograd.Function):
                 gconv: _Conv = rec["gconv"]
                 dh = _empty((B, T, gconv.cout), dout)
                 dgb = torch.empty((gconv.cout,), device=dout.device, dtype=torch.float32)
-                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), ptr(dgb), st)
+                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), ptr(dgb), None, st)
                 glu_grads[k] = gconv.backward_weight(dh, rec["x_new"], B, T, 1, dout, status, known_dbias=dgb)
                 g = _empty((B, T, gconv.cin), dout)
                 gconv.backward_data(dh, None, B, T, 1, g, status)
@@ -170,7 +170,7 @@ class _ConvSequenceFn(torch.autograd.Function):
                 if rec["act"] == ACT_GELU:
                     call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                          ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
-                         ptr(dy), ptr(dgamma), ptr(dbeta), st)
+                         ptr(dy), ptr(dgamma), ptr(dbeta), None, st)
                 else:
                     call("bm_bn_act_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                          ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout,

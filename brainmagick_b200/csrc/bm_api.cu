@@ -300,17 +300,26 @@ extern "C" int bm_bn_eval_stats(const float* running_mean, const float* running_
     return 0;
 }
 
+// amax_out (nullable, every producer below): a device float that receives max |output| -- the scale source of the F16-pipe
+// conv that consumes the tensor next (bm_tc_conv1d_f16's x_amax), folded into the producing kernel instead of a bm_amax pass
+static int amax_begin(float* amax_out, cudaStream_t st) {
+    if (amax_out) BM_CUDA(cudaMemsetAsync(amax_out, 0, sizeof(float), st));
+    return 0;
+}
+
 extern "C" int bm_bn_gelu_skip_fwd(const float* y, const float* mean, const float* invstd, const float* gamma,
                                    const float* beta, const float* x_old, float* x_new, long long rows, int C,
-                                   bm_stream_t stream) {
+                                   float* amax_out, bm_stream_t stream) {
     BM_CHECK_ARG(y && mean && invstd && gamma && beta && x_new && rows > 0 && C > 0);
     long long total = rows * C;
+    if (int rc = amax_begin(amax_out, ST(stream))) return rc;
     bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x_new) |
                                  reinterpret_cast<uintptr_t>(x_old)) % 16 == 0);
     if (vec && C / 4 <= 256 && aligned16(mean, invstd, gamma) && aligned16(beta)) {
         const int cx = C / 4, ry = std::max(1, 320 / cx);
         const unsigned nblk = (unsigned)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
-        bn_gelu_skip_fwd_cs_kernel<<<nblk, dim3(cx, ry), 0, ST(stream)>>>(y, mean, invstd, gamma, beta, x_old, x_new, rows, C);
+        bn_gelu_skip_fwd_cs_kernel<<<nblk, dim3(cx, ry), 0, ST(stream)>>>(y, mean, invstd, gamma, beta, x_old, x_new, rows, C,
+                                                                          reinterpret_cast<unsigned int*>(amax_out));
         BM_CHECK_LAUNCH();
         return 0;
     }
@@ -321,15 +330,18 @@ extern "C" int bm_bn_gelu_skip_fwd(const float* y, const float* mean, const floa
         bn_gelu_skip_fwd_kernel<1><<<ew_grid(total), 256, 0, ST(stream)>>>(y, mean, invstd, gamma, beta, x_old,
                                                                           x_new, total, C);
     BM_CHECK_LAUNCH();
+    if (amax_out) return tc::launch_amax(x_new, total, amax_out, ST(stream));
     return 0;
 }
 
 extern "C" int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* mean, const float* invstd,
                                    const float* gamma, const float* beta, int batch_stats, long long rows, int C,
-                                   double* sums, float* dy, float* dgamma, float* dbeta, bm_stream_t stream) {
+                                   double* sums, float* dy, float* dgamma, float* dbeta, float* amax_out,
+                                   bm_stream_t stream) {
     BM_CHECK_ARG(g && y && mean && invstd && gamma && beta && sums && dy && dgamma && dbeta && rows > 0 && C > 0);
     cudaStream_t st = ST(stream);
     BM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    if (int rc = amax_begin(amax_out, st)) return rc;
     const long long total = rows * C;
     const bool vec = (C % 4 == 0) && aligned16(g, y, dy) && aligned16(mean, invstd, gamma) && aligned16(beta);
     if (vec && C / 4 <= 256 && aligned16(dgamma, dbeta)) {
@@ -341,7 +353,8 @@ extern "C" int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* 
         bn_param_grad_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, dgamma, dbeta, C);
         BM_CHECK_LAUNCH();
         bn_gelu_bwd_apply_cs_kernel<<<nblk, dim3(cx, ry), 0, st>>>(g, y, mean, invstd, gamma, beta, dgamma, dbeta,
-                                                                   (float)(1.0 / (double)rows), batch_stats, dy, rows, C);
+                                                                   (float)(1.0 / (double)rows), batch_stats, dy, rows, C,
+                                                                   reinterpret_cast<unsigned int*>(amax_out));
         BM_CHECK_LAUNCH();
         return 0;
     }
@@ -363,6 +376,7 @@ extern "C" int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* 
         bn_gelu_bwd_apply_kernel<<<ew_grid(total), 256, 0, st>>>(g, y, mean, invstd, gamma, beta, sums, (double)rows,
                                                                batch_stats, dy, total, C);
     BM_CHECK_LAUNCH();
+    if (amax_out) return tc::launch_amax(dy, total, amax_out, st);
     return 0;
 }
 
@@ -408,14 +422,16 @@ extern "C" int bm_conv1d_glu_fwd(const float* x, const float* wf, const float* b
 }
 
 extern "C" int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh, float* dbias,
-                          bm_stream_t stream) {
+                          float* amax_out, bm_stream_t stream) {
     BM_CHECK_ARG(g && h && dh && rows > 0 && H > 0);
     cudaStream_t st = ST(stream);
     if (dbias) BM_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * 2 * H, st));
+    if (int rc = amax_begin(amax_out, st)) return rc;
     if (H % 4 == 0 && H / 4 <= 256 && aligned16(g, h, dh)) {
         const int cx = H / 4, ry = std::max(1, 320 / cx);
         const unsigned nblk = (unsigned)((rows + CS_ROWS_PER_BLOCK - 1) / CS_ROWS_PER_BLOCK);
-        glu_bwd_cs_kernel<<<nblk, dim3(cx, ry), dbias ? sizeof(float) * 2 * H * ry : 0, st>>>(g, h, dh, dbias, rows, H);
+        glu_bwd_cs_kernel<<<nblk, dim3(cx, ry), dbias ? sizeof(float) * 2 * H * ry : 0, st>>>(
+            g, h, dh, dbias, rows, H, reinterpret_cast<unsigned int*>(amax_out));
         BM_CHECK_LAUNCH();
         return 0;
     }
@@ -430,6 +446,7 @@ extern "C" int bm_glu_bwd(const float* g, const float* h, long long rows, int H,
         colsum_cl_kernel<<<grid, 128, 0, st>>>(dh, dbias, rows, 2 * H, 256);
         BM_CHECK_LAUNCH();
     }
+    if (amax_out) return tc::launch_amax(dh, rows * 2 * H, amax_out, st);
     return 0;
 }
 
@@ -972,7 +989,7 @@ extern "C" int bm_f16_split(const float* src, long long n, const float* amax, vo
 extern "C" int bm_tc_conv1d_f16(const float* x, const float* x_amax, const void* w_hi, const void* w_lo, const float* w_amax,
                                 const float* bias, int accumulate, int B, int T, int Cin, int Ntot, int Kw, int dilation,
                                 int sign, int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out,
-                                double* stats, int* status, bm_stream_t stream) {
+                                double* stats, float* amax_out, int* status, bm_stream_t stream) {
     BM_CHECK_ARG(x && x_amax && w_hi && w_lo && w_amax && B > 0 && T > 0 && dilation >= 1 && (sign == 1 || sign == -1));
     BM_CHECK_ARG(glu ? (glu_out != nullptr) : (y != nullptr));
     BM_CHECK_ARG(tc::conv_pp_supported(T, Cin, Ntot, Kw, glu));
@@ -981,7 +998,9 @@ extern "C" int bm_tc_conv1d_f16(const float* x, const float* x_amax, const void*
     a.x = x; a.w_raw = nullptr; a.bias = bias; a.B = B; a.T = T; a.Cin = Cin; a.Ntot = Ntot; a.taps = Kw;
     a.dilation = dilation; a.sign = sign; a.glu = glu; a.act = act; a.out_tmajor = out_tmajor; a.accumulate = accumulate;
     a.y = y; a.aux = aux; a.glu_out = glu_out; a.stats = stats; a.err = status;
-    h.x_amax = x_amax; h.w_hi = w_hi; h.w_lo = w_lo; h.w_amax = w_amax;
+    h.x_amax = x_amax; h.w_hi = w_hi; h.w_lo = w_lo; h.w_amax = w_amax; h.out_amax = amax_out;
+    BM_CHECK_ARG(!amax_out || ((glu || act) && !out_tmajor));      // the outputs another conv consumes: GLU out, GELU out
+    if (int rc = amax_begin(amax_out, ST(stream))) return rc;
     return tc::launch_conv_hp(h, ST(stream));
 }
 

@@ -506,15 +506,35 @@ constexpr int CS_ROWS_PER_BLOCK = 96, CS_U = 4;       // rows per block; rows pe
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float4 ld4s(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }   // streamed once
 
+// max |.| of what a block has just written -> ONE atomicMax per block on `cell` (the bits of a non-negative float order like
+// unsigned integers).  The consumer is the F16-pipe conv (tc_convh.cuh), which scales its operand by a power of two from it:
+// fusing the reduction here saves bm_amax's extra pass over the tensor.  Every thread of the block must call.
+__device__ __forceinline__ float amax4(float m, const float4& o) {
+    return fmaxf(fmaxf(m, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+}
+__device__ __forceinline__ void block_amax_commit(float m, unsigned int* cell) {
+    __shared__ float warp_max[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+    if ((tid & 31) == 0) warp_max[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < (nthr + 31) / 32; ++w) m = fmaxf(m, warp_max[w]);
+        if (m > 0.f) atomicMax(cell, __float_as_uint(m));
+    }
+}
+
 // x_new = GELU((y - mean) * invstd * gamma + beta) (+ x_old)
 __global__ void __launch_bounds__(320, 2)
 bn_gelu_skip_fwd_cs_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ invstd,
                            const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ x_old,
-                           float* __restrict__ x_new, long long rows, int C) {
+                           float* __restrict__ x_new, long long rows, int C, unsigned int* __restrict__ amax) {
     const int c = threadIdx.x * 4, RY = blockDim.y;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c), be = ld4(beta + c);
     const long long r0 = (long long)blockIdx.x * CS_ROWS_PER_BLOCK;
     const long long r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
+    float am = 0.f;
     for (long long r = r0 + threadIdx.y; r < r1; r += (long long)CS_U * RY) {
         float4 v[CS_U], u[CS_U];
 #pragma unroll
@@ -537,9 +557,11 @@ bn_gelu_skip_fwd_cs_kernel(const float* __restrict__ y, const float* __restrict_
                 o.w = gelu_f(fmaf((v[k].w - mu.w) * is.w, ga.w, be.w));
                 if (x_old) { o.x += u[k].x; o.y += u[k].y; o.z += u[k].z; o.w += u[k].w; }
                 *reinterpret_cast<float4*>(x_new + rr * C + c) = o;
+                am = amax4(am, o);
             }
         }
     }
+    if (amax) block_amax_commit(am, amax);
 }
 
 // backward pass 1: sums[c] += sum dz, sums[C+c] += sum dz*yhat  with dz = g * GELU'(z); fp32 per thread, combined over the
@@ -591,9 +613,10 @@ __global__ void __launch_bounds__(320, 2)
 bn_gelu_bwd_apply_cs_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ mean,
                             const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                             const float* __restrict__ dgamma, const float* __restrict__ dbeta, float rn, int use_batch_stats,
-                            float* __restrict__ dy, long long rows, int C) {
+                            float* __restrict__ dy, long long rows, int C, unsigned int* __restrict__ amax) {
     const int c = threadIdx.x * 4, RY = blockDim.y;
     const float4 mu = ld4(mean + c), is = ld4(invstd + c), ga = ld4(gamma + c), be = ld4(beta + c);
+    float am = 0.f;
     float4 m1 = make_float4(0.f, 0.f, 0.f, 0.f), m2 = m1;
     if (use_batch_stats) {
         const float4 db = ld4(dbeta + c), dg = ld4(dgamma + c);
@@ -621,9 +644,11 @@ bn_gelu_bwd_apply_cs_kernel(const float* __restrict__ g, const float* __restrict
                 yh = (yv[k].z - mu.z) * is.z; dz = gv[k].z * gelu_grad_f(fmaf(yh, ga.z, be.z)); o.z = kk.z * (dz - m1.z - yh * m2.z);
                 yh = (yv[k].w - mu.w) * is.w; dz = gv[k].w * gelu_grad_f(fmaf(yh, ga.w, be.w)); o.w = kk.w * (dz - m1.w - yh * m2.w);
                 *reinterpret_cast<float4*>(dy + rr * C + c) = o;
+                am = amax4(am, o);
             }
         }
     }
+    if (amax) block_amax_commit(am, amax);
 }
 
 // GLU backward, column-stationary (H % 4 == 0, H/4 <= 256): thread (cx, ry) owns a-columns 4cx.. and the matching gate columns;
@@ -631,12 +656,13 @@ bn_gelu_bwd_apply_cs_kernel(const float* __restrict__ g, const float* __restrict
 // it has just produced (shared-memory combine over the row lanes, one fp32 atomic per column per block; zeroed by the caller).
 __global__ void __launch_bounds__(320, 2)
 glu_bwd_cs_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ dh, float* __restrict__ dbias,
-                  long long rows, int H) {
+                  long long rows, int H, unsigned int* __restrict__ amax) {
     extern __shared__ float red[];                       // [RY][2H]
     const int c = threadIdx.x * 4, RY = blockDim.y;
     const long long r0 = (long long)blockIdx.x * CS_ROWS_PER_BLOCK;
     const long long r1 = min(rows, r0 + CS_ROWS_PER_BLOCK);
     float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+    float am = 0.f;
     for (long long r = r0 + threadIdx.y; r < r1; r += (long long)CS_U * RY) {
         float4 av[CS_U], bv[CS_U], gv[CS_U];
 #pragma unroll
@@ -659,9 +685,11 @@ glu_bwd_cs_kernel(const float* __restrict__ g, const float* __restrict__ h, floa
                 *reinterpret_cast<float4*>(dh + rr * 2 * H + H + c) = db;
                 sa.x += da.x; sa.y += da.y; sa.z += da.z; sa.w += da.w;
                 sb.x += db.x; sb.y += db.y; sb.z += db.z; sb.w += db.w;
+                am = amax4(amax4(am, da), db);
             }
         }
     }
+    if (amax) block_amax_commit(am, amax);
     if (!dbias) return;
     float* mine = red + (size_t)threadIdx.y * 2 * H;
     *reinterpret_cast<float4*>(mine + c) = sa;

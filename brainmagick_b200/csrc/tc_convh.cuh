@@ -101,6 +101,7 @@ struct ConvHP {
     ConvPP c;                   // geometry, epilogue mode and outputs as in conv_pp_kernel
     const float* x_amax;        // device scalars: largest |x|, largest |w| (what bm_amax wrote)
     const float* w_amax;
+    unsigned int* out_amax;     // nullable: max |glu_out| (mode 3) / max |y| (mode 2) for the conv that consumes it next
     int comp_off;               // debug: leave the accumulator's truncation gain uncorrected (profiles/accumulator_gain_probe.py)
 };
 
@@ -275,10 +276,12 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                            (1.0f / f16_scale_of(__ldg(hp.x_amax))) * (1.0f / f16_scale_of(__ldg(hp.w_amax)));
         int tcount = 0;
         bool ok = true;
+        float am = 0.f;                                               // max |output| this thread has produced
         for (int tile = pair; tile < ntiles && ok; tile += npairs, ++tcount) {
             const int n_tile = tile % p.ntn, m_tile = tile / p.ntn;
             const int row0 = m_tile * 2 * HP_BM + (int)rank * HP_BM;  // this CTA's first row
             const int r32 = row0 + q * 32;                            // this warp's first row
+            const bool row_live = row0 + row < p.R;                   // rows past the end are computed from zero-filled x
             ok = mbar_wait(&acc_full, (uint32_t)tcount & 1, p.err, 96);
             tc_fence_after();
             if (glu) {
@@ -312,6 +315,10 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
 #pragma unroll
                     for (int j = 0; j < 32; ++j) a[j] *= sigmoid_f(g[j]);
+                    if (hp.out_amax && row_live) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) am = fmaxf(am, fabsf(a[j]));
+                    }
                     pp_stage_store(buf, a, lane, &tmO, c0 + c * 32, r32, false);
                 }
             } else {
@@ -350,6 +357,10 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (p.save_aux) pp_stage_store(buf, v, lane, &tmO, n0 + c * 32, r32, false);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);
+                        if (hp.out_amax && row_live) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) am = fmaxf(am, fabsf(v[j]));
+                        }
                     }
                     pp_stage_store(buf, v, lane, &tmY, n0 + c * 32, r32, p.mode == 1);
                     if (p.stats) {
@@ -368,6 +379,11 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
+        }
+        if (hp.out_amax) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+            if (lane == 0 && am > 0.f) atomicMax(hp.out_amax, __float_as_uint(am));
         }
         if (lane == 0) bulk_wait<0>();
         __syncwarp();
@@ -441,6 +457,7 @@ inline bool make_tmap_f16(CUtensorMap* m, const void* base, const uint64_t* dims
 struct ConvHPArgs {
     ConvPPArgs c;                    // c.w_raw unused
     const float* x_amax; const void* w_hi; const void* w_lo; const float* w_amax;
+    float* out_amax;                 // nullable (zeroed by the caller)
 };
 
 inline int launch_conv_hp(const ConvHPArgs& h, cudaStream_t st) {
@@ -465,7 +482,8 @@ inline int launch_conv_hp(const ConvHPArgs& h, cudaStream_t st) {
     if (a.glu && (a.act || a.out_tmajor || a.aux || a.accumulate)) return set_error(2, "%s: GLU excludes the other epilogues%s", __func__);
     if (a.out_tmajor && (a.act || a.accumulate)) return set_error(2, "%s: channel-major output is a plain store%s", __func__);
     if (a.act && a.accumulate) return set_error(2, "%s: accumulate excludes the activation%s", __func__);
-    hp.x_amax = h.x_amax; hp.w_amax = h.w_amax; hp.comp_off = (g_debug_flags & 2) ? 1 : 0;
+    hp.x_amax = h.x_amax; hp.w_amax = h.w_amax; hp.out_amax = reinterpret_cast<unsigned int*>(h.out_amax);
+    hp.comp_off = (g_debug_flags & 2) ? 1 : 0;
 
     CUtensorMap tmA, tmBh, tmBl, tmY, tmO;
     {

@@ -124,6 +124,11 @@ def tensor_amax(x: torch.Tensor) -> torch.Tensor:
     return cell
 
 
+def amax_cell(like: torch.Tensor) -> tp.Optional[torch.Tensor]:
+    """A device float for a producer kernel to leave max |output| in (its `amax_out`), when the F16 pipe is in use."""
+    return _empty((1,), like) if USE_CONV_F16 else None
+
+
 class _Conv:
     """One conv layer's prepared operands + the kernel choice (tensor-core or FP32-FMA)."""
 
@@ -177,10 +182,11 @@ class _Conv:
             call("bm_conv_weight_prep", ptr(w), self.cout, self.cin, self.kw, ptr(self.wf), ptr(self.wb), st)
 
     def run_tc(self, fwd: bool, x, bias, addend, B, T, dilation, glu, act, tmajor, y, aux, glu_out, stats, status,
-               x_amax=None):
+               x_amax=None, out_amax=None):
         """One tensor-core conv launch: forward taps (fwd) or the data gradient; `addend` must be None or `y` itself
         (in-place accumulation) on the persistent kernel.  `x_amax` (F16 pipe): the device float holding max |x| when the
-        producer of x already knows it, else one bm_amax pass here."""
+        producer of x already knows it, else one bm_amax pass here; `out_amax`: a device float that receives max |output| of a
+        GLU / GELU epilogue for the conv that consumes it next (`amax_cell`)."""
         st = stream()
         if fwd:
             pp, hi, lo, cin, ntot, sign = self.fwd_pp, self.f_hi, self.f_lo, self.cin, self.cout, 1
@@ -193,7 +199,8 @@ class _Conv:
                 x_amax = tensor_amax(x)
             call("bm_tc_conv1d_f16", ptr(x), ptr(x_amax), ptr(h16[0]), ptr(h16[1]), ptr(self.w_amax), ptr(bias),
                  0 if addend is None else 1, B, T, cin, ntot, self.kw, dilation, sign, glu, act, tmajor, ptr(y), ptr(aux),
-                 ptr(glu_out), ptr(stats), ptr(status), st)
+                 ptr(glu_out), ptr(stats), ptr(out_amax), ptr(status), st)
+            return out_amax
         elif pp:
             assert addend is None or addend.data_ptr() == y.data_ptr(), "the persistent kernel accumulates in place only"
             call("bm_tc_conv1d_persistent", ptr(x), ptr(hi), ptr(bias), 0 if addend is None else 1, B, T, cin, ntot,
@@ -202,33 +209,37 @@ class _Conv:
             assert stats is None
             call("bm_tc_conv1d", ptr(x), ptr(hi), ptr(lo), ptr(bias), ptr(addend), B, T, cin, ntot, self.kw, dilation,
                  sign, glu, act, tmajor, ptr(y), ptr(aux), ptr(glu_out), None, ptr(status), st)
+        return None                        # the tf32 kernels do not report max |output|
 
     # y = conv(x) (+bias); optionally BatchNorm statistics into `stats`
-    def forward(self, x, bias, B, T, dilation, y, stats, status):
+    def forward(self, x, bias, B, T, dilation, y, stats, status, x_amax=None):
         st = stream()
         if self.fwd_tc:
             fused = stats is not None and self.fwd_pp          # BatchNorm statistics out of the conv epilogue
             if self.cout > 320:
                 fused = False                                   # the kernel keeps the statistics of ONE N tile in smem
-            self.run_tc(True, x, bias, None, B, T, dilation, 0, 0, 0, y, None, None, stats if fused else None, status)
+            self.run_tc(True, x, bias, None, B, T, dilation, 0, 0, 0, y, None, None, stats if fused else None, status,
+                        x_amax=x_amax)
             if stats is not None and not fused:
                 call("bm_col_stats", ptr(y), B * T, self.cout, ptr(stats), st)
         else:
             call("bm_conv1d_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout, self.kw, dilation,
                  ptr(y), ptr(stats), st)
 
-    def forward_glu(self, x, bias, B, T, h, out, status):
+    def forward_glu(self, x, bias, B, T, h, out, status, x_amax=None, out_amax=None):
+        """-> the device float holding max |out| when the kernel produced it (F16 pipe), else None."""
         st = stream()
         if self.fwd_tc:
-            self.run_tc(True, x, bias, None, B, T, 1, 1, 0, 0, h, None, out, None, status)
+            return self.run_tc(True, x, bias, None, B, T, 1, 1, 0, 0, h, None, out, None, status, x_amax=x_amax,
+                               out_amax=out_amax)
         else:
             call("bm_conv1d_glu_fwd", ptr(x), ptr(self.wf), ptr(bias), B, T, self.cin, self.cout // 2, self.kw,
                  ptr(h), ptr(out), st)
 
-    def backward_data(self, dy, addend, B, T, dilation, dx, status):
+    def backward_data(self, dy, addend, B, T, dilation, dx, status, dy_amax=None):
         st = stream()
         if self.bwd_tc:
-            self.run_tc(False, dy, None, addend, B, T, dilation, 0, 0, 0, dx, None, None, None, status)
+            self.run_tc(False, dy, None, addend, B, T, dilation, 0, 0, 0, dx, None, None, None, status, x_amax=dy_amax)
         else:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
                  dilation, ptr(dx), st)
@@ -482,13 +493,15 @@ class _EncoderFn(torch.autograd.Function):
         # K3/K4 ConvSequence
         stats = _empty((2 * H,), meg, torch.float64)
         saved_layers = []
+        x_amax = None                                   # device float with max |x| when x's producer reported it (F16 pipe)
         for k in range(depth):
             cw, cb, gamma, beta = conv_p[k]
             conv = conv0 if k == 0 else _Conv(cw, T, False, tc, want_bwd=save)
             cout = conv.cout
             y = _empty((B, T, cout), meg)
             if plan.bare_last and k == depth - 1:
-                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, None, status)
+                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, None, status, x_amax=x_amax)
+                x_amax = None
                 skip = plan.skip and conv.cin_true == cout
                 x_new = y
                 if skip:
@@ -501,7 +514,7 @@ class _EncoderFn(torch.autograd.Function):
                     gconv = _Conv(gw, T, True, tc, want_bwd=save)
                     h = _empty((B, T, gconv.cout), meg) if save else None
                     out = _empty((B, T, gconv.cout // 2), meg)
-                    gconv.forward_glu(x, gb.contiguous(), B, T, h, out, status)
+                    x_amax = gconv.forward_glu(x, gb.contiguous(), B, T, h, out, status, x_amax=x_amax, out_amax=amax_cell(meg))
                     rec.update(h=h, gconv=gconv)
                     x = out
                 saved_layers.append(rec if save else None)
@@ -510,17 +523,19 @@ class _EncoderFn(torch.autograd.Function):
             invstd = _empty((cout,), meg)
             rm, rv = plan.bn_buffers[k]
             if plan.training:
-                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, stats, status)
+                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, stats, status, x_amax=x_amax)
                 call("bm_bn_stats_finalize", ptr(stats), rows, float(plan.bn_eps), float(plan.bn_momentum),
                      ptr(rm), ptr(rv), ptr(mean), ptr(invstd), cout, st)
             else:
-                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, None, status)
+                conv.forward(x, cb.contiguous(), B, T, plan.dilations[k], y, None, status, x_amax=x_amax)
                 call("bm_bn_eval_stats", ptr(rm), ptr(rv), float(plan.bn_eps), ptr(mean), ptr(invstd), cout, st)
             skip = plan.skip and conv.cin_true == cout
             x_new = _empty((B, T, cout), meg)
+            x_amax = None
             if plan.act_code == 0:
+                x_amax = amax_cell(meg)
                 call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
-                     ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, st)
+                     ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, ptr(x_amax), st)
             else:
                 call("bm_bn_act_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
                      ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, plan.act_code,
@@ -532,7 +547,7 @@ class _EncoderFn(torch.autograd.Function):
                 gconv = _Conv(gw, T, True, tc, want_bwd=save)
                 h = _empty((B, T, gconv.cout), meg) if save else None
                 out = _empty((B, T, gconv.cout // 2), meg)
-                gconv.forward_glu(x, gb.contiguous(), B, T, h, out, status)
+                x_amax = gconv.forward_glu(x, gb.contiguous(), B, T, h, out, status, x_amax=x_amax, out_amax=amax_cell(meg))
                 rec.update(h=h, gconv=gconv)
                 x = out
             saved_layers.append(rec if save else None)
@@ -576,8 +591,9 @@ class _EncoderFn(torch.autograd.Function):
             call("bm_transpose_nt", ptr(est_cl), B, T, F, ptr(est), st)
             del est_cl
         elif head_tc:
-            head0.run_tc(True, x, b0.contiguous(), None, B, T, 1, 0, 1, 0, q, h1 if save else None, None, None, status)
-            head2.run_tc(True, q, b2.contiguous(), None, B, T, 1, 0, 0, 1, est, None, None, None, status)
+            q_amax = head0.run_tc(True, x, b0.contiguous(), None, B, T, 1, 0, 1, 0, q, h1 if save else None, None, None, status,
+                                  x_amax=x_amax, out_amax=amax_cell(meg))
+            head2.run_tc(True, q, b2.contiguous(), None, B, T, 1, 0, 0, 1, est, None, None, None, status, x_amax=q_amax)
         else:
             call("bm_head_fwd", ptr(x), ptr(w0_2), ptr(b0.contiguous()), ptr(w2_2), ptr(b2.contiguous()), B, T, H, F,
                  ptr(h1), ptr(q), ptr(est), st)
@@ -706,10 +722,11 @@ class _EncoderFn(torch.autograd.Function):
                 gconv: _Conv = rec["gconv"]
                 dh = _empty((B, T, gconv.cout), meg)
                 dgb = _empty((gconv.cout,), meg)          # the GLU conv's bias gradient, summed while dh is produced
-                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), ptr(dgb), st)
+                dh_amax = amax_cell(meg)
+                call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), ptr(dgb), ptr(dh_amax), st)
                 glu_grads[k] = weight_grad(gconv, dh, rec["x_new"], 1, False, dgb)
                 g = _empty((B, T, gconv.cin), meg)
-                gconv.backward_data(dh, None, B, T, 1, g, status)
+                gconv.backward_data(dh, None, B, T, 1, g, status, dy_amax=dh_amax)
                 del dh
             if rec.get("bare"):
                 # bare convolution (+ residual): dL/dy = dL/dx_new; no BatchNorm behind it, so the bias gradient is real
@@ -727,10 +744,12 @@ class _EncoderFn(torch.autograd.Function):
             dy = _empty((B, T, cout), meg)
             dgamma = _empty((cout,), meg)
             dbeta = _empty((cout,), meg)
+            dy_amax = None
             if plan.act_code == 0:
+                dy_amax = amax_cell(meg)
                 call("bm_bn_gelu_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                      ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout, ptr(sums),
-                     ptr(dy), ptr(dgamma), ptr(dbeta), st)
+                     ptr(dy), ptr(dgamma), ptr(dbeta), ptr(dy_amax), st)
             else:
                 call("bm_bn_act_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                      ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout,
@@ -738,10 +757,10 @@ class _EncoderFn(torch.autograd.Function):
             dcw, dcb = weight_grad(conv, dy, rec["x_in"], plan.dilations[k], plan.training)
             if rec["skip"]:
                 # in place: g += conv_transpose(dy) (addend == output: the pair kernel turns this into a TMA reduce-add)
-                conv.backward_data(dy, g, B, T, plan.dilations[k], g, status)
+                conv.backward_data(dy, g, B, T, plan.dilations[k], g, status, dy_amax=dy_amax)
             else:
                 g_in = _empty((B, T, conv.cin), meg)
-                conv.backward_data(dy, None, B, T, plan.dilations[k], g_in, status)
+                conv.backward_data(dy, None, B, T, plan.dilations[k], g_in, status, dy_amax=dy_amax)
                 g = g_in
             layer_grads[k] = (dcw, dcb, dgamma, dbeta)
             del dy

@@ -102,15 +102,19 @@ int bm_bn_stats_finalize(const double* stats, long long n, float eps, float mome
                          float* running_var, float* mean, float* invstd, int C, bm_stream_t stream);
 int bm_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* invstd,
                      int C, bm_stream_t stream);
-/* x_new = GELU(gamma*(y-mean)*invstd + beta) (+ x_old if not NULL); rows = B*T. */
+/* x_new = GELU(gamma*(y-mean)*invstd + beta) (+ x_old if not NULL); rows = B*T.
+ * amax_out (nullable; the same argument on bm_bn_gelu_skip_bwd, bm_glu_bwd, bm_tc_conv1d_f16): a device float that receives
+ * max |output| -- the x_amax of the F16-pipe conv (bm_tc_conv1d_f16) that consumes the tensor next, produced by the kernel
+ * that writes the tensor instead of a separate bm_amax pass over it. */
 int bm_bn_gelu_skip_fwd(const float* y, const float* mean, const float* invstd, const float* gamma,
-                        const float* beta, const float* x_old, float* x_new, long long rows, int C,
+                        const float* beta, const float* x_old, float* x_new, long long rows, int C, float* amax_out,
                         bm_stream_t stream);
 /* g = dL/dx_new -> dy (through GELU and BN), dgamma, dbeta.  batch_stats=1: training-mode BN backward.
  * sums: fp64 [2*C] scratch. */
 int bm_bn_gelu_skip_bwd(const float* g, const float* y, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, int batch_stats, long long rows, int C,
-                        double* sums, float* dy, float* dgamma, float* dbeta, bm_stream_t stream);
+                        double* sums, float* dy, float* dgamma, float* dbeta, float* amax_out /* of dy */,
+                        bm_stream_t stream);
 /* dx = conv_transpose(dy) (+ addend, the skip-path gradient, if not NULL). */
 int bm_conv1d_bwd_data(const float* dy, const float* wb, const float* addend, int B, int T, int Cin, int Cout,
                        int Kw, int dilation, float* dx, bm_stream_t stream);
@@ -124,7 +128,7 @@ int bm_conv1d_glu_fwd(const float* x, const float* wf, const float* bias, int B,
                       float* h, float* out, bm_stream_t stream);
 int bm_glu_bwd(const float* g, const float* h, long long rows, int H, float* dh,
                float* dbias /* nullable [2H]: sum over rows of dh = the GLU conv's bias gradient, from the same pass */,
-               bm_stream_t stream);
+               float* amax_out /* of dh */, bm_stream_t stream);
 
 /* ---- K5: head Conv1d(H,2H,1) -> GELU -> ConvTranspose1d(2H,F,1) (simpleconv.py:185-189,246-249) --------
  * x [B,T,H]; w0 [2H,H]; w2 [2H,F] (ConvTranspose1d weight is input-major); out h1,q [B,T,2H], est [B,F,T]. */
@@ -273,7 +277,8 @@ int bm_amax(const float* x, long long n, float* amax, bm_stream_t stream);
 int bm_f16_split(const float* src, long long n, const float* amax, void* hi, void* lo, bm_stream_t stream);
 int bm_tc_conv1d_f16(const float* x, const float* x_amax, const void* w_hi, const void* w_lo, const float* w_amax,
                      const float* bias, int accumulate, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
-                     int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, double* stats, int* status,
+                     int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, double* stats,
+                     float* amax_out /* nullable: max |glu_out| (glu) or max |y| (act), see bm_bn_gelu_skip_fwd */, int* status,
                      bm_stream_t stream);
 
 /* bm_tc_wgrad: weight gradient on the tensor cores (3xTF32): dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-Kw/2)*dil,n]

@@ -44,7 +44,7 @@ for flags,tag in ((2,"uncompensated"),(0,"compensated")):
             f,_=raw(w)
             amax,hi,lo=f16_ops(x,f)
             y=torch.empty(B,T,Cout,device=dev)
-            call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, 0, B,T,Cin,Cout,Kw,1,1,0,0,0, ptr(y),None,None,None,ptr(status),stream())
+            call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, 0, B,T,Cin,Cout,Kw,1,1,0,0,0, ptr(y),None,None,None,None,ptr(status),stream())
             torch.cuda.synchronize()
             ref=torch.nn.functional.conv1d(x.double().permute(0,2,1), w.double(), None, padding=Kw//2).permute(0,2,1)
             probe(tag+" "+label+" "+dist, y, ref)

@@ -89,12 +89,14 @@ elif which in ("bn_bwd", "bn_fwd"):   # -k regex:bn_gelu_bwd_(reduce|apply)_cs_k
     mean, invstd = torch.zeros(H, device=dev), torch.ones(H, device=dev)
     sums = torch.empty(2 * H, device=dev, dtype=torch.float64)
     dgam, dbet = torch.empty(H, device=dev), torch.empty(H, device=dev)
+    amax = torch.empty(1, device=dev)
     for _ in range(6):
         if which == "bn_bwd":
             call("bm_bn_gelu_skip_bwd", ptr(dy), ptr(x), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), 1, rows, H, ptr(sums),
-                 ptr(gy), ptr(dgam), ptr(dbet), stream())
+                 ptr(gy), ptr(dgam), ptr(dbet), ptr(amax), stream())
         else:
-            call("bm_bn_gelu_skip_fwd", ptr(dy), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), ptr(x), ptr(gy), rows, H, stream())
+            call("bm_bn_gelu_skip_fwd", ptr(dy), ptr(mean), ptr(invstd), ptr(gam), ptr(bet), ptr(x), ptr(gy), rows, H, ptr(amax),
+                 stream())
 torch.cuda.synchronize()
 assert int(status.item()) == 0
 print("done", which)

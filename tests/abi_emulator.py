@@ -209,8 +209,17 @@ class Emulator:
             a = a + _v(x_old, rows, C)
         _v(x_new, rows, C).copy_(a)
 
-    def bm_bn_gelu_skip_fwd(self, y, mean, invstd, gamma, beta, x_old, x_new, rows, C, stream):
+    def bm_bn_gelu_skip_fwd(self, y, mean, invstd, gamma, beta, x_old, x_new, rows, C, amax_out, stream):
         self.bm_bn_act_skip_fwd(y, mean, invstd, gamma, beta, x_old, x_new, rows, C, 0, 0.0, stream)
+        self._amax_out(amax_out, _v(x_new, rows * C))
+
+    @staticmethod
+    def _amax_out(cell, values):
+        """The producers' `amax_out`: max |output| of what they have just written."""
+        if cell is not None:
+            v = values.abs()
+            v = v[~torch.isnan(v)]
+            _v(cell, 1).fill_(float(v.max()) if v.numel() else 0.0)
 
     def bm_bn_act_skip_bwd(self, g, y, mean, invstd, gamma, beta, batch_stats, rows, C, act, slope, sums, dy, dgamma, dbeta,
                            stream):
@@ -228,8 +237,10 @@ class Emulator:
             v = dz - (s1 / rows).float() - yh * (s2 / rows).float()
         _v(dy, rows, C).copy_(_v(gamma, C) * _v(invstd, C) * v)
 
-    def bm_bn_gelu_skip_bwd(self, g, y, mean, invstd, gamma, beta, batch_stats, rows, C, sums, dy, dgamma, dbeta, stream):
+    def bm_bn_gelu_skip_bwd(self, g, y, mean, invstd, gamma, beta, batch_stats, rows, C, sums, dy, dgamma, dbeta, amax_out,
+                            stream):
         self.bm_bn_act_skip_bwd(g, y, mean, invstd, gamma, beta, batch_stats, rows, C, 0, 0.0, sums, dy, dgamma, dbeta, stream)
+        self._amax_out(amax_out, _v(dy, rows * C))
 
     def bm_conv1d_bwd_data(self, dy, wb, addend, B, T, Cin, Cout, Kw, dilation, dx, stream):
         w = _v(wb, Kw, Cout, Cin).permute(1, 2, 0)                        # [Cout, Cin, Kw]
@@ -255,13 +266,14 @@ class Emulator:
             _v(h, B, T, 2 * H).copy_(hh)
         _v(out, B, T, H).copy_(hh[..., :H] * torch.sigmoid(hh[..., H:]))
 
-    def bm_glu_bwd(self, g, h, rows, H, dh, dbias, stream):
+    def bm_glu_bwd(self, g, h, rows, H, dh, dbias, amax_out, stream):
         gg, hh = _v(g, rows, H), _v(h, rows, 2 * H)
         a, b = hh[:, :H], hh[:, H:]
         s = torch.sigmoid(b)
         _v(dh, rows, 2 * H).copy_(torch.cat([gg * s, gg * a * s * (1 - s)], dim=1))
         if dbias is not None:
             _v(dbias, 2 * H).copy_(_v(dh, rows, 2 * H).sum(0))
+        self._amax_out(amax_out, _v(dh, rows * 2 * H))
 
     # ---------------------------------------------------------------- K5
     def bm_head_fwd(self, x, w0, b0, w2, b2, B, T, H, F_, h1, q, est, stream):
@@ -404,7 +416,7 @@ class Emulator:
         _v(lo, n).copy_((v - h.float()).to(torch.float16))
 
     def bm_tc_conv1d_f16(self, x, x_amax, w_hi, w_lo, w_amax, bias, accumulate, B, T, Cin, Ntot, Kw, dilation, sign, glu, act,
-                         out_tmajor, y, aux, glu_out, stats, status, stream):
+                         out_tmajor, y, aux, glu_out, stats, amax_out, status, stream):
         sx, sw = self._f16_scale(float(_v(x_amax, 1))), self._f16_scale(float(_v(w_amax, 1)))
         n = Kw * Ntot * Cin
         w = (_v(w_hi, n).float() + _v(w_lo, n).float()) / sw            # what the tensor core multiplies by, unscaled
@@ -413,6 +425,9 @@ class Emulator:
         xq = (xh.float() + (xv - xh.float()).to(torch.float16).float()) / sx
         self.bm_tc_conv1d(xq.contiguous(), w.contiguous(), None, bias, y if accumulate else None, B, T, Cin, Ntot, Kw,
                           dilation, sign, glu, act, out_tmajor, y, aux, glu_out, stats, status, stream)
+        if amax_out is not None:
+            assert (glu or act) and not out_tmajor
+            self._amax_out(amax_out, _v(glu_out, B * T * (Ntot // 2)) if glu else _v(y, B * T * Ntot))
 
     def bm_col_stats(self, y, rows, C, stats, stream):
         o = _v(y, rows, C).double()

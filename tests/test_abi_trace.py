@@ -10,7 +10,14 @@ def test_full_size_step_runs_on_tensor_cores_only():
     names = {c[0] for c in abi_trace.simpleconv_step(abi_trace.CONFIGS["full"], True)}
     assert not names & {"bm_conv1d_fwd", "bm_conv1d_bwd_data", "bm_conv1d_bwd_weight", "bm_conv1d_glu_fwd", "bm_head_fwd",
                         "bm_head_bwd", "bm_sensor_chain_fwd", "bm_sensor_chain_bwd", "bm_attention_weights_fwd"}
-    assert {"bm_tc_conv1d_persistent", "bm_tc_wgrad", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
+    assert {"bm_tc_conv1d_f16", "bm_tc_wgrad_conv", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
+    # F16 pipe: the tensors between two kernels of the conv stack carry their max |.| from the producer; bm_amax passes are
+    # left only in front of the convs whose input comes from elsewhere (sensor chain, head gradient, ...)
+    calls = abi_trace.simpleconv_step(abi_trace.CONFIGS["full"], True)
+    n_conv = sum(c[0] == "bm_tc_conv1d_f16" for c in calls)
+    rows = abi_trace.CONFIGS["full"][0] * abi_trace.CONFIGS["full"][2]                    # B*T: passes over ACTIVATIONS
+    n_pass = sum(c[0] == "bm_amax" and c[2] % rows == 0 for c in calls)
+    assert n_conv >= 30 and n_pass <= 8, (n_conv, n_pass)
 
 
 @pytest.mark.parametrize("override", [dict(glu=0), dict(skip=False), dict(gelu=False), dict(complex_out=False),

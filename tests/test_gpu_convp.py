@@ -61,8 +61,14 @@ def _run(x, w_op, bias, accumulate, B, T, Cin, Ntot, Kw, dil, sign, glu, act, tm
     status = torch.zeros(1, dtype=torch.int32, device=DEV)
     if PIPE == "f16":
         amax, hi, lo = _f16_operands(x, w_op)
+        # the epilogues another conv consumes (GLU out, GELU out) also report max |output| for that conv's scale
+        out_amax = torch.full((1,), float("nan"), device=DEV) if (glu or act) and not tmajor else None
         call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), ptr(bias), accumulate, B, T, Cin,
-             Ntot, Kw, dil, sign, glu, act, tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), stream())
+             Ntot, Kw, dil, sign, glu, act, tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(out_amax), ptr(status),
+             stream())
+        if out_amax is not None:
+            produced = glu_out if glu else y
+            assert float(out_amax) == float(produced.abs().max()), (float(out_amax), float(produced.abs().max()))
     else:
         call("bm_tc_conv1d_persistent", ptr(x), ptr(w_op), ptr(bias), accumulate, B, T, Cin, Ntot, Kw, dil, sign, glu, act,
              tmajor, ptr(y), ptr(aux), ptr(glu_out), ptr(stats), ptr(status), stream())
@@ -167,6 +173,39 @@ def test_head_modes(B, T):
     assert rel_err(est.cpu(), ref.cpu()) < TOL
 
 
+def test_producers_report_amax(pipe):
+    """The elementwise kernels in front of a conv leave max |output| in `amax_out` (no separate pass over the tensor)."""
+    if pipe != "f16":
+        pytest.skip("one run is enough")
+    call, ptr, stream = _abi()
+    torch.manual_seed(5)
+    for rows, C in ((360 * 7 + 13, 320), (97, 64), (1000, 100)):             # column-stationary kernels and the generic ones
+        y, x_old = torch.randn(rows, C, device=DEV) * 3, torch.randn(rows, C, device=DEV)
+        mean, invstd = torch.randn(C, device=DEV) * 0.1, torch.rand(C, device=DEV) + 0.5
+        gamma, beta = torch.randn(C, device=DEV), torch.randn(C, device=DEV) * 0.1
+        x_new = torch.empty(rows, C, device=DEV)
+        cell = torch.full((1,), float("nan"), device=DEV)
+        call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), ptr(x_old), ptr(x_new), rows, C,
+             ptr(cell), stream())
+        assert float(cell) == float(x_new.abs().max())
+        g = torch.randn(rows, C, device=DEV) * 1e-3
+        sums = torch.empty(2 * C, device=DEV, dtype=torch.float64)
+        dy, dgamma, dbeta = torch.empty(rows, C, device=DEV), torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+        call("bm_bn_gelu_skip_bwd", ptr(g), ptr(y), ptr(mean), ptr(invstd), ptr(gamma), ptr(beta), 1, rows, C, ptr(sums),
+             ptr(dy), ptr(dgamma), ptr(dbeta), ptr(cell), stream())
+        assert float(cell) == float(dy.abs().max())
+        if C % 2 == 0:
+            H = C // 2
+            gg = torch.randn(rows, H, device=DEV)
+            dh, dbias = torch.empty(rows, C, device=DEV), torch.empty(C, device=DEV)
+            call("bm_glu_bwd", ptr(gg), ptr(y), rows, H, ptr(dh), ptr(dbias), ptr(cell), stream())
+            assert float(cell) == float(dh.abs().max())
+    z = torch.zeros(64, 320, device=DEV)                                      # an all-zero tensor reports 0 (scale 1)
+    cell = torch.full((1,), float("nan"), device=DEV)
+    call("bm_amax", ptr(z), z.numel(), ptr(cell), stream())
+    assert float(cell) == 0.0
+
+
 def test_speed_report(capsys):
     """Not a pass/fail on speed: per-launch times at the BASELINE shape (B=256, T=360), L2 flushed between launches."""
     call, ptr, stream = _abi()
@@ -187,9 +226,10 @@ def test_speed_report(capsys):
         """A closure that launches ONLY the conv kernel (f16: the operand preparation is done here, once)."""
         if PIPE == "f16":
             amax, hi, lo = _f16_operands(xt, w_op)
+            out_cell = torch.empty(1, device=DEV)
             return lambda: call("bm_tc_conv1d_f16", ptr(xt), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, acc, Bn,
                                 Tn, Cin, Ntot, Kw, dil, sign, glu, 0, 0, ptr(yt), None, ptr(glu_out), ptr(stats_t),
-                                ptr(status), st)
+                                ptr(out_cell) if glu else None, ptr(status), st)
         return lambda: call("bm_tc_conv1d_persistent", ptr(xt), ptr(w_op), None, acc, Bn, Tn, Cin, Ntot, Kw, dil, sign, glu,
                             0, 0, ptr(yt), None, ptr(glu_out), ptr(stats_t), ptr(status), st)
 
