@@ -203,7 +203,8 @@ def run_b200(args):
         t0 = time.perf_counter()
         for i in range(n_steps):
             fn(i)
-        host_ms[0] = (time.perf_counter() - t0) * 1e3 / n_steps      # host time to ENQUEUE a step (no sync inside the loop)
+            if i == 1:                     # host time to ENQUEUE a step, from the first two steps after the barrier: the launch
+                host_ms[0] = (time.perf_counter() - t0) * 1e3 / 2        # queue is still far from full, so nothing blocks
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -226,7 +227,7 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     ms_total = timed(args.steps, resident_step)
     launches = _lib.launch_count() - launches0
-    host_ms_value = host_ms[0]        # ~= ms_per_step means the host, not the GPU, paces the step
+    host_ms_value = host_ms[0]        # >= ms_per_step would mean the host, not the GPU, paces the step
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
     value = world * B / (ms_per_step / 1e3)
@@ -431,8 +432,8 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
     """The dominant kernel first (K3: Conv1d 320->320 k3 + BatchNorm statistics, half of the step with its data-gradient
     twin), then K4 (Conv1d 320->640 + GLU), K6 (CLIP scores + norms + softmax/CE), the weight-gradient kernel and the
     HBM-bound BatchNorm/GELU kernels.  Algorithmic work per SURVEY.md 8(d); the tensor pipe executes 3x the algorithmic
-    FLOPs (hi*hi + lo*hi + hi*lo) at the tf32 rate (= bf16 / 2), so a tensor-bound `frac` against the measured bf16 peak
-    tops out at 1/6: `frac_of_3xtf32_ceiling` is the same number against peak/6."""
+    FLOPs (hi*hi + lo*hi + hi*lo): at the f16 rate a tensor-bound `frac` against the measured bf16 peak tops out at 1/3, at
+    the tf32 rate (= bf16 / 2) at 1/6 -- `frac_of_scheme_ceiling` is the same number against that ceiling."""
     from brainmagick_b200._lib import call, ptr, stream, load
     lib = load()
     peaks = load_peaks()
@@ -456,12 +457,15 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
     h = torch.empty(B, T, 2 * H, device=dev)
     stats = torch.empty(2 * H, device=dev, dtype=torch.float64)
 
-    def tensor_entry(kernel, ms, flops, alg_bytes, traffic):
+    def tensor_entry(kernel, ms, flops, alg_bytes, traffic, pipe="tf32"):
+        """`frac` is against the measured dense bf16 peak.  An fp32-faithful product needs three MMAs (hi*hi + lo*hi + hi*lo):
+        on kind::tf32 (half the bf16 rate) the ceiling of `frac` is 1/6, on kind::f16 it is 1/3 -- `frac_of_scheme_ceiling`."""
         ach = flops / (ms / 1e3) / 1e12
+        ceil = peak_tf / (6 if pipe == "tf32" else 3)
         return dict(kernel=kernel, bound="tensor", achieved=ach, peak=peak_tf, unit="TFLOP/s", frac=ach / peak_tf,
                     traffic=traffic, algorithmic_bytes=alg_bytes, ms_per_launch=ms,
-                    peak_source=src + " cuBLAS bf16 burst (MEASURED_PEAKS.json)", executed_tflops=3 * ach,
-                    frac_of_3xtf32_ceiling=ach / (peak_tf / 6))
+                    peak_source=src + " cuBLAS bf16 burst (MEASURED_PEAKS.json)", pipe="kind::" + pipe,
+                    executed_tflops_bf16_equivalent=(6 if pipe == "tf32" else 3) * ach, frac_of_scheme_ceiling=ach / ceil)
 
     def hbm_entry(kernel, ms, alg_bytes, traffic):
         ach = alg_bytes / (ms / 1e3) / 1e9
@@ -469,24 +473,52 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
                     traffic=traffic, algorithmic_bytes=alg_bytes, ms_per_launch=ms,
                     peak_source=src + " copy bandwidth (MEASURED_PEAKS.json)")
 
-    ms = _time_kernel([lambda x=x, y=y: call("bm_tc_conv1d_persistent", ptr(x), ptr(f), ptr(bias), 0, B, T, H, H, Kw, 4, 1, 0,
-                                             0, 0, ptr(y), None, None, ptr(stats), ptr(status), st) for x, y in zip(xs, ys)])
-    main = tensor_entry("conv_pp_kernel via bm_tc_conv1d_persistent (K3: Conv1d 320->320 k3 d4 + BatchNorm statistics; "
-                        "persistent CTA pairs, tcgen05 cta_group::2 kind::tf32, 3xTF32)", ms, 2.0 * H * H * Kw * T * B,
-                        2.0 * B * T * H * 4, ncu_traffic_bytes("convp"))
-    main["note"] = ("achieved = ALGORITHMIC fp32 FLOPs (2*320*320*3*T*B per launch) / time. fp32-faithful parity (1e-4) needs 3 "
-                    "tf32 MMAs per product and kind::tf32 runs at half the bf16 rate, so the ceiling of `frac` for this scheme "
-                    "is 1/6 (frac_of_3xtf32_ceiling = achieved / (peak/6))")
+    def f16_weights(w_op):
+        amax = torch.empty(1, device=dev)
+        call("bm_amax", ptr(w_op), w_op.numel(), ptr(amax), st)
+        hi = torch.empty(w_op.shape, device=dev, dtype=torch.float16)
+        lo = torch.empty(w_op.shape, device=dev, dtype=torch.float16)
+        call("bm_f16_split", ptr(w_op), w_op.numel(), ptr(amax), ptr(hi), ptr(lo), st)
+        return hi, lo, amax
+
+    def amax_of(t):
+        cell = torch.empty(1, device=dev)
+        call("bm_amax", ptr(t), t.numel(), ptr(cell), st)
+        return cell
+
+    # the kernels the training step runs: the persistent CTA-pair conv on the F16 pipe (bm_tc_conv1d_f16)
+    fh, fl, fa = f16_weights(f)
+    gh, gl, ga = f16_weights(g)
+    fgh, fgl, fga = f16_weights(fg)
+    xa = [amax_of(x) for x in xs]
+    out_amax = torch.empty(1, device=dev)
+    ms = _time_kernel([lambda x=x, y=y, a=a: call("bm_tc_conv1d_f16", ptr(x), ptr(a), ptr(fh), ptr(fl), ptr(fa), ptr(bias), 0, B, T,
+                                                  H, H, Kw, 4, 1, 0, 0, 0, ptr(y), None, None, ptr(stats), None, ptr(status), st)
+                       for x, y, a in zip(xs, ys, xa)])
+    main = tensor_entry("conv_hp_kernel via bm_tc_conv1d_f16 (K3: Conv1d 320->320 k3 d4 + BatchNorm statistics; persistent CTA "
+                        "pairs, tcgen05 cta_group::2 kind::f16, fp32 operands as fp16 hi/lo pieces)", ms,
+                        2.0 * H * H * Kw * T * B, 2.0 * B * T * H * 4, ncu_traffic_bytes("convh"), pipe="f16")
+    main["note"] = ("achieved = ALGORITHMIC fp32 FLOPs (2*320*320*3*T*B per launch) / time; fp32-faithful parity (1e-4) takes "
+                    "three MMAs per product, so the ceiling of `frac` is 1/3 on kind::f16 (1/6 on kind::tf32): see "
+                    "frac_of_scheme_ceiling")
     others = []
     try:
-        ms = _time_kernel([lambda x=x, y=y: call("bm_tc_conv1d_persistent", ptr(x), ptr(fg), None, 0, B, T, H, 2 * H, Kw, 1, 1,
-                                                 1, 0, 0, ptr(h), None, ptr(y), None, ptr(status), st) for x, y in zip(xs, ys)])
-        others.append(tensor_entry("conv_pp_kernel GLU mode (K4: Conv1d 320->640 k3 + GLU, h saved)", ms,
-                                   4.0 * H * H * Kw * T * B, 4.0 * B * T * H * 4, ncu_traffic_bytes("convp_glu")))
-        ms = _time_kernel([lambda x=x, y=y: call("bm_tc_conv1d_persistent", ptr(x), ptr(g), None, 1, B, T, H, H, Kw, 4, -1, 0,
-                                                 0, 0, ptr(y), None, None, None, ptr(status), st) for x, y in zip(xs, ys)])
-        others.append(tensor_entry("conv_pp_kernel data gradient, y += tile (TMA reduce-add)", ms, 2.0 * H * H * Kw * T * B,
-                                   3.0 * B * T * H * 4, ncu_traffic_bytes("convp_acc")))
+        ms = _time_kernel([lambda x=x, y=y, a=a: call("bm_tc_conv1d_f16", ptr(x), ptr(a), ptr(fgh), ptr(fgl), ptr(fga), None, 0,
+                                                      B, T, H, 2 * H, Kw, 1, 1, 1, 0, 0, ptr(h), None, ptr(y), None,
+                                                      ptr(out_amax), ptr(status), st) for x, y, a in zip(xs, ys, xa)])
+        others.append(tensor_entry("conv_hp_kernel GLU mode (K4: Conv1d 320->640 k3 + GLU, h saved, max |out| reported)", ms,
+                                   4.0 * H * H * Kw * T * B, 4.0 * B * T * H * 4, ncu_traffic_bytes("convh_glu"), pipe="f16"))
+        ms = _time_kernel([lambda x=x, y=y, a=a: call("bm_tc_conv1d_f16", ptr(x), ptr(a), ptr(gh), ptr(gl), ptr(ga), None, 1, B,
+                                                      T, H, H, Kw, 4, -1, 0, 0, 0, ptr(y), None, None, None, None, ptr(status),
+                                                      st) for x, y, a in zip(xs, ys, xa)])
+        others.append(tensor_entry("conv_hp_kernel data gradient, y += tile (TMA reduce-add)", ms, 2.0 * H * H * Kw * T * B,
+                                   3.0 * B * T * H * 4, ncu_traffic_bytes("convh_acc"), pipe="f16"))
+        # the 3xTF32 variant of the same kernel (round 2's first half; still what runs where USE_CONV_F16 is off)
+        ms = _time_kernel([lambda x=x, y=y: call("bm_tc_conv1d_persistent", ptr(x), ptr(f), ptr(bias), 0, B, T, H, H, Kw, 4, 1,
+                                                 0, 0, 0, ptr(y), None, None, ptr(stats), ptr(status), st)
+                           for x, y in zip(xs, ys)])
+        others.append(tensor_entry("conv_pp_kernel via bm_tc_conv1d_persistent (K3 on kind::tf32, 3xTF32: for comparison)", ms,
+                                   2.0 * H * H * Kw * T * B, 2.0 * B * T * H * 4, ncu_traffic_bytes("convp")))
         # K6: CLIP scores + candidate norms + softmax / CE / mean at the training shape (Bn = local rows, Bc = global rows)
         KT = F * T
         est = torch.randn(B, KT, device=dev) * 0.01
@@ -512,19 +544,26 @@ def kernel_rooflines(dev, B, T, F, Bc, H=320, Kw=3):
         # the kernel the training step uses for this layer (functional.tc_wgrad's choice): CTA pairs, rows = (tap, x channel)
         assert lib.bm_tc_wgrad_conv_supported(T, H, H, Kw)
         wsg = torch.empty(int(lib.bm_tc_wgrad_conv_workspace(B, T, H, H, Kw)), device=dev)
+        dya = [amax_of(dy) for dy in dys]
+        ms = _time_kernel([lambda x=x, dy=dy, a=a, b=b: call("bm_tc_wgrad_conv_f16", ptr(dy), ptr(b), ptr(x), ptr(a), B, T, H, H, H,
+                                                             Kw, 4, ptr(wsg), ptr(dw), ptr(status), st)
+                           for x, dy, a, b in zip(xs, dys, xa, dya)])
+        others.append(tensor_entry("wgrad_hp_kernel (+reduce) via bm_tc_wgrad_conv_f16 (weight gradient of K3, kind::f16)", ms,
+                                   2.0 * H * H * Kw * T * B, 2.0 * B * T * H * 4, ncu_traffic_bytes("wgradh"), pipe="f16"))
         ms = _time_kernel([lambda x=x, dy=dy: call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, H, H, H, Kw, 4, ptr(wsg), ptr(dw),
                                                    ptr(status), st) for x, dy in zip(xs, dys)])
-        others.append(tensor_entry("wgrad_pp_kernel (+reduce) via bm_tc_wgrad_conv (weight gradient of K3)", ms,
+        others.append(tensor_entry("wgrad_pp_kernel (+reduce) via bm_tc_wgrad_conv (the same on kind::tf32: for comparison)", ms,
                                    2.0 * H * H * Kw * T * B, 2.0 * B * T * H * 4, ncu_traffic_bytes("wgrad")))
         del wsg
-        # ... and of the GLU conv (640 x 320 x 3): the second-largest share of the step after conv_pp
+        # ... and of the GLU conv (640 x 320 x 3): the second-largest share of the step after the convs
         dy2 = torch.randn(B, T, 2 * H, device=dev)
+        dy2a = amax_of(dy2)
         dw2 = torch.empty(2 * H, H, Kw, device=dev)
         wsg = torch.empty(int(lib.bm_tc_wgrad_conv_workspace(B, T, 2 * H, H, Kw)), device=dev)
-        ms = _time_kernel([lambda x=x: call("bm_tc_wgrad_conv", ptr(dy2), ptr(x), B, T, 2 * H, H, H, Kw, 1, ptr(wsg), ptr(dw2),
-                                            ptr(status), st) for x in xs])
-        others.append(tensor_entry("wgrad_pp_kernel (+reduce) via bm_tc_wgrad_conv (weight gradient of K4)", ms,
-                                   2.0 * 2 * H * H * Kw * T * B, 3.0 * B * T * H * 4, None))
+        ms = _time_kernel([lambda x=x, a=a: call("bm_tc_wgrad_conv_f16", ptr(dy2), ptr(dy2a), ptr(x), ptr(a), B, T, 2 * H, H, H,
+                                                 Kw, 1, ptr(wsg), ptr(dw2), ptr(status), st) for x, a in zip(xs, xa)])
+        others.append(tensor_entry("wgrad_hp_kernel (+reduce) via bm_tc_wgrad_conv_f16 (weight gradient of K4)", ms,
+                                   2.0 * 2 * H * H * Kw * T * B, 3.0 * B * T * H * 4, None, pipe="f16"))
         del wsg, dy2, dw2
         # HBM-bound: BatchNorm + GELU (+skip) backward and forward
         gam, bet = torch.ones(H, device=dev), torch.zeros(H, device=dev)

@@ -62,6 +62,7 @@ SIGNATURES = {
     "bm_tc_wgrad": [P, P, I, I, I, I, I, I, I, P, P, P, P, P],
     "bm_tc_wgrad_conv_supported": [I, I, I, I],
     "bm_tc_wgrad_conv": [P, P, I, I, I, I, I, I, I, P, P, P, P],
+    "bm_tc_wgrad_conv_f16": [P, P, P, P, I, I, I, I, I, I, I, P, P, P, P],
     "bm_col_sum": [P, L, I, P, P],
     "bm_tc_pointwise_sel": [P, P, P, P, I, I, I, I, I, P, P, P],
     "bm_tc_wgrad_grouped": [P, P, P, P, I, I, I, I, I, P, P, P],

@@ -9,6 +9,7 @@
 #include "tc_clip.cuh"
 #include "tc_convp.cuh"
 #include "tc_convh.cuh"
+#include "tc_wgradh.cuh"
 #include "tc_wgradp.cuh"
 #include "tc_gemm_nt.cuh"
 #include "retrieval.cuh"
@@ -930,6 +931,16 @@ extern "C" int bm_tc_wgrad_conv(const float* dy, const float* x, int B, int T, i
     BM_CHECK_ARG(dy && x && workspace && dw && B > 0 && T > 0 && dilation >= 1);
     BM_CHECK_ARG(tc::wgradp_supported(T, M, N, Kw) && Ntrue > 0 && Ntrue <= N);
     return tc::launch_wgrad_pp(dy, x, B, T, M, N, Ntrue, Kw, dilation, workspace, dw, status, ST(stream));
+}
+
+// the same weight gradient on the F16 pipe (csrc/tc_wgradh.cuh): dy_amax / x_amax = device floats with max |dy|, max |x|
+// (bm_amax, or the amax_out of the kernels that produced the tensors); same shape gate and workspace as bm_tc_wgrad_conv
+extern "C" int bm_tc_wgrad_conv_f16(const float* dy, const float* dy_amax, const float* x, const float* x_amax, int B, int T,
+                                    int M, int N, int Ntrue, int Kw, int dilation, float* workspace, float* dw, int* status,
+                                    bm_stream_t stream) {
+    BM_CHECK_ARG(dy && dy_amax && x && x_amax && workspace && dw && B > 0 && T > 0 && dilation >= 1);
+    BM_CHECK_ARG(tc::wgradp_supported(T, M, N, Kw) && Ntrue > 0 && Ntrue <= N);
+    return tc::launch_wgrad_hp(dy, dy_amax, x, x_amax, B, T, M, N, Ntrue, Kw, dilation, workspace, dw, status, ST(stream));
 }
 
 extern "C" int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream) {

@@ -94,12 +94,14 @@ def _round_up(n, m):
 
 
 USE_CONV_F16 = True    # the persistent conv on the F16 tensor pipe (tc_convh.cuh: fp16 hi/lo pieces, twice the MMA rate of 3xTF32)
+USE_WGRAD_F16 = True   # ... and the CTA-pair weight gradient (tc_wgradh.cuh)
 USE_WGRAD_PP = True    # CTA-pair weight-gradient kernel (tc_wgradp.cuh) where its 256-row tiling wastes < 10 %
 
 
-def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None):
+def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None, dy_amax=None, x_amax=None):
     """dw[m][n][tap] = sum_{b,t} dy[b,t,m] x[b,t+(tap-kw//2)*dilation,n] on the tensor cores -> [M, Ntrue, kw];
-    `dbias` [M] (optional) receives sum_{b,t} dy[b,t,m]."""
+    `dbias` [M] (optional) receives sum_{b,t} dy[b,t,m].  `dy_amax` / `x_amax` (F16 pipe): device floats with max |dy| /
+    max |x| when their producers reported them, else a bm_amax pass here."""
     lib = _lib.load()
     dw = _empty((M, Ntrue, kw), dy)
     rows = kw * N                                       # output rows of the pair kernel, tiled in blocks of 256
@@ -107,7 +109,13 @@ def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None):
         rows / (-(-rows // 256) * 256) >= 0.9            # else the single-CTA kernel wastes less on padding rows
     if pair_ok:
         ws = _empty((int(lib.bm_tc_wgrad_conv_workspace(B, T, M, N, kw)),), dy)
-        call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(status), stream())
+        if USE_WGRAD_F16:
+            dy_amax = tensor_amax(dy) if dy_amax is None else dy_amax
+            x_amax = tensor_amax(x) if x_amax is None else x_amax
+            call("bm_tc_wgrad_conv_f16", ptr(dy), ptr(dy_amax), ptr(x), ptr(x_amax), B, T, M, N, Ntrue, kw, dilation, ptr(ws),
+                 ptr(dw), ptr(status), stream())
+        else:
+            call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, Ntrue, kw, dilation, ptr(ws), ptr(dw), ptr(status), stream())
         if dbias is not None:
             call("bm_col_sum", ptr(dy), B * T, M, ptr(dbias), stream())
         return dw
@@ -244,18 +252,20 @@ class _Conv:
             call("bm_conv1d_bwd_data", ptr(dy), ptr(self.wb), ptr(addend), B, T, self.cin, self.cout, self.kw,
                  dilation, ptr(dx), st)
 
-    def backward_weight(self, dy, x, B, T, dilation, like, status, bias_grad_is_zero=False, known_dbias=None):
+    def backward_weight(self, dy, x, B, T, dilation, like, status, bias_grad_is_zero=False, known_dbias=None, dy_amax=None,
+                        x_amax=None):
         """`bias_grad_is_zero`: the conv feeds a training-mode BatchNorm, whose backward makes sum(dy) == 0 exactly
         (the reference's value there is rounding noise around 0); skip the reduction.  `known_dbias`: the producer of dy
-        already summed it over the rows."""
+        already summed it over the rows.  `dy_amax` / `x_amax`: see tc_wgrad."""
         if self.wgrad_tc:
+            am = dict(dy_amax=dy_amax, x_amax=x_amax)
             if known_dbias is not None:
-                return tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status), known_dbias
+                return tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status, **am), known_dbias
             if bias_grad_is_zero:
-                dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status)
+                dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status, **am)
                 return dw, torch.zeros((self.cout,), device=like.device)
             db = _empty((self.cout,), like)
-            dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status, dbias=db)
+            dw = tc_wgrad(dy, x, B, T, self.cout, self.cin, self.cin_true, self.kw, dilation, status, dbias=db, **am)
             return dw, db
         db = _empty((self.cout,), like)
         dw = _empty((self.cout, self.cin, self.kw), like)
@@ -531,7 +541,7 @@ class _EncoderFn(torch.autograd.Function):
                 call("bm_bn_eval_stats", ptr(rm), ptr(rv), float(plan.bn_eps), ptr(mean), ptr(invstd), cout, st)
             skip = plan.skip and conv.cin_true == cout
             x_new = _empty((B, T, cout), meg)
-            x_amax = None
+            x_in_amax, x_amax = x_amax, None
             if plan.act_code == 0:
                 x_amax = amax_cell(meg)
                 call("bm_bn_gelu_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
@@ -540,7 +550,8 @@ class _EncoderFn(torch.autograd.Function):
                 call("bm_bn_act_skip_fwd", ptr(y), ptr(mean), ptr(invstd), ptr(gamma.contiguous()),
                      ptr(beta.contiguous()), ptr(x) if skip else None, ptr(x_new), rows, cout, plan.act_code,
                      float(plan.act_slope), st)
-            rec = dict(x_in=x, y=y, mean=mean, invstd=invstd, conv=conv, skip=skip, x_new=x_new)
+            rec = dict(x_in=x, y=y, mean=mean, invstd=invstd, conv=conv, skip=skip, x_new=x_new, x_in_amax=x_in_amax,
+                       x_new_amax=x_amax)
             x = x_new
             if plan.glu_after[k]:
                 gw, gb = glu_p[k]
@@ -579,6 +590,7 @@ class _EncoderFn(torch.autograd.Function):
         w0_2 = w0.reshape(H2, H).contiguous()
         w2_2 = w2.reshape(H2, F).contiguous()
         head_generic = plan.act_code != 0
+        q_amax = None
         if head_generic:
             # simpleconv.gelu=False (simpleconv.py:85-90,187): conv -> activation kernel -> conv, channels-last, then one
             # transpose to the channel-major estimate (the fused GELU epilogues below do not apply)
@@ -604,7 +616,7 @@ class _EncoderFn(torch.autograd.Function):
             ctx.pads = (Op, ILp)
             ctx.saved = dict(meg=meg, emb=emb, att=att, u=u, v=v, il_w2=il_w2, subj_w=None if subj_w is None else subj_w.contiguous(), il_conv=il_conv,
                              subj_pad=subj_pad, megT=megT, heads_tc=heads_conv is not None,
-                             layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q,
+                             layers=saved_layers, x_last=x, w0_2=w0_2, w2_2=w2_2, h1=h1, q=q, q_amax=q_amax,
                              head0=head0, head2=head2, head_tc=head_tc, head_generic=head_generic,
                              conv_p=conv_p, glu_p=glu_p, il_shape=None if il_w is None else il_w.shape,
                              w0_shape=w0.shape, w2_shape=w2.shape, front=front, params=(heads, il_w, subj_w, sub_emb))
@@ -656,7 +668,8 @@ class _EncoderFn(torch.autograd.Function):
             dest_t = _empty((B, T, F), meg)
             call("bm_transpose_nt", ptr(dest), B, F, T, ptr(dest_t), st)
             # dq = dest_t @ w2^T  (w2_as_conv [F,2H,1]: its data-gradient operand is [1][2H][F])
-            head2.run_tc(False, dest_t, None, None, B, T, 1, 0, 0, 0, dq, None, None, None, status)
+            dest_amax = tensor_amax(dest_t) if USE_CONV_F16 else None      # one pass serves the dgrad and the wgrad below
+            head2.run_tc(False, dest_t, None, None, B, T, 1, 0, 0, 0, dq, None, None, None, status, x_amax=dest_amax)
             lib = _lib.load()
             if lib.bm_tc_wgrad_supported(H2, F) and lib.bm_tc_wgrad_supported(H2, H):
                 main0 = torch.cuda.current_stream()
@@ -674,7 +687,8 @@ class _EncoderFn(torch.autograd.Function):
                     return out
 
                 # dW2 / db2 only need dest_t and q: they overlap the dq contraction queued just before
-                dw2 = on_side(lambda: tc_wgrad(s["q"], dest_t, B, T, H2, F, F, 1, 1, status), s["q"], dest_t).reshape(H2, F)
+                dw2 = on_side(lambda: tc_wgrad(s["q"], dest_t, B, T, H2, F, F, 1, 1, status, dy_amax=s.get("q_amax"),
+                                               x_amax=dest_amax), s["q"], dest_t, dest_amax).reshape(H2, F)
                 call("bm_col_sum", ptr(dest_t), rows, F, ptr(db2), st)
                 call("bm_gelu_bwd", ptr(dq), ptr(s["h1"]), rows * H2, ptr(dq), st)           # dq <- dh1
                 dw0 = on_side(lambda: tc_wgrad(dq, s["x_last"], B, T, H2, H, H, 1, 1, status, dbias=db0), dq,
@@ -698,17 +712,17 @@ class _EncoderFn(torch.autograd.Function):
         side = _side_stream(meg.device) if (OVERLAP_WGRAD and plan.use_tensor_cores) else None
         keep_alive: tp.List[tp.Any] = ctx_keep
 
-        def weight_grad(conv_obj, dy_t, x_t, dil, bias_zero, known_dbias=None):
+        def weight_grad(conv_obj, dy_t, x_t, dil, bias_zero, known_dbias=None, dy_amax=None, x_amax=None):
             if side is None:
                 return conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero,
-                                                known_dbias=known_dbias)
+                                                known_dbias=known_dbias, dy_amax=dy_amax, x_amax=x_amax)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 out = conv_obj.backward_weight(dy_t, x_t, B, T, dil, meg, status, bias_grad_is_zero=bias_zero,
-                                               known_dbias=known_dbias)
+                                               known_dbias=known_dbias, dy_amax=dy_amax, x_amax=x_amax)
             # the big operands are kept alive until the streams join (no record_stream: with the host running steps ahead
             # it would block the allocator from reusing ~3 GB of blocks and force cudaMallocs in the timed loop)
-            keep_alive.append((dy_t, x_t))
+            keep_alive.append((dy_t, x_t, dy_amax, x_amax))
             for o in out:
                 o.record_stream(main)
             return out
@@ -724,7 +738,7 @@ class _EncoderFn(torch.autograd.Function):
                 dgb = _empty((gconv.cout,), meg)          # the GLU conv's bias gradient, summed while dh is produced
                 dh_amax = amax_cell(meg)
                 call("bm_glu_bwd", ptr(g), ptr(rec["h"]), rows, gconv.cout // 2, ptr(dh), ptr(dgb), ptr(dh_amax), st)
-                glu_grads[k] = weight_grad(gconv, dh, rec["x_new"], 1, False, dgb)
+                glu_grads[k] = weight_grad(gconv, dh, rec["x_new"], 1, False, dgb, dy_amax=dh_amax, x_amax=rec.get("x_new_amax"))
                 g = _empty((B, T, gconv.cin), meg)
                 gconv.backward_data(dh, None, B, T, 1, g, status, dy_amax=dh_amax)
                 del dh
@@ -754,7 +768,8 @@ class _EncoderFn(torch.autograd.Function):
                 call("bm_bn_act_skip_bwd", ptr(g), ptr(rec["y"]), ptr(rec["mean"]), ptr(rec["invstd"]),
                      ptr(gamma.contiguous()), ptr(beta.contiguous()), 1 if plan.training else 0, rows, cout,
                      plan.act_code, float(plan.act_slope), ptr(sums), ptr(dy), ptr(dgamma), ptr(dbeta), st)
-            dcw, dcb = weight_grad(conv, dy, rec["x_in"], plan.dilations[k], plan.training)
+            dcw, dcb = weight_grad(conv, dy, rec["x_in"], plan.dilations[k], plan.training, dy_amax=dy_amax,
+                                   x_amax=rec.get("x_in_amax"))
             if rec["skip"]:
                 # in place: g += conv_transpose(dy) (addend == output: the pair kernel turns this into a TMA reduce-add)
                 conv.backward_data(dy, g, B, T, plan.dilations[k], g, status, dy_amax=dy_amax)

@@ -298,6 +298,12 @@ int bm_tc_wgrad_conv_supported(int T, int M, int N, int Kw);
 long long bm_tc_wgrad_conv_workspace(int B, int T, int M, int N, int Kw);
 int bm_tc_wgrad_conv(const float* dy, const float* x, int B, int T, int M, int N, int Ntrue, int Kw, int dilation,
                      float* workspace, float* dw, int* status, bm_stream_t stream);
+/* bm_tc_wgrad_conv_f16: the same on the F16 pipe (csrc/tc_wgradh.cuh; see bm_tc_conv1d_f16 for the arithmetic): both
+ * operands as fp16 hi/lo pieces of the tensors scaled by powers of two from dy_amax / x_amax (device floats: bm_amax or a
+ * producer's amax_out); the dY tile is transposed to K-major rows while it is split.  Same gate and workspace. */
+int bm_tc_wgrad_conv_f16(const float* dy, const float* dy_amax, const float* x, const float* x_amax, int B, int T, int M,
+                         int N, int Ntrue, int Kw, int dilation, float* workspace, float* dw, int* status,
+                         bm_stream_t stream);
 int bm_col_sum(const float* x, long long rows, int C, float* out, bm_stream_t stream);
 /* SubjectLayers (common.py:55-58) on the tensor cores.
  * bm_tc_pointwise_sel: y[b,t,n] = sum_k x[b,t,k] W[wsel[b]][n][k] with tf32-split weight sets w_hi/w_lo [S][Ntot][Cin].

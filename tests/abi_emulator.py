@@ -451,6 +451,17 @@ class Emulator:
     def bm_tc_wgrad_conv(self, dy, x, B, T, M, N, Ntrue, Kw, dilation, ws, dw, status, stream):
         self.bm_tc_wgrad(dy, x, B, T, M, N, Ntrue, Kw, dilation, ws, dw, None, status, stream)
 
+    def _f16_pieces(self, t, n, amax):
+        """What the F16-pipe kernels multiply by: (hi + lo) / scale of t * scale, both pieces rounded to fp16."""
+        s = self._f16_scale(float(_v(amax, 1)))
+        v = _v(t, n) * s
+        h = v.to(torch.float16)
+        return ((h.float() + (v - h.float()).to(torch.float16).float()) / s).contiguous()
+
+    def bm_tc_wgrad_conv_f16(self, dy, dy_amax, x, x_amax, B, T, M, N, Ntrue, Kw, dilation, ws, dw, status, stream):
+        self.bm_tc_wgrad(self._f16_pieces(dy, B * T * M, dy_amax), self._f16_pieces(x, B * T * N, x_amax), B, T, M, N, Ntrue,
+                         Kw, dilation, ws, dw, None, status, stream)
+
     def bm_tc_pointwise_sel(self, x, w_hi, w_lo, wsel, n_sets, B, T, Cin, Ntot, y, status, stream):
         w = _v(w_hi, n_sets, Ntot, Cin) + _v(w_lo, n_sets, Ntot, Cin)
         _v(y, B, T, Ntot).copy_(torch.einsum("btk,bnk->btn", _v(x, B, T, Cin), w[wsel.long()[:B]]))

@@ -10,7 +10,7 @@ def test_full_size_step_runs_on_tensor_cores_only():
     names = {c[0] for c in abi_trace.simpleconv_step(abi_trace.CONFIGS["full"], True)}
     assert not names & {"bm_conv1d_fwd", "bm_conv1d_bwd_data", "bm_conv1d_bwd_weight", "bm_conv1d_glu_fwd", "bm_head_fwd",
                         "bm_head_bwd", "bm_sensor_chain_fwd", "bm_sensor_chain_bwd", "bm_attention_weights_fwd"}
-    assert {"bm_tc_conv1d_f16", "bm_tc_wgrad_conv", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
+    assert {"bm_tc_conv1d_f16", "bm_tc_wgrad_conv_f16", "bm_tc_pointwise_sel", "bm_tc_wgrad_grouped"} <= names
     # F16 pipe: the tensors between two kernels of the conv stack carry their max |.| from the producer; bm_amax passes are
     # left only in front of the convs whose input comes from elsewhere (sensor chain, head gradient, ...)
     calls = abi_trace.simpleconv_step(abi_trace.CONFIGS["full"], True)

@@ -217,8 +217,10 @@ def test_tc_wgrad_speed_report(capsys, trunc):
     dict(B=2, T=64, M=192, N=96, Kw=3, dil=1),
     dict(B=40, T=360, M=320, N=320, Kw=3, dil=8),
 ])
-def test_tc_wgrad_pair_kernel(case):
-    """bm_tc_wgrad_conv (csrc/tc_wgradp.cuh): rows = (tap, x channel), flattened reduction, CTA pairs."""
+@pytest.mark.parametrize("pipe", ["tf32", "f16"])
+def test_tc_wgrad_pair_kernel(case, pipe):
+    """bm_tc_wgrad_conv (csrc/tc_wgradp.cuh) and bm_tc_wgrad_conv_f16 (csrc/tc_wgradh.cuh): rows = (tap, x channel), flattened
+    reduction, CTA pairs."""
     call, ptr, stream = _call()
     from brainmagick_b200 import _lib
     torch.manual_seed(11)
@@ -230,7 +232,19 @@ def test_tc_wgrad_pair_kernel(case):
     ws = torch.full((int(_lib.load().bm_tc_wgrad_conv_workspace(B, T, M, N, Kw)),), float("nan"), device=dev)
     dw = torch.full((M, N, Kw), float("nan"), device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw), ptr(status), stream())
+    if pipe == "f16":
+        dy *= 3e-4                                                    # gradients are small: the per-tensor scales matter
+        amax = torch.empty(2, device=dev)
+        call("bm_amax", ptr(dy), dy.numel(), ptr(amax[0:1]), stream())
+        call("bm_amax", ptr(x), x.numel(), ptr(amax[1:2]), stream())
+
+        def run(out):
+            call("bm_tc_wgrad_conv_f16", ptr(dy), ptr(amax[0:1]), ptr(x), ptr(amax[1:2]), B, T, M, N, N, Kw, dil, ptr(ws),
+                 ptr(out), ptr(status), stream())
+    else:
+        def run(out):
+            call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(out), ptr(status), stream())
+    run(dw)
     torch.cuda.synchronize()
     assert int(status.item()) == 0, f"tcgen05 pipeline timed out at barrier code {int(status.item())}"
     ref = torch.zeros(M, N, Kw, dtype=torch.float64, device=dev)
@@ -240,10 +254,10 @@ def test_tc_wgrad_pair_kernel(case):
         lo, hi = max(0, -s), min(T, T - s)
         ref[:, :, j] = torch.einsum("btm,btn->mn", dyd[:, lo:hi], xd[:, lo + s:hi + s])
     e = rel_err(dw.cpu(), ref.cpu())
-    print(f"[tc wgrad pair {case}] rel_err vs fp64 = {e:.2e}")
+    print(f"[tc wgrad pair {pipe} {case}] rel_err vs fp64 = {e:.2e}")
     assert e < TOL
     dw2 = torch.empty_like(dw)
-    call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, dil, ptr(ws), ptr(dw2), ptr(status), stream())
+    run(dw2)
     torch.cuda.synchronize()
     assert torch.equal(dw, dw2)                                   # fixed-order reduction
 
@@ -262,7 +276,13 @@ def test_tc_wgrad_pair_speed_report(capsys):
         dw = torch.empty(M, N, Kw, device=dev)
         ws_new = torch.empty(int(_lib.load().bm_tc_wgrad_conv_workspace(B, T, M, N, Kw)), device=dev)
         ws_old = torch.empty(int(_lib.load().bm_tc_wgrad_workspace(B, M, N, Kw)), device=dev)
-        for name, fn in (("pair kernel", lambda: call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws_new),
+        amax = torch.empty(2, device=dev)
+        call("bm_amax", ptr(dy), dy.numel(), ptr(amax[0:1]), stream())
+        call("bm_amax", ptr(x), x.numel(), ptr(amax[1:2]), stream())
+        for name, fn in (("pair kernel, F16 pipe", lambda: call("bm_tc_wgrad_conv_f16", ptr(dy), ptr(amax[0:1]), ptr(x),
+                                                                 ptr(amax[1:2]), B, T, M, N, N, Kw, 4, ptr(ws_new), ptr(dw),
+                                                                 ptr(status), stream())),
+                         ("pair kernel", lambda: call("bm_tc_wgrad_conv", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws_new),
                                                        ptr(dw), ptr(status), stream())),
                          ("round-1 kernel", lambda: call("bm_tc_wgrad", ptr(dy), ptr(x), B, T, M, N, N, Kw, 4, ptr(ws_old),
                                                           ptr(dw), None, ptr(status), stream()))):
