@@ -127,7 +127,9 @@ def ptr(t):
 
 
 def stream():
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current CUDA stream's handle (raw C accessors: torch.cuda.current_stream() builds a Stream object and resolves the
+    device through several Python layers, 1.9 ms per step over the ~1 400 calls of one)."""
+    return c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def launch_count() -> int:

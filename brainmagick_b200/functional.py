@@ -125,6 +125,18 @@ def tc_wgrad(dy, x, B, T, M, N, Ntrue, kw, dilation, status, dbias=None, dy_amax
     return dw
 
 
+def group_layout(index: torch.Tensor, n_groups: int):
+    """CSR grouping of the samples by `index` (values 0..n_groups-1): (order [B] int32, offsets [n_groups+1] int32), computed
+    on the device WITHOUT a device->host synchronisation -- torch.bincount sizes its output from the data and stalls the host
+    until everything queued before it has run (8.6 ms of a 17.6 ms step, measured with profiles/host_profile.py)."""
+    order = torch.argsort(index, stable=True).to(torch.int32)
+    groups = torch.arange(n_groups, device=index.device, dtype=index.dtype)
+    counts = (index.reshape(-1, 1) == groups.reshape(1, -1)).sum(0)
+    off = torch.zeros(n_groups + 1, dtype=torch.int32, device=index.device)
+    off[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    return order, off
+
+
 def tensor_amax(x: torch.Tensor) -> torch.Tensor:
     """max |x| as a device float [1] (bm_amax: one pass over x): the F16 pipe's per-tensor scale comes from it."""
     cell = _empty((1,), x)
@@ -336,9 +348,7 @@ def _staged_front_backward(plan: "EncoderPlan", saved, g, heads, il_w, subj_w, s
     d_subj = None
     if subj_w is not None:
         S = subj_w.shape[0]
-        subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
-        subj_off = torch.zeros(S + 1, dtype=torch.int32, device=meg.device)
-        subj_off[1:] = torch.cumsum(torch.bincount(plan.subject, minlength=S), 0).to(torch.int32)
+        subj_order, subj_off = group_layout(plan.subject, S)
         d_subj = _empty((S, w_v, w_x), meg)
         dv = _empty((B, T, w_v), meg)
         call("bm_subject_layers_bwd", ptr(g), w_x, ptr(saved["v"]), w_v, ptr(subj_w.contiguous()), ptr(plan.subject),
@@ -790,10 +800,7 @@ class _EncoderFn(torch.autograd.Function):
         else:
             d_sub_emb = None
             # ---- sensor chain + attention ----
-            subj_order = torch.argsort(plan.subject, stable=True).to(torch.int32)
-            counts = torch.bincount(plan.subject, minlength=S)
-            subj_off = torch.zeros(S + 1, dtype=torch.int32, device=meg.device)
-            subj_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            subj_order, subj_off = group_layout(plan.subject, S)
             Op, ILp = ctx.pads
             d_subj = _empty((S, IL, D), meg)
             d_att = _empty((R, O, C), meg)
@@ -1060,9 +1067,7 @@ class _SubjectLayersFn(torch.autograd.Function):
         st = stream()
         g = _empty((B, T, D), xl)
         call("bm_transpose_nt", ptr(gout.contiguous()), B, D, T, ptr(g), st)
-        order = torch.argsort(subject, stable=True).to(torch.int32)
-        off = torch.zeros(S + 1, dtype=torch.int32, device=xl.device)
-        off[1:] = torch.cumsum(torch.bincount(subject, minlength=S), 0).to(torch.int32)
+        order, off = group_layout(subject, S)
         dxl, dw = _empty((B, T, Cin), xl), _empty((S, Cin, D), xl)
         call("bm_subject_layers_bwd", ptr(g), D, ptr(xl), Cin, ptr(w), ptr(subject), ptr(order), ptr(off), B, T, Cin, D, S,
              Cin, ptr(dxl), ptr(dw), st)
