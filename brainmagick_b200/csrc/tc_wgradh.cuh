@@ -10,6 +10,9 @@
 //       thread = dY channel reads its column of the raw [32 pos][32 ch] box (conflict-free) and writes one K-major row
 //       (32 fp16 = 64 B, SWIZZLE_64B) of the hi tile and of the lo tile -- the operand layout conv_hp_kernel already uses.
 // 12 kind::f16 MMAs per chunk (M = 256, N = h0 / h1, K = 16) instead of 24 kind::tf32 MMAs.
+// With the tensor-pipe time halved the CONVERTERS set the pace (~300 instructions per thread per chunk against 960 MMA
+// cycles): two warps share every converter row set (16 of the chunk's 32 positions each: 8 A warps + 10 B warps), and the
+// sample-edge test is one ballot per chunk (lane j = position j) instead of a compare chain per element.
 #pragma once
 #include "tc_wgradp.cuh"
 #include "tc_convh.cuh"
@@ -17,13 +20,19 @@
 namespace bm {
 namespace tc {
 
-constexpr int WH_BK = 32, WH_STAGES = 3, WH_ASTAGES = 5, WH_THREADS = 384;
+constexpr int WH_BK = 32, WH_STAGES = 3, WH_ASTAGES = 5, WH_THREADS = 672;        // 21 warps, see the kernel
 constexpr int WH_RAW_BYTES = WP_MAX_BLKS * WP_BLK_BYTES;        // 20 KB: this CTA's dY boxes, raw fp32
 constexpr int WH_BH_BYTES = WP_MAX_BLKS * 32 * WH_BK * 2;       // 10 KB: 160 K-major rows of 64 B (hi); the same again for lo
 constexpr int WH_STAGE_BYTES = WH_RAW_BYTES + 2 * WH_BH_BYTES;  // 40 KB
 constexpr int WH_ATILE_BYTES = 4 * WP_BLK_BYTES;                // 16 KB: X boxes of one chunk
 constexpr int WH_SMEM_BYTES = WH_STAGES * WH_STAGE_BYTES + WH_ASTAGES * WH_ATILE_BYTES + 1024;
 constexpr int WH_ACC_COLS = 320, WH_A_COLS = WH_BK;             // 16 packed hi columns + 16 packed lo columns
+
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 
 struct WgradHP {
     WgradPP c;
@@ -65,12 +74,12 @@ wgrad_hp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < WH_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&conv_bar[s], 2 * (4 + nblk));                // one elected lane per converter warp of both CTAs (LEADER's copy)
+            mbar_init(&conv_bar[s], 2 * (8 + 2 * nblk));            // one elected lane per converter warp of both CTAs (LEADER's copy)
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < WH_ASTAGES; ++s) {
             mbar_init(&afull_bar[s], 1);
-            mbar_init(&aempty_bar[s], 4);
+            mbar_init(&aempty_bar[s], 8);
         }
         mbar_init(&tmem_full_bar, 1);
         fence_barrier_init();
@@ -140,13 +149,15 @@ wgrad_hp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                 __syncwarp();
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 10) {
         // ------------------------------------------------ A: shifted X rows * s -> TMEM (fp16 pairs); then the epilogue --
-        const int q = warp & 3;
+        // warp pair (q, half): TMEM lane quarter q = warp % 4, positions [16 half, +16) of the chunk
+        const int q = warp & 3, half = (warp - 2) >> 2;
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         const int grow = m_tile * 256 + (int)rank * 128 + q * 32 + lane;      // output row (tap, n)
         const bool row_ok = grow < p.rows;
-        const int tap = row_ok ? grow / p.Nx : 0;
+        const int wrow = m_tile * 256 + (int)rank * 128 + q * 32;             // the warp's first row: one tap per warp (Nx % 32 == 0)
+        const int tap = wrow < p.rows ? wrow / p.Nx : 0;
         const int shift = (tap - p.taps / 2) * p.dilation;
         const float sx = f16_scale_of(__ldg(hp.x_amax));
         uint8_t* a_ring = smem + WH_STAGES * WH_STAGE_BYTES;
@@ -154,33 +165,34 @@ wgrad_hp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
         for (int it = 0; it < total && ok; ++it) {
             const int s = it % WH_STAGES, sa = it % WH_ASTAGES;
             const uint32_t ph = (it / WH_STAGES) & 1, pha = (it / WH_ASTAGES) & 1;
-            ok = mbar_wait(&afull_bar[sa], pha, p.err, 107);              // this chunk's X boxes have landed
-            const float* col = reinterpret_cast<const float*>(a_ring + sa * WH_ATILE_BYTES + q * WP_BLK_BYTES) + lane;
+            // which of the chunk's 32 positions stay inside their sample after the tap shift (else: the conv's zero padding)
             const int p0 = (it_begin + it) * WH_BK;
-            int t = p0 % p.T;                                            // time of the chunk's first row in its sample
-            uint32_t r[WH_BK];                                           // [0,16) hi pairs, [16,32) lo pairs
+            int tj = p0 % p.T + lane;                                    // T >= 32: at most one wrap inside a chunk
+            if (tj >= p.T) tj -= p.T;
+            const uint32_t inside = __ballot_sync(0xffffffffu, tj + shift >= 0 && tj + shift < p.T);
+            const uint32_t live = (row_ok ? inside : 0u) >> (half * 16);      // bit j = this half's position j
+            ok = mbar_wait(&afull_bar[sa], pha, p.err, 107);              // this chunk's X boxes have landed
+            const float* col = reinterpret_cast<const float*>(a_ring + sa * WH_ATILE_BYTES + q * WP_BLK_BYTES) + lane +
+                               half * 16 * 32;
+            uint32_t r[16];                                              // [0,8) hi pairs, [8,16) lo pairs of this half
 #pragma unroll
-            for (int j = 0; j < WH_BK; j += 2) {
-                float v0 = col[j * 32], v1 = col[(j + 1) * 32];
-                int ts = t + shift;
-                if (!(row_ok && ts >= 0 && ts < p.T)) v0 = 0.f;          // across a sample edge: the conv's zero padding
-                if (++t == p.T) t = 0;
-                ts = t + shift;
-                if (!(row_ok && ts >= 0 && ts < p.T)) v1 = 0.f;
-                if (++t == p.T) t = 0;
-                f16_split2(v0 * sx, v1 * sx, r[j / 2], r[16 + j / 2]);
+            for (int j = 0; j < 16; j += 2) {
+                const float v0 = ((live >> j) & 1u) ? col[j * 32] * sx : 0.f;
+                const float v1 = ((live >> (j + 1)) & 1u) ? col[(j + 1) * 32] * sx : 0.f;
+                f16_split2(v0, v1, r[j / 2], r[8 + j / 2]);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&aempty_bar[sa]);                 // the ring slot can be refilled
             ok = ok && mbar_wait(&empty_bar[s], ph ^ 1, p.err, 104);      // the MMAs of chunk it-STAGES have left this slot
             tc_fence_after();
-            tmem_st32u(tq + WH_ACC_COLS + s * WH_A_COLS, r);
+            tmem_st8u(tq + WH_ACC_COLS + s * WH_A_COLS + half * 8, r);
+            tmem_st8u(tq + WH_ACC_COLS + s * WH_A_COLS + WH_BK / 2 + half * 8, r + 8);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&conv_bar[s]), 0));
         }
-        // ---- epilogue: partial tile -> workspace [ks][mtiles*256][Mdy] ----
+        // ---- epilogue: partial tile -> workspace [ks][mtiles*256][Mdy]; the two warps of a quarter alternate column chunks ----
         if (!skip) {
             if (total > 0) mbar_wait(&tmem_full_bar, 0, p.err, 106);
             tc_fence_after();
@@ -188,7 +200,7 @@ wgrad_hp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
             const float comp = acc_trunc_comp(total * (WH_BK / 16) * 3) * (1.0f / sx) *
                                (1.0f / f16_scale_of(__ldg(hp.dy_amax)));
 #pragma unroll 1
-            for (int c = 0; c < p.nt / 32; ++c) {
+            for (int c = half; c < p.nt / 32; c += 2) {
                 float v[32];
                 if (total > 0) {
                     tmem_ld32(tq + c * 32, v);
@@ -204,9 +216,10 @@ wgrad_hp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
             }
             tc_fence_before();
         }
-    } else if (warp < 11) {
+    } else if (warp < 20) {
         // ------------------------------------------------ B: dY block w (32 channels) -> K-major fp16 hi / lo rows ------
-        const int w = warp - 6;                                          // block index 0..4
+        // warp pair (w, half): block w, positions [16 half, +16) = 16-byte chunks 2 half, 2 half + 1 of the 64-byte rows
+        const int w = (warp - 10) >> 1, half = (warp - 10) & 1;
         if (w < nblk) {
             const float sdy = f16_scale_of(__ldg(hp.dy_amax));
             const int brow = w * 32 + lane;                              // row of the CTA's B tile (half 0 rows, then half 1 rows)
@@ -221,7 +234,8 @@ wgrad_hp_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant_
                 uint8_t* hrow = st + WH_RAW_BYTES + brow * 64;
                 uint8_t* lrow = hrow + WH_BH_BYTES;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {                            // 8 positions = one 16-byte chunk of the row
+                for (int cc = 0; cc < 2; ++cc) {                         // 8 positions = one 16-byte chunk of the row
+                    const int c = 2 * half + cc;
                     uint4 h, l;
                     f16_split2(col[(8 * c + 0) * 32] * sdy, col[(8 * c + 1) * 32] * sdy, h.x, l.x);
                     f16_split2(col[(8 * c + 2) * 32] * sdy, col[(8 * c + 3) * 32] * sdy, h.y, l.y);
