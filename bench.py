@@ -667,6 +667,8 @@ def run_reference(args):
 
 
 def main():
+    # NCCL's own log lines (its version banner, NCCL_DEBUG=INFO output) go to stdout by default: keep stdout for the ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

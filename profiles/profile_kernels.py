@@ -1,5 +1,5 @@
 """Runs each hot kernel a few times at the BASELINE shape (B=256, T=360, H=320) so that one `ncu --set full`
-capture per kernel is short (which = conv | conv_glu | conv_acc | wgrad | prep | topk | scores | scores_train | bn_bwd | bn_fwd):   ncu --set full --clock-control none --import-source on -k regex:<name> -s 3 -c 2 \
+capture per kernel is short (which = convh | convh_glu | convh_acc | wgradh | conv | conv_glu | conv_acc | wgrad | prep | topk | scores | scores_train | bn_bwd | bn_fwd):   ncu --set full --clock-control none --import-source on -k regex:<name> -s 3 -c 2 \
                                -o gpurun_out/prof_<name> python profiles/profile_kernels.py <which>"""
 import os
 import sys
@@ -14,7 +14,42 @@ which = sys.argv[1] if len(sys.argv) > 1 else "conv"
 dev = "cuda"
 B, T, H, Kw = 256, 360, 320, 3
 status = torch.zeros(1, dtype=torch.int32, device=dev)
-if which in ("conv", "conv_glu", "conv_acc"):
+if which in ("convh", "convh_glu", "convh_acc", "wgradh"):
+    # -k regex:conv_hp_kernel / wgrad_hp_kernel: the F16-pipe kernels the training step runs (K3 forward with BatchNorm
+    # statistics | K4 GLU forward (h saved, amax reported) | K3 data gradient, y += tile | K3 weight gradient)
+    lib = _lib.load()
+    x = torch.randn(B, T, H, device=dev)
+    N = 2 * H if which == "convh_glu" else H
+    w = torch.randn(N, H, Kw, device=dev) * 0.03
+    f, g = torch.empty(Kw, N, H, device=dev), torch.empty(Kw, H, N, device=dev)
+    call("bm_tc_weight_split", ptr(w), N, H, Kw, ptr(f), None, ptr(g), None, stream())
+    op = g if which == "convh_acc" else f
+    amax = torch.empty(4, device=dev)
+    call("bm_amax", ptr(x), x.numel(), ptr(amax[0:1]), stream())
+    call("bm_amax", ptr(op), op.numel(), ptr(amax[1:2]), stream())
+    hi, lo = torch.empty(op.shape, device=dev, dtype=torch.float16), torch.empty(op.shape, device=dev, dtype=torch.float16)
+    call("bm_f16_split", ptr(op), op.numel(), ptr(amax[1:2]), ptr(hi), ptr(lo), stream())
+    y = torch.zeros(B, T, H, device=dev)
+    h = torch.empty(B, T, 2 * H, device=dev) if which == "convh_glu" else None
+    stats = torch.empty(2 * H, device=dev, dtype=torch.float64)
+    dy = torch.randn(B, T, H, device=dev) * 1e-3
+    call("bm_amax", ptr(dy), dy.numel(), ptr(amax[2:3]), stream())
+    ws = torch.empty(int(lib.bm_tc_wgrad_conv_workspace(B, T, H, H, Kw)), device=dev)
+    dw = torch.empty(H, H, Kw, device=dev)
+    for _ in range(6):
+        if which == "convh":
+            call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, 0, B, T, H, H, Kw, 4, 1, 0, 0,
+                 0, ptr(y), None, None, ptr(stats), None, ptr(status), stream())
+        elif which == "convh_glu":
+            call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, 0, B, T, H, 2 * H, Kw, 1, 1,
+                 1, 0, 0, ptr(h), None, ptr(y), None, ptr(amax[3:4]), ptr(status), stream())
+        elif which == "convh_acc":
+            call("bm_tc_conv1d_f16", ptr(x), ptr(amax[0:1]), ptr(hi), ptr(lo), ptr(amax[1:2]), None, 1, B, T, H, H, Kw, 4, -1, 0,
+                 0, 0, ptr(y), None, None, None, None, ptr(status), stream())
+        else:
+            call("bm_tc_wgrad_conv_f16", ptr(dy), ptr(amax[2:3]), ptr(x), ptr(amax[0:1]), B, T, H, H, H, Kw, 4, ptr(ws), ptr(dw),
+                 ptr(status), stream())
+elif which in ("conv", "conv_glu", "conv_acc"):
     # -k regex:conv_pp_kernel: K3 forward with BatchNorm statistics | K4 GLU forward (h saved) | K3 data gradient, y += tile
     x = torch.randn(B, T, H, device=dev)
     N = 2 * H if which == "conv_glu" else H
