@@ -82,7 +82,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             prefetch_tmap(&tmA);
             prefetch_tmap(&tmBhi);
             prefetch_tmap(&tmBlo);
-            const int wsel_base = p.wsel ? p.wsel[b] * p.taps : 0;
+            int wsel = p.wsel ? p.wsel[b] : 0;
+            if (wsel < 0 || wsel >= p.n_wsets) {             // a subject / recording index outside the weight sets: the TMA would
+                if (p.err) atomicCAS(p.err, 0, 900);         // zero-fill silently; report it like the reference's gather would raise
+                wsel = 0;
+            }
+            const int wsel_base = wsel * p.taps;
             for (int it = 0; it < total; ++it) {
                 const int s = it % CV_STAGES;
                 const uint32_t ph = (it / CV_STAGES) & 1;

@@ -71,6 +71,10 @@ def check_tc_status(device=None) -> None:
     for dev, t in _status.items():
         if device is None or torch.device(device) == dev:
             code = int(t.item())
+            if code == 900:
+                t.zero_()
+                raise IndexError(f"a subject / recording index is outside the weight sets of the per-sample 1x1 layer on {dev} "
+                                 "(bm/models/common.py:57 raises there too)")
             if code != 0:
                 raise _lib.BmB200Error(f"a tcgen05 kernel reported a pipeline timeout (barrier code {code}) on {dev}")
 

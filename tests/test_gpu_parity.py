@@ -216,3 +216,33 @@ def test_standalone_merger_and_subject_layers_match_oracle():
     """ChannelMerger.forward / SubjectLayers.forward on their own (bm/models/common.py:334-362, 55-58) run the stage kernels."""
     from test_emulated_host_path import _standalone_modules_case
     _standalone_modules_case(torch.device("cuda"))
+
+
+@pytest.mark.gpu
+def test_subject_index_out_of_range_is_reported():
+    """A subject index beyond n_subjects: the reference's weight gather raises (bm/models/common.py:57).  The tensor-core
+    per-sample 1x1 kernel must not read outside its weight sets and reports it through the status word (no host sync in the
+    forward pass): `functional.check_tc_status()` raises IndexError."""
+    from oracle import bm_oracle
+    from brainmagick_b200 import functional as BF, synthetic
+    cfg = bm_oracle.Config(in_channels=208, out_channels=1024, n_subjects=27)
+    params = bm_oracle.init_state_dict(cfg, seed=21)
+    d = bm_oracle.synthetic_batch(cfg, batch=4, T=120, seed=9)
+    d["rec_positions"] = synthetic.normalised_positions(cfg.n_subjects, cfg.in_channels, (), seed=4)
+    model = _build_model(cfg, params).eval()
+    meg = d["meg"].cuda()
+    bad = d["subject_index"].clone()
+    bad[1] = cfg.n_subjects                                          # one past the last subject
+    batch = synthetic.make_batch(meg, bad.cuda(), d["rec_positions"], d["rec_of_sample"])
+    with torch.no_grad():
+        model(dict(meg=meg), batch)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        BF.check_tc_status()
+    BF.check_tc_status()                                             # the flag is cleared once reported
+    batch = synthetic.make_batch(meg, d["subject_index"].cuda(), d["rec_positions"], d["rec_of_sample"])
+    with torch.no_grad():
+        est = model(dict(meg=meg), batch)
+    torch.cuda.synchronize()
+    BF.check_tc_status()
+    assert torch.isfinite(est).all()
