@@ -53,6 +53,7 @@ SIGNATURES = {
     "bm_tc_conv1d_persistent": [P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P],
     "bm_amax": [P, L, P, P],
     "bm_f16_split": [P, L, P, P, P, P],
+    "bm_tc_weight_split_f16": [P, P, I, I, I, P, P, P, P, P],
     "bm_tc_conv1d_f16": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, I, P, P, P, P, P, P, P],
     "bm_col_stats": [P, L, I, P, P],
     "bm_channel_mask": [P, P, I, I, I, P, P],

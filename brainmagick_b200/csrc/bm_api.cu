@@ -997,6 +997,16 @@ extern "C" int bm_f16_split(const float* src, long long n, const float* amax, vo
     BM_CHECK_ARG(src && amax && hi && lo && n > 0);
     return tc::launch_f16_split(src, n, amax, hi, lo, ST(stream));
 }
+extern "C" int bm_tc_weight_split_f16(const float* w, const float* w_amax, int Cout, int Cin, int Kw, void* f_hi, void* f_lo,
+                                      void* g_hi, void* g_lo, bm_stream_t stream) {
+    BM_CHECK_ARG(w && w_amax && Cout > 0 && Cin > 0 && Kw > 0);
+    BM_CHECK_ARG((f_hi || g_hi) && (!f_hi == !f_lo) && (!g_hi == !g_lo));
+    tc::weight_split_f16_kernel<<<ew_grid((long long)Cout * Cin * Kw), 256, 0, ST(stream)>>>(
+        w, w_amax, reinterpret_cast<__half*>(f_hi), reinterpret_cast<__half*>(f_lo), reinterpret_cast<__half*>(g_hi),
+        reinterpret_cast<__half*>(g_lo), Cout, Cin, Kw);
+    BM_CHECK_LAUNCH();
+    return 0;
+}
 extern "C" int bm_tc_conv1d_f16(const float* x, const float* x_amax, const void* w_hi, const void* w_lo, const float* w_amax,
                                 const float* bias, int accumulate, int B, int T, int Cin, int Ntot, int Kw, int dilation,
                                 int sign, int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out,

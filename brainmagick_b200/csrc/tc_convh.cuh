@@ -442,6 +442,29 @@ __global__ void __launch_bounds__(256) f16_split_kernel(const float* __restrict_
     }
 }
 
+// W[o][i][j] (nn.Conv1d layout) * scale(amax) -> fp16 hi / lo pieces in the K-major layouts of bm_tc_weight_split:
+//   forward operand F[j][o][i], data-gradient operand G[j][i][o]; either pair may be NULL.  One launch per layer and step
+//   instead of re-layout + two splits.
+__global__ void __launch_bounds__(256) weight_split_f16_kernel(const float* __restrict__ W, const float* __restrict__ amax,
+                                                               __half* __restrict__ f_hi, __half* __restrict__ f_lo,
+                                                               __half* __restrict__ g_hi, __half* __restrict__ g_lo, int O, int I,
+                                                               int Kw) {
+    const float s = f16_scale_of(__ldg(amax));
+    const long long total = (long long)O * I * Kw;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % Kw);
+        const long long oi = idx / Kw;
+        const int i = (int)(oi % I), o = (int)(oi / I);
+        const float v = W[idx] * s;
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        const long long fi = ((long long)j * O + o) * I + i, gi = ((long long)j * I + i) * O + o;
+        if (f_hi) { f_hi[fi] = h; f_lo[fi] = l; }
+        if (g_hi) { g_hi[gi] = h; g_lo[gi] = l; }
+    }
+}
+
 inline bool make_tmap_f16(CUtensorMap* m, const void* base, const uint64_t* dims, const uint64_t* strides_b,
                           const uint32_t* box, CUtensorMapSwizzle swizzle) {
     PFN_bm_encodeTiled enc = get_encode_tiled();

@@ -177,29 +177,36 @@ class _Conv:
         self.fwd_tc, self.bwd_tc = fwd_tc, bwd_tc
         self.wgrad_tc = allow_tc and bool(lib.bm_tc_wgrad_supported(self.cout, self.cin))
         self.f_hi = self.f_lo = self.g_hi = self.g_lo = self.wf = self.wb = None
-        if fwd_tc or (bwd_tc and want_bwd):
-            # K-major operands: RAW fp32 for the persistent kernel (it derives the tf32 lo part itself), a pre-split tf32
-            # hi/lo pair for the single-CTA kernel
-            if fwd_tc:
+        self.f_h16 = self.g_h16 = self.w_amax = None
+        f16_f = USE_CONV_F16 and self.fwd_pp                      # operands of the F16-pipe kernel (tc_convh.cuh)
+        f16_g = USE_CONV_F16 and self.bwd_pp and want_bwd
+        if f16_f or f16_g:
+            # fp16 hi/lo pieces of w * 2^k (k from the weights' largest magnitude), straight into the K-major layouts:
+            # bm_amax + ONE re-layout-and-split launch per layer and step
+            self.w_amax = _empty((1,), w)
+            call("bm_amax", ptr(w), w.numel(), ptr(self.w_amax), st)
+            half = dict(device=w.device, dtype=torch.float16)
+            if f16_f:
+                self.f_h16 = (torch.empty((self.kw, self.cout, self.cin), **half), torch.empty((self.kw, self.cout, self.cin), **half))
+            if f16_g:
+                self.g_h16 = (torch.empty((self.kw, self.cin, self.cout), **half), torch.empty((self.kw, self.cin, self.cout), **half))
+            fh, fl = self.f_h16 if f16_f else (None, None)
+            gh, gl = self.g_h16 if f16_g else (None, None)
+            call("bm_tc_weight_split_f16", ptr(w), ptr(self.w_amax), self.cout, self.cin, self.kw, ptr(fh), ptr(fl), ptr(gh),
+                 ptr(gl), st)
+        need_f = fwd_tc and not f16_f                              # fp32 K-major operands for the TF32-pipe kernels
+        need_g = bwd_tc and want_bwd and not f16_g
+        if need_f or need_g:
+            # RAW fp32 for the persistent kernel (it derives the tf32 lo part itself), a pre-split tf32 hi/lo pair for the
+            # single-CTA kernel
+            if need_f:
                 self.f_hi = _empty((self.kw, self.cout, self.cin), w)
                 self.f_lo = None if self.fwd_pp else _empty((self.kw, self.cout, self.cin), w)
-            if bwd_tc and want_bwd:
+            if need_g:
                 self.g_hi = _empty((self.kw, self.cin, self.cout), w)
                 self.g_lo = None if self.bwd_pp else _empty((self.kw, self.cin, self.cout), w)
             call("bm_tc_weight_split", ptr(w), self.cout, self.cin, self.kw, ptr(self.f_hi), ptr(self.f_lo),
                  ptr(self.g_hi), ptr(self.g_lo), st)
-        # F16 pipe: the raw K-major weights once more as fp16 hi/lo pieces of w * 2^k (k from the weights' largest magnitude)
-        self.f_h16 = self.g_h16 = self.w_amax = None
-        if USE_CONV_F16 and (self.fwd_pp or (self.bwd_pp and want_bwd)):
-            src = self.f_hi if self.fwd_pp else self.g_hi
-            self.w_amax = _empty((1,), w)
-            call("bm_amax", ptr(src), src.numel(), ptr(self.w_amax), st)
-            for name, raw_w, on in (("f_h16", self.f_hi, self.fwd_pp), ("g_h16", self.g_hi, self.bwd_pp and want_bwd)):
-                if on:
-                    hi = torch.empty(raw_w.shape, device=w.device, dtype=torch.float16)
-                    lo = torch.empty(raw_w.shape, device=w.device, dtype=torch.float16)
-                    call("bm_f16_split", ptr(raw_w), raw_w.numel(), ptr(self.w_amax), ptr(hi), ptr(lo), st)
-                    setattr(self, name, (hi, lo))
         if (not fwd_tc) or (want_bwd and not bwd_tc):
             self.wf = _empty((self.kw, self.cin, self.cout), w) if not fwd_tc else None
             self.wb = _empty((self.kw, self.cout, self.cin), w) if (want_bwd and not bwd_tc) else None

@@ -275,6 +275,11 @@ int bm_tc_conv1d_persistent(const float* x, const float* w_raw, const float* bia
  * x_amax = the device float bm_amax wrote for x; same shape gate. */
 int bm_amax(const float* x, long long n, float* amax, bm_stream_t stream);
 int bm_f16_split(const float* src, long long n, const float* amax, void* hi, void* lo, bm_stream_t stream);
+/* bm_tc_weight_split_f16: bm_tc_weight_split + bm_f16_split in one launch: w [Cout,Cin,Kw] (nn.Conv1d layout) times
+ * scale(w_amax[0]) -> fp16 pieces of the forward operand f [Kw,Cout,Cin] and of the data-gradient operand g [Kw,Cin,Cout]
+ * (either pair may be NULL); w_amax = bm_amax over w. */
+int bm_tc_weight_split_f16(const float* w, const float* w_amax, int Cout, int Cin, int Kw, void* f_hi, void* f_lo, void* g_hi,
+                           void* g_lo, bm_stream_t stream);
 int bm_tc_conv1d_f16(const float* x, const float* x_amax, const void* w_hi, const void* w_lo, const float* w_amax,
                      const float* bias, int accumulate, int B, int T, int Cin, int Ntot, int Kw, int dilation, int sign,
                      int glu, int act, int out_tmajor, float* y, float* aux, float* glu_out, double* stats,

@@ -415,6 +415,17 @@ class Emulator:
         _v(hi, n).copy_(h)
         _v(lo, n).copy_((v - h.float()).to(torch.float16))
 
+    def bm_tc_weight_split_f16(self, w, w_amax, Cout, Cin, Kw, f_hi, f_lo, g_hi, g_lo, stream):
+        v = _v(w, Cout, Cin, Kw) * self._f16_scale(float(_v(w_amax, 1)))
+        h = v.to(torch.float16)
+        lo = (v - h.float()).to(torch.float16)
+        if f_hi is not None:
+            _v(f_hi, Kw, Cout, Cin).copy_(h.permute(2, 0, 1))
+            _v(f_lo, Kw, Cout, Cin).copy_(lo.permute(2, 0, 1))
+        if g_hi is not None:
+            _v(g_hi, Kw, Cin, Cout).copy_(h.permute(2, 1, 0))
+            _v(g_lo, Kw, Cin, Cout).copy_(lo.permute(2, 1, 0))
+
     def bm_tc_conv1d_f16(self, x, x_amax, w_hi, w_lo, w_amax, bias, accumulate, B, T, Cin, Ntot, Kw, dilation, sign, glu, act,
                          out_tmajor, y, aux, glu_out, stats, amax_out, status, stream):
         sx, sw = self._f16_scale(float(_v(x_amax, 1))), self._f16_scale(float(_v(w_amax, 1)))

@@ -173,6 +173,27 @@ def test_head_modes(B, T):
     assert rel_err(est.cpu(), ref.cpu()) < TOL
 
 
+def test_fused_weight_split_matches_two_steps(pipe):
+    """bm_tc_weight_split_f16 (one launch) == bm_tc_weight_split (re-layout) + bm_f16_split, bit for bit."""
+    if pipe != "f16":
+        pytest.skip("one run is enough")
+    call, ptr, stream = _abi()
+    torch.manual_seed(3)
+    for Cout, Cin, Kw in ((320, 320, 3), (640, 320, 3), (1024, 640, 1)):
+        w = torch.randn(Cout, Cin, Kw, device=DEV) * 0.02
+        f, g = _raw_operands(w)
+        amax = torch.empty(1, device=DEV)
+        call("bm_amax", ptr(w), w.numel(), ptr(amax), stream())
+        outs = [torch.empty(t.shape, device=DEV, dtype=torch.float16) for t in (f, f, g, g)]
+        call("bm_f16_split", ptr(f), f.numel(), ptr(amax), ptr(outs[0]), ptr(outs[1]), stream())
+        call("bm_f16_split", ptr(g), g.numel(), ptr(amax), ptr(outs[2]), ptr(outs[3]), stream())
+        fused = [torch.full(t.shape, float("nan"), device=DEV, dtype=torch.float16) for t in (f, f, g, g)]
+        call("bm_tc_weight_split_f16", ptr(w), ptr(amax), Cout, Cin, Kw, ptr(fused[0]), ptr(fused[1]), ptr(fused[2]),
+             ptr(fused[3]), stream())
+        for a, b in zip(outs, fused):
+            assert torch.equal(a, b)
+
+
 def test_producers_report_amax(pipe):
     """The elementwise kernels in front of a conv leave max |output| in `amax_out` (no separate pass over the tensor)."""
     if pipe != "f16":
