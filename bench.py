@@ -313,6 +313,9 @@ def run_b200(args):
         ms_per_step=ms_per_step, higher_is_better=True, scaling=scaling, vs_baseline=None, dtype="f32", data="synthetic",
         config=dict(workload=cfg["name"], batch_per_gpu=B, global_batch=B * world, sensors=C, T=T, F=F,
                     subjects=S, model="clip_conv (random init)", negatives="global (all-gather)" if world > 1 else "local",
+                    arithmetic="fp32-faithful (parity 1e-4): every product = 3 tensor-core MMAs over two-piece operands, fp32 "
+                               "accumulation in tensor memory -- fp16 pieces on tcgen05 kind::f16 (convs, weight gradients), "
+                               "tf32 pieces on kind::tf32 (CLIP, grouped / per-sample 1x1); elementwise in fp32",
                     l2=f"per-step working set (inputs {h2d / 1e6:.0f} MB + ~{act_gb:.1f} GB saved activations) >> 126 MB L2; "
                        "two input batches rotate",
                     last_loss=last_loss[0]),

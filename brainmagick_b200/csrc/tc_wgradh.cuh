@@ -20,7 +20,7 @@
 namespace bm {
 namespace tc {
 
-constexpr int WH_BK = 32, WH_STAGES = 3, WH_ASTAGES = 5, WH_THREADS = 672;        // 21 warps, see the kernel
+constexpr int WH_BK = 32, WH_STAGES = 4, WH_ASTAGES = 3, WH_THREADS = 672;        // 21 warps, see the kernel
 constexpr int WH_RAW_BYTES = WP_MAX_BLKS * WP_BLK_BYTES;        // 20 KB: this CTA's dY boxes, raw fp32
 constexpr int WH_BH_BYTES = WP_MAX_BLKS * 32 * WH_BK * 2;       // 10 KB: 160 K-major rows of 64 B (hi); the same again for lo
 constexpr int WH_STAGE_BYTES = WH_RAW_BYTES + 2 * WH_BH_BYTES;  // 40 KB
