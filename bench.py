@@ -286,8 +286,21 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_e2e = float(tt.item())
     h2d = sum(t.numel() * t.element_size() for t in host[0][:3])
+    # the same pinned -> device copies ALONE (nothing else running): the floor the interconnect puts under an e2e step
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        keep = [t.to(dev, non_blocking=True) for t in host[0][:3]]
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_ms_alone = c0.elapsed_time(c1) / 3
+    del keep
     e2e = dict(value=world * B / (ms_e2e / 1e3), unit="segments/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-               ms_per_step=ms_e2e, note="inputs copied from pinned host memory on a copy stream one step ahead; one loss.item() per step, read one step behind")
+               ms_per_step=ms_e2e, h2d_ms_alone=h2d_ms_alone, h2d_gb_per_s_alone=h2d / h2d_ms_alone / 1e6,
+               note="inputs copied from pinned host memory on a copy stream one step ahead; one loss.item() per step, read one "
+                    "step behind; h2d_ms_alone = the step's host->device copies with nothing else running (when it approaches "
+                    "ms_per_step the interconnect, not the GPU, paces the e2e step)")
 
     # ---- rooflines: the dominant kernel (K3 dilated conv) + the other kernels the north star names --------
     roofline = None
