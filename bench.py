@@ -195,19 +195,29 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     host_ms = [0.0]
+    per_step = []
 
     def timed(n_steps, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t0 = time.perf_counter()
+        marks = []
         for i in range(n_steps):
             fn(i)
+            ev = torch.cuda.Event(enable_timing=True)               # per-step boundaries (diagnostic: drift inside the region)
+            ev.record()
+            marks.append(ev)
             if i == 1:                     # host time to ENQUEUE a step, from the first two steps after the barrier: the launch
                 host_ms[0] = (time.perf_counter() - t0) * 1e3 / 2        # queue is still far from full, so nothing blocks
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        prev = e0
+        per_step.clear()
+        for ev in marks:
+            per_step.append(round(prev.elapsed_time(ev), 3))
+            prev = ev
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -227,6 +237,7 @@ def run_b200(args):
     launches0 = _lib.launch_count()
     ms_total = timed(args.steps, resident_step)
     launches = _lib.launch_count() - launches0
+    step_ms = list(per_step)
     host_ms_value = host_ms[0]        # >= ms_per_step would mean the host, not the GPU, paces the step
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms_total / args.steps
@@ -332,7 +343,7 @@ def run_b200(args):
                     l2=f"per-step working set (inputs {h2d / 1e6:.0f} MB + ~{act_gb:.1f} GB saved activations) >> 126 MB L2; "
                        "two input batches rotate",
                     last_loss=last_loss[0]),
-        host_enqueue_ms_per_step=host_ms_value,
+        host_enqueue_ms_per_step=host_ms_value, step_ms=step_ms,
         clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline, also=also)
     print(json.dumps(out))
 
