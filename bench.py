@@ -261,7 +261,13 @@ def run_b200(args):
                         subj_h.to(dev, non_blocking=True), subj_l)
             ready[k].record(copy_stream)
 
-    pending = [None]
+    # device -> host read of a step's result EVERY step, pipelined by one step: the loss is copied into pinned host memory
+    # right behind the step that produced it and the host waits for THAT copy's event while the next step is already queued
+    # (like a training loop that logs the previous iteration's loss).  `loss.item()` would do the same copy but then
+    # synchronise the whole stream -- including the step just enqueued -- and leave the GPU idle between the ~60 tiny
+    # kernels at the start of the next forward pass while the host catches up (measured: +1.3-1.8 ms per step).
+    loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
     def e2e_run(n_steps):
         main = torch.cuda.current_stream()
@@ -276,13 +282,14 @@ def run_b200(args):
             meg_d, feats_d, subj_d, subj_l = slots[k]
             loss = step(meg_d, feats_d, subj_d, subj_l)
             consumed[k].record(main)
-            # device -> host read of a step's result EVERY step, pipelined by one step (the host reads step i-1's loss
-            # while step i is already queued, like a training loop that logs the previous iteration's loss)
-            if pending[0] is not None:
-                last_loss[0] = pending[0].item()
-            pending[0] = loss
-        last_loss[0] = pending[0].item()
-        pending[0] = None
+            loss_host[k].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_ready[k].record(main)
+            if i > 0:
+                loss_ready[1 - k].synchronize()                          # step i-1's loss has landed in host memory
+                last_loss[0] = float(loss_host[1 - k][0])
+        k = (n_steps - 1) % 2
+        loss_ready[k].synchronize()
+        last_loss[0] = float(loss_host[k][0])
 
     e2e_run(min(2, args.warmup))
     barrier()
@@ -309,8 +316,8 @@ def run_b200(args):
     del keep
     e2e = dict(value=world * B / (ms_e2e / 1e3), unit="segments/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                ms_per_step=ms_e2e, h2d_ms_alone=h2d_ms_alone, h2d_gb_per_s_alone=h2d / h2d_ms_alone / 1e6,
-               note="inputs copied from pinned host memory on a copy stream one step ahead; one loss.item() per step, read one "
-                    "step behind; h2d_ms_alone = the step's host->device copies with nothing else running (when it approaches "
+               note="inputs copied from pinned host memory on a copy stream one step ahead; the loss of every step is copied to "
+                    "pinned host memory and read by the host one step behind (event wait, not a stream synchronise); h2d_ms_alone = the step's host->device copies with nothing else running (when it approaches "
                     "ms_per_step the interconnect, not the GPU, paces the e2e step)")
 
     # ---- rooflines: the dominant kernel (K3 dilated conv) + the other kernels the north star names --------
