@@ -255,6 +255,10 @@ def run_b200(args):
     def issue_copy(i):
         meg_h, feats_h, subj_h, subj_l = host[i % n_host]
         k = i % 2
+        if diag == "no_copy":                          # diagnostic only: the e2e loop without the host->device copies
+            slots[k] = resident[i % n_host] + (subj_l,)
+            ready[k].record(copy_stream)
+            return
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[k])                         # the step that used this slot has finished
             slots[k] = (meg_h.to(dev, non_blocking=True), feats_h.to(dev, non_blocking=True),
@@ -266,6 +270,7 @@ def run_b200(args):
     # (like a training loop that logs the previous iteration's loss).  `loss.item()` would do the same copy but then
     # synchronise the whole stream -- including the step just enqueued -- and leave the GPU idle between the ~60 tiny
     # kernels at the start of the next forward pass while the host catches up (measured: +1.3-1.8 ms per step).
+    diag = os.environ.get("BM_E2E_DIAG", "")
     loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -280,11 +285,13 @@ def run_b200(args):
             k = i % 2
             main.wait_event(ready[k])
             meg_d, feats_d, subj_d, subj_l = slots[k]
+            if diag == "compute_on_resident":          # diagnostic only (BM_E2E_DIAG): copies still run, the step ignores them
+                meg_d, feats_d, subj_d = resident[i % n_host]
             loss = step(meg_d, feats_d, subj_d, subj_l)
             consumed[k].record(main)
             loss_host[k].copy_(loss.detach().reshape(1), non_blocking=True)
             loss_ready[k].record(main)
-            if i > 0:
+            if i > 0 and diag != "no_readback":
                 loss_ready[1 - k].synchronize()                          # step i-1's loss has landed in host memory
                 last_loss[0] = float(loss_host[1 - k][0])
         k = (n_steps - 1) % 2
