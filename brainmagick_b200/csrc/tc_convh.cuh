@@ -18,7 +18,6 @@
 //       the weights change once per step, so bm_f16_split prepares them once and no warp converts them here
 //     leader CTA, one elected lane: 12 x tcgen05.mma.cta_group::2.kind::f16 (M = 256, N = nh <= 160, K = 16; A from TMEM)
 //   TMEM: [0, 320) accumulator (two column halves of nh), [320 + 32 s, +32) x stage s (hi pairs | lo pairs).
-//   22 warps: TMA, MMA, 4 converters, 16 epilogue (4 per TMEM lane quarter); 4 operand stages.
 #pragma once
 #include <cuda_fp16.h>
 #include <cstring>
@@ -27,11 +26,11 @@
 namespace bm {
 namespace tc {
 
-constexpr int HP_BM = 128, HP_BK = 32, HP_STAGES = 4, HP_EPI_WARPS = 16, HP_THREADS = (6 + HP_EPI_WARPS) * 32;
+constexpr int HP_BM = 128, HP_BK = 32, HP_STAGES = 5, HP_THREADS = 448;
 constexpr int HP_A_BYTES = HP_BM * HP_BK * 4;                        // 16 KB fp32
 constexpr int HP_BQ_BYTES = (PP_MAX_NH / 2) * HP_BK * 2;             // 5 KB: half of one column half, fp16
 constexpr int HP_STAGE_BYTES = HP_A_BYTES + 4 * HP_BQ_BYTES;         // 36 KB: x | hi h0 | hi h1 | lo h0 | lo h1
-constexpr int HP_SMEM_BYTES = HP_STAGES * HP_STAGE_BYTES + HP_EPI_WARPS * PP_EPI_BUF + PP_STATS_BYTES + 1024;
+constexpr int HP_SMEM_BYTES = HP_STAGES * HP_STAGE_BYTES + PP_EPI_WARPS * PP_EPI_BUF + PP_STATS_BYTES + 1024;
 constexpr int HP_ACC_COLS = 2 * PP_MAX_NH, HP_A_COLS = HP_BK;        // 16 packed hi columns + 16 packed lo columns
 constexpr int HP_TARGET_EXP = 14;                                    // scaled maximum in [2^14, 2^15)
 
@@ -127,7 +126,7 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     uint8_t* epi_smem = smem + HP_STAGES * HP_STAGE_BYTES;
-    double* stats_smem = reinterpret_cast<double*>(epi_smem + HP_EPI_WARPS * PP_EPI_BUF);
+    double* stats_smem = reinterpret_cast<double*>(epi_smem + PP_EPI_WARPS * PP_EPI_BUF);
 
     const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
     const int ntiles = skip ? 0 : p.mtiles * p.ntn;
@@ -145,7 +144,7 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(&empty_bar[s], 1);
         }
         mbar_init(&acc_full, 1);
-        mbar_init(&acc_empty, 2 * HP_EPI_WARPS);
+        mbar_init(&acc_empty, 2 * PP_EPI_WARPS);
         fence_barrier_init();
     }
     if (p.stats)
@@ -265,13 +264,9 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ------------------------------------------------ epilogue: FOUR warps per TMEM lane quarter ---------------------
-        // The accumulator is single-buffered (320 of the 512 TMEM columns): the next tile's MMAs wait until every epilogue
-        // warp has READ its columns.  A warp reads a 32-column chunk, processes and stores it, then reads its next one, so
-        // the release comes after (chunks per warp - 1) rounds of processing: with two warps per quarter (5 chunks each)
-        // that bubble was ~3 us of every 21.8 us tile; four warps per quarter take 2-3 chunks each (round-robin).
-        const int ew = warp - 6;                                     // 0..15
-        const int q = warp & 3, cset = ew >> 2;                      // cset 0..3: chunks cset, cset + 4, ...
+        // ------------------------------------------------ epilogue: two warps per TMEM lane quarter ---------------------
+        const int ew = warp - 6;                                     // 0..7
+        const int q = warp & 3, cset = ew >> 2;
         const int row = q * 32 + lane;
         const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
         uint8_t* buf = epi_smem + ew * PP_EPI_BUF;
@@ -291,18 +286,14 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             if (glu) {
                 const int nch = nh / 32;
+                const int ch_begin = cset == 0 ? 0 : (nch + 1) / 2, ch_end = cset == 0 ? (nch + 1) / 2 : nch;
                 const int c0 = n_tile * nh;
-                if (cset >= nch) {                                    // no chunk for this warp: nothing to read, release at once
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
-                }
 #pragma unroll 1
-                for (int c = cset; c < nch; c += 4) {
+                for (int c = ch_begin; c < ch_end; ++c) {
                     float a[32], g[32];
                     tmem_ld32(tq + c * 32, a);
                     tmem_ld32(tq + nh + c * 32, g);
-                    if (c + 4 >= nch) {                               // last TMEM read of this thread: release the accumulator
+                    if (c + 1 == ch_end) {                            // last TMEM read of this thread: release the accumulator
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
@@ -331,20 +322,15 @@ conv_hp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     pp_stage_store(buf, a, lane, &tmO, c0 + c * 32, r32, false);
                 }
             } else {
-                const int ncol0 = 0;
-                const int n0 = n_tile * 2 * nh;
-                const int nch = 2 * nh / 32;                          // chunks of both column halves
+                const int ncol0 = cset * nh;
+                const int n0 = n_tile * 2 * nh + ncol0;
+                const int nch = nh / 32;
                 const int prow = row0 + row;
-                if (cset >= nch) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
-                }
 #pragma unroll 1
-                for (int c = cset; c < nch; c += 4) {
+                for (int c = 0; c < nch; ++c) {
                     float v[32];
                     tmem_ld32(tq + ncol0 + c * 32, v);
-                    if (c + 4 >= nch) {
+                    if (c + 1 == nch) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&acc_empty), 0));
