@@ -252,6 +252,13 @@ def run_b200(args):
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
+    # The big input (features, 377 MB) is split into chunks issued round-robin on SEVERAL copy streams: with one stream the
+    # copies of a step reached 55 GB/s alone but only 18-25 GB/s while the step's kernels were running on some boxes of the
+    # pool, which made the e2e step copy-bound (24.8 ms against 16.4 ms of compute); BM_E2E_COPY_STREAMS=1 restores that.
+    n_cs = max(1, int(os.environ.get("BM_E2E_COPY_STREAMS", "4")))
+    copy_streams = [copy_stream] + [torch.cuda.Stream(device=dev) for _ in range(n_cs - 1)]
+    joined = [[torch.cuda.Event() for _ in range(n_cs)] for _ in range(2)]
+
     def issue_copy(i):
         meg_h, feats_h, subj_h, subj_l = host[i % n_host]
         k = i % 2
@@ -261,8 +268,25 @@ def run_b200(args):
             return
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[k])                         # the step that used this slot has finished
-            slots[k] = (meg_h.to(dev, non_blocking=True), feats_h.to(dev, non_blocking=True),
-                        subj_h.to(dev, non_blocking=True), subj_l)
+            feats_d = torch.empty(feats_h.shape, device=dev, dtype=feats_h.dtype)
+            meg_d = meg_h.to(dev, non_blocking=True)
+            subj_d = subj_h.to(dev, non_blocking=True)
+            start = torch.cuda.Event()
+            start.record(copy_stream)
+        rows = feats_h.shape[0]
+        per = -(-rows // (2 * n_cs))
+        for c, r0 in enumerate(range(0, rows, per)):
+            cs = copy_streams[c % n_cs]
+            with torch.cuda.stream(cs):
+                if cs is not copy_stream and r0 < per * n_cs:
+                    cs.wait_event(start)                                # the destination exists and its slot is free
+                feats_d[r0:r0 + per].copy_(feats_h[r0:r0 + per], non_blocking=True)
+        for j, cs in enumerate(copy_streams):
+            joined[k][j].record(cs)
+        with torch.cuda.stream(copy_stream):
+            for j in range(1, n_cs):
+                copy_stream.wait_event(joined[k][j])
+            slots[k] = (meg_d, feats_d, subj_d, subj_l)
             ready[k].record(copy_stream)
 
     # device -> host read of a step's result EVERY step, pipelined by one step: the loss is copied into pinned host memory
