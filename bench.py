@@ -252,10 +252,11 @@ def run_b200(args):
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    # The big input (features, 377 MB) is split into chunks issued round-robin on SEVERAL copy streams: with one stream the
-    # copies of a step reached 55 GB/s alone but only 18-25 GB/s while the step's kernels were running on some boxes of the
-    # pool, which made the e2e step copy-bound (24.8 ms against 16.4 ms of compute); BM_E2E_COPY_STREAMS=1 restores that.
-    n_cs = max(1, int(os.environ.get("BM_E2E_COPY_STREAMS", "4")))
+    # The big input (features, 377 MB) is split into chunks issued round-robin on BM_E2E_COPY_STREAMS copy streams (default 2).
+    # The step's copies reach 55 GB/s alone (8.2 ms); on one box of the pool they fell to ~18 GB/s while the step's kernels
+    # were running and the e2e step became copy-bound (24.8 ms against 16.4 ms of compute) -- not reproduced on other boxes,
+    # where 1, 2 and 4 streams all give e2e = step + 1.2-1.5 ms (pipeline fill of the first batch + the loss read-back).
+    n_cs = max(1, int(os.environ.get("BM_E2E_COPY_STREAMS", "2")))
     copy_streams = [copy_stream] + [torch.cuda.Stream(device=dev) for _ in range(n_cs - 1)]
     joined = [[torch.cuda.Event() for _ in range(n_cs)] for _ in range(2)]
 
