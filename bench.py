@@ -174,6 +174,8 @@ def run_b200(args):
     resident = [tuple(t.to(dev) for t in hb[:3]) for hb in host]
     recs = [synthetic.SyntheticRecording(s, positions[s]) for s in range(S)]
 
+    diag_step = os.environ.get("BM_STEP_DIAG", "")
+
     def make_batch(meg_d, subj_d, subj_h):
         return synthetic.SyntheticBatch(meg_d, subj_d, [recs[s] for s in subj_h])
 
@@ -184,7 +186,7 @@ def run_b200(args):
         est = model(dict(meg=meg_d), batch)
         loss = clip(est, feats_d, mask)
         loss.backward()
-        if world > 1:
+        if world > 1 and diag_step != "no_allreduce":      # (BM_STEP_DIAG: diagnostic only)
             distrib.sync_gradients(model.parameters())
         opt.step()
         return loss
@@ -384,7 +386,7 @@ def run_b200(args):
                     last_loss=last_loss[0]),
         host_enqueue_ms_per_step=host_ms_value, step_ms=step_ms,
         clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roofline, cpu_baseline=cpu_baseline, also=also)
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 def also_measured(cfg, model, clip, make_batch, resident, host, n_host, mask, dev, B, iters=5):
@@ -729,12 +731,30 @@ def run_reference(args):
                          f"{threads} threads set with torch.set_num_threads (also under torchrun)"),
         cpu_baseline=res, also=also,
         e2e=dict(value=res["value"], unit="segments/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(out))
+    emit(json.dumps(out))
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: str) -> None:
+    """The result line, on the process's ORIGINAL stdout."""
+    data = (line + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line + "\n")
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
-    # NCCL's own log lines (its version banner, NCCL_DEBUG=INFO output) go to stdout by default: keep stdout for the ONE JSON line
+    # stdout carries ONE JSON line.  Libraries write there too (NCCL's version banner at communicator creation, NCCL_DEBUG
+    # output): file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -750,7 +770,7 @@ def main():
     args = ap.parse_args()
     if args.next_rows:
         from profiles import bench_next_rows      # its CPU legs are this file's cpu_baseline leg for those rows
-        bench_next_rows.main()
+        bench_next_rows.main(emit=emit)
         return
     if args.impl == "reference":
         run_reference(args)

@@ -196,7 +196,7 @@ def bench_deepmel():
                                   sample=f"{nb} segments, 1 step"))
 
 
-def main():
+def main(emit=print):
     out = dict(device=torch.cuda.get_device_name(0))
     for name, fn in (("prep", bench_prep), ("deepmel", bench_deepmel), ("retrieval", bench_retrieval)):
         try:
@@ -207,7 +207,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "next_rows.json"), "w") as f:
         json.dump(out, f, indent=1)
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 if __name__ == "__main__":
