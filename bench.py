@@ -751,6 +751,10 @@ def main():
     # stdout carries ONE JSON line.  Libraries write there too (NCCL's version banner at communicator creation, NCCL_DEBUG
     # output): file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor.
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # The step uses ~7 streams per rank (main, weight-gradient side stream, candidate gather, NCCL, input copies).  With
+    # the default 8 hardware work queues streams alias: at N = 2 the resident loop then showed 20-50 ms stalls every few
+    # steps (a spinning symmetric-memory barrier kernel ahead of an NCCL kernel in the same queue); none with 32 queues.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
