@@ -133,9 +133,13 @@ class _ConvSequenceFn(torch.autograd.Function):
         return out_cm
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dout):
         plan: SequencePlan = ctx.plan
         s = ctx.saved
+        if s is None:
+            raise RuntimeError("brainmagick_b200.ConvSequence: backward through the graph a second time -- the saved "
+                               "activations are released by the first backward; retain_graph is not supported")
         B, C0, Cp, T, C_last = ctx.dims
         depth = len(plan.dilations)
         rows = B * T

@@ -644,9 +644,13 @@ class _EncoderFn(torch.autograd.Function):
         return est
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dest):
         plan: EncoderPlan = ctx.plan
         s = ctx.saved
+        if s is None:
+            raise RuntimeError("brainmagick_b200.SimpleConv: backward through the graph a second time -- the saved activations "
+                               "(~5 GB at B=256) are released by the first backward; retain_graph is not supported")
         B, C, T, R, O, P, IL, S, D, Dp, H, F = ctx.dims
         depth = len(plan.dilations)
         st = stream()

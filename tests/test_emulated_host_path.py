@@ -414,3 +414,26 @@ def _standalone_modules_case(device):
 def test_standalone_merger_and_subject_layers_on_the_emulator():
     with abi_emulator.emulated():
         _standalone_modules_case(torch.device("cpu"))
+
+
+def test_second_backward_raises_a_clear_error():
+    """The fused encoder releases its saved activations in backward (ctx.saved, not save_for_backward): a second backward
+    through the same graph must say so instead of failing with an opaque TypeError."""
+    import brainmagick_b200 as bb
+    from brainmagick_b200 import synthetic
+    cfg, train, t = load_golden(GOLDEN_CASES[0])
+    model = bb.SimpleConv(
+        in_channels=dict(meg=cfg.in_channels), out_channels=cfg.out_channels, hidden=dict(meg=cfg.hidden),
+        depth=cfg.depth, dilation_period=cfg.dilation_period, kernel_size=cfg.kernel_size, skip=True,
+        subject_layers=True, subject_dim=0, complex_out=True, glu=cfg.glu, glu_context=cfg.glu_context, merger=True,
+        initial_linear=cfg.initial_linear, merger_channels=cfg.merger_channels, gelu=True, batch_norm=True,
+        merger_pos_dim=cfg.merger_pos_dim, merger_dropout=cfg.merger_dropout, n_subjects=cfg.n_subjects)
+    model.load_state_dict({k[2:]: v for k, v in t.items() if k.startswith("p.")}, strict=True)
+    model.train(True)
+    batch = synthetic.make_batch(t["meg"], t["subject_index"], t["rec_positions"], t["rec_of_sample"])
+    with abi_emulator.emulated():
+        est = model(dict(meg=t["meg"]), batch)
+        loss = est.square().mean()
+        loss.backward(retain_graph=True)
+        with pytest.raises(RuntimeError, match="second time"):
+            loss.backward()
