@@ -47,3 +47,31 @@ def test_ablation_rows_run_through_the_host_path(override):
     if "complex_out" in override:
         assert not any("head" in n for n in names)
         assert names.count("bm_bn_gelu_skip_fwd") == 9                # the 10th layer is a bare convolution
+
+
+def test_group_layout_matches_bincount_without_a_sync():
+    """functional.group_layout = argsort + CSR offsets of the subject / recording groups with static shapes (torch.bincount
+    sizes its output from the data: a device->host sync in the middle of the backward pass)."""
+    import torch
+    from brainmagick_b200.functional import group_layout
+    g = torch.Generator().manual_seed(0)
+    for n_groups, B in ((27, 256), (4, 7), (175, 1024), (3, 1)):
+        idx = torch.randint(0, n_groups, (B,), generator=g, dtype=torch.int32)
+        order, off = group_layout(idx, n_groups)
+        want = torch.zeros(n_groups + 1, dtype=torch.int64)
+        want[1:] = torch.cumsum(torch.bincount(idx.long(), minlength=n_groups), 0)
+        assert off.dtype == torch.int32 and torch.equal(off.long(), want)
+        assert torch.equal(order.long(), torch.argsort(idx.long(), stable=True))
+        for s in range(n_groups):
+            assert (idx[order.long()[off[s]:off[s + 1]]] == s).all()
+
+
+def test_weight_preparation_is_two_launches_per_layer():
+    """F16 pipe: per conv layer and step, one bm_amax over the nn.Conv1d weight and ONE re-layout-and-split launch."""
+    calls = abi_trace.simpleconv_step(abi_trace.CONFIGS["full"], True)
+    names = [c[0] for c in calls]
+    n_f16_layers = names.count("bm_tc_weight_split_f16")
+    assert n_f16_layers >= 17                                   # 10 conv + 5 GLU + 2 head (+ the sensor-chain 1x1 convs)
+    assert names.count("bm_f16_split") == 0                      # the two-step preparation is not used by the training step
+    # one bm_amax per prepared weight set + the few activation tensors whose producer does not report its maximum
+    assert n_f16_layers <= names.count("bm_amax") <= n_f16_layers + 10
