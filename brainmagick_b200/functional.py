@@ -144,6 +144,8 @@ def group_layout(index: torch.Tensor, n_groups: int):
 def tensor_amax(x: torch.Tensor) -> torch.Tensor:
     """max |x| as a device float [1] (bm_amax: one pass over x): the F16 pipe's per-tensor scale comes from it."""
     cell = _empty((1,), x)
+    if x.data_ptr() % 16:                       # the kernel reads float4: a view at an odd offset goes through an aligned copy
+        x = x.clone()
     call("bm_amax", ptr(x), x.numel(), ptr(cell), stream())
     return cell
 
