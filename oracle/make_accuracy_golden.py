@@ -7,7 +7,7 @@ oracle cannot train at this size in seconds on the GPU box:
 The oracle (oracle/bm_oracle.py, pinned to the verbatim reference by tests/test_oracle_vs_reference.py) trains from a seeded
 state_dict on the learnable synthetic retrieval task (oracle/accuracy_task.py) with a fixed batch order and spatial-dropout
 centres, then is evaluated with scripts/run_eval_probs.py:237-264 semantics (top-k over all held-out candidates).
-tests/test_gpu_accuracy.py::test_top10_accuracy_parity_at_baseline_widths regenerates the same task and schedule from the same
+tests/test_gpu_zy_accuracy.py::test_top10_accuracy_parity_at_baseline_widths regenerates the same task and schedule from the same
 seeds, trains the CUDA drop-in, and compares top-10 / top-1 accuracy and the loss trajectory with the numbers stored here."""
 from __future__ import annotations
 
